@@ -1,0 +1,178 @@
+/* qb200.h - C ABI of the B200-native LBG codebook-training / index-assignment path.
+ *
+ * This is the drop-in boundary for the hot path of coodie/quant: everything the reference does
+ * between "RGB bytes of an image" and "(codebook, per-block indices, distortion)" - i.e.
+ *   getBlocksAsVectorsFromImage        /root/reference/src/Compressor.cpp:31-62
+ *   LBGQuantizer::quantize             /root/reference/src/Quantizer.cpp:121-143
+ *     Solution::assignCodeVectors      /root/reference/src/Quantizer.cpp:24-32  (+ src/KDTree.cpp)
+ *     Solution::updateDistortion       /root/reference/src/Quantizer.cpp:9-22
+ *     Solution::fixCodeVectors         /root/reference/src/Quantizer.cpp:72-87
+ *     split step                       /root/reference/src/Quantizer.cpp:134-138
+ * runs behind these entry points on one B200 (sm_100a).  Plain pointers and sizes only; no C++
+ * or torch types; no exceptions cross this boundary.  The caller owns every host buffer; the
+ * library owns device memory inside an opaque context.  A context is not re-entrant: use one per
+ * host thread / per GPU.  There is NO CPU fallback: without a usable CUDA device qb200_create
+ * fails with QB200_ERR_NODEV.
+ *
+ * Multi-GPU: each process (one per GPU) gives its context a SHARD of the image's block rows
+ * (qb200_set_image_shard) and passes an all-reduce callback to qb200_train; the library calls it
+ * once per split level on K*(dim+2) 64-bit integers that live in device memory.
+ */
+#ifndef QB200_H
+#define QB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_VERSION 100 /* major*100 + minor */
+
+/* Status codes (0 = success, negative = failure; qb200_last_error gives the text). */
+#define QB200_OK 0
+#define QB200_ERR_ARG (-1)    /* bad argument (null pointer, empty training set, nbits out of range...) */
+#define QB200_ERR_NODEV (-2)  /* no CUDA device / device is not sm_100 */
+#define QB200_ERR_CUDA (-3)   /* a CUDA runtime call or kernel failed */
+#define QB200_ERR_OOM (-4)    /* device or pinned-host allocation failed */
+#define QB200_ERR_STATE (-5)  /* call sequence error (e.g. train before set_image) */
+#define QB200_ERR_COMM (-6)   /* the all-reduce callback reported failure */
+
+/* Colour spaces: same integer values as the reference's `enum class ColorSpaces`
+ * (/root/reference/include/ColorSpace.hpp:6).  CIE1931 (2) is rejected with QB200_ERR_ARG. */
+#define QB200_CS_NORMAL 0 /* value = (double)(int8)byte        src/ColorSpace.cpp:4-6   */
+#define QB200_CS_SCALED 1 /* value = ((int8)byte + 128.0)/255  src/ColorSpace.cpp:16-21 */
+
+/* Training schedule. */
+#define QB200_MODE_PARITY 0 /* the reference's HEAD schedule: ONE assignment per split level,
+                               no empty-cell repair (src/Quantizer.cpp:98-108). */
+
+typedef struct qb200_ctx qb200_ctx;
+
+/* Per-level report filled by qb200_train (all optional diagnostics). */
+typedef struct qb200_level_report {
+  uint32_t K;             /* codebook size of this level */
+  uint32_t flagged;       /* queries whose FP32 top-2 gap was inside the error margin (this rank) */
+  uint32_t changed;       /* of those, how many the exact FP64 resolver moved to another index */
+  uint32_t dead_cells;    /* cells with no member after the (global) reduction */
+  uint32_t kd_depth;      /* depth of the nanoflann-order KD tree built for the resolver */
+  float ms_assign;        /* device time of the FP32 assignment kernel */
+  float ms_resolve;       /* device time of the exact resolver kernel */
+  float ms_accumulate;    /* device time of the per-cell statistics kernel */
+  double distortion_pre;  /* updateDistortion() before fixCodeVectors (src/Quantizer.cpp:100) */
+  double distortion_post; /* updateDistortion() after fixCodeVectors  (src/Quantizer.cpp:104) */
+} qb200_level_report;
+
+/* In-place sum all-reduce over `count` unsigned 64-bit integers at device address `dev_u64`.
+ * On entry the data is complete (the library has synchronised its stream); on return the reduced
+ * values must be visible to later work on `cuda_stream`.  Two's-complement wrap-around makes the
+ * same call correct for the signed sums.  Return 0 on success. */
+typedef int (*qb200_allreduce_fn)(void *dev_u64, size_t count, void *cuda_stream, void *user);
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int qb200_version(void);
+/* Creates a context on CUDA device `device`.  Replaces nothing in the reference (it has no
+ * device state); it is the analogue of constructing `Solution` (src/Quantizer.cpp:89-96). */
+int qb200_create(int device, qb200_ctx **out);
+void qb200_destroy(qb200_ctx *ctx);
+/* Last error text of this context (or of the failed qb200_create when ctx == NULL). */
+const char *qb200_last_error(const qb200_ctx *ctx);
+/* Run all device work on an existing CUDA stream (cudaStream_t); NULL restores the context's own. */
+int qb200_set_stream(qb200_ctx *ctx, void *cuda_stream);
+int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                      size_t *total_mem);
+
+/* ---- training set ------------------------------------------------------------------------
+ * Replaces getBlocksAsVectorsFromImage (src/Compressor.cpp:31-62).  The N x dim double vectors
+ * are never materialised: kernels gather the raw bytes with the reference's layout rule (pixel
+ * index x*ySize + y, vector index i*hBlocks + j, y-overflow wraps, past-the-end elements are 0.0).
+ * `rgb` holds n_images consecutive images of xSize*ySize*3 bytes each (n_images >= 1); the
+ * training set is the concatenation of their block vectors.  rgb_is_device != 0 means `rgb` is a
+ * device pointer that stays valid until the next set_image/destroy (no copy is made). */
+int qb200_set_image(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth,
+                    int blockHeight, int colorspace, int n_images, int rgb_is_device);
+/* Same for one image, but this context only owns block rows [row_begin, row_end) of the
+ * wBlocks = ceil(xSize/blockWidth) rows (multi-GPU sharding).  `rgb` is the WHOLE
+ * host image; only the byte range the shard needs is copied to the device. */
+int qb200_set_image_shard(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth,
+                          int blockHeight, int colorspace, size_t row_begin, size_t row_end);
+/* Training set given as an N x dim matrix of lattice bytes (row-major): element value is
+ * decoded with `colorspace` exactly like an image byte.  Used by the generic
+ * AbstractQuantizer::quantize(vector<Vector>) entry (include/Quantizer.hpp:12-14). */
+int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors, int dim,
+                         int colorspace, int bytes_is_device);
+/* Number of vectors this context holds / their dimension. */
+size_t qb200_num_vectors(const qb200_ctx *ctx);
+int qb200_dim(const qb200_ctx *ctx);
+
+/* ---- the hot path -------------------------------------------------------------------------
+ * qb200_train replaces LBGQuantizer::quantize (src/Quantizer.cpp:121-143): initial codevector =
+ * mean, then nbits levels of {split by (1 + 0.2) / (1 - 0.2), assign, accumulate, fix}.
+ *   n_total       total number of vectors over all ranks (0 = this context's own count)
+ *   allreduce     NULL for a single GPU
+ *   codebook_out  K*dim doubles (K = 1 << nbits), colour-space domain, as quantize() returns
+ *   distortion_out  last updateDistortion() value (src/Quantizer.cpp:142)
+ *   reports       nbits entries or NULL
+ * The assignment of the LAST level (w.r.t. that level's pre-fix codebook, src/Quantizer.cpp:142)
+ * stays on the device; fetch it with qb200_get_assign. */
+int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_total,
+                qb200_allreduce_fn allreduce, void *allreduce_user, double *codebook_out,
+                double *distortion_out, qb200_level_report *reports);
+/* Copies this context's assignment (one uint32 per vector) to host memory. */
+int qb200_get_assign(qb200_ctx *ctx, uint32_t *assign_out);
+/* Same, widened to the reference's std::vector<size_t> element type. */
+int qb200_get_assign_u64(qb200_ctx *ctx, uint64_t *assign_out);
+/* Device address of the assignment array (uint32[num_vectors]); valid until the next call that
+ * changes the training set. */
+int qb200_assign_device_ptr(qb200_ctx *ctx, void **dev_ptr);
+
+/* One level's worth of work against a caller-supplied codebook (K x dim doubles, colour-space
+ * domain): Solution::assignCodeVectors (src/Quantizer.cpp:24-32, i.e. KDTree(dim, cb) +
+ * nearestNeighbour per vector, src/KDTree.cpp:16-29) followed by the integer statistics
+ * fixCodeVectors/updateDistortion are derived from.  Any output pointer may be NULL.
+ *   assign_out  num_vectors uint32
+ *   count_out   K uint64          members per cell
+ *   sum_out     K*dim int64       per-cell sums of the lattice value L = (int8)byte
+ *   sqsum_out   K uint64          per-cell sums over members and dims of L*L
+ *   flagged_out queries that went through the exact FP64 resolver
+ * This is also the encode-only entry (BASELINE config 5): pass only assign_out. */
+int qb200_assign_accumulate(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32_t *assign_out,
+                            uint64_t *count_out, int64_t *sum_out, uint64_t *sqsum_out,
+                            uint32_t *flagged_out);
+/* Assignment only, result left on the device (timed by bench.py without D2H). */
+int qb200_assign_only(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32_t *flagged_out,
+                      float *ms_assign_out, float *ms_resolve_out);
+
+/* fixCodeVectors + the two updateDistortion values from integer statistics (O(K*dim) FP64 on the
+ * host; SURVEY.md 8a "key simplification"): centroid = (S_t/255.0)/n for SCALED, S/n for NORMAL,
+ * zero vector for an empty cell.  codebook_pre may be NULL (then *dist_pre is not written). */
+int qb200_finalize_level(int colorspace, uint32_t K, int dim, uint64_t n_total,
+                         const uint64_t *count, const int64_t *sum, const uint64_t *sqsum,
+                         const double *codebook_pre, double *codebook_post, double *dist_pre,
+                         double *dist_post);
+
+/* Codebook doubles -> bytes exactly as vectorsToCharVectorsColorSpaced + colorSpaceToRGB do
+ * (src/Compressor.cpp:12-29, src/ColorSpace.cpp:8-11,23-28). Host-side, O(K*dim). */
+int qb200_codebook_to_bytes(const double *codebook, size_t K, int dim, int colorspace,
+                            uint8_t *bytes_out);
+
+/* CompressedImage::decompress + getImageFromVectors (src/Compressor.cpp:64-92,156-165) on the
+ * device: rebuilds the RGB image from codebook bytes and indices.  Also returns the pixel-domain
+ * mean squared error against the context's current image when mse_out != NULL (the report's
+ * "Distortion", src/Compressor.cpp:137-146).  rgb_out: n_images*xSize*ySize*3 host bytes or NULL. */
+int qb200_decode(qb200_ctx *ctx, const uint8_t *codebook_bytes, uint32_t K, uint8_t *rgb_out,
+                 double *mse_out);
+
+/* Measured FP32 FMA throughput of this device (TFLOP/s, FMA = 2 flop): the in-run roofline
+ * denominator for the assignment kernel. */
+int qb200_measure_fp32_peak(qb200_ctx *ctx, double *tflops_out);
+
+/* Number of kernels this library has launched in this process since the last reset
+ * (bench.py's "gpu_launches"). */
+int qb200_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QB200_H */

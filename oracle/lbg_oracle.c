@@ -267,7 +267,7 @@ static int32_t orc_divide(orc_kdtree *t, size_t left, size_t right, orc_interval
     nd->divlow = lb[cutfeat].high;
     nd->divhigh = rb[cutfeat].low;
     for (int i = 0; i < dim; ++i) {
-      bbox[i].low = lb[i].low < rb[i].low ? lb[i].low : rb[i].low;       /* std::min(l, r) */
+      bbox[i].low = rb[i].low < lb[i].low ? rb[i].low : lb[i].low;       /* std::min(l, r) */
       bbox[i].high = lb[i].high < rb[i].high ? rb[i].high : lb[i].high; /* std::max(l, r) */
     }
     free(lb);

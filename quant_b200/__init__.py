@@ -1,0 +1,14 @@
+"""quant_b200 - B200-native LBG codebook training / index assignment behind the reference's
+Quantizer / Compressor interface.  The compute path is libqb200.so (hand-written sm_100a CUDA,
+C ABI in include/qb200.h); this package is the host-side mirror of the reference's API.
+"""
+from ._lib import CS_NORMAL, CS_SCALED, LIB_PATH, Qb200Error, load
+from .context import Context, codebook_to_bytes, finalize_level, launch_count
+from .rgbimage import RGBImage
+from .quantizer import (AbstractQuantizer, LBGQuantizer, Quantizers, getQuantizer,
+                        vectors_to_lattice_bytes)
+from .compressor import (ColorSpaces, CompressedImage, CompressionRaport,
+                         getBlocksAsVectorsFromImage, getImageFromVectors,
+                         vectorsToCharVectorsColorSpaced)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,196 @@
+"""Python mirror of the codec layer around the hot path
+(/root/reference/include/Compressor.hpp:9-48, src/Compressor.cpp, include/ColorSpace.hpp).
+
+Only ``compress`` touches the GPU (through the C ABI); block extraction, byte conversion, decode
+and the ``.quant`` container are restated here as host logic with the reference's exact layout
+rules so that the parity tests read like the reference's own test (src/test.cpp).
+"""
+from __future__ import annotations
+
+import enum
+import time
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+from ._lib import CS_NORMAL, CS_SCALED
+from .context import codebook_to_bytes
+from .quantizer import Quantizers, getQuantizer
+from .rgbimage import RGBImage
+
+
+class ColorSpaces(enum.IntEnum):
+    NORMAL = 0
+    SCALED = 1
+    CIE1931 = 2
+
+
+def _check_cs(cs) -> int:
+    cs = int(cs)
+    if cs not in (CS_NORMAL, CS_SCALED):
+        raise NotImplementedError("CIE1931 is outside the accelerated path (SURVEY.md 8f row 3)")
+    return cs
+
+
+def _block_index_map(xSize: int, ySize: int, w: int, h: int):
+    """img index of every (vector, pixel-in-block) pair: (N, w*h) int64, per src/Compressor.cpp:44-50."""
+    wB, hB = (xSize + w - 1) // w, (ySize + h - 1) // h
+    i = np.arange(wB, dtype=np.int64)[:, None, None, None]
+    j = np.arange(hB, dtype=np.int64)[None, :, None, None]
+    dx = np.arange(w, dtype=np.int64)[None, None, :, None]
+    dy = np.arange(h, dtype=np.int64)[None, None, None, :]
+    idx = (i * w + dx) * ySize + (j * h + dy)
+    return idx.reshape(wB * hB, w * h)
+
+
+def getBlocksAsVectorsFromImage(image: RGBImage, w: int, h: int, cs) -> np.ndarray:
+    """src/Compressor.cpp:31-62 -> (N, 3*w*h) float64."""
+    cs = _check_cs(cs)
+    idx = _block_index_map(image.xSize, image.ySize, w, h)
+    npix = image.xSize * image.ySize
+    valid = idx < npix
+    px = image.img[np.where(valid, idx, 0)].astype(np.int8).astype(np.float64)  # signed char
+    if cs == CS_SCALED:
+        px = (px + 128.0) / 255
+    px = np.where(valid[..., None], px, 0.0)
+    return px.reshape(idx.shape[0], -1)
+
+
+def vectorsToCharVectorsColorSpaced(vectors: np.ndarray, cs) -> np.ndarray:
+    """src/Compressor.cpp:12-29 -> (K, dim) uint8 (the reference's chars, reinterpreted)."""
+    return codebook_to_bytes(vectors, _check_cs(cs))
+
+
+def getImageFromVectors(blocks: np.ndarray, xSize: int, ySize: int, w: int, h: int) -> RGBImage:
+    """src/Compressor.cpp:64-92; writes happen in (i, j, x, y) order, later writes win."""
+    blocks = np.ascontiguousarray(blocks, np.uint8)
+    idx = _block_index_map(xSize, ySize, w, h)
+    npix = xSize * ySize
+    out = np.zeros((npix, 3), np.uint8)
+    flat_idx = idx.reshape(-1)
+    vals = blocks.reshape(-1, 3)
+    keep = flat_idx < npix
+    # numpy fancy assignment applies duplicates in order, i.e. the last one wins, like the loops
+    out[flat_idx[keep]] = vals[keep]
+    return RGBImage.from_array(out, xSize, ySize)
+
+
+@dataclass
+class CompressionRaport:
+    distortion: float
+    bitsPerPixel: float
+    uncompressedSize: int
+    compressedSize: int
+    compressionTime: float
+
+    def __str__(self):  # src/Compressor.cpp:290-305
+        return ("Compression raport: \n"
+                f"Distortion        = {self.distortion:.10f}\n"
+                f"Bits per pixel    = {self.bitsPerPixel:.10f}\n"
+                f"Uncompressed size = {_pretty(self.uncompressedSize)}\n"
+                f"Compressed size   = {_pretty(self.compressedSize)}\n"
+                f"Compression ratio = {self.compressedSize / self.uncompressedSize:.3f}\n"
+                f"Compression time  = {self.compressionTime:.3f}s\n")
+
+
+def _pretty(b: int) -> str:  # src/Compressor.cpp:269-288 (including its odd Mb remainder)
+    if b < 1024:
+        return f"{b}b"
+    if b < 1024 * 1024:
+        return f"{b // 1024},{b % 1024}Kb"
+    return f"{b // (1024 * 1024)},{b % (1024 * 1024)}Mb"
+
+
+def _smallest_pow2(n: int) -> int:  # src/Compressor.cpp:167-172
+    p = 0
+    while n // 2:
+        n //= 2
+        p += 1
+    return p
+
+
+class CompressedImage:
+    def __init__(self):
+        self.codeVectors = np.zeros((0, 0), np.uint8)       # (K, dim) bytes
+        self.assignedCodeVector = np.zeros(0, np.uint64)     # N indices (size_t)
+        self.xSize = self.ySize = 0
+        self.blockWidth = self.blockHeight = 0
+        self.colorSpace = ColorSpaces.SCALED
+        self.quantizer = Quantizers.LBG
+
+    # -- the hot path --------------------------------------------------------------------------
+    @staticmethod
+    def compress(image: RGBImage, quantizer, colorSpace, blockWidth: int, blockHeight: int,
+                 eps: float, N: int, device: int = 0, context=None
+                 ) -> Tuple["CompressedImage", CompressionRaport]:
+        """src/Compressor.cpp:107-154.  The timed region is the reference's: block extraction +
+        quantize, here = host bytes -> GPU -> codebook and indices back on the host."""
+        cs = _check_cs(colorSpace)
+        q = getQuantizer(quantizer, device, context)
+        if q is None:
+            raise ValueError("quantizer not implemented (the reference returns nullptr and crashes)")
+        t0 = time.perf_counter()
+        codeVectors, assigned, _ = q.quantize_image(image.img, image.xSize, image.ySize, blockWidth,
+                                                    blockHeight, cs, N, eps)
+        dt = time.perf_counter() - t0
+        res = CompressedImage()
+        res.codeVectors = vectorsToCharVectorsColorSpaced(codeVectors, cs)
+        res.assignedCodeVector = assigned
+        res.xSize, res.ySize = image.xSize, image.ySize
+        res.blockWidth, res.blockHeight = blockWidth, blockHeight
+        res.colorSpace = ColorSpaces(cs)  # the reference leaves this member uninitialised
+        res.quantizer = Quantizers(int(quantizer))
+        res.last_reports = q.last_reports
+        bpp = np.float32(res.sizeInBits()) / np.float32(image.xSize * image.ySize)
+        # report distortion: decode on the GPU and compare bytes as signed chars (:137-146)
+        _, mse = q.context.decode(res.codeVectors, want_image=False)
+        rap = CompressionRaport(mse, float(bpp), image.sizeInBytes(), res.sizeInBits() // 8, dt)
+        return res, rap
+
+    @staticmethod
+    def decompress(cImg: "CompressedImage") -> RGBImage:
+        """src/Compressor.cpp:156-165."""
+        blocks = cImg.codeVectors[np.asarray(cImg.assignedCodeVector, np.int64)]
+        return getImageFromVectors(blocks, cImg.xSize, cImg.ySize, cImg.blockWidth, cImg.blockHeight)
+
+    def sizeInBits(self) -> int:
+        """src/Compressor.cpp:174-182 (approximate, bit-packed size)."""
+        bits = (_smallest_pow2(len(self.codeVectors)) * len(self.assignedCodeVector)
+                + self.blockWidth * self.blockHeight * len(self.codeVectors) * 8 * 3)
+        return ((bits + 7) // 8) * 8
+
+    # -- .quant container (src/Compressor.cpp:190-267) ------------------------------------------
+    def to_bytes(self) -> bytes:
+        bits = _smallest_pow2(len(self.codeVectors))
+        assert bits <= 24
+        hdr = b"%d %d %d %d %d %d %d\n" % (bits, int(self.colorSpace), len(self.assignedCodeVector),
+                                          self.xSize, self.ySize, self.blockWidth, self.blockHeight)
+        bpi = (bits + 7) // 8
+        a = np.asarray(self.assignedCodeVector, "<u8")
+        idx = a.view(np.uint8).reshape(-1, 8)[:, :bpi]  # low bytes of a little-endian size_t
+        return hdr + np.ascontiguousarray(self.codeVectors, np.uint8).tobytes() + idx.tobytes()
+
+    def saveToFile(self, path: str):
+        with open(path, "wb") as f:
+            f.write(self.to_bytes())
+
+    def loadFromFile(self, path: str):
+        with open(path, "rb") as f:
+            data = f.read()
+        nl = data.index(b"\n")
+        bits, cs, n, xs, ys, bw, bh = (int(t) for t in data[:nl].split())
+        self.xSize, self.ySize, self.blockWidth, self.blockHeight = xs, ys, bw, bh
+        try:
+            self.colorSpace = ColorSpaces(cs)
+        except ValueError:  # files written by the reference carry an uninitialised value here
+            self.colorSpace = cs
+        dim, K = bw * bh * 3, 1 << bits
+        pos = nl + 1
+        self.codeVectors = np.frombuffer(data, np.uint8, K * dim, pos).reshape(K, dim).copy()
+        pos += K * dim
+        bpi = (bits + 7) // 8
+        raw = np.frombuffer(data, np.uint8, n * bpi, pos).reshape(n, bpi)
+        a = np.zeros((n, 8), np.uint8)
+        a[:, :bpi] = raw
+        self.assignedCodeVector = a.view("<u8").reshape(-1).astype(np.uint64)

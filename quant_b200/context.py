@@ -1,0 +1,203 @@
+"""Thin object wrapper over the C ABI: one ``Context`` per GPU (include/qb200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import ALLREDUCE_FN, CS_NORMAL, CS_SCALED, LevelReport, MODE_PARITY, Qb200Error
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """Owns one ``qb200_ctx``. ``device`` is the CUDA ordinal."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.qb200_create(device, C.byref(h))
+        if rc != 0:
+            raise Qb200Error(rc, (self.lib.qb200_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+        self._keep = None  # keeps host/device buffers alive while the context borrows them
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise Qb200Error(rc, (self.lib.qb200_last_error(self.h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.qb200_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def device_info(self):
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._check(self.lib.qb200_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi),
+                                               C.byref(mem)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), total_mem=mem.value)
+
+    # -- training set -----------------------------------------------------------------------
+    def set_image(self, rgb: np.ndarray, xSize: int, ySize: int, w: int, h: int,
+                  colorspace: int = CS_SCALED, n_images: int = 1):
+        rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1)
+        if rgb.size != n_images * xSize * ySize * 3:
+            raise ValueError("rgb has the wrong number of bytes")
+        self._keep = rgb
+        self._check(self.lib.qb200_set_image(self.h, _ptr(rgb), xSize, ySize, w, h, colorspace,
+                                             n_images, 0))
+
+    def set_image_device(self, dev_ptr: int, xSize: int, ySize: int, w: int, h: int,
+                         colorspace: int = CS_SCALED, n_images: int = 1, keep=None):
+        self._keep = keep
+        self._check(self.lib.qb200_set_image(self.h, C.c_void_p(dev_ptr), xSize, ySize, w, h,
+                                             colorspace, n_images, 1))
+
+    def set_image_shard(self, rgb: np.ndarray, xSize: int, ySize: int, w: int, h: int,
+                        colorspace: int, row_begin: int, row_end: int):
+        rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1)
+        self._keep = rgb
+        self._check(self.lib.qb200_set_image_shard(self.h, _ptr(rgb), xSize, ySize, w, h,
+                                                   colorspace, row_begin, row_end))
+
+    def set_vectors_u8(self, mat: np.ndarray, colorspace: int = CS_SCALED):
+        mat = np.ascontiguousarray(mat, np.uint8)
+        n, dim = mat.shape
+        self._keep = mat
+        self._check(self.lib.qb200_set_vectors_u8(self.h, _ptr(mat), n, dim, colorspace, 0))
+
+    @property
+    def num_vectors(self) -> int:
+        return int(self.lib.qb200_num_vectors(self.h))
+
+    @property
+    def dim(self) -> int:
+        return int(self.lib.qb200_dim(self.h))
+
+    # -- hot path ---------------------------------------------------------------------------
+    def train(self, nbits: int, eps: float = float(np.float32(1e-6)), n_total: int = 0,
+              allreduce: Optional[Callable[[int, int, int], int]] = None, reports: bool = True):
+        """LBGQuantizer::quantize. Returns (codebook[K,dim] f64, distortion, [LevelReport...])."""
+        K, dim = 1 << nbits, self.dim
+        cb = np.empty((K, dim), np.float64)
+        dist = C.c_double()
+        rep = (LevelReport * max(nbits, 1))() if reports else None
+        cb_fn = None
+        if allreduce is not None:
+            def tramp(dev, count, stream, user):
+                try:
+                    return int(allreduce(dev, count, stream or 0) or 0)
+                except Exception:  # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb_fn = ALLREDUCE_FN(tramp)
+        self._check(self.lib.qb200_train(self.h, nbits, eps, MODE_PARITY, n_total,
+                                         C.cast(cb_fn, C.c_void_p) if cb_fn else None, None,
+                                         _ptr(cb), C.byref(dist),
+                                         C.cast(rep, C.c_void_p) if rep is not None else None))
+        out = []
+        if rep is not None:
+            for i in range(nbits):
+                r = rep[i]
+                out.append({f: getattr(r, f) for f, _ in LevelReport._fields_})
+        return cb, dist.value, out
+
+    def get_assign(self) -> np.ndarray:
+        a = np.empty(self.num_vectors, np.uint32)
+        self._check(self.lib.qb200_get_assign(self.h, _ptr(a)))
+        return a
+
+    def get_assign_u64(self) -> np.ndarray:
+        a = np.empty(self.num_vectors, np.uint64)
+        self._check(self.lib.qb200_get_assign_u64(self.h, _ptr(a)))
+        return a
+
+    def assign_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.qb200_assign_device_ptr(self.h, C.byref(p)))
+        return p.value or 0
+
+    def assign_accumulate(self, codebook: np.ndarray, want_assign=True, want_stats=True):
+        cb = np.ascontiguousarray(codebook, np.float64)
+        K, dim = cb.shape
+        if dim != self.dim:
+            raise ValueError("codebook dimension mismatch")
+        a = np.empty(self.num_vectors, np.uint32) if want_assign else None
+        n = np.empty(K, np.uint64) if want_stats else None
+        S = np.empty((K, dim), np.int64) if want_stats else None
+        Q = np.empty(K, np.uint64) if want_stats else None
+        fl = C.c_uint32()
+        self._check(self.lib.qb200_assign_accumulate(self.h, _ptr(cb), K, _ptr(a), _ptr(n), _ptr(S),
+                                                     _ptr(Q), C.byref(fl)))
+        return dict(assign=a, count=n, sum=S, sqsum=Q, flagged=fl.value)
+
+    def assign_only(self, codebook: np.ndarray):
+        cb = np.ascontiguousarray(codebook, np.float64)
+        fl, ma, mr = C.c_uint32(), C.c_float(), C.c_float()
+        self._check(self.lib.qb200_assign_only(self.h, _ptr(cb), cb.shape[0], C.byref(fl),
+                                               C.byref(ma), C.byref(mr)))
+        return dict(flagged=fl.value, ms_assign=ma.value, ms_resolve=mr.value)
+
+    def decode(self, codebook_bytes: np.ndarray, want_image=True):
+        cbb = np.ascontiguousarray(codebook_bytes, np.uint8)
+        out = np.empty(len(self._keep) if self._keep is not None else 0, np.uint8) if want_image else None
+        mse = C.c_double()
+        self._check(self.lib.qb200_decode(self.h, _ptr(cbb), cbb.shape[0], _ptr(out), C.byref(mse)))
+        return out, mse.value
+
+    def measure_fp32_peak(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.qb200_measure_fp32_peak(self.h, C.byref(v)))
+        return v.value
+
+
+def finalize_level(colorspace, n_total, count, sums, sqsum, codebook_pre=None):
+    lib = _lib.load()
+    count = np.ascontiguousarray(count, np.uint64)
+    sums = np.ascontiguousarray(sums, np.int64)
+    sqsum = np.ascontiguousarray(sqsum, np.uint64)
+    K, dim = sums.shape
+    post = np.empty((K, dim), np.float64)
+    pre = None if codebook_pre is None else np.ascontiguousarray(codebook_pre, np.float64)
+    d0, d1 = C.c_double(float("nan")), C.c_double()
+    rc = lib.qb200_finalize_level(colorspace, K, dim, n_total, _ptr(count), _ptr(sums), _ptr(sqsum),
+                                  _ptr(pre), _ptr(post), C.byref(d0), C.byref(d1))
+    if rc != 0:
+        raise Qb200Error(rc, "qb200_finalize_level")
+    return post, d0.value, d1.value
+
+
+def codebook_to_bytes(codebook, colorspace=CS_SCALED):
+    lib = _lib.load()
+    cb = np.ascontiguousarray(codebook, np.float64)
+    out = np.empty(cb.shape, np.uint8)
+    rc = lib.qb200_codebook_to_bytes(_ptr(cb), cb.shape[0], cb.shape[1], colorspace, _ptr(out))
+    if rc != 0:
+        raise Qb200Error(rc, "qb200_codebook_to_bytes")
+    return out
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_lib.load().qb200_launch_count(1 if reset else 0))

@@ -1,0 +1,180 @@
+// See kd_host.hpp.  Compiled as plain C++ with strict IEEE double (no -ffast-math, no FMA
+// contraction: all comparisons and the midpoint below must round exactly like the reference's).
+#include "kd_host.hpp"
+
+#include <algorithm>
+#include <utility>
+
+namespace qb {
+namespace {
+
+struct Range {
+  double lo, hi;
+};
+
+class Builder {
+ public:
+  Builder(const double *pts, size_t n, int dim, int leaf_max, KdHostTree &out)
+      : pts_(pts), n_(n), dim_(dim), leaf_max_((size_t)leaf_max), out_(out) {}
+
+  void run() {
+    out_.nodes.clear();
+    out_.nodes.reserve(2 * n_ / (leaf_max_ ? leaf_max_ : 1) + 8);
+    out_.order.resize(n_);
+    for (size_t i = 0; i < n_; i++) out_.order[i] = (unsigned int)i;
+    out_.depth = 0;
+    std::vector<Range> box(dim_);
+    if (n_ == 0) {
+      out_.box_low.assign(dim_, 0.0);
+      out_.box_high.assign(dim_, 0.0);
+      return;
+    }
+    // computeBoundingBox: strict < / > updates starting from point 0.
+    for (int d = 0; d < dim_; d++) box[d].lo = box[d].hi = at(0, d);
+    for (size_t k = 1; k < n_; k++)
+      for (int d = 0; d < dim_; d++) {
+        double v = at(k, d);
+        if (v < box[d].lo) box[d].lo = v;
+        if (v > box[d].hi) box[d].hi = v;
+      }
+    subdivide(0, n_, box, 1);
+    out_.box_low.resize(dim_);
+    out_.box_high.resize(dim_);
+    for (int d = 0; d < dim_; d++) {
+      out_.box_low[d] = box[d].lo;
+      out_.box_high[d] = box[d].hi;
+    }
+  }
+
+ private:
+  double at(size_t point, int d) const { return pts_[point * (size_t)dim_ + d]; }
+  double via(size_t pos, int d) const { return at(out_.order[pos], d); }
+
+  void span_of(size_t first, size_t count, int d, double &mn, double &mx) const {
+    mn = mx = via(first, d);
+    for (size_t i = 1; i < count; i++) {
+      double v = via(first + i, d);
+      if (v < mn) mn = v;
+      if (v > mx) mx = v;
+    }
+  }
+
+  // planeSplit on order[first .. first+count): two Hoare-style sweeps with unsigned indices
+  // (the "!right" exits are part of the behaviour being reproduced).
+  void partition(size_t first, size_t count, int feat, double cut, size_t &lim1, size_t &lim2) {
+    unsigned int *ind = out_.order.data() + first;
+    auto val = [&](size_t p) { return at(ind[p], feat); };
+    size_t left = 0, right = count - 1;
+    for (;;) {
+      while (left <= right && val(left) < cut) ++left;
+      while (right && left <= right && val(right) >= cut) --right;
+      if (left > right || !right) break;
+      std::swap(ind[left], ind[right]);
+      ++left;
+      --right;
+    }
+    lim1 = left;
+    right = count - 1;
+    for (;;) {
+      while (left <= right && val(left) <= cut) ++left;
+      while (right && left <= right && val(right) > cut) --right;
+      if (left > right || !right) break;
+      std::swap(ind[left], ind[right]);
+      ++left;
+      --right;
+    }
+    lim2 = left;
+  }
+
+  // middleSplit_: cut the dimension of (nearly) largest box span with the largest actual spread
+  // at the box midpoint clamped into the data range; balance by count when the plane is lopsided.
+  size_t choose_split(size_t first, size_t count, const std::vector<Range> &box, int &feat,
+                      double &cut) {
+    const double kEps = static_cast<double>(0.00001);
+    double max_span = box[0].hi - box[0].lo;
+    for (int d = 1; d < dim_; d++) {
+      double span = box[d].hi - box[d].lo;
+      if (span > max_span) max_span = span;
+    }
+    double best_spread = -1;
+    feat = 0;
+    for (int d = 0; d < dim_; d++) {
+      double span = box[d].hi - box[d].lo;
+      if (span > (1 - kEps) * max_span) {
+        double mn, mx;
+        span_of(first, count, d, mn, mx);
+        double spread = mx - mn;
+        if (spread > best_spread) {
+          feat = d;
+          best_spread = spread;
+        }
+      }
+    }
+    double mid = (box[feat].lo + box[feat].hi) / 2;
+    double mn, mx;
+    span_of(first, count, feat, mn, mx);
+    cut = mid < mn ? mn : (mid > mx ? mx : mid);
+    size_t lim1, lim2;
+    partition(first, count, feat, cut, lim1, lim2);
+    if (lim1 > count / 2) return lim1;
+    if (lim2 < count / 2) return lim2;
+    return count / 2;
+  }
+
+  // divideTree: `box` is in/out - on return it is the tight box of the subtree.
+  int subdivide(size_t first, size_t last, std::vector<Range> &box, int level) {
+    int me = (int)out_.nodes.size();
+    out_.nodes.emplace_back();
+    if (level > out_.depth) out_.depth = level;
+    if (last - first <= leaf_max_) {
+      KdNode &nd = out_.nodes[me];
+      nd.child1 = nd.child2 = -1;
+      nd.a = (int)first;
+      nd.b = (int)last;
+      nd.divlow = nd.divhigh = 0.0;
+      for (int d = 0; d < dim_; d++) box[d].lo = box[d].hi = via(first, d);
+      for (size_t p = first + 1; p < last; p++)
+        for (int d = 0; d < dim_; d++) {
+          double v = via(p, d);
+          if (box[d].lo > v) box[d].lo = v;
+          if (box[d].hi < v) box[d].hi = v;
+        }
+      return me;
+    }
+    int feat;
+    double cut;
+    size_t nleft = choose_split(first, last - first, box, feat, cut);
+    std::vector<Range> lbox(box);
+    lbox[feat].hi = cut;
+    int c1 = subdivide(first, first + nleft, lbox, level + 1);
+    std::vector<Range> rbox(box);
+    rbox[feat].lo = cut;
+    int c2 = subdivide(first + nleft, last, rbox, level + 1);
+    KdNode &nd = out_.nodes[me];
+    nd.child1 = c1;
+    nd.child2 = c2;
+    nd.a = feat;
+    nd.b = 0;
+    nd.divlow = lbox[feat].hi;
+    nd.divhigh = rbox[feat].lo;
+    for (int d = 0; d < dim_; d++) {
+      box[d].lo = std::min(lbox[d].lo, rbox[d].lo);
+      box[d].hi = std::max(lbox[d].hi, rbox[d].hi);
+    }
+    return me;
+  }
+
+  const double *pts_;
+  size_t n_;
+  int dim_;
+  size_t leaf_max_;
+  KdHostTree &out_;
+};
+
+}  // namespace
+
+void build_kd_tree(const double *points, size_t K, int dim, int leaf_max, KdHostTree &out) {
+  Builder(points, K, dim, leaf_max, out).run();
+}
+
+}  // namespace qb

@@ -1,0 +1,761 @@
+// C ABI of libqb200 (include/qb200.h) and the host-side level driver.
+//
+// The driver restates LBGQuantizer::quantize + Solution::LBGIterate
+// (/root/reference/src/Quantizer.cpp:98-143) around three kernels per split level
+// (assign -> resolve -> accumulate) and an O(K*dim) FP64 finalisation on the host.
+#include "../../include/qb200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kd_host.hpp"
+#include "qb200_launch.hpp"
+
+using namespace qb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct qb200_ctx {
+  int device = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+
+  // training set
+  bool have_set = false;
+  VecSource src{};
+  int colorspace = QB200_CS_SCALED;
+  bool is_image = false, is_shard = false;
+  DecodeGeom geom{};
+  DevBuf d_img;               // owned copy of the bytes (unless borrowed)
+  const uint8_t *borrowed = nullptr;
+
+  // per-vector
+  DevBuf d_assign, d_flags;
+  // per-level
+  DevBuf d_rows, d_cb64, d_nodes, d_vind, d_bbox, d_stats, d_counters, d_misc;
+  // pinned staging
+  void *h_pin = nullptr;
+  size_t h_pin_cap = 0;
+  bool assign_valid = false;
+};
+
+namespace {
+
+int fail(qb200_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? QB200_ERR_OOM : QB200_ERR_CUDA, "%s: %s", \
+                  #call, cudaGetErrorString(e_));                                                  \
+  } while (0)
+
+int ensure(qb200_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return QB200_OK;
+  if (b.p) {
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, QB200_ERR_OOM, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return QB200_OK;
+}
+
+int ensure_pinned(qb200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->h_pin_cap) return QB200_OK;
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  ctx->h_pin = nullptr;
+  ctx->h_pin_cap = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMallocHost(&ctx->h_pin, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, QB200_ERR_OOM, "cudaMallocHost(%zu bytes): %s", want, cudaGetErrorString(e));
+  }
+  ctx->h_pin_cap = want;
+  return QB200_OK;
+}
+
+void free_buf(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+// ---- level machinery --------------------------------------------------------------------------
+
+struct LevelOut {
+  unsigned int flagged = 0, changed = 0;
+  int kd_depth = 0;
+  float ms_assign = 0, ms_resolve = 0, ms_accumulate = 0;
+};
+
+// Colour-space codebook (FP64) -> staged FP32 rows in lattice coordinates.
+//   SCALED: value = (L + 128)/255  =>  C = 255*c - 128 ;  NORMAL: C = c.
+void make_rows(const double *cb, uint32_t K, int dim, int colorspace, float *rows, float *c_max_norm) {
+  const int row = assign_row_floats(dim);
+  double max_n2 = 0;
+  for (uint32_t k = 0; k < K; k++) {
+    float *r = rows + (size_t)k * row;
+    double n2 = 0;
+    for (int e = 0; e < dim; e++) {
+      const double c = cb[(size_t)k * dim + e];
+      const double C = colorspace == QB200_CS_SCALED ? 255.0 * c - 128.0 : c;
+      const float Cf = (float)C;
+      r[e] = -2.0f * Cf;
+      n2 += (double)Cf * (double)Cf;
+    }
+    r[dim] = (float)n2;
+    for (int e = dim + 1; e < row; e++) r[e] = 0.f;
+    if (n2 > max_n2) max_n2 = n2;
+  }
+  *c_max_norm = (float)(std::sqrt(max_n2) * 1.000001 + 1e-3);
+}
+
+// Runs assign (+ resolve) (+ accumulate) for one codebook.  Leaves the assignment in d_assign and,
+// when want_stats, the K*(dim+2) statistics words in d_stats (NOT yet all-reduced / copied).
+int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, bool timed, LevelOut *out) {
+  const int dim = ctx->src.dim;
+  const int row = assign_row_floats(dim);
+  const size_t rows_bytes = (size_t)K * row * 4, cb_bytes = (size_t)K * dim * 8;
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_rows, rows_bytes))) return rc;
+  if ((rc = ensure(ctx, ctx->d_cb64, cb_bytes))) return rc;
+  if ((rc = ensure(ctx, ctx->d_counters, 64))) return rc;
+  if (want_stats && (rc = ensure(ctx, ctx->d_stats, stats_words(K, dim) * 8))) return rc;
+  // pinned layout: [rows | cb64 | kd nodes | vind | bbox | counters(64B)]
+  const size_t max_nodes = 2 * (size_t)K + 8;
+  const size_t off_cb = (rows_bytes + 255) & ~(size_t)255;
+  const size_t off_nodes = (off_cb + cb_bytes + 255) & ~(size_t)255;
+  const size_t off_vind = off_nodes + max_nodes * sizeof(KdNode);
+  const size_t off_bbox = (off_vind + (size_t)K * 4 + 255) & ~(size_t)255;
+  const size_t off_cnt = off_bbox + 2 * (size_t)dim * 8;
+  if ((rc = ensure_pinned(ctx, off_cnt + 64))) return rc;
+  char *pin = (char *)ctx->h_pin;
+  float *h_rows = (float *)pin;
+  double *h_cb = (double *)(pin + off_cb);
+
+  float c_max = 0;
+  make_rows(cb, K, dim, ctx->colorspace, h_rows, &c_max);
+  std::memcpy(h_cb, cb, cb_bytes);
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->d_rows.p, h_rows, rows_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_cb64.p, h_cb, cb_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+
+  AssignLaunch a{};
+  a.src = ctx->src;
+  a.cb_rows = (const float *)ctx->d_rows.p;
+  a.K = (int)K;
+  // 2 scores * (dim+3) * 2^-24 * (|X|+|C|)^2, with 25% head-room (see qb200_kernels.cu)
+  a.margin_coef = 2.5f * (float)(dim + 3) * 5.9604645e-8f;
+  a.c_max_norm = c_max;
+  a.assign = (uint32_t *)ctx->d_assign.p;
+  a.flag_list = (uint32_t *)ctx->d_flags.p;
+  a.flag_count = (unsigned int *)ctx->d_counters.p;
+  a.sm_count = ctx->sm_count;
+  a.stream = st;
+  if (timed) CU(cudaEventRecord(ctx->ev[0], st));
+  CU(launch_assign(a));
+  if (timed) CU(cudaEventRecord(ctx->ev[1], st));
+
+  // While the filter runs: build the reference's KD tree for this codebook on the host.
+  KdHostTree tree;
+  build_kd_tree(cb, K, dim, 10 /* src/KDTree.cpp:4 */, tree);
+  if (tree.depth > kResolveDepthCap)
+    return fail(ctx, QB200_ERR_ARG, "KD tree depth %d exceeds the resolver's stack (%d)", tree.depth,
+                kResolveDepthCap);
+  if (tree.nodes.size() > max_nodes) return fail(ctx, QB200_ERR_STATE, "KD tree larger than expected");
+  if ((rc = ensure(ctx, ctx->d_nodes, tree.nodes.size() * sizeof(KdNode)))) return rc;
+  if ((rc = ensure(ctx, ctx->d_vind, (size_t)K * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_bbox, 2 * (size_t)dim * 8))) return rc;
+  std::memcpy(pin + off_nodes, tree.nodes.data(), tree.nodes.size() * sizeof(KdNode));
+  std::memcpy(pin + off_vind, tree.order.data(), (size_t)K * 4);
+  std::memcpy(pin + off_bbox, tree.box_low.data(), (size_t)dim * 8);
+  std::memcpy(pin + off_bbox + (size_t)dim * 8, tree.box_high.data(), (size_t)dim * 8);
+  CU(cudaMemcpyAsync(ctx->d_nodes.p, pin + off_nodes, tree.nodes.size() * sizeof(KdNode), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_vind.p, pin + off_vind, (size_t)K * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_bbox.p, pin + off_bbox, 2 * (size_t)dim * 8, cudaMemcpyHostToDevice, st));
+  KdDevice kd{};
+  kd.nodes = (const KdNode *)ctx->d_nodes.p;
+  kd.vind = (const unsigned int *)ctx->d_vind.p;
+  kd.bbox_low = (const double *)ctx->d_bbox.p;
+  kd.bbox_high = kd.bbox_low + dim;
+  kd.n_nodes = (int)tree.nodes.size();
+  kd.depth = tree.depth;
+  unsigned int *cnt = (unsigned int *)ctx->d_counters.p;
+  CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p, kd,
+                    (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, cnt + 1, 0xffffffffu,
+                    ctx->sm_count, st));
+  if (timed) CU(cudaEventRecord(ctx->ev[2], st));
+  if (want_stats) {
+    CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(K, dim) * 8, st));
+    CU(launch_accumulate(ctx->src, (const uint32_t *)ctx->d_assign.p, (int)K, (unsigned long long *)ctx->d_stats.p,
+                         ctx->sm_count, st));
+  }
+  if (timed) CU(cudaEventRecord(ctx->ev[3], st));
+  CU(cudaMemcpyAsync(pin + off_cnt, ctx->d_counters.p, 8, cudaMemcpyDeviceToHost, st));
+  ctx->assign_valid = true;
+  if (out) {
+    // the caller synchronises before reading these
+    out->kd_depth = tree.depth;
+  }
+  return QB200_OK;
+}
+
+// after a stream sync: counters and timings of the level just run
+int collect_level(qb200_ctx *ctx, uint32_t K, bool timed, LevelOut *out) {
+  const int dim = ctx->src.dim;
+  const int row = assign_row_floats(dim);
+  const size_t rows_bytes = (size_t)K * row * 4, cb_bytes = (size_t)K * dim * 8;
+  const size_t max_nodes = 2 * (size_t)K + 8;
+  const size_t off_cb = (rows_bytes + 255) & ~(size_t)255;
+  const size_t off_nodes = (off_cb + cb_bytes + 255) & ~(size_t)255;
+  const size_t off_vind = off_nodes + max_nodes * sizeof(KdNode);
+  const size_t off_bbox = (off_vind + (size_t)K * 4 + 255) & ~(size_t)255;
+  const size_t off_cnt = off_bbox + 2 * (size_t)dim * 8;
+  const unsigned int *c = (const unsigned int *)((char *)ctx->h_pin + off_cnt);
+  out->flagged = c[0];
+  out->changed = c[1];
+  if (timed) {
+    CU(cudaEventElapsedTime(&out->ms_assign, ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(&out->ms_resolve, ctx->ev[1], ctx->ev[2]));
+    CU(cudaEventElapsedTime(&out->ms_accumulate, ctx->ev[2], ctx->ev[3]));
+  }
+  return QB200_OK;
+}
+
+int fetch_stats(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void *ar_user, std::vector<unsigned long long> &host) {
+  const size_t words = stats_words(K, ctx->src.dim);
+  if (ar) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ar(ctx->d_stats.p, words, (void *)ctx->stream, ar_user) != 0)
+      return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed at K=%u", K);
+  }
+  host.resize(words);
+  CU(cudaMemcpyAsync(host.data(), ctx->d_stats.p, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return QB200_OK;
+}
+
+void split_stats(const std::vector<unsigned long long> &w, uint32_t K, int dim, std::vector<uint64_t> &n,
+                 std::vector<int64_t> &S, std::vector<uint64_t> &Q) {
+  n.resize(K);
+  S.resize((size_t)K * dim);
+  Q.resize(K);
+  for (uint32_t k = 0; k < K; k++) {
+    const unsigned long long *r = w.data() + (size_t)k * (dim + 2);
+    n[k] = r[0];
+    for (int e = 0; e < dim; e++) S[(size_t)k * dim + e] = (int64_t)r[1 + e];
+    Q[k] = r[dim + 1];
+  }
+}
+
+int set_common(qb200_ctx *ctx, size_t n_local) {
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_assign, (n_local ? n_local : 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_flags, (n_local ? n_local : 1) * 4))) return rc;
+  ctx->assign_valid = false;
+  ctx->have_set = true;
+  return QB200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int qb200_version(void) { return QB200_VERSION; }
+
+int qb200_create(int device, qb200_ctx **out) {
+  qb200_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, QB200_ERR_ARG, "qb200_create: out == NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, QB200_ERR_NODEV, "no CUDA device (%s); libqb200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return fail(nullptr, QB200_ERR_ARG, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, QB200_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, QB200_ERR_NODEV, "device %d is sm_%d%d; libqb200 is built for sm_100a only", device,
+                prop.major, prop.minor);
+  ctx = new (std::nothrow) qb200_ctx();
+  if (!ctx) return fail(nullptr, QB200_ERR_OOM, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->total_mem = prop.totalGlobalMem;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    delete ctx;
+    return fail(nullptr, QB200_ERR_CUDA, "stream creation: %s", msg.c_str());
+  }
+  ctx->stream = ctx->own_stream;
+  for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  *out = ctx;
+  return QB200_OK;
+}
+
+void qb200_destroy(qb200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_rows, &ctx->d_cb64, &ctx->d_nodes,
+                    &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc})
+    free_buf(*b);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  for (auto &ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char *qb200_last_error(const qb200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int qb200_set_stream(qb200_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return QB200_ERR_ARG;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return QB200_OK;
+}
+
+int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = ctx->total_mem;
+  return QB200_OK;
+}
+
+static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int w, int h, int colorspace,
+                          int n_images, int on_device, bool shard, size_t row_begin, size_t row_end) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (!rgb) return fail(ctx, QB200_ERR_ARG, "set_image: rgb == NULL");
+  if (xSize <= 0 || ySize <= 0 || w <= 0 || h <= 0 || n_images <= 0)
+    return fail(ctx, QB200_ERR_ARG, "set_image: sizes must be positive (x=%d y=%d w=%d h=%d n=%d)", xSize, ySize, w,
+                h, n_images);
+  if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED)
+    return fail(ctx, QB200_ERR_ARG, "set_image: colour space %d is not supported (NORMAL=0, SCALED=1)", colorspace);
+  const long long dim = 3LL * w * h;
+  if (dim > kMaxDim) return fail(ctx, QB200_ERR_ARG, "set_image: block %dx%d gives dim %lld > %d", w, h, dim, kMaxDim);
+  CU(cudaSetDevice(ctx->device));
+  const unsigned long long wB = ((unsigned long long)xSize + w - 1) / w, hB = ((unsigned long long)ySize + h - 1) / h;
+  if (hB > 0xffffffffull) return fail(ctx, QB200_ERR_ARG, "set_image: too many blocks per row");
+  if (!shard) {
+    row_begin = 0;
+    row_end = wB;
+  }
+  if (row_begin > row_end || row_end > wB)
+    return fail(ctx, QB200_ERR_ARG, "set_image_shard: rows [%zu,%zu) outside [0,%llu)", row_begin, row_end, wB);
+  VecSource s{};
+  s.img_bytes = (unsigned long long)xSize * ySize * 3;
+  s.per_image = wB * hB;
+  s.first_vec = (unsigned long long)row_begin * hB;
+  s.n_local = shard ? (unsigned long long)(row_end - row_begin) * hB : s.per_image * (unsigned long long)n_images;
+  s.row_stride = (unsigned long long)w * ySize * 3;
+  s.col_stride = (unsigned int)(h * 3);
+  s.hB = (unsigned int)hB;
+  s.dim = (int)dim;
+  s.pad_lattice = colorspace == QB200_CS_SCALED ? -128 : 0;
+  for (int e = 0; e < dim; e++) {
+    const int pix = e / 3, ch = e % 3, dx = pix / h, dy = pix % h;
+    s.elem_off[e] = (unsigned int)(((unsigned long long)dx * ySize + dy) * 3 + ch);
+  }
+  if (s.n_local > 0xffffffffull) return fail(ctx, QB200_ERR_ARG, "set_image: more than 2^32 vectors");
+  // byte range this context needs
+  unsigned long long lo = 0, hi = s.img_bytes * (unsigned long long)n_images;
+  if (shard) {
+    lo = (unsigned long long)row_begin * s.row_stride;
+    if (row_end > row_begin) {
+      unsigned long long last = (unsigned long long)(row_end - 1) * s.row_stride + (hB - 1) * s.col_stride +
+                                s.elem_off[dim - 1] + 1;
+      hi = last < s.img_bytes ? last : s.img_bytes;
+    } else {
+      hi = lo;
+    }
+    if (lo > s.img_bytes) lo = s.img_bytes;
+    if (hi < lo) hi = lo;
+  }
+  s.origin = lo;
+  ctx->borrowed = nullptr;
+  if (on_device) {
+    if (shard) return fail(ctx, QB200_ERR_ARG, "set_image_shard takes a host image");
+    ctx->borrowed = rgb;
+    s.buf = rgb;
+  } else {
+    int rc = ensure(ctx, ctx->d_img, (size_t)(hi - lo) + 16);
+    if (rc) return rc;
+    if (hi > lo) CU(cudaMemcpyAsync(ctx->d_img.p, rgb + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+    s.buf = (const uint8_t *)ctx->d_img.p;
+  }
+  ctx->src = s;
+  ctx->colorspace = colorspace;
+  ctx->is_image = true;
+  ctx->is_shard = shard && !(row_begin == 0 && row_end == wB);
+  ctx->geom.xSize = xSize;
+  ctx->geom.ySize = ySize;
+  ctx->geom.w = w;
+  ctx->geom.h = h;
+  ctx->geom.wB = (unsigned int)wB;
+  ctx->geom.hB = (unsigned int)hB;
+  ctx->geom.n_pixels = (unsigned long long)xSize * ySize;
+  ctx->geom.n_images = n_images;
+  return set_common(ctx, (size_t)s.n_local);
+}
+
+int qb200_set_image(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth, int blockHeight,
+                    int colorspace, int n_images, int rgb_is_device) {
+  return set_image_impl(ctx, rgb, xSize, ySize, blockWidth, blockHeight, colorspace, n_images, rgb_is_device, false, 0,
+                        0);
+}
+
+int qb200_set_image_shard(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth, int blockHeight,
+                          int colorspace, size_t row_begin, size_t row_end) {
+  return set_image_impl(ctx, rgb, xSize, ySize, blockWidth, blockHeight, colorspace, 1, 0, true, row_begin, row_end);
+}
+
+int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors, int dim, int colorspace,
+                         int bytes_is_device) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (!bytes && n_vectors) return fail(ctx, QB200_ERR_ARG, "set_vectors_u8: bytes == NULL");
+  if (dim <= 0 || dim > kMaxDim) return fail(ctx, QB200_ERR_ARG, "set_vectors_u8: dim %d outside [1,%d]", dim, kMaxDim);
+  if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED)
+    return fail(ctx, QB200_ERR_ARG, "set_vectors_u8: colour space %d is not supported", colorspace);
+  if (n_vectors > 0xffffffffull) return fail(ctx, QB200_ERR_ARG, "set_vectors_u8: more than 2^32 vectors");
+  CU(cudaSetDevice(ctx->device));
+  VecSource s{};
+  s.img_bytes = (unsigned long long)n_vectors * dim;
+  s.per_image = n_vectors ? n_vectors : 1;
+  s.first_vec = 0;
+  s.n_local = n_vectors;
+  s.row_stride = (unsigned long long)dim;
+  s.col_stride = 0;
+  s.hB = 1;
+  s.dim = dim;
+  s.pad_lattice = colorspace == QB200_CS_SCALED ? -128 : 0;
+  for (int e = 0; e < dim; e++) s.elem_off[e] = (unsigned int)e;
+  s.origin = 0;
+  ctx->borrowed = nullptr;
+  if (bytes_is_device) {
+    ctx->borrowed = bytes;
+    s.buf = bytes;
+  } else {
+    int rc = ensure(ctx, ctx->d_img, (size_t)s.img_bytes + 16);
+    if (rc) return rc;
+    if (s.img_bytes) CU(cudaMemcpyAsync(ctx->d_img.p, bytes, (size_t)s.img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    s.buf = (const uint8_t *)ctx->d_img.p;
+  }
+  ctx->src = s;
+  ctx->colorspace = colorspace;
+  ctx->is_image = false;
+  ctx->is_shard = false;
+  return set_common(ctx, n_vectors);
+}
+
+size_t qb200_num_vectors(const qb200_ctx *ctx) { return ctx && ctx->have_set ? (size_t)ctx->src.n_local : 0; }
+int qb200_dim(const qb200_ctx *ctx) { return ctx && ctx->have_set ? ctx->src.dim : 0; }
+
+int qb200_finalize_level(int colorspace, uint32_t K, int dim, uint64_t n_total, const uint64_t *count,
+                         const int64_t *sum, const uint64_t *sqsum, const double *codebook_pre, double *codebook_post,
+                         double *dist_pre, double *dist_post) {
+  if (!count || !sum || !sqsum || dim <= 0 || K == 0) return QB200_ERR_ARG;
+  if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED) return QB200_ERR_ARG;
+  const bool scaled = colorspace == QB200_CS_SCALED;
+  // Work in the colour space's integer lattice: SCALED t = L + 128 in [0,255] (value t/255),
+  // NORMAL t = L (value t).  Sums stay exact in 64-bit integers.
+  const double unit = scaled ? 255.0 : 1.0;
+  long double acc_pre = 0, acc_post = 0;
+  for (uint32_t k = 0; k < K; k++) {
+    const uint64_t n = count[k];
+    long double st2 = 0, cross = 0, c2 = 0;
+    int64_t s_all = 0;
+    for (int e = 0; e < dim; e++) s_all += sum[(size_t)k * dim + e];
+    // Q in the t lattice: sum (L+128)^2 = Q_L + 256*S_L + 128^2 * dim * n
+    const long double Qt = scaled ? (long double)sqsum[k] + 256.0L * (long double)s_all +
+                                        16384.0L * (long double)dim * (long double)n
+                                  : (long double)sqsum[k];
+    for (int e = 0; e < dim; e++) {
+      const int64_t St = sum[(size_t)k * dim + e] + (scaled ? (int64_t)(128 * n) : 0);
+      // centroid: the reference divides the Kahan sum of the members by their count
+      // (src/Quantizer.cpp:81-85); an empty cell keeps the zero vector.
+      double c = 0.0;
+      if (n) c = ((double)St / unit) / (double)n;
+      if (codebook_post) codebook_post[(size_t)k * dim + e] = c;
+      st2 += (long double)St * (long double)St;
+      if (codebook_pre) {
+        const long double cp = codebook_pre[(size_t)k * dim + e];
+        cross += cp * (long double)St;
+        c2 += cp * cp;
+      }
+    }
+    if (n) acc_post += Qt - st2 / (long double)n;
+    if (codebook_pre) acc_pre += Qt - 2.0L * unit * cross + (long double)unit * unit * (long double)n * c2;
+  }
+  const long double denom = (long double)unit * unit * (long double)n_total * (long double)dim;
+  if (dist_post) *dist_post = (double)(acc_post / denom);
+  if (dist_pre && codebook_pre) *dist_pre = (double)(acc_pre / denom);
+  return QB200_OK;
+}
+
+int qb200_codebook_to_bytes(const double *codebook, size_t K, int dim, int colorspace, uint8_t *bytes_out) {
+  if (!codebook || !bytes_out || dim <= 0) return QB200_ERR_ARG;
+  if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED) return QB200_ERR_ARG;
+  for (size_t i = 0; i < K * (size_t)dim; i++) {
+    // ScaledColor::colorSpaceToRGB: (char)std::round((c - 128.0) * 255); ColorSpace: (char)std::round(c)
+    const double r = colorspace == QB200_CS_SCALED ? std::round((codebook[i] - 128.0) * 255) : std::round(codebook[i]);
+    bytes_out[i] = (uint8_t)(int8_t)(int)r;
+  }
+  return QB200_OK;
+}
+
+int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_total, qb200_allreduce_fn allreduce,
+                void *allreduce_user, double *codebook_out, double *distortion_out, qb200_level_report *reports) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_train: no training set (call qb200_set_image first)");
+  if (mode != QB200_MODE_PARITY) return fail(ctx, QB200_ERR_ARG, "qb200_train: unknown mode %d", mode);
+  if (nbits < 0 || nbits > 16) return fail(ctx, QB200_ERR_ARG, "qb200_train: nbits %d outside [0,16]", nbits);
+  if (!codebook_out) return fail(ctx, QB200_ERR_ARG, "qb200_train: codebook_out == NULL");
+  (void)eps;  // HEAD schedule: the eps test only decides between one and two identical fix rounds
+  const uint64_t N = n_total ? n_total : (uint64_t)ctx->src.n_local;
+  // Solution's constructor does trainingSet.at(0) (src/Quantizer.cpp:91): empty input is an error.
+  if (N == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
+  if (!allreduce && ctx->src.n_local == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
+  CU(cudaSetDevice(ctx->device));
+  const int dim = ctx->src.dim;
+  const uint32_t maxK = 1u << nbits;
+  std::vector<double> cb((size_t)maxK * dim), post((size_t)maxK * dim);
+  std::vector<unsigned long long> words;
+  std::vector<uint64_t> n;
+  std::vector<int64_t> S;
+  std::vector<uint64_t> Q;
+  int rc;
+  // initial codevector = mean of the training set (src/Quantizer.cpp:129-130)
+  if ((rc = ensure(ctx, ctx->d_stats, stats_words(1, dim) * 8))) return rc;
+  CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(1, dim) * 8, ctx->stream));
+  CU(launch_accumulate(ctx->src, nullptr, 1, (unsigned long long *)ctx->d_stats.p, ctx->sm_count, ctx->stream));
+  if ((rc = fetch_stats(ctx, 1, allreduce, allreduce_user, words))) return rc;
+  split_stats(words, 1, dim, n, S, Q);
+  if (n[0] != N) return fail(ctx, QB200_ERR_STATE, "vector count mismatch: reduced %llu, expected %llu",
+                             (unsigned long long)n[0], (unsigned long long)N);
+  double dpost = 0, dpre = 0;
+  qb200_finalize_level(ctx->colorspace, 1, dim, N, n.data(), S.data(), Q.data(), nullptr, cb.data(), nullptr, &dpost);
+  uint32_t K = 1;
+  int level = 0;
+  ctx->assign_valid = false;
+  while (K < maxK) {
+    // split (src/Quantizer.cpp:134-138): entry k and entry k+K are (1 + 0.2) and (1 - 0.2) times parent k
+    for (size_t i = 0; i < (size_t)K * dim; i++) {
+      const double v = cb[i];
+      cb[i] = v * (double)(1 + 0.2);
+      cb[(size_t)K * dim + i] = v * (double)(1 - 0.2);
+    }
+    K *= 2;
+    LevelOut lo;
+    if ((rc = run_level(ctx, cb.data(), K, true, reports != nullptr, &lo))) return rc;
+    if ((rc = fetch_stats(ctx, K, allreduce, allreduce_user, words))) return rc;
+    if ((rc = collect_level(ctx, K, reports != nullptr, &lo))) return rc;
+    split_stats(words, K, dim, n, S, Q);
+    qb200_finalize_level(ctx->colorspace, K, dim, N, n.data(), S.data(), Q.data(), cb.data(), post.data(), &dpre,
+                         &dpost);
+    if (reports) {
+      qb200_level_report &r = reports[level];
+      r.K = K;
+      r.flagged = lo.flagged;
+      r.changed = lo.changed;
+      r.kd_depth = (uint32_t)lo.kd_depth;
+      r.ms_assign = lo.ms_assign;
+      r.ms_resolve = lo.ms_resolve;
+      r.ms_accumulate = lo.ms_accumulate;
+      r.distortion_pre = dpre;
+      r.distortion_post = dpost;
+      uint32_t dead = 0;
+      for (uint32_t k = 0; k < K; k++) dead += n[k] == 0;
+      r.dead_cells = dead;
+    }
+    std::memcpy(cb.data(), post.data(), (size_t)K * dim * 8);
+    level++;
+  }
+  std::memcpy(codebook_out, cb.data(), (size_t)K * dim * 8);
+  if (distortion_out) *distortion_out = dpost;
+  if (nbits == 0) {
+    // K == 1: the reference returns the mean, an all-zero assignment and an uninitialised distortion
+    CU(cudaMemsetAsync(ctx->d_assign.p, 0, (size_t)ctx->src.n_local * 4, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->assign_valid = true;
+  }
+  return QB200_OK;
+}
+
+int qb200_get_assign(qb200_ctx *ctx, uint32_t *assign_out) {
+  if (!ctx || !assign_out) return QB200_ERR_ARG;
+  if (!ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_get_assign: no assignment computed yet");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(assign_out, ctx->d_assign.p, (size_t)ctx->src.n_local * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return QB200_OK;
+}
+
+int qb200_get_assign_u64(qb200_ctx *ctx, uint64_t *assign_out) {
+  if (!ctx || !assign_out) return QB200_ERR_ARG;
+  const size_t n = (size_t)ctx->src.n_local;
+  // copy into the upper half of the caller's buffer, then widen in place front to back
+  uint32_t *tmp = reinterpret_cast<uint32_t *>(assign_out) + n;
+  int rc = qb200_get_assign(ctx, tmp);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) assign_out[i] = tmp[i];
+  return QB200_OK;
+}
+
+int qb200_assign_device_ptr(qb200_ctx *ctx, void **dev_ptr) {
+  if (!ctx || !dev_ptr) return QB200_ERR_ARG;
+  if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "no training set");
+  *dev_ptr = ctx->d_assign.p;
+  return QB200_OK;
+}
+
+int qb200_assign_accumulate(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32_t *assign_out,
+                            uint64_t *count_out, int64_t *sum_out, uint64_t *sqsum_out, uint32_t *flagged_out) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_assign_accumulate: no training set");
+  if (!codebook || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_assign_accumulate: empty codebook");
+  if (K > (1u << 24)) return fail(ctx, QB200_ERR_ARG, "qb200_assign_accumulate: K too large");
+  CU(cudaSetDevice(ctx->device));
+  const bool want_stats = count_out || sum_out || sqsum_out;
+  LevelOut lo;
+  int rc = run_level(ctx, codebook, K, want_stats, false, &lo);
+  if (rc) return rc;
+  const int dim = ctx->src.dim;
+  if (want_stats) {
+    std::vector<unsigned long long> words;
+    if ((rc = fetch_stats(ctx, K, nullptr, nullptr, words))) return rc;
+    for (uint32_t k = 0; k < K; k++) {
+      const unsigned long long *r = words.data() + (size_t)k * (dim + 2);
+      if (count_out) count_out[k] = r[0];
+      if (sum_out)
+        for (int e = 0; e < dim; e++) sum_out[(size_t)k * dim + e] = (int64_t)r[1 + e];
+      if (sqsum_out) sqsum_out[k] = r[dim + 1];
+    }
+  } else {
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if ((rc = collect_level(ctx, K, false, &lo))) return rc;
+  if (flagged_out) *flagged_out = lo.flagged;
+  if (assign_out) return qb200_get_assign(ctx, assign_out);
+  return QB200_OK;
+}
+
+int qb200_assign_only(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32_t *flagged_out, float *ms_assign_out,
+                      float *ms_resolve_out) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_assign_only: no training set");
+  if (!codebook || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_assign_only: empty codebook");
+  CU(cudaSetDevice(ctx->device));
+  LevelOut lo;
+  int rc = run_level(ctx, codebook, K, false, true, &lo);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if ((rc = collect_level(ctx, K, true, &lo))) return rc;
+  if (flagged_out) *flagged_out = lo.flagged;
+  if (ms_assign_out) *ms_assign_out = lo.ms_assign;
+  if (ms_resolve_out) *ms_resolve_out = lo.ms_resolve;
+  return QB200_OK;
+}
+
+int qb200_decode(qb200_ctx *ctx, const uint8_t *codebook_bytes, uint32_t K, uint8_t *rgb_out, double *mse_out) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (!ctx->have_set || !ctx->is_image) return fail(ctx, QB200_ERR_STATE, "qb200_decode: the training set is not an image");
+  if (ctx->is_shard) return fail(ctx, QB200_ERR_STATE, "qb200_decode: not available on a sharded context");
+  if (!ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_decode: no assignment computed yet");
+  if (!codebook_bytes || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_decode: empty codebook");
+  CU(cudaSetDevice(ctx->device));
+  const int dim = ctx->src.dim;
+  const size_t cbb = (size_t)K * dim;
+  const size_t img_total = (size_t)ctx->geom.n_pixels * 3 * ctx->geom.n_images;
+  int rc;
+  // d_misc layout: [sq_err (8) | pad to 256 | codebook bytes | pad | decoded image]
+  const size_t off_cb = 256, off_img = (off_cb + cbb + 255) & ~(size_t)255;
+  if ((rc = ensure(ctx, ctx->d_misc, off_img + (rgb_out ? img_total : 0) + 16))) return rc;
+  char *m = (char *)ctx->d_misc.p;
+  CU(cudaMemsetAsync(m, 0, 8, ctx->stream));
+  CU(cudaMemcpyAsync(m + off_cb, codebook_bytes, cbb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_decode(ctx->geom, ctx->src.buf, (const uint32_t *)ctx->d_assign.p, (const uint8_t *)(m + off_cb),
+                   rgb_out ? (uint8_t *)(m + off_img) : nullptr, (unsigned long long *)m, ctx->sm_count, ctx->stream));
+  unsigned long long sq = 0;
+  CU(cudaMemcpyAsync(&sq, m, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (rgb_out) CU(cudaMemcpyAsync(rgb_out, m + off_img, img_total, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (mse_out) *mse_out = (double)sq / (double)img_total;
+  return QB200_OK;
+}
+
+int qb200_measure_fp32_peak(qb200_ctx *ctx, double *tflops_out) {
+  if (!ctx || !tflops_out) return QB200_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 4, iters = 4096;
+  int rc = ensure(ctx, ctx->d_misc, (size_t)blocks * 512 * 4);
+  if (rc) return rc;
+  CU(launch_ffma_probe((float *)ctx->d_misc.p, blocks, 64, 0.999f, 1e-4f, ctx->stream));  // warm-up
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CU(launch_ffma_probe((float *)ctx->d_misc.p, blocks, iters, 0.999f, 1e-4f, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    if (ms < best_ms) best_ms = ms;
+  }
+  const double flops = 2.0 * 8.0 * 16.0 * (double)iters * 512.0 * (double)blocks;
+  *tflops_out = flops / (best_ms * 1e-3) / 1e12;
+  return QB200_OK;
+}
+
+int qb200_launch_count(int reset) {
+  int n = launch_count();
+  if (reset) reset_launch_count();
+  return n;
+}
+
+}  // extern "C"

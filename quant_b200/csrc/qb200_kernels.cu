@@ -1,0 +1,763 @@
+// Hand-written sm_100a kernels of the LBG hot path and their launchers.
+//
+//   assign_kernel      Solution::assignCodeVectors   (/root/reference/src/Quantizer.cpp:24-32)
+//                      brute-force FP32 nearest-codevector FILTER over raw image bytes
+//   resolve_kernel     KDTree::nearestNeighbour      (/root/reference/src/KDTree.cpp:20-29 ->
+//                      nanoflann.hpp:906-920,1188-1270,320-345) exact FP64 re-solve of the queries
+//                      the filter could not decide
+//   accumulate_*       fixCodeVectors / updateDistortion as integer per-cell statistics
+//                      (/root/reference/src/Quantizer.cpp:9-22,59-87)
+//   decode_kernel      decompress + getImageFromVectors (/root/reference/src/Compressor.cpp:64-92,156-165)
+//
+// Why a filter + resolver: the reference computes everything in FP64 (include/VectorOperations.hpp:10)
+// and breaks exact ties by KD-tree traversal order.  FP32 cannot reproduce that bit-for-bit, so the
+// FP32 pass only decides queries whose best and second-best scores differ by more than a rigorous
+// bound on its own rounding error; all others are appended to a list and re-solved by walking the
+// reference's tree with the reference's arithmetic.
+#include "qb200_launch.hpp"
+
+#include <cfloat>
+#include <cstdio>
+
+namespace qb {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared through the TMA unit (SASS: UBLKCP); bytes % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// assign_kernel: FP32 filter
+// ------------------------------------------------------------------------------------------------
+// Lattice coordinates: every training-vector element is the integer L = (int8)byte in [-128,127]
+// (SCALED value = (L+128)/255, NORMAL value = L), codevectors are mapped to the same axis
+// (C = 255*c - 128 resp. C = c) on the host in FP64 and rounded once to FP32.  The score
+//     s_k = |C_k|^2 - 2 <X, C_k>   ( = |X - C_k|^2 - |X|^2 )
+// is one FFMA per dimension: row k of the staged codebook is [-2*C_k[0..DIM), |C_k|^2, pad].
+// |s_k(fp32) - s_k(exact, FP64 codebook)| <= (DIM+3) * 2^-24 * (|X| + max_k|C_k|)^2, so a query is
+// decided here only when  second - best > 2 * that bound (margin_coef carries the constant).
+template <int DIM>
+struct AssignCfg {
+  static constexpr int ROW = ((DIM + 1 + 3) / 4) * 4;  // floats per staged codebook row
+  static constexpr int Q = DIM <= 6 ? 8 : (DIM <= 12 ? 4 : (DIM <= 27 ? 2 : 2));
+  static constexpr int THREADS = DIM <= 27 ? 512 : 256;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
+    assign_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int k_chunk,
+                  const float margin_coef, const float c_max_norm, uint32_t *__restrict__ assign,
+                  uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count,
+                  const unsigned long long tiles) {
+  using Cfg = AssignCfg<DIM>;
+  constexpr int ROW = Cfg::ROW, Q = Cfg::Q, THREADS = Cfg::THREADS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *s_cb = reinterpret_cast<float *>(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x;
+  const int n_chunks = (K + k_chunk - 1) / k_chunk;
+  uint32_t phase = 0;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // stage a codebook chunk with the TMA unit; one elected thread issues, everyone waits on the mbarrier
+  auto stage_chunk = [&](int chunk) {
+    const int k0 = chunk * k_chunk;
+    const int kn = min(k_chunk, K - k0);
+    if (tid == 0) {
+      const uint32_t total = (uint32_t)kn * ROW * 4u;
+      mbar_expect_tx(&s_bar, total);
+      const char *g = reinterpret_cast<const char *>(cb_rows + (size_t)k0 * ROW);
+      char *s = reinterpret_cast<char *>(s_cb);
+      for (uint32_t off = 0; off < total; off += 32768u) {
+        uint32_t n = min(32768u, total - off);
+        tma_load_1d(s + off, g + off, n, &s_bar);
+      }
+    }
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+    return kn;
+  };
+
+  int staged = -1;
+  if (n_chunks == 1) {
+    stage_chunk(0);
+    staged = 0;
+  }
+
+  for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const unsigned long long v0 = tile * (unsigned long long)(THREADS * Q);
+    float x[Q][DIM];
+    float xn[Q];
+    bool live[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const unsigned long long v = v0 + (unsigned long long)q * THREADS + tid;
+      live[q] = v < src.n_local;
+      xn[q] = 0.f;
+      if (live[q]) {
+        unsigned long long base, img;
+        vec_base(src, v, base, img);
+#pragma unroll
+        for (int e = 0; e < DIM; e++) {
+          float f = (float)load_lattice(src, img, base, e);
+          x[q][e] = f;
+          xn[q] = fmaf(f, f, xn[q]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < DIM; e++) x[q][e] = 0.f;
+      }
+    }
+    float best[Q], second[Q];
+    int bidx[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      best[q] = FLT_MAX;
+      second[q] = FLT_MAX;
+      bidx[q] = 0;
+    }
+
+    for (int chunk = 0; chunk < n_chunks; chunk++) {
+      int kn;
+      if (n_chunks == 1) {
+        kn = K;
+      } else {
+        if (staged != chunk) {
+          __syncthreads();  // everyone is done reading the previous chunk
+          kn = stage_chunk(chunk);
+          staged = chunk;
+        } else {
+          kn = min(k_chunk, K - chunk * k_chunk);
+        }
+      }
+      const int k0 = chunk * k_chunk;
+      const float4 *rows = reinterpret_cast<const float4 *>(s_cb);
+#pragma unroll 2
+      for (int k = 0; k < kn; k++) {
+        float c[ROW];
+#pragma unroll
+        for (int r = 0; r < ROW / 4; r++) {
+          float4 t = rows[k * (ROW / 4) + r];
+          c[4 * r + 0] = t.x;
+          c[4 * r + 1] = t.y;
+          c[4 * r + 2] = t.z;
+          c[4 * r + 3] = t.w;
+        }
+        const int kg = k0 + k;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+          float s = c[DIM];
+#pragma unroll
+          for (int e = 0; e < DIM; e++) s = fmaf(x[q][e], c[e], s);
+          second[q] = fminf(second[q], fmaxf(s, best[q]));
+          const bool better = s < best[q];
+          best[q] = fminf(best[q], s);
+          bidx[q] = better ? kg : bidx[q];
+        }
+      }
+    }
+
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const unsigned long long v = v0 + (unsigned long long)q * THREADS + tid;
+      float r = sqrtf(xn[q]) + c_max_norm;
+      const float margin = margin_coef * r * r;
+      const bool flag = live[q] && !((second[q] - best[q]) > margin);
+      if (live[q]) assign[v] = (uint32_t)bidx[q];
+      // warp-aggregated append
+      const unsigned int m = __ballot_sync(0xffffffffu, flag);
+      if (m) {
+        const int lane = tid & 31;
+        const int leader = __ffs(m) - 1;
+        unsigned int basepos = 0;
+        if (lane == leader) basepos = atomicAdd(flag_count, (unsigned int)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+      }
+    }
+  }
+}
+
+// Generic-dimension filter (any dim <= kMaxDim that has no template instance): one query per
+// thread, the query lives in shared memory (column per thread), codebook rows streamed from L2.
+// Same score, same margin rule; slower, only there so that every block shape works.
+__global__ void __launch_bounds__(128, 1)
+    assign_generic_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int row,
+                          const float margin_coef, const float c_max_norm, uint32_t *__restrict__ assign,
+                          uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *s_x = reinterpret_cast<float *>(smem_raw);  // [dim][128]
+  const int dim = src.dim, tid = threadIdx.x;
+  for (unsigned long long v0 = (unsigned long long)blockIdx.x * 128; v0 < src.n_local;
+       v0 += (unsigned long long)gridDim.x * 128) {
+    const unsigned long long v = v0 + tid;
+    const bool live = v < src.n_local;
+    float xn = 0.f;
+    if (live) {
+      unsigned long long base, img;
+      vec_base(src, v, base, img);
+      for (int e = 0; e < dim; e++) {
+        float f = (float)load_lattice(src, img, base, e);
+        s_x[e * 128 + tid] = f;
+        xn = fmaf(f, f, xn);
+      }
+    } else {
+      for (int e = 0; e < dim; e++) s_x[e * 128 + tid] = 0.f;
+    }
+    float best = FLT_MAX, second = FLT_MAX;
+    int bidx = 0;
+    for (int k = 0; k < K; k++) {
+      const float *c = cb_rows + (size_t)k * row;
+      float s = __ldg(c + dim);
+      for (int e = 0; e < dim; e++) s = fmaf(s_x[e * 128 + tid], __ldg(c + e), s);
+      second = fminf(second, fmaxf(s, best));
+      const bool better = s < best;
+      best = fminf(best, s);
+      bidx = better ? k : bidx;
+    }
+    float r = sqrtf(xn) + c_max_norm;
+    const bool flag = live && !((second - best) > margin_coef * r * r);
+    if (live) assign[v] = (uint32_t)bidx;
+    const unsigned int m = __ballot_sync(0xffffffffu, flag);
+    if (m) {
+      const int lane = tid & 31, leader = __ffs(m) - 1;
+      unsigned int basepos = 0;
+      if (lane == leader) basepos = atomicAdd(flag_count, (unsigned int)__popc(m));
+      basepos = __shfl_sync(0xffffffffu, basepos, leader);
+      if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// resolve_kernel: exact FP64 nearest neighbour in nanoflann's traversal order
+// ------------------------------------------------------------------------------------------------
+// One thread per flagged query.  Arithmetic is spelled with the round-to-nearest intrinsics so
+// that nvcc cannot contract a*b+c into an FMA: the reference's x86-64 build has none.
+__device__ __forceinline__ double sq_diff(double a, double b) {
+  const double d = __dsub_rn(a, b);
+  return __dmul_rn(d, d);
+}
+
+// L2_Adaptor::operator() (nanoflann.hpp:320-345) with worst_dist = -1: groups of four summed as
+// ((d0^2 + d1^2) + d2^2) + d3^2 and added to the running result, then a scalar tail.
+__device__ __forceinline__ double nanoflann_l2(const double *a, const double *__restrict__ b, int dim) {
+  double result = 0.0;
+  int d = 0;
+  for (; d + 3 < dim; d += 4) {
+    const double g = __dadd_rn(__dadd_rn(__dadd_rn(sq_diff(a[d], b[d]), sq_diff(a[d + 1], b[d + 1])),
+                                         sq_diff(a[d + 2], b[d + 2])),
+                               sq_diff(a[d + 3], b[d + 3]));
+    result = __dadd_rn(result, g);
+  }
+  for (; d < dim; d++) result = __dadd_rn(result, sq_diff(a[d], b[d]));
+  return result;
+}
+
+struct Frame {
+  int node, other, feat, phase;
+  double mind, cut, saved;
+};
+
+template <int DIMCAP, int DEPTHCAP>
+__global__ void __launch_bounds__(128)
+    resolve_kernel(const VecSource src, const int scaled, const double *__restrict__ cb, const KdDevice tree,
+                   const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
+                   uint32_t *__restrict__ assign, unsigned int *__restrict__ changed) {
+  const int dim = src.dim;
+  const unsigned int total = *flag_count;
+  double x[DIMCAP], dists[DIMCAP];
+  Frame stack[DEPTHCAP];
+  for (unsigned int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    const unsigned long long v = flag_list[f];
+    unsigned long long base, img;
+    vec_base(src, v, base, img);
+    for (int e = 0; e < dim; e++) {
+      const double L = (double)load_lattice(src, img, base, e);
+      // ScaledColor::RGBtoColorSpace: ((double)c + 128.0) / 255 (src/ColorSpace.cpp:16-21);
+      // a past-the-end element is the literal 0.0 and (-128 + 128)/255 == 0.0 as well.
+      x[e] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+    }
+    // computeInitialDistances (nanoflann.hpp:1188-1205)
+    double distsq = 0.0;
+    for (int e = 0; e < dim; e++) {
+      dists[e] = 0.0;
+      if (x[e] < tree.bbox_low[e]) {
+        dists[e] = sq_diff(x[e], tree.bbox_low[e]);
+        distsq = __dadd_rn(distsq, dists[e]);
+      }
+      if (x[e] > tree.bbox_high[e]) {
+        dists[e] = sq_diff(x[e], tree.bbox_high[e]);
+        distsq = __dadd_rn(distsq, dists[e]);
+      }
+    }
+    // KNNResultSet with capacity 1 (nanoflann.hpp:78-144)
+    double best = DBL_MAX;
+    unsigned int best_idx = 0;
+    bool have = false;
+    // searchLevel (nanoflann.hpp:1213-1270), recursion unrolled onto an explicit stack
+    int sp = 0;
+    stack[0].node = 0;
+    stack[0].mind = distsq;
+    stack[0].phase = 0;
+    while (sp >= 0) {
+      Frame &fr = stack[sp];
+      const KdNode nd = tree.nodes[fr.node];
+      if (fr.phase == 0) {
+        if (nd.child1 < 0 && nd.child2 < 0) {
+          const double worst = best;  // read once per leaf (:1219)
+          for (int p = nd.a; p < nd.b; p++) {
+            const unsigned int index = tree.vind[p];
+            const double dist = nanoflann_l2(x, cb + (size_t)index * dim, dim);
+            if (dist < worst) {
+              if (!have || best > dist) {  // addPoint: strict '>' (:121)
+                best = dist;
+                best_idx = index;
+              }
+              have = true;
+            }
+          }
+          sp--;
+          continue;
+        }
+        const int feat = nd.a;
+        const double val = x[feat];
+        const double diff1 = __dsub_rn(val, nd.divlow);
+        const double diff2 = __dsub_rn(val, nd.divhigh);
+        int first;
+        if (__dadd_rn(diff1, diff2) < 0) {
+          first = nd.child1;
+          fr.other = nd.child2;
+          fr.cut = sq_diff(val, nd.divhigh);
+        } else {
+          first = nd.child2;
+          fr.other = nd.child1;
+          fr.cut = sq_diff(val, nd.divlow);
+        }
+        fr.feat = feat;
+        fr.phase = 1;
+        const double m = fr.mind;
+        sp++;
+        stack[sp].node = first;
+        stack[sp].mind = m;
+        stack[sp].phase = 0;
+      } else if (fr.phase == 1) {
+        const double dst = dists[fr.feat];
+        fr.saved = dst;
+        const double m2 = __dsub_rn(__dadd_rn(fr.mind, fr.cut), dst);  // mindistsq + cut_dist - dst
+        dists[fr.feat] = fr.cut;
+        fr.phase = 2;
+        if (m2 <= best) {  // mindistsq*epsError <= worstDist(), epsError == 1
+          const int other = fr.other;
+          sp++;
+          stack[sp].node = other;
+          stack[sp].mind = m2;
+          stack[sp].phase = 0;
+        }
+      } else {
+        dists[fr.feat] = fr.saved;
+        sp--;
+      }
+    }
+    const uint32_t old = assign[v];
+    if (old != best_idx) {
+      assign[v] = best_idx;
+      atomicAdd(changed, 1u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulate: per-cell integer statistics  {n_k, S_k[d] = sum L, Q_k = sum_d sum L^2}
+// ------------------------------------------------------------------------------------------------
+// Small codebooks (KT*(DIM+2) accumulators fit in registers): every thread keeps all cells'
+// partial sums, predicated adds, one shuffle tree per accumulator at the end - no atomics while
+// streaming, so K = 1, 2, 4, 8 (where every vector lands in a handful of cells) run at HBM speed.
+template <int DIM, int KT>
+__global__ void __launch_bounds__(256)
+    accumulate_reg_kernel(const VecSource src, const uint32_t *__restrict__ assign,
+                          unsigned long long *__restrict__ stats) {
+  int n[KT], S[KT][DIM];
+  unsigned long long Qs[KT];
+#pragma unroll
+  for (int k = 0; k < KT; k++) {
+    n[k] = 0;
+    Qs[k] = 0;
+#pragma unroll
+    for (int e = 0; e < DIM; e++) S[k][e] = 0;
+  }
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < src.n_local;
+       v += (unsigned long long)gridDim.x * blockDim.x) {
+    const int a = (KT == 1 || assign == nullptr) ? 0 : (int)assign[v];
+    unsigned long long base, img;
+    vec_base(src, v, base, img);
+    int L[DIM];
+    int q = 0;
+#pragma unroll
+    for (int e = 0; e < DIM; e++) {
+      L[e] = load_lattice(src, img, base, e);
+      q += L[e] * L[e];
+    }
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+      const bool hit = (a == k);
+      n[k] += hit ? 1 : 0;
+      Qs[k] += hit ? (unsigned long long)q : 0ull;
+#pragma unroll
+      for (int e = 0; e < DIM; e++) S[k][e] += hit ? L[e] : 0;
+    }
+  }
+  // warp tree, then one 64-bit global atomic per accumulator per warp
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < KT; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      n[k] += __shfl_xor_sync(0xffffffffu, n[k], o);
+      Qs[k] += __shfl_xor_sync(0xffffffffu, Qs[k], o);
+#pragma unroll
+      for (int e = 0; e < DIM; e++) S[k][e] += __shfl_xor_sync(0xffffffffu, S[k][e], o);
+    }
+    if (lane == 0 && n[k] != 0) {
+      unsigned long long *row = stats + (size_t)k * (DIM + 2);
+      atomicAdd(row, (unsigned long long)n[k]);
+#pragma unroll
+      for (int e = 0; e < DIM; e++)
+        if (S[k][e] != 0) atomicAdd(row + 1 + e, (unsigned long long)(long long)S[k][e]);
+      atomicAdd(row + DIM + 1, Qs[k]);
+    }
+  }
+}
+
+// General case: per-CTA privatised table in shared memory (cells [k_base, k_base + k_count) only,
+// so codebooks whose table exceeds shared memory are handled by blockIdx.y slices that each re-read
+// the 4 + dim bytes per vector), shared-memory atomics while streaming, 64-bit global atomics of
+// the non-zero entries at the end.
+__global__ void __launch_bounds__(256)
+    accumulate_smem_kernel(const VecSource src, const uint32_t *__restrict__ assign, const int K,
+                           const int k_slice, unsigned long long *__restrict__ stats) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int dim = src.dim;
+  const int k_base = blockIdx.y * k_slice;
+  const int k_count = min(k_slice, K - k_base);
+  unsigned long long *s_q = reinterpret_cast<unsigned long long *>(smem_raw);  // [k_slice]
+  int *s_n = reinterpret_cast<int *>(s_q + k_slice);                           // [k_slice]
+  int *s_s = s_n + k_slice;                                                    // [k_slice][dim]
+  for (int i = threadIdx.x; i < k_slice; i += blockDim.x) {
+    s_q[i] = 0;
+    s_n[i] = 0;
+  }
+  for (int i = threadIdx.x; i < k_slice * dim; i += blockDim.x) s_s[i] = 0;
+  __syncthreads();
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < src.n_local;
+       v += (unsigned long long)gridDim.x * blockDim.x) {
+    const int a = (assign ? (int)assign[v] : 0) - k_base;
+    if (a < 0 || a >= k_count) continue;
+    unsigned long long base, img;
+    vec_base(src, v, base, img);
+    int q = 0;
+    int *row = s_s + a * dim;
+    for (int e = 0; e < dim; e++) {
+      const int L = load_lattice(src, img, base, e);
+      q += L * L;
+      if (L != 0) atomicAdd(row + e, L);
+    }
+    atomicAdd(s_n + a, 1);
+    atomicAdd(s_q + a, (unsigned long long)q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k_count; i += blockDim.x) {
+    if (s_n[i] != 0) {
+      unsigned long long *row = stats + (size_t)(k_base + i) * (dim + 2);
+      atomicAdd(row, (unsigned long long)s_n[i]);
+      atomicAdd(row + dim + 1, s_q[i]);
+    }
+  }
+  for (int i = threadIdx.x; i < k_count * dim; i += blockDim.x) {
+    const int sv = s_s[i];
+    if (sv != 0) {
+      const int k = i / dim, e = i - k * dim;
+      atomicAdd(stats + (size_t)(k_base + k) * (dim + 2) + 1 + e, (unsigned long long)(long long)sv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode: indices + codebook bytes -> RGB bytes, and the report's pixel-domain squared error
+// ------------------------------------------------------------------------------------------------
+// getImageFromVectors (src/Compressor.cpp:64-92) PUSHES block elements into pixels in (i, j, x, y)
+// loop order; on shapes where ySize is not a multiple of h a block overflows in y and its writes
+// wrap into the next x line, so a pixel can be written twice and the later write wins.  One thread
+// per pixel PULLS instead: it enumerates the (x, y) pairs with x*ySize + y == p that some block
+// covers and takes the one the sequential loops would have executed last.
+__global__ void __launch_bounds__(256)
+    decode_kernel(const DecodeGeom g, const uint8_t *__restrict__ orig, const uint32_t *__restrict__ assign,
+                  const uint8_t *__restrict__ cb_bytes, uint8_t *__restrict__ out,
+                  unsigned long long *__restrict__ sq_err) {
+  unsigned long long err = 0;
+  const unsigned long long total = g.n_pixels * (unsigned long long)g.n_images;
+  const unsigned long long per_image_vecs = (unsigned long long)g.wB * g.hB;
+  const long long y_cover = (long long)g.hB * g.h;  // blocks cover y in [0, y_cover)
+  const int dim = 3 * g.w * g.h;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long img = t / g.n_pixels;
+    const long long p = (long long)(t - img * g.n_pixels);
+    long long x = p / g.ySize, y = p - x * g.ySize;
+    // candidates: (x, y), (x-1, y+ySize), ... while y < y_cover; keep the lexicographically largest (i, j, x, y)
+    long long bi = -1, bj = -1, bx = 0, by = 0;
+    while (x >= 0 && y < y_cover) {
+      const long long i = x / g.w, j = y / g.h;
+      if (i > bi || (i == bi && (j > bj || (j == bj && (x > bx || (x == bx && y > by)))))) {
+        bi = i; bj = j; bx = x; by = y;
+      }
+      x -= 1;
+      y += g.ySize;
+    }
+    uint8_t px[3] = {0, 0, 0};  // a pixel nobody writes keeps RGB{} == 0
+    if (bi >= 0) {
+      const unsigned long long vec = img * per_image_vecs + (unsigned long long)bi * g.hB + (unsigned long long)bj;
+      const int e = (int)(((bx - bi * g.w) * g.h + (by - bj * g.h)) * 3);
+      const uint8_t *c = cb_bytes + (size_t)assign[vec] * dim + e;
+      px[0] = __ldg(c); px[1] = __ldg(c + 1); px[2] = __ldg(c + 2);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      if (out) out[t * 3 + ch] = px[ch];
+      // the report compares the bytes as SIGNED chars (src/Compressor.cpp:141-143)
+      const int d = (int)(signed char)__ldg(orig + t * 3 + ch) - (int)(signed char)px[ch];
+      err += (unsigned long long)(d * d);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+  if ((threadIdx.x & 31) == 0 && err) atomicAdd(sq_err, err);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 FMA peak probe (roofline denominator measured in the same run)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) ffma_probe_kernel(float *out, int iters, const float m, const float c) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      a0 = fmaf(a0, m, c);
+      a1 = fmaf(a1, m, c);
+      a2 = fmaf(a2, m, c);
+      a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c);
+      a5 = fmaf(a5, m, c);
+      a6 = fmaf(a6, m, c);
+      a7 = fmaf(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int g_launch_count = 0;
+int launch_count() { return g_launch_count; }
+void reset_launch_count() { g_launch_count = 0; }
+
+int assign_row_floats(int dim) { return ((dim + 1 + 3) / 4) * 4; }
+
+template <int DIM>
+static cudaError_t launch_assign_t(const AssignLaunch &a) {
+  using Cfg = AssignCfg<DIM>;
+  const size_t row_bytes = (size_t)Cfg::ROW * 4;
+  const size_t smem_cap = 200 * 1024;
+  int k_chunk = a.K;
+  if ((size_t)k_chunk * row_bytes > smem_cap) k_chunk = (int)(smem_cap / row_bytes) & ~7;
+  const size_t smem = (size_t)k_chunk * row_bytes;
+  {
+    cudaError_t e = cudaFuncSetAttribute(assign_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_cap);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned long long per_tile = (unsigned long long)Cfg::THREADS * Cfg::Q;
+  const unsigned long long tiles = (a.src.n_local + per_tile - 1) / per_tile;
+  unsigned long long grid = tiles < (unsigned long long)a.sm_count ? tiles : (unsigned long long)a.sm_count;
+  if (grid == 0) return cudaSuccess;
+  assign_kernel<DIM><<<(unsigned int)grid, Cfg::THREADS, smem, a.stream>>>(
+      a.src, a.cb_rows, a.K, k_chunk, a.margin_coef, a.c_max_norm, a.assign, a.flag_list, a.flag_count, tiles);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assign(const AssignLaunch &a) {
+  switch (a.src.dim) {
+    case 3: return launch_assign_t<3>(a);
+    case 6: return launch_assign_t<6>(a);
+    case 9: return launch_assign_t<9>(a);
+    case 12: return launch_assign_t<12>(a);
+    case 24: return launch_assign_t<24>(a);
+    case 27: return launch_assign_t<27>(a);
+    case 48: return launch_assign_t<48>(a);
+    default: break;
+  }
+  const size_t smem = (size_t)a.src.dim * 128 * 4;
+  {
+    cudaError_t e = cudaFuncSetAttribute(assign_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kMaxDim * 128 * 4);
+    if (e != cudaSuccess) return e;
+  }
+  unsigned long long blocks = (a.src.n_local + 127) / 128;
+  const unsigned long long cap = (unsigned long long)a.sm_count * 2;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return cudaSuccess;
+  assign_generic_kernel<<<(unsigned int)blocks, 128, smem, a.stream>>>(a.src, a.cb_rows, a.K,
+                                                                        assign_row_floats(a.src.dim), a.margin_coef,
+                                                                        a.c_max_norm, a.assign, a.flag_list,
+                                                                        a.flag_count);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const KdDevice &tree,
+                           const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
+                           unsigned int *changed, unsigned int flagged_hint, int sm_count, cudaStream_t stream) {
+  unsigned int blocks = (unsigned int)sm_count * 4;
+  if (flagged_hint != 0xffffffffu) {
+    unsigned int need = (flagged_hint + 127) / 128;
+    if (need == 0) return cudaSuccess;
+    if (need < blocks) blocks = need;
+  }
+  const bool deep = tree.depth > 92;
+  if (src.dim <= 16) {
+    if (!deep)
+      resolve_kernel<16, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+    else
+      resolve_kernel<16, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+  } else if (src.dim <= 48) {
+    if (!deep)
+      resolve_kernel<48, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+    else
+      resolve_kernel<48, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+  } else {
+    if (!deep)
+      resolve_kernel<kMaxDim, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+    else
+      resolve_kernel<kMaxDim, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+  }
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+template <int DIM, int KT>
+static cudaError_t launch_acc_reg(const VecSource &src, const uint32_t *assign, unsigned long long *stats,
+                                  int sm_count, cudaStream_t stream) {
+  unsigned long long blocks = (src.n_local + 255) / 256;
+  const unsigned long long cap = (unsigned long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return cudaSuccess;
+  accumulate_reg_kernel<DIM, KT><<<(unsigned int)blocks, 256, 0, stream>>>(src, assign, stats);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+template <int DIM>
+static bool try_acc_reg(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats, int sm_count,
+                        cudaStream_t stream, cudaError_t &err) {
+  if (K == 1) { err = launch_acc_reg<DIM, 1>(src, assign, stats, sm_count, stream); return true; }
+  if (K == 2) { err = launch_acc_reg<DIM, 2>(src, assign, stats, sm_count, stream); return true; }
+  if constexpr (DIM <= 12) {
+    if (K == 4) { err = launch_acc_reg<DIM, 4>(src, assign, stats, sm_count, stream); return true; }
+    if (K == 8) { err = launch_acc_reg<DIM, 8>(src, assign, stats, sm_count, stream); return true; }
+  }
+  return false;
+}
+
+cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats,
+                              int sm_count, cudaStream_t stream) {
+  cudaError_t err = cudaSuccess;
+  bool done = false;
+  if (K <= 8) {
+    switch (src.dim) {
+      case 3: done = try_acc_reg<3>(src, assign, K, stats, sm_count, stream, err); break;
+      case 6: done = try_acc_reg<6>(src, assign, K, stats, sm_count, stream, err); break;
+      case 9: done = try_acc_reg<9>(src, assign, K, stats, sm_count, stream, err); break;
+      case 12: done = try_acc_reg<12>(src, assign, K, stats, sm_count, stream, err); break;
+      case 24: done = try_acc_reg<24>(src, assign, K, stats, sm_count, stream, err); break;
+      case 27: done = try_acc_reg<27>(src, assign, K, stats, sm_count, stream, err); break;
+      case 48: done = try_acc_reg<48>(src, assign, K, stats, sm_count, stream, err); break;
+      default: break;
+    }
+  }
+  if (done) return err;
+  if (assign == nullptr && K != 1) return cudaErrorInvalidValue;
+  const int dim = src.dim;
+  const size_t per_cell = 8 + 4 + 4 * (size_t)dim;
+  const size_t smem_cap = 200 * 1024;
+  int k_slice = K;
+  if ((size_t)k_slice * per_cell > smem_cap) k_slice = (int)(smem_cap / per_cell);
+  const int slices = (K + k_slice - 1) / k_slice;
+  const size_t smem = (size_t)k_slice * per_cell;
+  err = cudaFuncSetAttribute(accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+  if (err != cudaSuccess) return err;
+  unsigned long long blocks = (src.n_local + 255) / 256;
+  unsigned long long cap = (unsigned long long)sm_count * (smem > 100 * 1024 ? 1 : 2);
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return cudaSuccess;
+  dim3 grid((unsigned int)blocks, (unsigned int)slices);
+  accumulate_smem_kernel<<<grid, 256, smem, stream>>>(src, assign, K, k_slice, stats);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32_t *assign, const uint8_t *cb_bytes,
+                          uint8_t *out, unsigned long long *sq_err, int sm_count, cudaStream_t stream) {
+  const unsigned long long total = g.n_pixels * (unsigned long long)g.n_images;
+  unsigned long long blocks = (total + 255) / 256;
+  const unsigned long long cap = (unsigned long long)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return cudaSuccess;
+  decode_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(g, orig, assign, cb_bytes, out, sq_err);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ffma_probe(float *out, int blocks, int iters, float m, float c, cudaStream_t stream) {
+  ffma_probe_kernel<<<blocks, 512, 0, stream>>>(out, iters, m, c);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+}  // namespace qb

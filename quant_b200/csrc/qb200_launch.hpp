@@ -1,0 +1,48 @@
+// Host-callable launchers of the kernels in qb200_kernels.cu.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "qb200_device.cuh"
+
+namespace qb {
+
+struct AssignLaunch {
+  VecSource src;
+  const float *cb_rows;      // K rows of assign_row_floats(dim) floats: [-2*C_k, |C_k|^2, pad]
+  int K;
+  float margin_coef;         // flag when second - best <= margin_coef * (|X| + c_max_norm)^2
+  float c_max_norm;          // max_k |C_k| (lattice units), rounded up
+  uint32_t *assign;          // n_local
+  uint32_t *flag_list;       // n_local (capacity)
+  unsigned int *flag_count;  // device counter, zeroed by the caller
+  int sm_count;
+  cudaStream_t stream;
+};
+
+int assign_row_floats(int dim);
+cudaError_t launch_assign(const AssignLaunch &a);
+cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const KdDevice &tree,
+                           const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
+                           unsigned int *changed, unsigned int flagged_hint, int sm_count, cudaStream_t stream);
+// stats must be zeroed by the caller; assign may be null only for K == 1.
+cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats,
+                              int sm_count, cudaStream_t stream);
+
+struct DecodeGeom {
+  int xSize, ySize, w, h;
+  unsigned int wB, hB;
+  unsigned long long n_pixels;  // per image
+  int n_images;
+};
+cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32_t *assign, const uint8_t *cb_bytes,
+                          uint8_t *out, unsigned long long *sq_err, int sm_count, cudaStream_t stream);
+cudaError_t launch_ffma_probe(float *out, int blocks, int iters, float m, float c, cudaStream_t stream);
+
+constexpr int kResolveDepthCap = 512;
+
+int launch_count();
+void reset_launch_count();
+
+}  // namespace qb
