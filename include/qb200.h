@@ -168,6 +168,12 @@ int qb200_decode(qb200_ctx *ctx, const uint8_t *codebook_bytes, uint32_t K, uint
  * denominator for the assignment kernel. */
 int qb200_measure_fp32_peak(qb200_ctx *ctx, double *tflops_out);
 
+/* Host-only diagnostic: builds the nanoflann-order KD tree (leaf size 10, src/KDTree.cpp:4;
+ * nanoflann.hpp:1046-1186) the resolver walks and returns its point order (K entries), node count
+ * and depth, so that the host logic can be checked without a GPU. */
+int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *order_out,
+                         int *n_nodes_out, int *depth_out);
+
 /* Number of kernels this library has launched in this process since the last reset
  * (bench.py's "gpu_launches"). */
 int qb200_launch_count(int reset);

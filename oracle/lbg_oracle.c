@@ -307,6 +307,9 @@ void orc_kd_free(orc_kdtree *t) {
 }
 
 int orc_kd_depth(const orc_kdtree *t) { return t->max_depth; }
+void orc_kd_order(const orc_kdtree *t, uint32_t *out) {
+  for (size_t i = 0; i < t->n; i++) out[i] = (uint32_t)t->vind[i];
+}
 size_t orc_kd_num_nodes(const orc_kdtree *t) { return t->n_nodes; }
 
 /* nanoflann.hpp:320-345 L2_Adaptor::operator() with worst_dist = -1 (no early exit): groups of

@@ -325,3 +325,13 @@ class PortLib:
         r = (self.lib.orc_kd_depth(t), self.lib.orc_kd_num_nodes(t))
         self.lib.orc_kd_free(t)
         return r
+
+    def kd_order(self, cb):
+        cb = np.ascontiguousarray(cb, np.float64)
+        t = self.lib.orc_kd_build(cb.reshape(-1), cb.shape[0], cb.shape[1])
+        out = np.empty(cb.shape[0], np.uint32)
+        self.lib.orc_kd_order.argtypes = [C.c_void_p, _u32p]
+        self.lib.orc_kd_order(t, out)
+        r = (self.lib.orc_kd_depth(t), self.lib.orc_kd_num_nodes(t), out)
+        self.lib.orc_kd_free(t)
+        return r

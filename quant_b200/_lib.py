@@ -60,6 +60,8 @@ SIGNATURES = {
     "qb200_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                C.POINTER(C.c_double)]),
     "qb200_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "qb200_debug_kd_build": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "qb200_launch_count": (C.c_int, [C.c_int]),
 }
 

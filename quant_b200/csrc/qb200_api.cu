@@ -752,6 +752,18 @@ int qb200_measure_fp32_peak(qb200_ctx *ctx, double *tflops_out) {
   return QB200_OK;
 }
 
+int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *order_out, int *n_nodes_out,
+                         int *depth_out) {
+  if (!points || K == 0 || dim <= 0) return QB200_ERR_ARG;
+  KdHostTree t;
+  build_kd_tree(points, K, dim, 10, t);
+  if (order_out)
+    for (size_t i = 0; i < K; i++) order_out[i] = t.order[i];
+  if (n_nodes_out) *n_nodes_out = (int)t.nodes.size();
+  if (depth_out) *depth_out = t.depth;
+  return QB200_OK;
+}
+
 int qb200_launch_count(int reset) {
   int n = launch_count();
   if (reset) reset_launch_count();

@@ -1,0 +1,86 @@
+"""The C-ABI shared library: loads, exports every symbol include/qb200.h declares, and its
+host-only entry points agree with the oracle.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import quant_b200 as qb
+from quant_b200 import _lib
+from conftest import HAVE_GPU, ROOT, load_golden
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "qb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qb200_[a-z0-9_]+)\s*\(", src)) - {"qb200_allreduce_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    lib = qb.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/qb200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "python binding and header disagree"
+    assert lib.qb200_version() == 100
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libqb200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="this box has a GPU")
+def test_no_device_is_an_error_not_a_fallback():
+    with pytest.raises(qb.Qb200Error) as e:
+        qb.Context(0)
+    assert e.value.code == _lib.ERR_NODEV
+
+
+def test_null_arguments_are_rejected():
+    lib = qb.load()
+    assert lib.qb200_create(0, None) == _lib.ERR_ARG
+    assert lib.qb200_codebook_to_bytes(None, 1, 3, 1, None) == _lib.ERR_ARG
+    assert lib.qb200_get_assign(None, None) == _lib.ERR_ARG
+    assert lib.qb200_num_vectors(None) == 0
+
+
+@pytest.mark.parametrize("cs", [0, 1])
+def test_codebook_to_bytes_matches_oracle(port, cs):
+    rng = np.random.default_rng(3)
+    if cs == 1:
+        cb = rng.random((300, 12)) * 1.3 - 0.1
+        cb[:40] = (rng.integers(0, 255, (40, 12)) + 0.5) / 255.0     # exact halves
+        cb[40] = 0.0                                                 # dead cell
+    else:
+        cb = rng.random((300, 12)) * 255 - 128
+        cb[:40] = rng.integers(-128, 127, (40, 12)) + 0.5
+    assert np.array_equal(qb.codebook_to_bytes(cb, cs), port.codebook_to_bytes(cb, cs))
+
+
+def test_kd_build_matches_oracle_tree(port):
+    g = load_golden("kodim01_crop_2x2_n10")
+    for i in (3, 6, 9):
+        cb = g.level(i)["cb_pre"]
+        K = cb.shape[0]
+        order = np.empty(K, np.uint32)
+        nn, dp = C.c_int(), C.c_int()
+        rc = qb.load().qb200_debug_kd_build(cb.ctypes.data_as(C.c_void_p), K, cb.shape[1],
+                                            order.ctypes.data_as(C.c_void_p), C.byref(nn), C.byref(dp))
+        assert rc == 0
+        depth, nodes, oorder = port.kd_order(cb)
+        assert (dp.value, nn.value) == (depth, nodes)
+        assert np.array_equal(order, oorder)
+    # degenerate: all points identical -> balanced count/2 splits
+    cb = np.zeros((64, 12))
+    order = np.empty(64, np.uint32)
+    nn, dp = C.c_int(), C.c_int()
+    assert qb.load().qb200_debug_kd_build(cb.ctypes.data_as(C.c_void_p), 64, 12,
+                                          order.ctypes.data_as(C.c_void_p), C.byref(nn), C.byref(dp)) == 0
+    depth, nodes, oorder = port.kd_order(cb)
+    assert (dp.value, nn.value) == (depth, nodes) and np.array_equal(order, oorder)
