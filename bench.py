@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py - LBG codebook-training throughput on B200 (the metric BASELINE.json names).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+
+A STEP is one complete LBG codebook train (LBGQuantizer::quantize, /root/reference/src/Quantizer.cpp:
+121-143: mean -> nbits x {split, assign, accumulate, fix}) over one synthetic image.  Per step the
+brute-force-equivalent work is N*(2K-2) distance evaluations (one assignment pass per split level,
+SURVEY.md D2); `value` = that / device time, in Gdist-evals/s, whole job over all ranks.
+
+  value      image already resident in HBM (borrowed device pointer); codebook comes back to the host
+             every level because the next level's KD tree is built there (it is part of the path)
+  e2e        the same train through the reference-facing call sequence with HOST buffers: pinned host
+             RGB bytes -> qb200_set_image_band (H2D) -> qb200_train -> qb200_get_assign (D2H indices)
+  roofline   the assignment kernel of the LAST level (K = 2^nbits), timed live by CUDA events on the
+             library's stream: algorithmic flops = N*K*3*dim (sub, mul, add per dimension, SURVEY.md
+             8d) against the FP32 FMA peak measured in the same run (MEASURED_PEAKS.json has no FP32
+             figure); `hbm` = the accumulate kernel of that level against the measured copy bandwidth
+  cpu_baseline / --impl reference
+             the UNMODIFIED reference (oracle/_ref/libquantref_release.so: its sources + its Release
+             flags, driven through CompressedImage::compress) on the box's host cores, on a bounded
+             band of the same image; else the plain-C oracle port (1 thread)
+
+Multi-GPU (torchrun, one rank per GPU): weak scaling - every rank owns one workload-sized band of a
+`world` times taller image; the only exchange is one NCCL all-reduce of K*(dim+2) 64-bit integers
+per split level.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> (band xSize per rank, ySize, w, h, nbits, description)
+WORKLOADS = {
+    "c1": (768, 512, 2, 2, 10, "synthetic noise 768x512 PPM, 2x2 block, 1024 codevectors (Kodak shape)"),
+    "c2": (4096, 4096, 2, 2, 10, "synthetic noise 4096x4096 PPM, 2x2 block (12-dim), 1024 codevectors, 4.2M vectors"),
+    "c3": (16384, 16384, 2, 2, 12, "synthetic noise 16384x16384 PPM, 2x2 block, 4096 codevectors, 67M vectors"),
+    "c4": (8192, 8192, 4, 4, 8, "synthetic noise 8192x8192 PPM, 4x4 block (48-dim), 256 codevectors"),
+}
+METRIC = "LBG Gdist-evals/s (N*K summed over split levels = N*(2K-2) per codebook train)"
+UNIT = "Gdist-evals/s"
+EPS = float(np.float32(1e-6))
+
+
+def noise_band(xs, ys, seed):
+    """`xs` pixel lines of `ys` pixels (the reference addresses pixel (x, y) at x*ySize + y)."""
+    return np.random.default_rng(seed).integers(0, 256, (xs, ys, 3), dtype=np.uint8)
+
+
+def evals_per_train(n_vectors, nbits):
+    return float(n_vectors) * (2.0 * (1 << nbits) - 2.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx.append(float(f[1]))
+                if t0 <= t <= t1 + 0.1:
+                    sm.append(float(f[0]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if t0 <= t <= t1 + 0.1 and v.lower().startswith("active"):
+                    reasons.add(name)
+        if not mx:
+            return None
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------
+def cpu_engine():
+    """('reference', RefLib release) when oracle/_ref travelled here, else ('port', PortLib)."""
+    from oracle.pyoracle import PortLib, RefLib, have_ref
+    if have_ref("release"):
+        try:
+            return "reference", RefLib("release")
+        except OSError:
+            pass
+    so = os.path.join(ROOT, "oracle", "liblbg_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
+    return "port", PortLib()
+
+
+def cpu_train_seconds(kind, eng, band, xs, ys, w, h, nbits):
+    """One train on the CPU, timed over the reference's own scope (block extraction + quantize,
+    src/Compressor.cpp:118-123)."""
+    if kind == "reference":
+        return eng.compress(band, xs, ys, w, h, nbits, want_outputs=False)["seconds"]
+    t = time.perf_counter()
+    X = eng.blocks(band, xs, ys, w, h)
+    eng.quantize(X, nbits)
+    return time.perf_counter() - t
+
+
+def cpu_sample(kind, eng, wl, budget_s, steps, warmup):
+    """Times `steps` trains (after `warmup`) on a band of the workload image sized to fit budget_s."""
+    bx, ys, w, h, nbits, _ = WORKLOADS[wl]
+    cores = eng.max_threads() if kind == "reference" else 1
+    # calibrate t(lines) = a + b*lines on two small bands (the first call also warms the OpenMP pool)
+    p1 = max(w * 8, min(bx, 64 if kind == "reference" else 16))
+    p2 = min(bx, 4 * p1)
+    cpu_train_seconds(kind, eng, noise_band(p1, ys, 1234), p1, ys, w, h, nbits)
+    t1 = cpu_train_seconds(kind, eng, noise_band(p1, ys, 1234), p1, ys, w, h, nbits)
+    t2 = cpu_train_seconds(kind, eng, noise_band(p2, ys, 1234), p2, ys, w, h, nbits) if p2 > p1 else t1
+    b = max((t2 - t1) / max(p2 - p1, 1), 1e-9)
+    a = max(t1 - b * p1, 0.0)
+    xs = int((budget_s / (steps + warmup) - a) / b)
+    xs = max(p1, min(bx, (xs // (8 * w)) * 8 * w))
+    band = noise_band(xs, ys, 1234)
+    n_vec = ((xs + w - 1) // w) * ((ys + h - 1) // h)
+    for _ in range(warmup):
+        cpu_train_seconds(kind, eng, band, xs, ys, w, h, nbits)
+    times = [cpu_train_seconds(kind, eng, band, xs, ys, w, h, nbits) for _ in range(steps)]
+    sec = float(np.mean(times))
+    val = evals_per_train(n_vec, nbits) / sec / 1e9
+    sample = (f"first {xs} of {bx} pixel lines of the {wl} image ({n_vec} of "
+              f"{(bx // w) * (ys // h)} vectors), full K={1 << nbits} train, {steps} timed run(s), mean")
+    return dict(value=val, unit=UNIT, cores=cores, kind=kind, sample=sample), sec, xs, n_vec
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind, eng = cpu_engine()
+    wl = args.workload
+    bx, ys, w, h, nbits, desc = WORKLOADS[wl]
+    base, sec, xs, n_vec = cpu_sample(kind, eng, wl, args.cpu_budget, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "bounded_sample": base["sample"], "block": [w, h], "nbits": nbits,
+                   "colorspace": "SCALED", "cpu_threads": base["cores"]},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import quant_b200 as qb
+    from quant_b200.distributed import make_allreduce
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl = args.workload
+    bx, ys, w, h, nbits, desc = WORKLOADS[wl]
+    K, dim = 1 << nbits, 3 * w * h
+    xs_total = bx * world                      # weak scaling: one band per rank
+    wB_band = bx // w
+    row_begin, row_end = rank * wB_band, (rank + 1) * wB_band
+    n_local = wB_band * (ys // h)
+    n_total = n_local * world
+
+    stream = torch.cuda.Stream()
+    ctx = qb.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    allreduce = make_allreduce() if world > 1 else None
+
+    band_np = noise_band(bx, ys, 1234 + rank).reshape(-1)
+    host_band = torch.empty(band_np.size, dtype=torch.uint8, pin_memory=True)
+    host_band.numpy()[:] = band_np
+    host_assign = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    host_assign_np = host_assign.numpy().view(np.uint32)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n, mode, collect=None):
+        """mode 'resident': device image borrowed; 'e2e': host bytes in, indices out. Returns device ms."""
+        total = 0.0
+        for _ in range(n):
+            with torch.cuda.stream(stream):
+                flush.zero_()                                  # evict the image and codebook from L2
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                if mode == "resident":
+                    cb, d, rep = ctx.train(nbits, EPS, n_total=n_total, allreduce=allreduce)
+                else:
+                    ctx.set_image_band(host_band.numpy(), xs_total, ys, w, h, qb.CS_SCALED, row_begin, row_end)
+                    cb, d, rep = ctx.train(nbits, EPS, n_total=n_total, allreduce=allreduce)
+                    ctx.get_assign(out=host_assign_np)
+                e1.record(stream)
+                e1.synchronize()
+                total += e0.elapsed_time(e1)
+                if collect is not None:
+                    collect.append(rep)
+        return total, cb, d
+
+    def timed(mode, steps, warmup):
+        if mode == "resident":
+            with torch.cuda.stream(stream):
+                dev_band = host_band.to("cuda", non_blocking=True)
+            stream.synchronize()
+            ctx.set_image_band(None, xs_total, ys, w, h, qb.CS_SCALED, row_begin, row_end,
+                               device_ptr=dev_band.data_ptr(), nbytes=dev_band.numel(), keep=dev_band)
+        run_steps(warmup, mode)
+        reps = []
+        barrier()
+        qb.launch_count(reset=True)
+        t0 = time.time()
+        ms, cb, d = run_steps(steps, mode, reps)
+        barrier()
+        t1 = time.time()
+        launches = qb.launch_count()
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, reps, launches, (t0, t1), cb, d
+
+    fp32_peak = ctx.measure_fp32_peak() if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_res, reps, launches, (t0, t1), cb_res, d_res = timed("resident", args.steps, args.warmup)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_e2e, _, _, _, cb_e2e, d_e2e = timed("e2e", args.steps, args.warmup)
+    assert np.array_equal(cb_res, cb_e2e) and d_res == d_e2e, "resident and e2e trains disagree"
+
+    if rank == 0:
+        evals = evals_per_train(n_total, nbits)
+        value = evals * args.steps / (ms_res * 1e-3) / 1e9
+        e2e = evals * args.steps / (ms_e2e * 1e-3) / 1e9
+        last = [r[-1] for r in reps]
+        ms_assign = float(np.mean([r["ms_assign"] for r in last]))
+        ms_acc = float(np.mean([r["ms_accumulate"] for r in last]))
+        per_level = {str(r["K"]): {k: round(float(np.mean([x[i][k] for x in reps])), 4)
+                                   for k in ("ms_assign", "ms_resolve", "ms_accumulate")}
+                     for i, r in enumerate(reps[0])}
+        flagged_last = int(last[-1]["flagged"])
+        flops = float(n_local) * K * 3.0 * dim
+        ach = flops / (ms_assign * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        acc_gbs = float(n_local) * (dim + 4) / (ms_acc * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 filter + f64 exact re-check; i64 sums",
+            "data": "synthetic",
+            "config": {"workload": desc + (f"; weak scaling: {world} such bands, one per rank" if world > 1 else ""),
+                       "block": [w, h], "nbits": nbits, "colorspace": "SCALED", "vectors_per_rank": n_local,
+                       "schedule": "reference HEAD: one assignment pass per split level, no empty-cell repair",
+                       "l2": "512 MiB flush (memset) before every timed step, outside the timed events"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(host_band.numel()) * world,
+                    "d2h_bytes_per_step": (n_local * 4) * world,
+                    "seconds_per_train": ms_e2e / args.steps / 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "kernel": f"assign_kernel<{dim}> at K={K} (last split level)",
+                         "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                         "peak_source": "FP32 FFMA probe in this run (FMA = 2 flop); MEASURED_PEAKS.json has no FP32 figure",
+                         "algorithmic": "3*dim flop per distance evaluation x N*K evaluations",
+                         "ms_per_launch": ms_assign, "gdist_evals_per_s": float(n_local) * K / (ms_assign * 1e-3) / 1e9,
+                         "traffic": None,
+                         "hbm": {"kernel": "accumulate (per-cell integer statistics), same level",
+                                 "achieved": acc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": acc_gbs / hbm_peak,
+                                 "peak_source": hbm_src, "ms_per_launch": ms_acc,
+                                 "algorithmic": "(dim + 4) bytes per vector"}},
+            "per_level_ms": per_level, "flagged_last_level": flagged_last,
+            "distortion": d_res, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            kind, eng = cpu_engine()
+            base, _, _, _ = cpu_sample(kind, eng, wl, args.cpu_budget, 1, 1)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=None, help="seconds of CPU work for the CPU arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.cpu_budget is None:
+        args.cpu_budget = 120.0 if args.impl == "reference" else 20.0
+    sys.exit(run_reference_arm(args) if args.impl == "reference" else run_gpu_arm(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,12 @@ int qb200_set_image(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, in
  * host image; only the byte range the shard needs is copied to the device. */
 int qb200_set_image_shard(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth,
                           int blockHeight, int colorspace, size_t row_begin, size_t row_end);
+/* Same shard, but the caller passes ONLY the shard's bytes: band[0] is image byte
+ * row_begin*blockWidth*ySize*3 and band_len covers the shard (a rank that loaded just its own band
+ * of a large image).  band_is_device != 0: `band` is a device pointer that is borrowed, not copied. */
+int qb200_set_image_band(qb200_ctx *ctx, const uint8_t *band, size_t band_len, int band_is_device,
+                         int xSize, int ySize, int blockWidth, int blockHeight, int colorspace,
+                         size_t row_begin, size_t row_end);
 /* Training set given as an N x dim matrix of lattice bytes (row-major): element value is
  * decoded with `colorspace` exactly like an image byte.  Used by the generic
  * AbstractQuantizer::quantize(vector<Vector>) entry (include/Quantizer.hpp:12-14). */

@@ -39,6 +39,8 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int]),
     "qb200_set_image_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_size_t, C.c_size_t]),
+    "qb200_set_image_band": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t]),
     "qb200_set_vectors_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                        C.c_int]),
     "qb200_num_vectors": (C.c_size_t, [C.c_void_p]),

@@ -81,6 +81,20 @@ class Context:
         self._check(self.lib.qb200_set_image_shard(self.h, _ptr(rgb), xSize, ySize, w, h,
                                                    colorspace, row_begin, row_end))
 
+    def set_image_band(self, band, xSize: int, ySize: int, w: int, h: int, colorspace: int,
+                       row_begin: int, row_end: int, device_ptr: int | None = None,
+                       nbytes: int | None = None, keep=None):
+        """This rank's own bytes of a sharded image: a host array, or (device_ptr, nbytes)."""
+        if device_ptr is not None:
+            self._keep = keep
+            self._check(self.lib.qb200_set_image_band(self.h, C.c_void_p(device_ptr), nbytes, 1, xSize,
+                                                      ySize, w, h, colorspace, row_begin, row_end))
+            return
+        band = np.ascontiguousarray(band, np.uint8).reshape(-1)
+        self._keep = band
+        self._check(self.lib.qb200_set_image_band(self.h, _ptr(band), band.size, 0, xSize, ySize, w, h,
+                                                  colorspace, row_begin, row_end))
+
     def set_vectors_u8(self, mat: np.ndarray, colorspace: int = CS_SCALED):
         mat = np.ascontiguousarray(mat, np.uint8)
         n, dim = mat.shape
@@ -124,8 +138,11 @@ class Context:
                 out.append({f: getattr(r, f) for f, _ in LevelReport._fields_})
         return cb, dist.value, out
 
-    def get_assign(self) -> np.ndarray:
-        a = np.empty(self.num_vectors, np.uint32)
+    def get_assign(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Indices as uint32; ``out`` may be a caller-owned (e.g. pinned) uint32 array."""
+        a = np.empty(self.num_vectors, np.uint32) if out is None else out
+        if a.dtype != np.uint32 or a.size < self.num_vectors or not a.flags.c_contiguous:
+            raise ValueError("out must be a contiguous uint32 array of num_vectors elements")
         self._check(self.lib.qb200_get_assign(self.h, _ptr(a)))
         return a
 

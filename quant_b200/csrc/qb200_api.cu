@@ -369,8 +369,11 @@ int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *c
   return QB200_OK;
 }
 
+// band_only: `rgb` points at the first byte the shard needs (image byte row_begin*w*ySize*3) and
+// holds `band_len` bytes, instead of being the whole image.
 static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int w, int h, int colorspace,
-                          int n_images, int on_device, bool shard, size_t row_begin, size_t row_end) {
+                          int n_images, int on_device, bool shard, size_t row_begin, size_t row_end,
+                          bool band_only = false, size_t band_len = 0) {
   if (!ctx) return QB200_ERR_ARG;
   if (!rgb) return fail(ctx, QB200_ERR_ARG, "set_image: rgb == NULL");
   if (xSize <= 0 || ySize <= 0 || w <= 0 || h <= 0 || n_images <= 0)
@@ -420,14 +423,18 @@ static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySi
   }
   s.origin = lo;
   ctx->borrowed = nullptr;
+  if (band_only && band_len < (size_t)(hi - lo))
+    return fail(ctx, QB200_ERR_ARG, "set_image_band: %zu bytes given, rows [%zu,%zu) need %llu", band_len, row_begin,
+                row_end, hi - lo);
+  const uint8_t *first = band_only ? rgb : rgb + lo;  // address of image byte `lo`
   if (on_device) {
-    if (shard) return fail(ctx, QB200_ERR_ARG, "set_image_shard takes a host image");
-    ctx->borrowed = rgb;
-    s.buf = rgb;
+    if (shard && !band_only) return fail(ctx, QB200_ERR_ARG, "set_image_shard takes a host image");
+    ctx->borrowed = first;
+    s.buf = first;
   } else {
     int rc = ensure(ctx, ctx->d_img, (size_t)(hi - lo) + 16);
     if (rc) return rc;
-    if (hi > lo) CU(cudaMemcpyAsync(ctx->d_img.p, rgb + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+    if (hi > lo) CU(cudaMemcpyAsync(ctx->d_img.p, first, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream));
     s.buf = (const uint8_t *)ctx->d_img.p;
   }
   ctx->src = s;
@@ -454,6 +461,13 @@ int qb200_set_image(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, in
 int qb200_set_image_shard(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth, int blockHeight,
                           int colorspace, size_t row_begin, size_t row_end) {
   return set_image_impl(ctx, rgb, xSize, ySize, blockWidth, blockHeight, colorspace, 1, 0, true, row_begin, row_end);
+}
+
+int qb200_set_image_band(qb200_ctx *ctx, const uint8_t *band, size_t band_len, int band_is_device, int xSize,
+                         int ySize, int blockWidth, int blockHeight, int colorspace, size_t row_begin,
+                         size_t row_end) {
+  return set_image_impl(ctx, band, xSize, ySize, blockWidth, blockHeight, colorspace, 1, band_is_device, true,
+                        row_begin, row_end, true, band_len);
 }
 
 int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors, int dim, int colorspace,
