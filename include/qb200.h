@@ -55,10 +55,11 @@ typedef struct qb200_level_report {
   uint32_t K;             /* codebook size of this level */
   uint32_t flagged;       /* queries whose FP32 top-2 gap was inside the error margin (this rank) */
   uint32_t changed;       /* of those, how many the exact FP64 resolver moved to another index */
+  uint32_t ties;          /* of those, how many had (near-)exact FP64 ties and took the KD-tree walk */
   uint32_t dead_cells;    /* cells with no member after the (global) reduction */
   uint32_t kd_depth;      /* depth of the nanoflann-order KD tree built for the resolver */
   float ms_assign;        /* device time of the FP32 assignment kernel */
-  float ms_resolve;       /* device time of the exact resolver kernel */
+  float ms_resolve;       /* device time of the exact resolver kernels (brute force + tree walk) */
   float ms_accumulate;    /* device time of the per-cell statistics kernel */
   double distortion_pre;  /* updateDistortion() before fixCodeVectors (src/Quantizer.cpp:100) */
   double distortion_post; /* updateDistortion() after fixCodeVectors  (src/Quantizer.cpp:104) */

@@ -19,7 +19,7 @@ MODE_PARITY = 0
 
 class LevelReport(C.Structure):
     _fields_ = [("K", C.c_uint32), ("flagged", C.c_uint32), ("changed", C.c_uint32),
-                ("dead_cells", C.c_uint32), ("kd_depth", C.c_uint32), ("ms_assign", C.c_float),
+                ("ties", C.c_uint32), ("dead_cells", C.c_uint32), ("kd_depth", C.c_uint32), ("ms_assign", C.c_float),
                 ("ms_resolve", C.c_float), ("ms_accumulate", C.c_float),
                 ("distortion_pre", C.c_double), ("distortion_post", C.c_double)]
 

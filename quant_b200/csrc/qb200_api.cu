@@ -47,7 +47,7 @@ struct qb200_ctx {
   const uint8_t *borrowed = nullptr;
 
   // per-vector
-  DevBuf d_assign, d_flags;
+  DevBuf d_assign, d_flags, d_ties;
   // per-level
   DevBuf d_rows, d_cb64, d_nodes, d_vind, d_bbox, d_stats, d_counters, d_misc;
   // pinned staging
@@ -120,7 +120,7 @@ void free_buf(DevBuf &b) {
 // ---- level machinery --------------------------------------------------------------------------
 
 struct LevelOut {
-  unsigned int flagged = 0, changed = 0;
+  unsigned int flagged = 0, changed = 0, ties = 0;
   int kd_depth = 0;
   float ms_assign = 0, ms_resolve = 0, ms_accumulate = 0;
 };
@@ -144,6 +144,11 @@ void make_rows(const double *cb, uint32_t K, int dim, int colorspace, float *row
     for (int e = dim + 1; e < row; e++) r[e] = 0.f;
     if (n2 > max_n2) max_n2 = n2;
   }
+  if (K & 1) {  // the kernel consumes codevectors in pairs: pad with a row that can never win
+    float *r = rows + (size_t)K * row;
+    for (int e = 0; e < row; e++) r[e] = 0.f;
+    r[dim] = 3.0e38f;
+  }
   *c_max_norm = (float)(std::sqrt(max_n2) * 1.000001 + 1e-3);
 }
 
@@ -152,7 +157,8 @@ void make_rows(const double *cb, uint32_t K, int dim, int colorspace, float *row
 int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, bool timed, LevelOut *out) {
   const int dim = ctx->src.dim;
   const int row = assign_row_floats(dim);
-  const size_t rows_bytes = (size_t)K * row * 4, cb_bytes = (size_t)K * dim * 8;
+  const uint32_t K_rows = K + (K & 1u);  // staged rows (even)
+  const size_t rows_bytes = (size_t)K_rows * row * 4, cb_bytes = (size_t)K * dim * 8;
   int rc;
   if ((rc = ensure(ctx, ctx->d_rows, rows_bytes))) return rc;
   if ((rc = ensure(ctx, ctx->d_cb64, cb_bytes))) return rc;
@@ -181,7 +187,7 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   AssignLaunch a{};
   a.src = ctx->src;
   a.cb_rows = (const float *)ctx->d_rows.p;
-  a.K = (int)K;
+  a.K = (int)K_rows;
   // 2 scores * (dim+3) * 2^-24 * (|X|+|C|)^2, with 25% head-room (see qb200_kernels.cu)
   a.margin_coef = 2.5f * (float)(dim + 3) * 5.9604645e-8f;
   a.c_max_norm = c_max;
@@ -219,9 +225,9 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   kd.n_nodes = (int)tree.nodes.size();
   kd.depth = tree.depth;
   unsigned int *cnt = (unsigned int *)ctx->d_counters.p;
-  CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p, kd,
-                    (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, cnt + 1, 0xffffffffu,
-                    ctx->sm_count, st));
+  CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p, (int)K, kd,
+                    (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
+                    cnt + 2, cnt + 1, ctx->sm_count, st));
   if (timed) CU(cudaEventRecord(ctx->ev[2], st));
   if (want_stats) {
     CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(K, dim) * 8, st));
@@ -229,7 +235,7 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
                          ctx->sm_count, st));
   }
   if (timed) CU(cudaEventRecord(ctx->ev[3], st));
-  CU(cudaMemcpyAsync(pin + off_cnt, ctx->d_counters.p, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(pin + off_cnt, ctx->d_counters.p, 12, cudaMemcpyDeviceToHost, st));
   ctx->assign_valid = true;
   if (out) {
     // the caller synchronises before reading these
@@ -242,7 +248,7 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
 int collect_level(qb200_ctx *ctx, uint32_t K, bool timed, LevelOut *out) {
   const int dim = ctx->src.dim;
   const int row = assign_row_floats(dim);
-  const size_t rows_bytes = (size_t)K * row * 4, cb_bytes = (size_t)K * dim * 8;
+  const size_t rows_bytes = (size_t)(K + (K & 1u)) * row * 4, cb_bytes = (size_t)K * dim * 8;
   const size_t max_nodes = 2 * (size_t)K + 8;
   const size_t off_cb = (rows_bytes + 255) & ~(size_t)255;
   const size_t off_nodes = (off_cb + cb_bytes + 255) & ~(size_t)255;
@@ -252,6 +258,7 @@ int collect_level(qb200_ctx *ctx, uint32_t K, bool timed, LevelOut *out) {
   const unsigned int *c = (const unsigned int *)((char *)ctx->h_pin + off_cnt);
   out->flagged = c[0];
   out->changed = c[1];
+  out->ties = c[2];
   if (timed) {
     CU(cudaEventElapsedTime(&out->ms_assign, ctx->ev[0], ctx->ev[1]));
     CU(cudaEventElapsedTime(&out->ms_resolve, ctx->ev[1], ctx->ev[2]));
@@ -290,6 +297,7 @@ int set_common(qb200_ctx *ctx, size_t n_local) {
   int rc;
   if ((rc = ensure(ctx, ctx->d_assign, (n_local ? n_local : 1) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->d_flags, (n_local ? n_local : 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_ties, (n_local ? n_local : 1) * 4))) return rc;
   ctx->assign_valid = false;
   ctx->have_set = true;
   return QB200_OK;
@@ -342,7 +350,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_rows, &ctx->d_cb64, &ctx->d_nodes,
+  for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_ties, &ctx->d_rows, &ctx->d_cb64, &ctx->d_nodes,
                     &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc})
     free_buf(*b);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -618,6 +626,7 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
       r.K = K;
       r.flagged = lo.flagged;
       r.changed = lo.changed;
+      r.ties = lo.ties;
       r.kd_depth = (uint32_t)lo.kd_depth;
       r.ms_assign = lo.ms_assign;
       r.ms_resolve = lo.ms_resolve;

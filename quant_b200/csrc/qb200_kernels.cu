@@ -66,13 +66,47 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 // is one FFMA per dimension: row k of the staged codebook is [-2*C_k[0..DIM), |C_k|^2, pad].
 // |s_k(fp32) - s_k(exact, FP64 codebook)| <= (DIM+3) * 2^-24 * (|X| + max_k|C_k|)^2, so a query is
 // decided here only when  second - best > 2 * that bound (margin_coef carries the constant).
+// Packed FP32 pairs (Blackwell FFMA2, PTX fma.rn.f32x2): one instruction = two IEEE round-to-nearest
+// FMAs.  A three-register scalar FFMA issues every other cycle per SM sub-partition, so a scalar
+// kernel tops out at half the FP32 lanes; FFMA2 is what fills all 128.  ptxas folds a pair built
+// from one register twice ({c, c}) into a broadcast operand (SASS "R.F32"), so the codevector element
+// needs no duplicate register.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {  // SASS FMNMX3
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 template <int DIM>
 struct AssignCfg {
   static constexpr int ROW = ((DIM + 1 + 3) / 4) * 4;  // floats per staged codebook row
-  static constexpr int Q = DIM <= 6 ? 8 : (DIM <= 12 ? 4 : (DIM <= 27 ? 2 : 2));
+  static constexpr int Q = DIM <= 12 ? 4 : 2;          // queries per thread (even: processed as pairs)
   static constexpr int THREADS = DIM <= 27 ? 512 : 256;
 };
 
+// Inner loop, per thread and per PAIR of codevectors (k, k+1), for each pair of its queries (q0, q1):
+//   (s_k[q0], s_k[q1])     = FFMA2 chain over the dimensions, addend initialised with |C_k|^2
+//   (s_k+1[q0], s_k+1[q1]) = same with row k+1
+// and per query, with lo/hi = min/max(s_k, s_k+1):
+//   second = min3(second, hi, max(lo, best));  pair = lo < best ? k : pair;  best = min(best, lo)
+// i.e. DIM/2 FFMA2 (fma pipe) + 3.5 min/max/select (alu pipe) per distance evaluation.  Which of
+// the two codevectors of the winning pair it was is recovered after the loop by recomputing the
+// two scores with the identical FMA sequence (bit-identical), so the loop carries no per-codevector
+// index bookkeeping.  The staged codebook always holds an even number of rows (the host pads an odd
+// K with a row that can never win).
 template <int DIM>
 __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
     assign_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int k_chunk,
@@ -81,6 +115,7 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
                   const unsigned long long tiles) {
   using Cfg = AssignCfg<DIM>;
   constexpr int ROW = Cfg::ROW, Q = Cfg::Q, THREADS = Cfg::THREADS;
+  static_assert(Q % 2 == 0, "queries are processed in pairs");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *s_cb = reinterpret_cast<float *>(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
@@ -121,35 +156,42 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
 
   for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const unsigned long long v0 = tile * (unsigned long long)(THREADS * Q);
-    float x[Q][DIM];
+    unsigned long long xp[Q / 2][DIM];  // (x[q0][e], x[q1][e]) pairs
     float xn[Q];
     bool live[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) {
-      const unsigned long long v = v0 + (unsigned long long)q * THREADS + tid;
-      live[q] = v < src.n_local;
-      xn[q] = 0.f;
-      if (live[q]) {
-        unsigned long long base, img;
-        vec_base(src, v, base, img);
+    for (int qp = 0; qp < Q / 2; qp++) {
+      float x[2][DIM];
 #pragma unroll
-        for (int e = 0; e < DIM; e++) {
-          float f = (float)load_lattice(src, img, base, e);
-          x[q][e] = f;
-          xn[q] = fmaf(f, f, xn[q]);
+      for (int h = 0; h < 2; h++) {
+        const int q = 2 * qp + h;
+        const unsigned long long v = v0 + (unsigned long long)q * THREADS + tid;
+        live[q] = v < src.n_local;
+        xn[q] = 0.f;
+        if (live[q]) {
+          unsigned long long base, img;
+          vec_base(src, v, base, img);
+#pragma unroll
+          for (int e = 0; e < DIM; e++) {
+            float f = (float)load_lattice(src, img, base, e);
+            x[h][e] = f;
+            xn[q] = fmaf(f, f, xn[q]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < DIM; e++) x[h][e] = 0.f;
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < DIM; e++) x[q][e] = 0.f;
       }
+#pragma unroll
+      for (int e = 0; e < DIM; e++) xp[qp][e] = pack2(x[0][e], x[1][e]);
     }
     float best[Q], second[Q];
-    int bidx[Q];
+    int bpair[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       best[q] = FLT_MAX;
       second[q] = FLT_MAX;
-      bidx[q] = 0;
+      bpair[q] = 0;
     }
 
     for (int chunk = 0; chunk < n_chunks; chunk++) {
@@ -167,27 +209,37 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
       }
       const int k0 = chunk * k_chunk;
       const float4 *rows = reinterpret_cast<const float4 *>(s_cb);
-#pragma unroll 2
-      for (int k = 0; k < kn; k++) {
-        float c[ROW];
+#pragma unroll 1
+      for (int k = 0; k < kn; k += 2) {
+        float c0[ROW], c1[ROW];
 #pragma unroll
         for (int r = 0; r < ROW / 4; r++) {
-          float4 t = rows[k * (ROW / 4) + r];
-          c[4 * r + 0] = t.x;
-          c[4 * r + 1] = t.y;
-          c[4 * r + 2] = t.z;
-          c[4 * r + 3] = t.w;
+          const float4 t = rows[k * (ROW / 4) + r];
+          const float4 u = rows[(k + 1) * (ROW / 4) + r];
+          c0[4 * r + 0] = t.x; c0[4 * r + 1] = t.y; c0[4 * r + 2] = t.z; c0[4 * r + 3] = t.w;
+          c1[4 * r + 0] = u.x; c1[4 * r + 1] = u.y; c1[4 * r + 2] = u.z; c1[4 * r + 3] = u.w;
         }
         const int kg = k0 + k;
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-          float s = c[DIM];
+        for (int qp = 0; qp < Q / 2; qp++) {
+          unsigned long long a0 = pack2(c0[DIM], c0[DIM]);
+          unsigned long long a1 = pack2(c1[DIM], c1[DIM]);
 #pragma unroll
-          for (int e = 0; e < DIM; e++) s = fmaf(x[q][e], c[e], s);
-          second[q] = fminf(second[q], fmaxf(s, best[q]));
-          const bool better = s < best[q];
-          best[q] = fminf(best[q], s);
-          bidx[q] = better ? kg : bidx[q];
+          for (int e = 0; e < DIM; e++) {
+            a0 = ffma2(xp[qp][e], pack2(c0[e], c0[e]), a0);
+            a1 = ffma2(xp[qp][e], pack2(c1[e], c1[e]), a1);
+          }
+          float s0[2], s1[2];
+          unpack2(a0, s0[0], s0[1]);
+          unpack2(a1, s1[0], s1[1]);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int q = 2 * qp + h;
+            const float lo = fminf(s0[h], s1[h]), hi = fmaxf(s0[h], s1[h]);
+            second[q] = fmin3(second[q], hi, fmaxf(lo, best[q]));
+            bpair[q] = lo < best[q] ? kg : bpair[q];
+            best[q] = fminf(best[q], lo);
+          }
         }
       }
     }
@@ -195,10 +247,23 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
 #pragma unroll
     for (int q = 0; q < Q; q++) {
       const unsigned long long v = v0 + (unsigned long long)q * THREADS + tid;
+      // which member of the winning pair: the same FMA sequence on the same operands gives the
+      // same bits as the loop did (rows come from global memory: the chunk may be gone from smem)
+      const float *r0 = cb_rows + (size_t)bpair[q] * ROW;
+      float t0 = __ldg(r0 + DIM), t1 = __ldg(r0 + ROW + DIM);
+#pragma unroll
+      for (int e = 0; e < DIM; e++) {
+        float lo_, hi_;
+        unpack2(xp[q / 2][e], lo_, hi_);
+        const float xe = (q & 1) ? hi_ : lo_;
+        t0 = fmaf(xe, __ldg(r0 + e), t0);
+        t1 = fmaf(xe, __ldg(r0 + ROW + e), t1);
+      }
+      const int bidx = bpair[q] + (t1 < t0 ? 1 : 0);
       float r = sqrtf(xn[q]) + c_max_norm;
       const float margin = margin_coef * r * r;
       const bool flag = live[q] && !((second[q] - best[q]) > margin);
-      if (live[q]) assign[v] = (uint32_t)bidx[q];
+      if (live[q]) assign[v] = (uint32_t)bidx;
       // warp-aggregated append
       const unsigned int m = __ballot_sync(0xffffffffu, flag);
       if (m) {
@@ -267,7 +332,7 @@ __global__ void __launch_bounds__(128, 1)
 // ------------------------------------------------------------------------------------------------
 // resolve_kernel: exact FP64 nearest neighbour in nanoflann's traversal order
 // ------------------------------------------------------------------------------------------------
-// One thread per flagged query.  Arithmetic is spelled with the round-to-nearest intrinsics so
+// Phase B: one thread per query phase A (below) could not decide.  Arithmetic is spelled with the round-to-nearest intrinsics so
 // that nvcc cannot contract a*b+c into an FMA: the reference's x86-64 build has none.
 __device__ __forceinline__ double sq_diff(double a, double b) {
   const double d = __dsub_rn(a, b);
@@ -287,6 +352,75 @@ __device__ __forceinline__ double nanoflann_l2(const double *a, const double *__
   }
   for (; d < dim; d++) result = __dadd_rn(result, sq_diff(a[d], b[d]));
   return result;
+}
+
+// Phase A of the resolver: one WARP per flagged query, exact FP64 distances (nanoflann's arithmetic,
+// so the values are the ones the reference's leaf loop computes) to ALL K codevectors, lanes strided
+// over k.  nanoflann's search is exact, so whenever the smallest distance is separated from every
+// other one the tree walk must return that codevector and no walk is needed: the only FP64 roundings
+// that differ between the walk and this loop are in the walk's pruning bound (mindistsq + cut_dist -
+// dists[feat], nanoflann.hpp:1254-1262), whose intermediates are distances from the query to actual
+// codevector coordinates, i.e. bounded by dmax = max_k dist_k; their accumulated error is below
+// ~4*dim*2^-53*dmax.  A query is decided here when it has exactly one candidate within
+// band = 2^-30 * dmax of the minimum (orders of magnitude above that error, orders of magnitude
+// below the FP32 filter's margin); otherwise (exact or near-exact FP64 ties: duplicated codevectors,
+// children 1.2c / 0.8c of a single-member cell) it goes to the tie list and phase B walks the tree.
+template <int DIMCAP>
+__global__ void __launch_bounds__(128)
+    resolve_bruteforce_kernel(const VecSource src, const int scaled, const double *__restrict__ cb, const int K,
+                              const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
+                              uint32_t *__restrict__ assign, uint32_t *__restrict__ tie_list,
+                              unsigned int *__restrict__ tie_count, unsigned int *__restrict__ changed) {
+  const int dim = src.dim;
+  const unsigned int total = *flag_count;
+  const int lane = threadIdx.x & 31;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+  double x[DIMCAP];
+  for (unsigned int f = warp; f < total; f += n_warps) {
+    const unsigned long long v = flag_list[f];
+    unsigned long long base, img;
+    vec_base(src, v, base, img);
+    for (int e = 0; e < dim; e++) {
+      const double L = (double)load_lattice(src, img, base, e);
+      x[e] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+    }
+    double d1 = DBL_MAX, d2 = DBL_MAX, dmax = 0.0;  // this lane's smallest, second smallest, largest
+    int k1 = 0;
+    for (int k = lane; k < K; k += 32) {
+      const double d = nanoflann_l2(x, cb + (size_t)k * dim, dim);
+      dmax = fmax(dmax, d);
+      if (d < d1) {
+        d2 = d1;
+        d1 = d;
+        k1 = k;
+      } else if (d < d2) {
+        d2 = d;
+      }
+    }
+    double wmin = d1, wmax = dmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+      wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    }
+    const double lim = wmin + wmax * 9.313225746154785e-10;  // 2^-30
+    const int mine = (d1 <= lim ? 1 : 0) + (d2 <= lim ? 1 : 0);
+    const unsigned int holders = __ballot_sync(0xffffffffu, mine > 0);
+    const unsigned int multi = __ballot_sync(0xffffffffu, mine > 1);
+    if (__popc(holders) == 1 && multi == 0) {
+      const int win = __shfl_sync(0xffffffffu, k1, __ffs(holders) - 1);
+      if (lane == 0) {
+        const uint32_t old = assign[v];
+        if (old != (uint32_t)win) {
+          assign[v] = (uint32_t)win;
+          atomicAdd(changed, 1u);
+        }
+      }
+    } else if (lane == 0) {
+      tie_list[atomicAdd(tie_count, 1u)] = (uint32_t)v;
+    }
+  }
 }
 
 struct Frame {
@@ -605,7 +739,7 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
   const size_t row_bytes = (size_t)Cfg::ROW * 4;
   const size_t smem_cap = 200 * 1024;
   int k_chunk = a.K;
-  if ((size_t)k_chunk * row_bytes > smem_cap) k_chunk = (int)(smem_cap / row_bytes) & ~7;
+  if ((size_t)k_chunk * row_bytes > smem_cap) k_chunk = (int)(smem_cap / row_bytes) & ~7;  // even
   const size_t smem = (size_t)k_chunk * row_bytes;
   {
     cudaError_t e = cudaFuncSetAttribute(assign_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -651,31 +785,39 @@ cudaError_t launch_assign(const AssignLaunch &a) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const KdDevice &tree,
+cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, int K, const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
-                           unsigned int *changed, unsigned int flagged_hint, int sm_count, cudaStream_t stream) {
-  unsigned int blocks = (unsigned int)sm_count * 4;
-  if (flagged_hint != 0xffffffffu) {
-    unsigned int need = (flagged_hint + 127) / 128;
-    if (need == 0) return cudaSuccess;
-    if (need < blocks) blocks = need;
-  }
+                           uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed, int sm_count,
+                           cudaStream_t stream) {
+  // phase A: brute force, one warp per flagged query (the count is only known on the device)
+  const unsigned int blocks_a = (unsigned int)sm_count * 8;
+  if (src.dim <= 16)
+    resolve_bruteforce_kernel<16><<<blocks_a, 128, 0, stream>>>(src, scaled, cb, K, flag_list, flag_count, assign, tie_list, tie_count, changed);
+  else if (src.dim <= 48)
+    resolve_bruteforce_kernel<48><<<blocks_a, 128, 0, stream>>>(src, scaled, cb, K, flag_list, flag_count, assign, tie_list, tie_count, changed);
+  else
+    resolve_bruteforce_kernel<kMaxDim><<<blocks_a, 128, 0, stream>>>(src, scaled, cb, K, flag_list, flag_count, assign, tie_list, tie_count, changed);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // phase B: the reference's tree walk for the queries phase A left undecided
+  const unsigned int blocks = (unsigned int)sm_count * 4;
   const bool deep = tree.depth > 92;
   if (src.dim <= 16) {
     if (!deep)
-      resolve_kernel<16, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+      resolve_kernel<16, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
     else
-      resolve_kernel<16, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+      resolve_kernel<16, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
   } else if (src.dim <= 48) {
     if (!deep)
-      resolve_kernel<48, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+      resolve_kernel<48, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
     else
-      resolve_kernel<48, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+      resolve_kernel<48, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
   } else {
     if (!deep)
-      resolve_kernel<kMaxDim, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+      resolve_kernel<kMaxDim, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
     else
-      resolve_kernel<kMaxDim, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, flag_list, flag_count, assign, changed);
+      resolve_kernel<kMaxDim, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
   }
   g_launch_count++;
   return cudaGetLastError();

@@ -23,9 +23,12 @@ struct AssignLaunch {
 
 int assign_row_floats(int dim);
 cudaError_t launch_assign(const AssignLaunch &a);
-cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const KdDevice &tree,
+// Exact re-solve of the flagged queries: brute-force FP64 phase, then the reference's KD walk for
+// the (near-)exact ties it leaves in tie_list (capacity: n_local).  Counters are device words.
+cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, int K, const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
-                           unsigned int *changed, unsigned int flagged_hint, int sm_count, cudaStream_t stream);
+                           uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed, int sm_count,
+                           cudaStream_t stream);
 // stats must be zeroed by the caller; assign may be null only for K == 1.
 cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats,
                               int sm_count, cudaStream_t stream);
