@@ -1,0 +1,103 @@
+"""The C++ drop-in host layer (quant_b200/host: Quantizer.hpp / Compressor.hpp / `quant` CLI over the C ABI).
+
+CPU part: the reference's own unit test restated (layout round trips), .quant decode through the CLI against
+the reference's decoded image, and a loud failure (no CPU fallback) when compressing without a GPU.
+GPU part: the CLI's .quant file and decoded PPM must be byte-identical to the reference's on every fixture."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, HAVE_GPU, golden_names, load_golden
+
+HOST = os.path.join(ROOT, "quant_b200", "host")
+QUANT = os.path.join(HOST, "quant")
+HOST_TEST = os.path.join(HOST, "host_test")
+
+
+@pytest.fixture(scope="module")
+def host_built():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "quant_b200", "csrc"), "-j4"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", HOST], stdout=subprocess.DEVNULL)
+    return True
+
+
+def write_ppm(path, rgb, xs, ys):
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (xs, ys))
+        f.write(np.ascontiguousarray(rgb, np.uint8).tobytes())
+
+
+def ppm_payload(path, xs, ys):
+    data = open(path, "rb").read()
+    return data[len(data) - xs * ys * 3:]
+
+
+def test_layout_roundtrips_like_the_reference_unit_test(host_built):
+    out = subprocess.run([HOST_TEST, "layout"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("name", ["odd_101x67_2x2_n6", "odd_101x67_1x3_n5_normal", "kodim23_crop_4x4_n8"])
+def test_cli_decompress_matches_reference_decode(host_built, tmp_path, name):
+    """loadFromFile + decompress + saveToFile are host code: a .quant built from the reference's codebook
+    bytes and indices must decode to the reference's image."""
+    import quant_b200 as qb
+    g = load_golden(name)
+    ci = qb.CompressedImage()
+    ci.codeVectors, ci.assignedCodeVector = g.z["codebook_bytes"], g.z["assign"].astype(np.uint64)
+    ci.xSize, ci.ySize, ci.blockWidth, ci.blockHeight = g.xs, g.ys, g.w, g.h
+    ci.colorSpace = qb.ColorSpaces(g.cs)
+    blob = ci.to_bytes()
+    assert hashlib.sha256(blob).hexdigest() == str(g.z["quant_sha"])
+    q, p = str(tmp_path / "a.quant"), str(tmp_path / "a.ppm")
+    open(q, "wb").write(blob)
+    r = subprocess.run([QUANT, q, "-o", p], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(ppm_payload(p, g.xs, g.ys)).hexdigest() == str(g.z["decoded_sha"])
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the behaviour on a machine WITHOUT a GPU")
+def test_compress_without_gpu_fails_loudly(host_built, tmp_path):
+    g = load_golden("tiny_8x8_2x2_n6")
+    p = str(tmp_path / "t.ppm")
+    write_ppm(p, g.rgb, g.xs, g.ys)
+    r = subprocess.run([QUANT, p, "-o", str(tmp_path / "t.quant"), "-n", "4"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU" in r.stderr and not os.path.exists(str(tmp_path / "t.quant"))
+
+
+def test_cli_rejects_bad_arguments(host_built, tmp_path):
+    r = subprocess.run([QUANT, "x.ppm"], capture_output=True, text=True)
+    assert r.returncode == 2 and "saveto" in r.stderr
+    r = subprocess.run([QUANT, "x.txt", "-o", "y.bin"], capture_output=True, text=True)
+    assert r.returncode == 1 and "File type not supported" in r.stderr
+    assert subprocess.run([QUANT, "--help"], capture_output=True).returncode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_names())
+def test_cli_compress_writes_the_reference_quant_file(host_built, tmp_path, name):
+    g = load_golden(name)
+    p, q, d = str(tmp_path / "i.ppm"), str(tmp_path / "o.quant"), str(tmp_path / "o.ppm")
+    write_ppm(p, g.rgb, g.xs, g.ys)
+    args = ["-n", str(g.nbits), "-w", str(g.w), "-h", str(g.h), "--c", str(g.cs)]
+    r = subprocess.run([QUANT, p, "-o", q, "-r", "1"] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(open(q, "rb").read()).hexdigest() == str(g.z["quant_sha"])
+    rep = dict(l.split("=", 1) for l in r.stdout.splitlines() if "=" in l)
+    dist = float([v for k, v in rep.items() if k.startswith("Distortion")][0])
+    assert dist == pytest.approx(float(g.z["report_distortion"]), abs=1e-9)
+    r = subprocess.run([QUANT, p, "-o", d] + args, capture_output=True, text=True)   # "showcase": ppm -> ppm
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(ppm_payload(d, g.xs, g.ys)).hexdigest() == str(g.z["decoded_sha"])
+
+
+@pytest.mark.gpu
+def test_plugin_quantize_entry_agrees_with_compress(host_built, tmp_path):
+    g = load_golden("odd_101x67_2x2_n6")
+    p = str(tmp_path / "i.ppm")
+    write_ppm(p, g.rgb, g.xs, g.ys)
+    r = subprocess.run([HOST_TEST, "quantize", p, str(g.w), str(g.h), str(g.nbits)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
