@@ -33,6 +33,7 @@ SIGNATURES = {
     "qb200_destroy": (None, [C.c_void_p]),
     "qb200_last_error": (C.c_char_p, [C.c_void_p]),
     "qb200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qb200_set_tensor_cores": (C.c_int, [C.c_void_p, C.c_int]),
     "qb200_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "qb200_set_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

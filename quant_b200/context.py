@@ -52,6 +52,10 @@ class Context:
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.qb200_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
 
+    def set_tensor_cores(self, enable: bool):
+        """Filter engine for K >= 16: tcgen05 tensor-core kernel (default) or the FP32 CUDA-core kernel."""
+        self._check(self.lib.qb200_set_tensor_cores(self.h, 1 if enable else 0))
+
     def device_info(self):
         sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
         self._check(self.lib.qb200_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi),

@@ -33,6 +33,30 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, i
 cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats,
                               int sm_count, cudaStream_t stream);
 
+// Tensor-core (tcgen05) variant of the filter, qb200_assign_tc.cu.  Same contract as launch_assign;
+// b_staged holds the codebook as three bf16 limbs in the UMMA shared-memory layout (see
+// tc_stage_codebook in qb200_api.cu), rows32 the FP32 rows padded to tc_padded_rows(K) rows.
+struct AssignTcLaunch {
+  VecSource src;
+  const unsigned char *b_staged;
+  const float *rows32;
+  int K;              // real codevectors
+  float margin_coef, c_max_norm;
+  float *state;       // n_local * 3 floats, only touched when the codebook needs more than one pass
+  uint32_t *assign, *flag_list;
+  unsigned int *flag_count;
+  int sm_count;
+  cudaStream_t stream;
+};
+bool tc_supported(int dim, int K);
+int tc_kblocks(int dim);
+size_t tc_row_bytes(int dim);
+int tc_padded_rows(int K);
+int tc_n_tile(int K);
+int tc_chunk_rows(int dim, int K);
+cudaError_t launch_assign_tc(const AssignTcLaunch &a);
+void count_launch();
+
 struct DecodeGeom {
   int xSize, ySize, w, h;
   unsigned int wB, hB;
