@@ -221,10 +221,20 @@ bool tc_enabled() {
   }();
   return on;
 }
+// Smallest codebook the tensor-core filter is used for; below it the per-tile pipeline overhead outweighs
+// the saved FMAs and the CUDA-core kernel is faster (measured crossover; QB200_TC_MIN_K overrides).
+int tc_min_k() {
+  static const int k = [] {
+    const char *e = std::getenv("QB200_TC_MIN_K");
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 16 ? v : 256;
+  }();
+  return k;
+}
 
 LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
   LevelLayout L;
-  L.use_tc = ctx->use_tc && tc_enabled() && tc_supported(dim, (int)K);
+  L.use_tc = ctx->use_tc && tc_enabled() && (int)K >= tc_min_k() && tc_supported(dim, (int)K);
   L.K_rows = L.use_tc ? (uint32_t)tc_padded_rows((int)K) : K + (K & 1u);
   L.rows_bytes = (size_t)L.K_rows * assign_row_floats(dim) * 4;
   L.tc_bytes = L.use_tc ? (size_t)L.K_rows * tc_row_bytes(dim) : 0;

@@ -223,12 +223,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         int bidx = chunk * 8;
         if (live_cur && !flag) {
           float sb = FLT_MAX;
-          const float *rows = rows32 + (size_t)chunk * 8 * Cfg::ROW32;
+          const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * Cfg::ROW32);
 #pragma unroll
           for (int c = 0; c < 8; c++) {
-            float s = __ldg(rows + c * Cfg::ROW32 + DIM);
+            float cr[Cfg::ROW32];
 #pragma unroll
-            for (int e = 0; e < DIM; e++) s = fmaf(x_cur[e], __ldg(rows + c * Cfg::ROW32 + e), s);
+            for (int q4 = 0; q4 < Cfg::ROW32 / 4; q4++) {
+              const float4 t = __ldg(rows + c * (Cfg::ROW32 / 4) + q4);
+              cr[4 * q4] = t.x; cr[4 * q4 + 1] = t.y; cr[4 * q4 + 2] = t.z; cr[4 * q4 + 3] = t.w;
+            }
+            float s = cr[DIM];
+#pragma unroll
+            for (int e = 0; e < DIM; e++) s = fmaf(x_cur[e], cr[e], s);
             if (s < sb) {
               sb = s;
               bidx = chunk * 8 + c;
@@ -268,29 +274,53 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           chunk = __float_as_int(state[v * 3 + 2]);
         }
       }
-      for (int jt = 0; jt < n_tiles_n; jt++, it++) {
-        const int buf = it & 1;
-        mbar_wait_bounded(&sh.tmem_full[buf], (it >> 1) & 1, 6);
-        tc_fence_after();
-        const int col0 = half * half_cols;
-        const int cid0 = (k_base + jt * n_tile + col0) >> 3;
-        for (int c = 0; c < half_cols; c += 32) {
-          float v[32];
-          const uint32_t taddr = lane_addr + (uint32_t)(buf * 256 + col0 + c);
-          const int ncol = min(32, half_cols - c);
+      // Flat sequence of column chunks (<= 32 columns each) over the N tiles of this query tile, software
+      // pipelined over two register buffers: the tcgen05.ld of chunk g+1 is in flight while chunk g is reduced.
+      const int col0 = half * half_cols;
+      const int ncol = min(32, half_cols);
+      const int ch_shift = half_cols >= 128 ? 2 : (half_cols >= 64 ? 1 : 0);  // chunks per N tile = 1 << ch_shift
+      const int total = n_tiles_n << ch_shift;
+      auto issue = [&](int g, float *v) {
+        const int jt = g >> ch_shift, c = (g & ((1 << ch_shift) - 1)) * 32;
+        const unsigned int itg = it + jt;
+        const int buf = itg & 1;
+        if (c == 0) {
+          mbar_wait_bounded(&sh.tmem_full[buf], (itg >> 1) & 1, 6);
+          tc_fence_after();
+        }
+        const uint32_t taddr = lane_addr + (uint32_t)(buf * 256 + col0 + c);
 #pragma unroll
-          for (int g = 0; g < 4; g++)
-            if (g * 8 < ncol) tmem_ld8(taddr + g * 8, v + g * 8);
-          tmem_ld_wait();
-          if (c + 32 >= half_cols) {  // everything of this buffer is in registers: hand it back to the MMA
-            tc_fence_before();
-            mbar_arrive(&sh.tmem_empty[buf]);
-          }
+        for (int q = 0; q < 4; q++)
+          if (q * 8 < ncol) tmem_ld8(taddr + q * 8, v + q * 8);
+      };
+      auto landed = [&](int g, float *v) {  // after this the chunk is in registers
+        tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; g++)
-            if (g * 8 < ncol) top2_update8(v + g * 8, cid0 + (c >> 3) + g, best, second, chunk);
+        for (int q = 0; q < 4; q++) tmem_ld_pin8(v + q * 8);
+        if ((g & ((1 << ch_shift) - 1)) == (1 << ch_shift) - 1) {  // last chunk of its N tile: hand the buffer back
+          tc_fence_before();
+          mbar_arrive(&sh.tmem_empty[(it + (g >> ch_shift)) & 1]);
+        }
+      };
+      auto reduce = [&](int g, const float *v) {
+        const int cid = (k_base + (g >> ch_shift) * n_tile + col0 + (g & ((1 << ch_shift) - 1)) * 32) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (q * 8 < ncol) top2_update8(v + q * 8, cid + q, best, second, chunk);
+      };
+      float va[32], vb[32];
+      issue(0, va);
+      for (int g = 0; g < total; g += 2) {
+        landed(g, va);
+        if (g + 1 < total) issue(g + 1, vb);
+        reduce(g, va);
+        if (g + 1 < total) {
+          landed(g + 1, vb);
+          if (g + 2 < total) issue(g + 2, va);
+          reduce(g + 1, vb);
         }
       }
+      it += n_tiles_n;
       const int rb = tile_seq & 1;
       if (tile_seq >= 2) mbar_wait_bounded(&sh.res_empty[rb], ((tile_seq >> 1) & 1) ^ 1, 7);
       sh.res_best[rb][half][r] = best;

@@ -135,6 +135,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
+// Ties eight loaded values to the preceding wait: asm volatile statements keep their order, and the
+// "+f" operands make every later use of v[] depend on this statement, so the compiler cannot hoist
+// arithmetic on the registers above tcgen05.wait::ld.
+__device__ __forceinline__ void tmem_ld_pin8(float *v) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace qb
