@@ -127,86 +127,7 @@ struct LevelOut {
   float ms_assign = 0, ms_resolve = 0, ms_accumulate = 0;
 };
 
-// Colour-space codebook (FP64) -> staged FP32 rows in lattice coordinates.
-//   SCALED: value = (L + 128)/255  =>  C = 255*c - 128 ;  NORMAL: C = c.
-// Rows K .. K_rows-1 are padding that can never win (the kernels consume rows in pairs / tiles).
-inline double lattice_coord(double c, int colorspace) { return colorspace == QB200_CS_SCALED ? 255.0 * c - 128.0 : c; }
-
-void make_rows(const double *cb, uint32_t K, uint32_t K_rows, int dim, int colorspace, float *rows, float *c_max_norm) {
-  const int row = assign_row_floats(dim);
-  double max_n2 = 0;
-  for (uint32_t k = 0; k < K; k++) {
-    float *r = rows + (size_t)k * row;
-    double n2 = 0;
-    for (int e = 0; e < dim; e++) {
-      const float Cf = (float)lattice_coord(cb[(size_t)k * dim + e], colorspace);
-      r[e] = -2.0f * Cf;
-      n2 += (double)Cf * (double)Cf;
-    }
-    r[dim] = (float)n2;
-    for (int e = dim + 1; e < row; e++) r[e] = 0.f;
-    if (n2 > max_n2) max_n2 = n2;
-  }
-  for (uint32_t k = K; k < K_rows; k++) {
-    float *r = rows + (size_t)k * row;
-    for (int e = 0; e < row; e++) r[e] = 0.f;
-    r[dim] = 3.0e38f;
-  }
-  *c_max_norm = (float)(std::sqrt(max_n2) * 1.000001 + 1e-3);
-}
-
-// bf16 helpers for the tensor-core staging (round to nearest even)
-inline uint16_t bf16_bits(float f) {
-  uint32_t u;
-  std::memcpy(&u, &f, 4);
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-inline double bf16_value(uint16_t b) {
-  uint32_t u = (uint32_t)b << 16;
-  float f;
-  std::memcpy(&f, &u, 4);
-  return (double)f;
-}
-
-// Codebook for assign_tc_kernel: per N tile, per limb l in {hi, mid, lo}, per 16-wide K block, an
-// N x 16 bf16 block in the UMMA K-major no-swizzle layout (8-row x 16-byte core matrices; the two core
-// matrices of a K block 128 B apart, 8-row groups 256 B apart).  Logical row k =
-// [-2*C_k[0..dim), |C_k|^2, 0 ...]; the three limbs of a value v are bf16(v), bf16(v - hi),
-// bf16(v - hi - mid): their sum carries 24 mantissa bits of v.
-void tc_stage_codebook(const double *cb, uint32_t K, int dim, int colorspace, unsigned char *out) {
-  const int KB = tc_kblocks(dim), N = tc_n_tile((int)K), Kp = tc_padded_rows((int)K);
-  const size_t block = (size_t)N * 32;
-  std::memset(out, 0, (size_t)Kp * tc_row_bytes(dim));
-  for (int k = 0; k < Kp; k++) {
-    const int jt = k / N, r = k % N;
-    double n2 = 0;
-    for (int e = 0; e <= dim; e++) {
-      double v;
-      if (k >= (int)K) {
-        v = e == dim ? 3.0e38 : 0.0;  // padding row: never the minimum
-      } else if (e < dim) {
-        const double C = (double)(float)lattice_coord(cb[(size_t)k * dim + e], colorspace);  // same FP32 C as make_rows
-        v = -2.0 * C;
-        n2 += C * C;
-      } else {
-        v = n2;
-      }
-      const int kb = e / 16, kk = e % 16;
-      double rem = v;
-      for (int l = 0; l < 3; l++) {
-        const uint16_t b = bf16_bits((float)rem);
-        rem -= bf16_value(b);
-        unsigned char *p = out + (size_t)((jt * 3 + l) * KB + kb) * block + (size_t)(r >> 3) * 256 + (size_t)(kk >> 3) * 128 +
-                           (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
-        std::memcpy(p, &b, 2);
-        if (k >= (int)K) break;  // the padding value fits one limb
-      }
-    }
-  }
-}
-
-// Pinned staging layout of one level: [rows32 | tc rows | cb64 | kd nodes | vind | bbox | counters(64B)]
+// Per-level sizes and the pinned staging layout: [cb64 | kd nodes | vind | bbox | counters(64B)]
 struct LevelLayout {
   uint32_t K_rows;  // staged FP32 rows
   bool use_tc;
@@ -241,8 +162,8 @@ LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
   L.cb_bytes = (size_t)K * dim * 8;
   L.max_nodes = 2 * (size_t)K + 8;
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  L.off_tc = up(L.rows_bytes);
-  L.off_cb = up(L.off_tc + L.tc_bytes);
+  L.off_tc = 0;
+  L.off_cb = 0;
   L.off_nodes = up(L.off_cb + L.cb_bytes);
   L.off_vind = L.off_nodes + L.max_nodes * sizeof(KdNode);
   L.off_bbox = up(L.off_vind + (size_t)K * 4);
@@ -265,23 +186,22 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   if (want_stats && (rc = ensure(ctx, ctx->d_stats, stats_words(K, dim) * 8))) return rc;
   if ((rc = ensure_pinned(ctx, L.total))) return rc;
   char *pin = (char *)ctx->h_pin;
-  float *h_rows = (float *)pin;
   double *h_cb = (double *)(pin + L.off_cb);
 
-  float c_max = 0;
-  make_rows(cb, K, L.K_rows, dim, ctx->colorspace, h_rows, &c_max);
+  // The FP64 codebook is the only thing uploaded; FP32 rows, bf16 limb tiles and max|C| are derived on the device.
   std::memcpy(h_cb, cb, cb_bytes);
   cudaStream_t st = ctx->stream;
-  CU(cudaMemcpyAsync(ctx->d_rows.p, h_rows, rows_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_cb64.p, h_cb, cb_bytes, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+  unsigned int *cnt = (unsigned int *)ctx->d_counters.p;  // [0] flagged, [1] changed, [2] ties, [4] max|C| (float)
+  const float *c_max_ptr = reinterpret_cast<const float *>(cnt + 4);
+  if (L.use_tc && (rc = ensure(ctx, ctx->d_rows_tc, L.tc_bytes))) return rc;
+  if (L.use_tc && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 12))) return rc;
   if (timed) CU(cudaEventRecord(ctx->ev[0], st));
+  CU(launch_stage_codebook((const double *)ctx->d_cb64.p, (int)K, (int)L.K_rows, L.use_tc ? (int)L.K_rows : 0, dim,
+                           ctx->colorspace == QB200_CS_SCALED, (float *)ctx->d_rows.p,
+                           L.use_tc ? (unsigned char *)ctx->d_rows_tc.p : nullptr, reinterpret_cast<float *>(cnt + 4), st));
   if (L.use_tc) {
-    // tensor-core filter: 3 bf16 limbs of the same FP32 rows, staged in the MMA's shared-memory layout
-    if ((rc = ensure(ctx, ctx->d_rows_tc, L.tc_bytes))) return rc;
-    tc_stage_codebook(cb, K, dim, ctx->colorspace, (unsigned char *)(pin + L.off_tc));
-    CU(cudaMemcpyAsync(ctx->d_rows_tc.p, pin + L.off_tc, L.tc_bytes, cudaMemcpyHostToDevice, st));
-    const bool multi_pass = tc_chunk_rows(dim, (int)K) < (int)L.K_rows;
-    if (multi_pass && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 12))) return rc;
     AssignTcLaunch a{};
     a.src = ctx->src;
     a.b_staged = (const unsigned char *)ctx->d_rows_tc.p;
@@ -290,11 +210,11 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
     // per-score bound: 3*(dim+1) exact products accumulated in FP32 (allowing truncation: 2^-23 each) plus
     // the limb residual, relative to (|X| + |C|)^2; the margin is three times that (see qb200_assign_tc.cu)
     a.margin_coef = 3.0f * (float)(3 * (dim + 1) + 2) * 1.1920929e-7f;
-    a.c_max_norm = c_max;
+    a.c_max_ptr = c_max_ptr;
     a.state = (float *)ctx->d_state.p;
     a.assign = (uint32_t *)ctx->d_assign.p;
     a.flag_list = (uint32_t *)ctx->d_flags.p;
-    a.flag_count = (unsigned int *)ctx->d_counters.p;
+    a.flag_count = cnt;
     a.sm_count = ctx->sm_count;
     a.stream = st;
     CU(launch_assign_tc(a));
@@ -305,16 +225,16 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
     a.K = (int)L.K_rows;
     // 2 scores * (dim+3) * 2^-24 * (|X|+|C|)^2, with 25% head-room (see qb200_kernels.cu)
     a.margin_coef = 2.5f * (float)(dim + 3) * 5.9604645e-8f;
-    a.c_max_norm = c_max;
+    a.c_max_ptr = c_max_ptr;
     a.assign = (uint32_t *)ctx->d_assign.p;
     a.flag_list = (uint32_t *)ctx->d_flags.p;
-    a.flag_count = (unsigned int *)ctx->d_counters.p;
+    a.flag_count = cnt;
     a.sm_count = ctx->sm_count;
     a.stream = st;
     CU(launch_assign(a));
   }
   if (timed) CU(cudaEventRecord(ctx->ev[1], st));
-  CU(cudaMemcpyAsync(ctx->d_cb64.p, h_cb, cb_bytes, cudaMemcpyHostToDevice, st));
+
 
   // While the filter runs: build the reference's KD tree for this codebook on the host.
   KdHostTree tree;
@@ -340,7 +260,6 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   kd.bbox_high = kd.bbox_low + dim;
   kd.n_nodes = (int)tree.nodes.size();
   kd.depth = tree.depth;
-  unsigned int *cnt = (unsigned int *)ctx->d_counters.p;
   CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
                     cnt + 2, cnt + 1, ctx->sm_count, st));

@@ -1,8 +1,8 @@
 // assign_tc_kernel: the nearest-codevector FILTER on the 5th-generation tensor cores (tcgen05).
 //
 // Replaces the distance loop of Solution::assignCodeVectors (/root/reference/src/Quantizer.cpp:24-32,
-// i.e. KDTree::nearestNeighbour per vector, src/KDTree.cpp:20-29) for codebooks of 16 or more
-// entries.  Like the CUDA-core assign_kernel it only DECIDES queries whose two best scores are
+// i.e. KDTree::nearestNeighbour per vector, src/KDTree.cpp:20-29) for codebooks of 64 or more
+// entries (padded to a multiple of 256 with rows that cannot win).  Like the CUDA-core assign_kernel it only DECIDES queries whose two best scores are
 // further apart than a bound on its own rounding error; the rest go to the exact FP64 resolver.
 //
 // Score  s_k = |C_k|^2 - 2 <X, C_k>  as a 128 x N x 16*KB GEMM per tile:
@@ -12,17 +12,18 @@
 // the three limbs are three accumulating MMAs into the same FP32 accumulator in tensor memory.
 // All products are exact in FP32; the error is limb truncation + FP32 accumulation of 3*(dim+1) terms.
 //
-// Roles inside the one persistent CTA per SM (416 threads):
+// Roles inside the one persistent CTA per SM (544 threads):
 //   warp 0        barrier setup, TMEM allocation, one lane issues TMA staging of the codebook and all MMAs
-//   warps 1-4     "service": thread r owns query r of a tile - gathers its bytes, writes the bf16 A row,
-//                 and after the epilogue merges/finalises the result (margin test, index, flag list)
-//   warps 5-12    epilogue: two warps per TMEM lane quarter, each scanning half of the N columns with
+//   warps 1-4     producers: thread r gathers the bytes of query r of a tile and writes its bf16 A row
+//   warps 5-8     mergers: thread r merges the two column halves of query r and stores its record
+//                 (best, second, chunk) - tc_finalize_kernel turns records into indices and flags
+//   warps 9-16    epilogue: two warps per TMEM lane quarter, each scanning half of the N columns with
 //                 tcgen05.ld and tracking (best, second, chunk-of-8 index) in registers with min/max ops:
 //                 2.75 alu operations per distance evaluation - this, not the tensor pipe, is the bound
-// Pipelines: A tile double-buffered in shared memory (a_full/a_empty), accumulator double-buffered in
-// TMEM (2 x 256 columns; tmem_full/tmem_empty), per-tile results double-buffered (res_full/res_empty).
+// Pipelines: ring of 4 A tiles in shared memory (a_full/a_empty), accumulator double-buffered in
+// TMEM (2 x 256 columns; tmem_full/tmem_empty), ring of 4 per-tile result records (res_full/res_empty).
 //
-// The member of the winning chunk of 8 is identified by the service thread with eight FP32 scores
+// The member of the winning chunk of 8 is identified by tc_finalize_kernel with eight FP32 scores
 // from the FP32 rows (the same rows the CUDA-core kernel uses): a query that passes the margin test has
 // its best score separated from every other score of the chunk by more than the tensor-core bound, which
 // is itself more than twice the FP32 bound, so the FP32 argmin over the chunk is the same codevector.
@@ -35,8 +36,11 @@ namespace qb {
 
 namespace {
 
-constexpr int kTcThreads = 32 * 13;
+constexpr int kTcThreads = 32 * 17;  // 1 MMA + 4 producer + 4 finaliser + 8 epilogue warps
+constexpr int kAStages = 4;            // A tiles in flight (shared memory ring)
+constexpr int kResStages = 4;          // per-tile result records in flight
 constexpr int kTileQ = 128;  // queries per tile = MMA M = TMEM lanes
+constexpr int kTileN = 256;  // codevectors per MMA = accumulator columns per TMEM buffer
 
 template <int DIM>
 struct TcCfg {
@@ -47,11 +51,12 @@ struct TcCfg {
 };
 
 struct TcShared {
-  uint64_t b_full, a_full[2], a_empty[2], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2];
+  uint64_t b_full, a_full[kAStages], a_empty[kAStages], tmem_full[2], tmem_empty[2], res_full[kResStages],
+      res_empty[kResStages];
   uint32_t tmem_base;
   uint32_t pad;
-  float res_best[2][2][kTileQ], res_second[2][2][kTileQ];
-  int res_chunk[2][2][kTileQ];
+  float res_best[kResStages][2][kTileQ], res_second[kResStages][2][kTileQ];
+  int res_chunk[kResStages][2][kTileQ];
 };
 
 // top-2 of eight scores merged into the running (best, second); `chunk` remembers which group of 8 held the best
@@ -70,31 +75,32 @@ __device__ __forceinline__ void top2_update8(const float *a, int cid, float &bes
 
 template <int DIM>
 __global__ void __launch_bounds__(kTcThreads, 1)
-    assign_tc_kernel(const VecSource src, const unsigned char *__restrict__ b_staged, const float *__restrict__ rows32,
-                     const int k_rows, const int k_base, const int n_tile, const int first_pass, const int last_pass,
-                     const float margin_coef, const float c_max_norm, float *__restrict__ state,
-                     uint32_t *__restrict__ assign, uint32_t *__restrict__ flag_list,
-                     unsigned int *__restrict__ flag_count, const unsigned long long tiles) {
+    assign_tc_kernel(const VecSource src, const unsigned char *__restrict__ b_staged, const int k_rows, const int k_base,
+                     const int first_pass, float *__restrict__ state, const unsigned long long tiles) {
   using Cfg = TcCfg<DIM>;
   constexpr int KB = Cfg::KB;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // [ B chunk | A tile 0 | A tile 1 | TcShared ]
+  // [ B chunk | A tile ring | TcShared ]
   const uint32_t b_bytes = (uint32_t)k_rows * Cfg::ROW_BYTES;
   unsigned char *s_b = smem_raw;
   unsigned char *s_a = smem_raw + ((b_bytes + 1023u) & ~1023u);
-  TcShared &sh = *reinterpret_cast<TcShared *>(s_a + 2 * Cfg::A_BYTES);
+  TcShared &sh = *reinterpret_cast<TcShared *>(s_a + kAStages * Cfg::A_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles_n = k_rows / n_tile;  // N tiles per query tile
+  const int n_tiles_n = k_rows / kTileN;  // N tiles per query tile (the host pads the codebook to a multiple)
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(&sh.b_full, 1);
-      for (int i = 0; i < 2; i++) {
+      for (int i = 0; i < kAStages; i++) {
         mbar_init(&sh.a_full[i], kTileQ);
         mbar_init(&sh.a_empty[i], 1);
+      }
+      for (int i = 0; i < 2; i++) {
         mbar_init(&sh.tmem_full[i], 1);
         mbar_init(&sh.tmem_empty[i], 256);
+      }
+      for (int i = 0; i < kResStages; i++) {
         mbar_init(&sh.res_full[i], 256);
         mbar_init(&sh.res_empty[i], kTileQ);
       }
@@ -115,17 +121,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (uint32_t off = 0; off < b_bytes; off += 32768u)
         tma_load_1d(s_b + off, b_staged + off, min(32768u, b_bytes - off), &sh.b_full);
       mbar_wait_bounded(&sh.b_full, 0, 1);
-      const uint32_t idesc = umma_idesc_bf16_f32(n_tile);
+      const uint32_t idesc = umma_idesc_bf16_f32(kTileN);
       const uint32_t a_addr = smem_u32(s_a), b_addr = smem_u32(s_b);
-      const uint32_t b_tile_bytes = (uint32_t)n_tile * 32u;  // one (limb, K block) of one N tile
+      const uint32_t b_tile_bytes = (uint32_t)kTileN * 32u;  // one (limb, K block) of one N tile
       unsigned int it = 0, tile_seq = 0;
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
-        const int ab = tile_seq & 1;
-        mbar_wait_bounded(&sh.a_full[ab], (tile_seq >> 1) & 1, 2);
+        const int ab = tile_seq % kAStages;
+        mbar_wait_bounded<true>(&sh.a_full[ab], (tile_seq / kAStages) & 1, 2);
         tc_fence_after();
         for (int jt = 0; jt < n_tiles_n; jt++, it++) {
           const int buf = it & 1;
-          mbar_wait_bounded(&sh.tmem_empty[buf], ((it >> 1) & 1) ^ 1, 3);
+          mbar_wait_bounded<true>(&sh.tmem_empty[buf], ((it >> 1) & 1) ^ 1, 3);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
@@ -144,15 +150,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
     }
   } else if (warp <= 4) {
-    // =========================== service: produce A rows, finalise results ===========================
+    // =========================== producers: gather query bytes, write bf16 A rows ===========================
     const int r = (warp - 1) * 32 + lane;  // query row inside a tile
     const uint32_t row_off = (uint32_t)(r >> 3) * 256u + (uint32_t)(r & 7) * 16u;
-    float x_cur[DIM], x_next[DIM];
-    bool live_cur = false, live_next = false;
-    auto gather = [&](unsigned long long tile, float *x, bool &live) {
+    unsigned int tile_seq = 0;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
+      float x[DIM];
       const unsigned long long v = tile * kTileQ + r;
-      live = v < src.n_local;
-      if (live) {
+      if (v < src.n_local) {
         unsigned long long base, img;
         vec_base(src, v, base, img);
 #pragma unroll
@@ -161,10 +166,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
         for (int e = 0; e < DIM; e++) x[e] = 0.f;
       }
-    };
-    auto produce = [&](unsigned int tile_seq, const float *x) {
-      const int ab = tile_seq & 1;
-      if (tile_seq >= 2) mbar_wait_bounded(&sh.a_empty[ab], ((tile_seq >> 1) & 1) ^ 1, 4);
+      const int ab = tile_seq % kAStages;
+      const unsigned int use = tile_seq / kAStages;
+      if (use >= 1) mbar_wait_bounded<true>(&sh.a_empty[ab], (use - 1) & 1, 4);
       unsigned char *a_tile = s_a + ab * Cfg::A_BYTES;
 #pragma unroll
       for (int kb = 0; kb < KB; kb++) {
@@ -182,85 +186,32 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&sh.a_full[ab]);
-    };
-
-    unsigned int tile_seq = 0;
-    unsigned long long tile = blockIdx.x;
-    if (tile < tiles) {
-      gather(tile, x_cur, live_cur);
-      produce(0, x_cur);
     }
-    for (; tile < tiles; tile += gridDim.x, tile_seq++) {
-      const unsigned long long next = tile + gridDim.x;
-      if (next < tiles) {
-        gather(next, x_next, live_next);
-        produce(tile_seq + 1, x_next);
-      }
-      // results of this tile
-      const int rb = tile_seq & 1;
-      mbar_wait_bounded(&sh.res_full[rb], (tile_seq >> 1) & 1, 5);
+  } else if (warp <= 8) {
+    // =========================== mergers: combine the two column halves, store the per-query record ===========================
+    // No dependent global loads here (they would serialise one tile per memory round trip); the margin
+    // test and the index inside the winning chunk are done by tc_finalize_kernel after the last pass.
+    const int r = (warp - 5) * 32 + lane;
+    unsigned int tile_seq = 0;
+    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
+      const unsigned long long v = tile * kTileQ + r;
+      const int rb = tile_seq % kResStages;
+      mbar_wait_bounded<true>(&sh.res_full[rb], (tile_seq / kResStages) & 1, 5);
       const float b0 = sh.res_best[rb][0][r], b1 = sh.res_best[rb][1][r];
       const float s0 = sh.res_second[rb][0][r], s1 = sh.res_second[rb][1][r];
       const int c0 = sh.res_chunk[rb][0][r], c1 = sh.res_chunk[rb][1][r];
       mbar_arrive(&sh.res_empty[rb]);
-      const float best = fminf(b0, b1);
-      const float second = fmin3(fmaxf(b0, b1), s0, s1);
-      const int chunk = b1 < b0 ? c1 : c0;
-      const unsigned long long v = tile * kTileQ + r;
-      bool flag = false;
-      if (!last_pass) {
-        if (live_cur) {
-          state[v * 3 + 0] = best;
-          state[v * 3 + 1] = second;
-          state[v * 3 + 2] = __int_as_float(chunk);
-        }
-      } else {
-        float xn = 0.f;
-#pragma unroll
-        for (int e = 0; e < DIM; e++) xn = fmaf(x_cur[e], x_cur[e], xn);
-        const float rr = sqrtf(xn) + c_max_norm;
-        flag = live_cur && !((second - best) > margin_coef * rr * rr);
-        int bidx = chunk * 8;
-        if (live_cur && !flag) {
-          float sb = FLT_MAX;
-          const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * Cfg::ROW32);
-#pragma unroll
-          for (int c = 0; c < 8; c++) {
-            float cr[Cfg::ROW32];
-#pragma unroll
-            for (int q4 = 0; q4 < Cfg::ROW32 / 4; q4++) {
-              const float4 t = __ldg(rows + c * (Cfg::ROW32 / 4) + q4);
-              cr[4 * q4] = t.x; cr[4 * q4 + 1] = t.y; cr[4 * q4 + 2] = t.z; cr[4 * q4 + 3] = t.w;
-            }
-            float s = cr[DIM];
-#pragma unroll
-            for (int e = 0; e < DIM; e++) s = fmaf(x_cur[e], cr[e], s);
-            if (s < sb) {
-              sb = s;
-              bidx = chunk * 8 + c;
-            }
-          }
-        }
-        if (live_cur) assign[v] = (uint32_t)bidx;
+      if (v < src.n_local) {
+        state[v * 3 + 0] = fminf(b0, b1);
+        state[v * 3 + 1] = fmin3(fmaxf(b0, b1), s0, s1);
+        state[v * 3 + 2] = __int_as_float(b1 < b0 ? c1 : c0);
       }
-      const unsigned int m = __ballot_sync(0xffffffffu, flag);
-      if (m) {
-        const int leader = __ffs(m) - 1;
-        unsigned int basepos = 0;
-        if (lane == leader) basepos = atomicAdd(flag_count, (unsigned int)__popc(m));
-        basepos = __shfl_sync(0xffffffffu, basepos, leader);
-        if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
-      }
-#pragma unroll
-      for (int e = 0; e < DIM; e++) x_cur[e] = x_next[e];
-      live_cur = live_next;
     }
   } else {
     // =========================== epilogue: TMEM -> registers -> running top-2 ===========================
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter + 32) are the ones this warp may read
-    const int half = (warp - 5) >> 2;      // which half of the N columns
+    const int half = (warp - 9) >> 2;      // which half of the N columns
     const int r = quarter * 32 + lane;     // query row = TMEM lane
-    const int half_cols = n_tile >> 1;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     unsigned int it = 0, tile_seq = 0;
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
@@ -276,12 +227,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       // Flat sequence of column chunks (<= 32 columns each) over the N tiles of this query tile, software
       // pipelined over two register buffers: the tcgen05.ld of chunk g+1 is in flight while chunk g is reduced.
+      constexpr int half_cols = kTileN / 2, ch_shift = 2, ch_mask = 3;  // 4 chunks of 32 columns per N tile and half
       const int col0 = half * half_cols;
-      const int ncol = min(32, half_cols);
-      const int ch_shift = half_cols >= 128 ? 2 : (half_cols >= 64 ? 1 : 0);  // chunks per N tile = 1 << ch_shift
       const int total = n_tiles_n << ch_shift;
       auto issue = [&](int g, float *v) {
-        const int jt = g >> ch_shift, c = (g & ((1 << ch_shift) - 1)) * 32;
+        const int jt = g >> ch_shift, c = (g & ch_mask) * 32;
         const unsigned int itg = it + jt;
         const int buf = itg & 1;
         if (c == 0) {
@@ -290,23 +240,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         const uint32_t taddr = lane_addr + (uint32_t)(buf * 256 + col0 + c);
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (q * 8 < ncol) tmem_ld8(taddr + q * 8, v + q * 8);
+        for (int q = 0; q < 4; q++) tmem_ld8(taddr + q * 8, v + q * 8);
       };
       auto landed = [&](int g, float *v) {  // after this the chunk is in registers
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; q++) tmem_ld_pin8(v + q * 8);
-        if ((g & ((1 << ch_shift) - 1)) == (1 << ch_shift) - 1) {  // last chunk of its N tile: hand the buffer back
+        if ((g & ch_mask) == ch_mask) {  // last chunk of its N tile: hand the buffer back to the MMA
           tc_fence_before();
           mbar_arrive(&sh.tmem_empty[(it + (g >> ch_shift)) & 1]);
         }
       };
       auto reduce = [&](int g, const float *v) {
-        const int cid = (k_base + (g >> ch_shift) * n_tile + col0 + (g & ((1 << ch_shift) - 1)) * 32) >> 3;
+        const int cid = (k_base + (g >> ch_shift) * kTileN + col0 + (g & ch_mask) * 32) >> 3;
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (q * 8 < ncol) top2_update8(v + q * 8, cid + q, best, second, chunk);
+        for (int q = 0; q < 4; q++) top2_update8(v + q * 8, cid + q, best, second, chunk);
       };
       float va[32], vb[32];
       issue(0, va);
@@ -321,8 +269,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
       }
       it += n_tiles_n;
-      const int rb = tile_seq & 1;
-      if (tile_seq >= 2) mbar_wait_bounded(&sh.res_empty[rb], ((tile_seq >> 1) & 1) ^ 1, 7);
+      const int rb = tile_seq % kResStages;
+      if (tile_seq >= kResStages) mbar_wait_bounded(&sh.res_empty[rb], ((tile_seq / kResStages) - 1) & 1, 7);
       sh.res_best[rb][half][r] = best;
       sh.res_second[rb][half][r] = second;
       sh.res_chunk[rb][half][r] = chunk;
@@ -335,6 +283,137 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// After the last pass: per query, read its (best, second, chunk) record, apply the margin test and - for
+// decided queries - find the member of the winning chunk of 8 with FP32 scores from the FP32 rows.
+// Undecided queries go to the flag list for the exact resolver.
+//
+// The chunk's 8 rows are contiguous (8 * ROW32 floats).  Gathering them one query per thread touches 32
+// different cache lines per warp-wide load and the L1 tag stage (one line per clock) becomes the bound,
+// so for 16-float rows (dim 12..15) EIGHT LANES SHARE ONE QUERY: at step i lane j reads float4 number
+// 8*i + j of the chunk (8 lanes = one 128-byte line), which is columns 4*(j%4).. of row 2*i + j/4; the four
+// lanes of a row add their partial dot products with two shuffles, each half-group keeps the best of its
+// four rows and one more shuffle merges the halves.  4 lines per warp-wide load instead of 32.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+    tc_finalize_kernel(const VecSource src, const float *__restrict__ rows32, const float *__restrict__ state,
+                       const float margin_coef, const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
+                       uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count) {
+  constexpr int ROW32 = TcCfg<DIM>::ROW32;
+  const float c_max_norm = *c_max_ptr;
+  const int lane = threadIdx.x & 31;
+  if constexpr (ROW32 == 16) {
+    const int j = lane & 7, cb = j & 3;  // lane inside the query group; column block of this lane
+    const unsigned int gmask = 0xFFu << (lane & 24);  // the eight lanes of this group: a dead group skips the shuffles
+    const unsigned long long gthread = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n_groups = (unsigned long long)gridDim.x * blockDim.x / 8;
+    const unsigned long long n_round = (src.n_local + 3ull) & ~3ull;  // 4 queries per warp per round
+    for (unsigned long long v = gthread >> 3; v < n_round; v += n_groups) {
+      const bool live = v < src.n_local;
+      bool flag = false;
+      if (live) {
+        const float best = state[v * 3 + 0], second = state[v * 3 + 1];
+        const int chunk = __float_as_int(state[v * 3 + 2]);
+        unsigned long long base, img;
+        vec_base(src, v, base, img);
+        // this lane's four extended coordinates [x, 1, 0, 0][4*cb .. 4*cb+3], and |x|^2 via the group
+        float xe[4], part = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int e = 4 * cb + t;
+          xe[t] = e < DIM ? (float)load_lattice(src, img, base, e < DIM ? e : 0) : (e == DIM ? 1.f : 0.f);
+          part = e < DIM ? fmaf(xe[t], xe[t], part) : part;
+        }
+        part += __shfl_xor_sync(gmask, part, 1);
+        part += __shfl_xor_sync(gmask, part, 2);
+        const float rr = sqrtf(part) + c_max_norm;
+        flag = !((second - best) > margin_coef * rr * rr);
+        const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * ROW32);
+        float sb = FLT_MAX;
+        int rbest = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float4 c = __ldg(rows + i * 8 + j);
+          float p = xe[0] * c.x;
+          p = fmaf(xe[1], c.y, p);
+          p = fmaf(xe[2], c.z, p);
+          p = fmaf(xe[3], c.w, p);
+          p += __shfl_xor_sync(gmask, p, 1);
+          p += __shfl_xor_sync(gmask, p, 2);
+          const int row = 2 * i + (j >> 2);
+          if (p < sb) {
+            sb = p;
+            rbest = row;
+          }
+        }
+        const float so = __shfl_xor_sync(gmask, sb, 4);
+        const int ro = __shfl_xor_sync(gmask, rbest, 4);
+        if (so < sb || (so == sb && ro < rbest)) rbest = ro;
+        if (j == 0) assign[v] = (uint32_t)(chunk * 8 + rbest);
+        flag = flag && j == 0;
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, flag);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned int basepos = 0;
+        if (lane == leader) basepos = atomicAdd(flag_count, (unsigned int)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+      }
+    }
+  } else {
+    const unsigned long long n_round = (src.n_local + 31ull) & ~31ull;  // whole warps stay in the loop for the ballot
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_round;
+         v += (unsigned long long)gridDim.x * blockDim.x) {
+      const bool live = v < src.n_local;
+      bool flag = false;
+      if (live) {
+        const float best = state[v * 3 + 0], second = state[v * 3 + 1];
+        const int chunk = __float_as_int(state[v * 3 + 2]);
+        unsigned long long base, img;
+        vec_base(src, v, base, img);
+        float x[DIM], xn = 0.f;
+#pragma unroll
+        for (int e = 0; e < DIM; e++) {
+          x[e] = (float)load_lattice(src, img, base, e);
+          xn = fmaf(x[e], x[e], xn);
+        }
+        const float rr = sqrtf(xn) + c_max_norm;
+        flag = !((second - best) > margin_coef * rr * rr);
+        int bidx = chunk * 8;
+        if (!flag) {
+          float sb = FLT_MAX;
+          const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * ROW32);
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            float cr[ROW32];
+#pragma unroll
+            for (int q4 = 0; q4 < ROW32 / 4; q4++) {
+              const float4 t = __ldg(rows + c * (ROW32 / 4) + q4);
+              cr[4 * q4] = t.x; cr[4 * q4 + 1] = t.y; cr[4 * q4 + 2] = t.z; cr[4 * q4 + 3] = t.w;
+            }
+            float s = cr[DIM];
+#pragma unroll
+            for (int e = 0; e < DIM; e++) s = fmaf(x[e], cr[e], s);
+            if (s < sb) {
+              sb = s;
+              bidx = chunk * 8 + c;
+            }
+          }
+        }
+        assign[v] = (uint32_t)bidx;
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, flag);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned int basepos = 0;
+        if (lane == leader) basepos = atomicAdd(flag_count, (unsigned int)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -342,16 +421,16 @@ int tc_kblocks(int dim) { return (dim + 1 + 15) / 16; }
 size_t tc_row_bytes(int dim) { return (size_t)tc_kblocks(dim) * 3 * 32; }
 bool tc_supported(int dim, int K) {
   switch (dim) {
-    case 3: case 6: case 9: case 12: case 24: case 27: case 48: return K >= 16;
+    case 3: case 6: case 9: case 12: case 24: case 27: case 48: return K >= 64;
     default: return false;
   }
 }
-int tc_padded_rows(int K) { return K < 256 ? ((K + 15) / 16) * 16 : ((K + 255) / 256) * 256; }
-int tc_n_tile(int K) { return K < 256 ? ((K + 15) / 16) * 16 : 256; }
+int tc_padded_rows(int K) { return ((K + kTileN - 1) / kTileN) * kTileN; }
+int tc_n_tile(int K) { (void)K; return kTileN; }
 // Rows per launch: what fits in shared memory next to the two A tiles, a multiple of the N tile.
 int tc_chunk_rows(int dim, int K) {
   const int kp = tc_padded_rows(K), nt = tc_n_tile(K);
-  const size_t budget = 200 * 1024 - 2 * (size_t)tc_kblocks(dim) * 4096;
+  const size_t budget = 208 * 1024 - kAStages * (size_t)tc_kblocks(dim) * 4096;
   int rows = (int)(budget / tc_row_bytes(dim));
   rows = (rows / nt) * nt;
   return rows < kp ? rows : kp;
@@ -360,23 +439,29 @@ int tc_chunk_rows(int dim, int K) {
 template <int DIM>
 static cudaError_t launch_tc_t(const AssignTcLaunch &a) {
   using Cfg = TcCfg<DIM>;
-  const int kp = tc_padded_rows(a.K), nt = tc_n_tile(a.K), chunk = tc_chunk_rows(DIM, a.K);
+  const int kp = tc_padded_rows(a.K), chunk = tc_chunk_rows(DIM, a.K);
   const unsigned long long tiles = (a.src.n_local + kTileQ - 1) / kTileQ;
   if (tiles == 0) return cudaSuccess;
-  const size_t smem_max = (((size_t)chunk * Cfg::ROW_BYTES + 1023) & ~(size_t)1023) + 2 * Cfg::A_BYTES + sizeof(TcShared) + 1024;
+  const size_t smem_max = (((size_t)chunk * Cfg::ROW_BYTES + 1023) & ~(size_t)1023) + kAStages * Cfg::A_BYTES + sizeof(TcShared) + 1024;
   cudaError_t e = cudaFuncSetAttribute(assign_tc_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return e;
   const unsigned int grid = (unsigned int)(tiles < (unsigned long long)a.sm_count ? tiles : a.sm_count);
   for (int k0 = 0; k0 < kp; k0 += chunk) {
     const int rows = kp - k0 < chunk ? kp - k0 : chunk;
-    assign_tc_kernel<DIM><<<grid, kTcThreads, smem_max, a.stream>>>(
-        a.src, a.b_staged + (size_t)k0 * Cfg::ROW_BYTES, a.rows32, rows, k0, nt, k0 == 0, k0 + rows >= kp, a.margin_coef,
-        a.c_max_norm, a.state, a.assign, a.flag_list, a.flag_count, tiles);
+    assign_tc_kernel<DIM><<<grid, kTcThreads, smem_max, a.stream>>>(a.src, a.b_staged + (size_t)k0 * Cfg::ROW_BYTES, rows,
+                                                                    k0, k0 == 0, a.state, tiles);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  return cudaSuccess;
+  const unsigned long long per_block = Cfg::ROW32 == 16 ? 32 : 256;  // queries per 256-thread block per round
+  unsigned long long blocks = (a.src.n_local + per_block - 1) / per_block;
+  const unsigned long long cap = (unsigned long long)a.sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  tc_finalize_kernel<DIM><<<(unsigned int)blocks, 256, 0, a.stream>>>(a.src, a.rows32, a.state, a.margin_coef, a.c_max_ptr,
+                                                                      a.assign, a.flag_list, a.flag_count);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_assign_tc(const AssignTcLaunch &a) {

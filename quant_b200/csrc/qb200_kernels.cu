@@ -52,10 +52,11 @@ struct AssignCfg {
 template <int DIM>
 __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
     assign_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int k_chunk,
-                  const float margin_coef, const float c_max_norm, uint32_t *__restrict__ assign,
+                  const float margin_coef, const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
                   uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count,
                   const unsigned long long tiles) {
   using Cfg = AssignCfg<DIM>;
+  const float c_max_norm = *c_max_ptr;
   constexpr int ROW = Cfg::ROW, Q = Cfg::Q, THREADS = Cfg::THREADS;
   static_assert(Q % 2 == 0, "queries are processed in pairs");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -225,8 +226,9 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
 // Same score, same margin rule; slower, only there so that every block shape works.
 __global__ void __launch_bounds__(128, 1)
     assign_generic_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int row,
-                          const float margin_coef, const float c_max_norm, uint32_t *__restrict__ assign,
+                          const float margin_coef, const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
                           uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count) {
+  const float c_max_norm = *c_max_ptr;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *s_x = reinterpret_cast<float *>(smem_raw);  // [dim][128]
   const int dim = src.dim, tid = threadIdx.x;
@@ -645,6 +647,64 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// stage_codebook_kernel: FP64 codebook -> what the filters consume, on the device (one thread per row)
+// ------------------------------------------------------------------------------------------------
+// Lattice coordinates C = 255*c - 128 (SCALED) or c (NORMAL), rounded once to FP32.
+//   rows32   k_rows32 rows of `row32` floats: [-2*C_k, |C_k|^2, 0 ..]; rows >= K can never win
+//   tc_out   (optional) k_rows_tc rows as three bf16 limbs in the UMMA K-major no-swizzle layout, per N tile
+//            of 256 rows, per limb, per 16-wide K block: 8-row x 16-byte core matrices, the two core matrices
+//            of a K block 128 B apart, 8-row groups 256 B apart.  Limbs of v: bf16(v), bf16(v - hi),
+//            bf16(v - hi - mid) - together 24 mantissa bits.
+//   c_max    max_k |C_k| (slightly rounded up), as float bits via atomicMax (non-negative floats order as ints)
+__device__ __forceinline__ unsigned short bf16_rn_bits(float f) {
+  unsigned int u = __float_as_uint(f);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
+__global__ void __launch_bounds__(128)
+    stage_codebook_kernel(const double *__restrict__ cb, const int K, const int k_rows32, const int k_rows_tc,
+                          const int dim, const int scaled, float *__restrict__ rows32, const int row32,
+                          unsigned char *__restrict__ tc_out, const int kblocks, unsigned int *__restrict__ c_max_bits) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_rows = k_rows32 > k_rows_tc ? k_rows32 : k_rows_tc;
+  if (k >= n_rows) return;
+  const size_t block = (size_t)256 * 32;  // bytes of one (N tile, limb, K block)
+  const int jt = k >> 8, r = k & 255;
+  auto put_tc = [&](int e, double v, bool single) {
+    if (!tc_out || k >= k_rows_tc) return;
+    const int kb = e >> 4, kk = e & 15;
+    double rem = v;
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+      const unsigned short b = (single && l > 0) ? (unsigned short)0 : bf16_rn_bits((float)rem);
+      rem = __dsub_rn(rem, (double)__uint_as_float((unsigned int)b << 16));
+      unsigned char *p = tc_out + (size_t)((jt * 3 + l) * kblocks + kb) * block + (size_t)(r >> 3) * 256 +
+                         (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
+      *reinterpret_cast<unsigned short *>(p) = b;
+    }
+  };
+  double n2 = 0.0;
+  for (int e = 0; e < dim; e++) {
+    float Cf = 0.f;
+    if (k < K) {
+      const double c = cb[(size_t)k * dim + e];
+      Cf = (float)(scaled ? __dsub_rn(__dmul_rn(255.0, c), 128.0) : c);
+      n2 = __dadd_rn(n2, __dmul_rn((double)Cf, (double)Cf));
+    }
+    if (k < k_rows32) rows32[(size_t)k * row32 + e] = -2.0f * Cf;
+    put_tc(e, -2.0 * (double)Cf, false);
+  }
+  const bool pad = k >= K;
+  if (k < k_rows32) {
+    rows32[(size_t)k * row32 + dim] = pad ? 3.0e38f : (float)n2;
+    for (int e = dim + 1; e < row32; e++) rows32[(size_t)k * row32 + e] = 0.f;
+  }
+  put_tc(dim, pad ? 3.0e38 : n2, pad);
+  for (int e = dim + 1; e < kblocks * 16; e++) put_tc(e, 0.0, true);
+  if (!pad) atomicMax(c_max_bits, __float_as_uint((float)(sqrt(n2) * 1.000001 + 1e-3)));
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP32 FMA peak probe (roofline denominator measured in the same run)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) ffma_probe_kernel(float *out, int iters, const float m, const float c) {
@@ -694,7 +754,7 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
   unsigned long long grid = tiles < (unsigned long long)a.sm_count ? tiles : (unsigned long long)a.sm_count;
   if (grid == 0) return cudaSuccess;
   assign_kernel<DIM><<<(unsigned int)grid, Cfg::THREADS, smem, a.stream>>>(
-      a.src, a.cb_rows, a.K, k_chunk, a.margin_coef, a.c_max_norm, a.assign, a.flag_list, a.flag_count, tiles);
+      a.src, a.cb_rows, a.K, k_chunk, a.margin_coef, a.c_max_ptr, a.assign, a.flag_list, a.flag_count, tiles);
   g_launch_count++;
   return cudaGetLastError();
 }
@@ -722,7 +782,7 @@ cudaError_t launch_assign(const AssignLaunch &a) {
   if (blocks == 0) return cudaSuccess;
   assign_generic_kernel<<<(unsigned int)blocks, 128, smem, a.stream>>>(a.src, a.cb_rows, a.K,
                                                                         assign_row_floats(a.src.dim), a.margin_coef,
-                                                                        a.c_max_norm, a.assign, a.flag_list,
+                                                                        a.c_max_ptr, a.assign, a.flag_list,
                                                                         a.flag_count);
   g_launch_count++;
   return cudaGetLastError();
@@ -835,6 +895,17 @@ cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32
   if (blocks > cap) blocks = cap;
   if (blocks == 0) return cudaSuccess;
   decode_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(g, orig, assign, cb_bytes, out, sq_err);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_rows_tc, int dim, int scaled,
+                                  float *rows32, unsigned char *tc_out, float *c_max, cudaStream_t stream) {
+  const int n_rows = k_rows32 > k_rows_tc ? k_rows32 : k_rows_tc;
+  if (n_rows == 0) return cudaSuccess;
+  stage_codebook_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(cb, K, k_rows32, k_rows_tc, dim, scaled, rows32,
+                                                                   assign_row_floats(dim), tc_out, tc_kblocks(dim),
+                                                                   reinterpret_cast<unsigned int *>(c_max));
   g_launch_count++;
   return cudaGetLastError();
 }

@@ -13,7 +13,7 @@ struct AssignLaunch {
   const float *cb_rows;      // K rows of assign_row_floats(dim) floats: [-2*C_k, |C_k|^2, pad]
   int K;
   float margin_coef;         // flag when second - best <= margin_coef * (|X| + c_max_norm)^2
-  float c_max_norm;          // max_k |C_k| (lattice units), rounded up
+  const float *c_max_ptr;    // device: max_k |C_k| (lattice units), rounded up (written by stage_codebook_kernel)
   uint32_t *assign;          // n_local
   uint32_t *flag_list;       // n_local (capacity)
   unsigned int *flag_count;  // device counter, zeroed by the caller
@@ -22,6 +22,9 @@ struct AssignLaunch {
 };
 
 int assign_row_floats(int dim);
+// FP64 codebook (device) -> FP32 rows (+ bf16 limb tiles when tc_out != null) + max codevector norm; c_max must be zeroed.
+cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_rows_tc, int dim, int scaled,
+                                  float *rows32, unsigned char *tc_out, float *c_max, cudaStream_t stream);
 cudaError_t launch_assign(const AssignLaunch &a);
 // Exact re-solve of the flagged queries: brute-force FP64 phase, then the reference's KD walk for
 // the (near-)exact ties it leaves in tie_list (capacity: n_local).  Counters are device words.
@@ -41,8 +44,9 @@ struct AssignTcLaunch {
   const unsigned char *b_staged;
   const float *rows32;
   int K;              // real codevectors
-  float margin_coef, c_max_norm;
-  float *state;       // n_local * 3 floats, only touched when the codebook needs more than one pass
+  float margin_coef;
+  const float *c_max_ptr;  // device
+  float *state;       // n_local * 3 floats: per-query (best, second, chunk) records between the passes and the finalise kernel
   uint32_t *assign, *flag_list;
   unsigned int *flag_count;
   int sm_count;

@@ -68,10 +68,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug must end the kernel with an error, never hang the GPU.
+// RELAXED waiters (roles that run far ahead of the role they wait for) sleep between polls so that
+// their spinning does not take issue slots from the warps doing the work on the same sub-partition.
+template <bool RELAXED = false>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, int tag) {
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
-  for (unsigned int spin = 0; spin < (1u << 26); spin++) {
+  for (unsigned int spin = 0; spin < (RELAXED ? (1u << 22) : (1u << 26)); spin++) {
     uint32_t ok;
     asm volatile(
         "{\n"
@@ -83,6 +86,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
+    if (RELAXED) __nanosleep(128);
   }
   printf("libqb200: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, (int)blockIdx.x, (int)threadIdx.x);
   __trap();
