@@ -292,6 +292,7 @@ def run_gpu_arm(args):
                                    for k in ("ms_assign", "ms_resolve", "ms_accumulate")}
                      for i, r in enumerate(reps[0])}
         flagged_last = int(last[-1]["flagged"])
+        ties_last = int(last[-1]["ties"])
         flops = float(n_local) * K * 3.0 * dim
         ach = flops / (ms_assign * 1e-3) / 1e12
         peaks = {}
@@ -326,7 +327,7 @@ def run_gpu_arm(args):
                                  "achieved": acc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": acc_gbs / hbm_peak,
                                  "peak_source": hbm_src, "ms_per_launch": ms_acc,
                                  "algorithmic": "(dim + 4) bytes per vector"}},
-            "per_level_ms": per_level, "flagged_last_level": flagged_last,
+            "per_level_ms": per_level, "flagged_last_level": flagged_last, "kd_walk_ties_last_level": ties_last,
             "distortion": d_res, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

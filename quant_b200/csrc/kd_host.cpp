@@ -154,7 +154,7 @@ class Builder {
     nd.child1 = c1;
     nd.child2 = c2;
     nd.a = feat;
-    nd.b = 0;
+    nd.b = (int)(first + nleft);  // child1 covers order[first, b), child2 order[b, last)
     nd.divlow = lbox[feat].hi;
     nd.divhigh = rbox[feat].lo;
     for (int d = 0; d < dim_; d++) {

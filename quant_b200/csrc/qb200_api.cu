@@ -166,7 +166,7 @@ LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
   L.off_cb = 0;
   L.off_nodes = up(L.off_cb + L.cb_bytes);
   L.off_vind = L.off_nodes + L.max_nodes * sizeof(KdNode);
-  L.off_bbox = up(L.off_vind + (size_t)K * 4);
+  L.off_bbox = up(L.off_vind + (size_t)K * 8);
   L.off_cnt = L.off_bbox + 2 * (size_t)dim * 8;
   L.total = L.off_cnt + 64;
   return L;
@@ -181,7 +181,7 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   const size_t off_nodes = L.off_nodes, off_vind = L.off_vind, off_bbox = L.off_bbox, off_cnt = L.off_cnt;
   int rc;
   if ((rc = ensure(ctx, ctx->d_rows, rows_bytes))) return rc;
-  if ((rc = ensure(ctx, ctx->d_cb64, cb_bytes))) return rc;
+  if ((rc = ensure(ctx, ctx->d_cb64, 2 * cb_bytes))) return rc;  // row-major | transposed
   if ((rc = ensure(ctx, ctx->d_counters, 64))) return rc;
   if (want_stats && (rc = ensure(ctx, ctx->d_stats, stats_words(K, dim) * 8))) return rc;
   if ((rc = ensure_pinned(ctx, L.total))) return rc;
@@ -200,7 +200,8 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   if (timed) CU(cudaEventRecord(ctx->ev[0], st));
   CU(launch_stage_codebook((const double *)ctx->d_cb64.p, (int)K, (int)L.K_rows, L.use_tc ? (int)L.K_rows : 0, dim,
                            ctx->colorspace == QB200_CS_SCALED, (float *)ctx->d_rows.p,
-                           L.use_tc ? (unsigned char *)ctx->d_rows_tc.p : nullptr, reinterpret_cast<float *>(cnt + 4), st));
+                           L.use_tc ? (unsigned char *)ctx->d_rows_tc.p : nullptr, reinterpret_cast<float *>(cnt + 4),
+                           (double *)ctx->d_cb64.p + (size_t)K * dim, st));
   if (L.use_tc) {
     AssignTcLaunch a{};
     a.src = ctx->src;
@@ -244,23 +245,29 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
                 kResolveDepthCap);
   if (tree.nodes.size() > max_nodes) return fail(ctx, QB200_ERR_STATE, "KD tree larger than expected");
   if ((rc = ensure(ctx, ctx->d_nodes, tree.nodes.size() * sizeof(KdNode)))) return rc;
-  if ((rc = ensure(ctx, ctx->d_vind, (size_t)K * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_vind, (size_t)K * 8))) return rc;  // vind | inverse
   if ((rc = ensure(ctx, ctx->d_bbox, 2 * (size_t)dim * 8))) return rc;
   std::memcpy(pin + off_nodes, tree.nodes.data(), tree.nodes.size() * sizeof(KdNode));
   std::memcpy(pin + off_vind, tree.order.data(), (size_t)K * 4);
+  {
+    unsigned int *inv = reinterpret_cast<unsigned int *>(pin + off_vind) + K;
+    for (uint32_t p = 0; p < K; p++) inv[tree.order[p]] = p;
+  }
   std::memcpy(pin + off_bbox, tree.box_low.data(), (size_t)dim * 8);
   std::memcpy(pin + off_bbox + (size_t)dim * 8, tree.box_high.data(), (size_t)dim * 8);
   CU(cudaMemcpyAsync(ctx->d_nodes.p, pin + off_nodes, tree.nodes.size() * sizeof(KdNode), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_vind.p, pin + off_vind, (size_t)K * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_vind.p, pin + off_vind, (size_t)K * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_bbox.p, pin + off_bbox, 2 * (size_t)dim * 8, cudaMemcpyHostToDevice, st));
   KdDevice kd{};
   kd.nodes = (const KdNode *)ctx->d_nodes.p;
   kd.vind = (const unsigned int *)ctx->d_vind.p;
+  kd.inv = kd.vind + K;
   kd.bbox_low = (const double *)ctx->d_bbox.p;
   kd.bbox_high = kd.bbox_low + dim;
   kd.n_nodes = (int)tree.nodes.size();
   kd.depth = tree.depth;
-  CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p, (int)K, kd,
+  CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p,
+                    (const double *)ctx->d_cb64.p + (size_t)K * dim, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
                     cnt + 2, cnt + 1, ctx->sm_count, st));
   if (timed) CU(cudaEventRecord(ctx->ev[2], st));
@@ -318,6 +325,22 @@ void split_stats(const std::vector<unsigned long long> &w, uint32_t K, int dim, 
     for (int e = 0; e < dim; e++) S[(size_t)k * dim + e] = (int64_t)r[1 + e];
     Q[k] = r[dim + 1];
   }
+}
+
+// Fills the fast-path fields of a VecSource (qb200_device.cuh).  `no_padding`: no element of any vector
+// lies outside its image.  buf is rebased so that offsets start at 0 (origin folded into the pointer).
+void finish_source(VecSource &s, unsigned long long n_images, bool no_padding) {
+  const unsigned long long span = s.img_bytes * n_images;
+  s.fast = no_padding && span < (1ull << 31) && s.per_image * n_images < (1ull << 32) && s.row_stride < (1ull << 31);
+  s.multi = n_images > 1;
+  if (!s.fast) return;
+  fastdiv_make(s.hB, s.hb_mul, s.hb_shift);
+  fastdiv_make((unsigned int)s.per_image, s.pi_mul, s.pi_shift);
+  s.row_stride32 = (unsigned int)s.row_stride;
+  s.img_bytes32 = (unsigned int)s.img_bytes;
+  s.first_vec32 = (unsigned int)s.first_vec;
+  s.per_image32 = (unsigned int)s.per_image;
+  s.origin32 = (unsigned int)s.origin;
 }
 
 int set_common(qb200_ctx *ctx, size_t n_local) {
@@ -478,6 +501,7 @@ static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySi
     if (hi > lo) CU(cudaMemcpyAsync(ctx->d_img.p, first, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream));
     s.buf = (const uint8_t *)ctx->d_img.p;
   }
+  finish_source(s, (unsigned long long)n_images, xSize % w == 0 && ySize % h == 0);
   ctx->src = s;
   ctx->colorspace = colorspace;
   ctx->is_image = true;
@@ -542,6 +566,7 @@ int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors,
     if (s.img_bytes) CU(cudaMemcpyAsync(ctx->d_img.p, bytes, (size_t)s.img_bytes, cudaMemcpyHostToDevice, ctx->stream));
     s.buf = (const uint8_t *)ctx->d_img.p;
   }
+  finish_source(s, 1, true);
   ctx->src = s;
   ctx->colorspace = colorspace;
   ctx->is_image = false;

@@ -158,10 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       float x[DIM];
       const unsigned long long v = tile * kTileQ + r;
       if (v < src.n_local) {
-        unsigned long long base, img;
-        vec_base(src, v, base, img);
-#pragma unroll
-        for (int e = 0; e < DIM; e++) x[e] = (float)load_lattice(src, img, base, e);
+        gather_lattice<DIM>(src, v, x);
       } else {
 #pragma unroll
         for (int e = 0; e < DIM; e++) x[e] = 0.f;
@@ -313,16 +310,26 @@ __global__ void __launch_bounds__(256)
       if (live) {
         const float best = state[v * 3 + 0], second = state[v * 3 + 1];
         const int chunk = __float_as_int(state[v * 3 + 2]);
-        unsigned long long base, img;
-        vec_base(src, v, base, img);
         // this lane's four extended coordinates [x, 1, 0, 0][4*cb .. 4*cb+3], and |x|^2 via the group
         float xe[4], part = 0.f;
+        if (src.fast) {
+          const signed char *p = fast_vec_ptr(src, v);
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const int e = 4 * cb + t;
-          xe[t] = e < DIM ? (float)load_lattice(src, img, base, e < DIM ? e : 0) : (e == DIM ? 1.f : 0.f);
-          part = e < DIM ? fmaf(xe[t], xe[t], part) : part;
+          for (int t = 0; t < 4; t++) {
+            const int e = 4 * cb + t;
+            xe[t] = e < DIM ? (float)(int)__ldg(p + src.elem_off[e < DIM ? e : 0]) : (e == DIM ? 1.f : 0.f);
+          }
+        } else {
+          unsigned long long base, img;
+          vec_base(src, v, base, img);
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int e = 4 * cb + t;
+            xe[t] = e < DIM ? (float)load_lattice(src, img, base, e < DIM ? e : 0) : (e == DIM ? 1.f : 0.f);
+          }
         }
+#pragma unroll
+        for (int t = 0; t < 4; t++) part = (4 * cb + t) < DIM ? fmaf(xe[t], xe[t], part) : part;
         part += __shfl_xor_sync(gmask, part, 1);
         part += __shfl_xor_sync(gmask, part, 2);
         const float rr = sqrtf(part) + c_max_norm;
@@ -369,14 +376,10 @@ __global__ void __launch_bounds__(256)
       if (live) {
         const float best = state[v * 3 + 0], second = state[v * 3 + 1];
         const int chunk = __float_as_int(state[v * 3 + 2]);
-        unsigned long long base, img;
-        vec_base(src, v, base, img);
         float x[DIM], xn = 0.f;
+        gather_lattice<DIM>(src, v, x);
 #pragma unroll
-        for (int e = 0; e < DIM; e++) {
-          x[e] = (float)load_lattice(src, img, base, e);
-          xn = fmaf(x[e], x[e], xn);
-        }
+        for (int e = 0; e < DIM; e++) xn = fmaf(x[e], x[e], xn);
         const float rr = sqrtf(xn) + c_max_norm;
         flag = !((second - best) > margin_coef * rr * rr);
         int bidx = chunk * 8;

@@ -26,7 +26,29 @@ struct VecSource {
   // Byte offset of element e relative to the block's first byte:
   // ((e/3)/h)*ySize*3 + ((e/3)%h)*3 + e%3.  Lives in the kernel parameter (constant) bank.
   unsigned int elem_off[kMaxDim];
+  // Fast path (set by the host when no element of any vector falls outside its image - block sizes divide
+  // the image - and every byte offset fits 31 bits): 32-bit address arithmetic, no per-element checks,
+  // divisions by hB / per_image through precomputed multipliers.
+  unsigned int fast;
+  unsigned int multi;                  // more than one image in the batch
+  unsigned int hb_mul, hb_shift;       // v / hB        (fastdiv)
+  unsigned int pi_mul, pi_shift;       // v / per_image (fastdiv)
+  unsigned int row_stride32, img_bytes32, first_vec32, per_image32, origin32;
 };
+
+// Division of a 32-bit n by an invariant d (Granlund-Montgomery): q = (t + ((n - t) >> 1)) >> (l - 1),
+// t = umulhi(m, n), l = ceil(log2 d), m = floor(2^32 * (2^l - d) / d) + 1.  d == 1: mul = 0, shift = 0.
+__host__ inline void fastdiv_make(unsigned int d, unsigned int &mul, unsigned int &shift) {
+  unsigned int l = 0;
+  while ((1ull << l) < d) l++;
+  mul = (unsigned int)((((1ull << l) - d) << 32) / d + 1);
+  shift = l;
+}
+__device__ __forceinline__ unsigned int fastdiv(unsigned int n, unsigned int mul, unsigned int shift) {
+  if (shift == 0) return n;  // d == 1
+  const unsigned int t = __umulhi(mul, n);
+  return (t + ((n - t) >> 1)) >> (shift - 1);
+}
 
 // Base byte offset (inside its image) and image number of local vector v.
 __device__ __forceinline__ void vec_base(const VecSource &s, unsigned long long v_local,
@@ -57,17 +79,45 @@ __device__ __forceinline__ int load_lattice(const VecSource &s, unsigned long lo
   return (int)(signed char)__ldg(s.buf + (img * s.img_bytes + o - s.origin));
 }
 
+// Fast path only (s.fast != 0): address of the first byte of local vector v's block.
+__device__ __forceinline__ const signed char *fast_vec_ptr(const VecSource &s, unsigned long long v_local) {
+  unsigned int v = s.first_vec32 + (unsigned int)v_local, img_off = 0;
+  if (s.multi) {
+    const unsigned int img = fastdiv(v, s.pi_mul, s.pi_shift);
+    v -= img * s.per_image32;
+    img_off = img * s.img_bytes32;
+  }
+  const unsigned int i = fastdiv(v, s.hb_mul, s.hb_shift), j = v - i * s.hB;
+  return reinterpret_cast<const signed char *>(s.buf) + (img_off + i * s.row_stride32 + j * s.col_stride - s.origin32);
+}
+
+// All DIM lattice values of local vector v (template DIM: fully unrolled, values stay in registers).
+template <int DIM, typename T>
+__device__ __forceinline__ void gather_lattice(const VecSource &s, unsigned long long v_local, T *out) {
+  if (s.fast) {
+    const signed char *p = fast_vec_ptr(s, v_local);
+#pragma unroll
+    for (int e = 0; e < DIM; e++) out[e] = (T)(int)__ldg(p + s.elem_off[e]);
+  } else {
+    unsigned long long base, img;
+    vec_base(s, v_local, base, img);
+#pragma unroll
+    for (int e = 0; e < DIM; e++) out[e] = (T)load_lattice(s, img, base, e);
+  }
+}
+
 // Flattened KD tree in nanoflann's shape (see kd_host.hpp); 32 bytes per node.
 struct KdNode {
   int child1, child2;  // -1/-1: leaf
   int a;               // inner: divfeat; leaf: left (first position in vind)
-  int b;               // leaf: right (one past the last position in vind)
+  int b;               // leaf: right (one past the last position in vind); inner: first position of child2's range
   double divlow, divhigh;
 };
 
 struct KdDevice {
   const KdNode *nodes;
   const unsigned int *vind;
+  const unsigned int *inv;   // inverse of vind: position of codevector k in traversal (leaf) order
   const double *bbox_low, *bbox_high;  // root bounding box, dim entries each
   int n_nodes;
   int depth;

@@ -112,14 +112,9 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
         live[q] = v < src.n_local;
         xn[q] = 0.f;
         if (live[q]) {
-          unsigned long long base, img;
-          vec_base(src, v, base, img);
+          gather_lattice<DIM>(src, v, x[h]);
 #pragma unroll
-          for (int e = 0; e < DIM; e++) {
-            float f = (float)load_lattice(src, img, base, e);
-            x[h][e] = f;
-            xn[q] = fmaf(f, f, xn[q]);
-          }
+          for (int e = 0; e < DIM; e++) xn[q] = fmaf(x[h][e], x[h][e], xn[q]);
         } else {
 #pragma unroll
           for (int e = 0; e < DIM; e++) x[h][e] = 0.f;
@@ -276,7 +271,7 @@ __global__ void __launch_bounds__(128, 1)
 // ------------------------------------------------------------------------------------------------
 // resolve_kernel: exact FP64 nearest neighbour in nanoflann's traversal order
 // ------------------------------------------------------------------------------------------------
-// Phase B: one thread per query phase A (below) could not decide.  Arithmetic is spelled with the round-to-nearest intrinsics so
+// Phase B: one warp per query phase A (below) could not decide.  Arithmetic is spelled with the round-to-nearest intrinsics so
 // that nvcc cannot contract a*b+c into an FMA: the reference's x86-64 build has none.
 __device__ __forceinline__ double sq_diff(double a, double b) {
   const double d = __dsub_rn(a, b);
@@ -298,6 +293,22 @@ __device__ __forceinline__ double nanoflann_l2(const double *a, const double *__
   return result;
 }
 
+// Same arithmetic on the TRANSPOSED codebook (element e of codevector k at bt[e * stride + k]): lanes that
+// hold consecutive k read consecutive doubles, so a warp-wide load touches 2 cache lines instead of 32.
+__device__ __forceinline__ double nanoflann_l2_t(const double *a, const double *__restrict__ bt, size_t stride, int dim) {
+  double result = 0.0;
+  int d = 0;
+  for (; d + 3 < dim; d += 4) {
+    const double g = __dadd_rn(__dadd_rn(__dadd_rn(sq_diff(a[d], bt[d * stride]), sq_diff(a[d + 1], bt[(d + 1) * stride])),
+                                         sq_diff(a[d + 2], bt[(d + 2) * stride])),
+                               sq_diff(a[d + 3], bt[(d + 3) * stride]));
+    result = __dadd_rn(result, g);
+  }
+  for (; d < dim; d++) result = __dadd_rn(result, sq_diff(a[d], bt[d * stride]));
+  return result;
+}
+
+
 // Phase A of the resolver: one WARP per flagged query, exact FP64 distances (nanoflann's arithmetic,
 // so the values are the ones the reference's leaf loop computes) to ALL K codevectors, lanes strided
 // over k.  nanoflann's search is exact, so whenever the smallest distance is separated from every
@@ -307,14 +318,16 @@ __device__ __forceinline__ double nanoflann_l2(const double *a, const double *__
 // codevector coordinates, i.e. bounded by dmax = max_k dist_k; their accumulated error is below
 // ~4*dim*2^-53*dmax.  A query is decided here when it has exactly one candidate within
 // band = 2^-30 * dmax of the minimum (orders of magnitude above that error, orders of magnitude
-// below the FP32 filter's margin); otherwise (exact or near-exact FP64 ties: duplicated codevectors,
-// children 1.2c / 0.8c of a single-member cell) it goes to the tie list and phase B walks the tree.
+// below the FP32 filter's margin).  EXACT ties (all candidates bitwise equal) are decided by the tree's
+// visiting order without a walk (see below); what remains - distinct distances closer than the band, or
+// more than 32 candidates - goes to the tie list and phase B walks the tree.
 template <int DIMCAP>
 __global__ void __launch_bounds__(128)
-    resolve_bruteforce_kernel(const VecSource src, const int scaled, const double *__restrict__ cb, const int K,
-                              const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
-                              uint32_t *__restrict__ assign, uint32_t *__restrict__ tie_list,
-                              unsigned int *__restrict__ tie_count, unsigned int *__restrict__ changed) {
+    resolve_bruteforce_kernel(const VecSource src, const int scaled, const double *__restrict__ cbt, const int K,
+                              const KdDevice tree, const uint32_t *__restrict__ flag_list,
+                              const unsigned int *__restrict__ flag_count, uint32_t *__restrict__ assign,
+                              uint32_t *__restrict__ tie_list, unsigned int *__restrict__ tie_count,
+                              unsigned int *__restrict__ changed) {
   const int dim = src.dim;
   const unsigned int total = *flag_count;
   const int lane = threadIdx.x & 31;
@@ -332,7 +345,7 @@ __global__ void __launch_bounds__(128)
     double d1 = DBL_MAX, d2 = DBL_MAX, dmax = 0.0;  // this lane's smallest, second smallest, largest
     int k1 = 0;
     for (int k = lane; k < K; k += 32) {
-      const double d = nanoflann_l2(x, cb + (size_t)k * dim, dim);
+      const double d = nanoflann_l2_t(x, cbt + k, (size_t)K, dim);
       dmax = fmax(dmax, d);
       if (d < d1) {
         d2 = d1;
@@ -352,8 +365,74 @@ __global__ void __launch_bounds__(128)
     const int mine = (d1 <= lim ? 1 : 0) + (d2 <= lim ? 1 : 0);
     const unsigned int holders = __ballot_sync(0xffffffffu, mine > 0);
     const unsigned int multi = __ballot_sync(0xffffffffu, mine > 1);
+    int win = -1;
     if (__popc(holders) == 1 && multi == 0) {
-      const int win = __shfl_sync(0xffffffffu, k1, __ffs(holders) - 1);
+      win = __shfl_sync(0xffffffffu, k1, __ffs(holders) - 1);
+    } else {
+      // EXACT ties only (every candidate's distance is bitwise the minimum: duplicated codevectors - dead
+      // cells - or children 1.2c / 0.8c of a single-member cell): the walk keeps the FIRST candidate it
+      // visits (leaf test `dist < worst` and KNNResultSet::addPoint are strict, nanoflann.hpp:1219-1224,
+      // :121) and it cannot prune that candidate's subtree, whose bound is below the running worst by the
+      // band.  Visiting order = near child first at every inner node (nanoflann.hpp:1242-1251), leaf points
+      // in vind order - so descend from the root through the subtrees that still contain candidates.
+      unsigned int my_pos = 0xffffffffu;  // up to 32 candidates, one per lane
+      int n_cand = 0;
+      bool exact = true;
+      for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        bool cand = false;
+        if (k < K) {
+          const double d = nanoflann_l2_t(x, cbt + k, (size_t)K, dim);
+          cand = d <= lim;
+          exact = exact && (!cand || d == wmin);
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, cand);
+        const int slot = n_cand + __popc(m & ((1u << lane) - 1u));
+        const unsigned int pos = cand ? tree.inv[k] : 0xffffffffu;
+        // hand candidate `pos` to lane `slot` (slots >= 32 are dropped and force the slow walk)
+#pragma unroll 1
+        for (unsigned int mm = m; mm; mm &= mm - 1) {
+          const int srcl = __ffs(mm) - 1;
+          const int s_slot = __shfl_sync(0xffffffffu, slot, srcl);
+          const unsigned int s_pos = __shfl_sync(0xffffffffu, pos, srcl);
+          if (lane == s_slot) my_pos = s_pos;
+        }
+        n_cand += __popc(m);
+      }
+      const bool all_exact = __all_sync(0xffffffffu, exact);
+      if (all_exact && n_cand <= 32) {
+        int node = 0, lo = 0, hi = K;
+        for (int guard = 0; guard < 4096; guard++) {
+          const KdNode nd = tree.nodes[node];
+          if (nd.child1 < 0 && nd.child2 < 0) break;
+          const int mid = nd.b;
+          const bool in1 = my_pos != 0xffffffffu && (int)my_pos >= lo && (int)my_pos < mid;
+          const bool in2 = my_pos != 0xffffffffu && (int)my_pos >= mid && (int)my_pos < hi;
+          const bool any1 = __any_sync(0xffffffffu, in1), any2 = __any_sync(0xffffffffu, in2);
+          bool go1;
+          if (any1 && any2) {
+            const double val = x[nd.a];
+            go1 = __dadd_rn(__dsub_rn(val, nd.divlow), __dsub_rn(val, nd.divhigh)) < 0;  // nearer child first
+          } else {
+            go1 = any1;
+          }
+          if (go1) {
+            node = nd.child1;
+            hi = mid;
+            if (!in1) my_pos = 0xffffffffu;
+          } else {
+            node = nd.child2;
+            lo = mid;
+            if (!in2) my_pos = 0xffffffffu;
+          }
+        }
+        unsigned int first = my_pos;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        win = (int)tree.vind[first];
+      }
+    }
+    if (win >= 0) {
       if (lane == 0) {
         const uint32_t old = assign[v];
         if (old != (uint32_t)win) {
@@ -377,11 +456,18 @@ __global__ void __launch_bounds__(128)
     resolve_kernel(const VecSource src, const int scaled, const double *__restrict__ cb, const KdDevice tree,
                    const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
                    uint32_t *__restrict__ assign, unsigned int *__restrict__ changed) {
+  // One WARP per query: every lane runs the same (sequential) tree walk; at a leaf the lanes compute the
+  // distances of its <= 10 points in parallel.  nanoflann's leaf loop (read worstDist once, add points in
+  // order, strict comparisons) keeps the first point that attains the leaf minimum, and only if that
+  // minimum is strictly below the best so far - which is what the lane-ordered reduction below returns.
   const int dim = src.dim;
   const unsigned int total = *flag_count;
+  const int lane = threadIdx.x & 31;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
   double x[DIMCAP], dists[DIMCAP];
   Frame stack[DEPTHCAP];
-  for (unsigned int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+  for (unsigned int f = warp; f < total; f += n_warps) {
     const unsigned long long v = flag_list[f];
     unsigned long long base, img;
     vec_base(src, v, base, img);
@@ -418,17 +504,30 @@ __global__ void __launch_bounds__(128)
       const KdNode nd = tree.nodes[fr.node];
       if (fr.phase == 0) {
         if (nd.child1 < 0 && nd.child2 < 0) {
-          const double worst = best;  // read once per leaf (:1219)
-          for (int p = nd.a; p < nd.b; p++) {
-            const unsigned int index = tree.vind[p];
-            const double dist = nanoflann_l2(x, cb + (size_t)index * dim, dim);
-            if (dist < worst) {
-              if (!have || best > dist) {  // addPoint: strict '>' (:121)
-                best = dist;
-                best_idx = index;
-              }
-              have = true;
+          const int p = nd.a + lane;
+          double dist = DBL_MAX;
+          unsigned int index = 0;
+          if (p < nd.b) {
+            index = tree.vind[p];
+            dist = nanoflann_l2(x, cb + (size_t)index * dim, dim);
+          }
+          // leaf minimum, first position on ties (lanes are in vind order)
+          double m = dist;
+          int ml = lane;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double om = __shfl_xor_sync(0xffffffffu, m, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, ml, o);
+            if (om < m || (om == m && ol < ml)) {
+              m = om;
+              ml = ol;
             }
+          }
+          const unsigned int mi = __shfl_sync(0xffffffffu, index, ml);
+          if (nd.b > nd.a && (!have || m < best)) {  // dist < worstDist at leaf entry, then addPoint's strict '>'
+            best = m;
+            best_idx = mi;
+            have = true;
           }
           sp--;
           continue;
@@ -472,10 +571,12 @@ __global__ void __launch_bounds__(128)
         sp--;
       }
     }
-    const uint32_t old = assign[v];
-    if (old != best_idx) {
-      assign[v] = best_idx;
-      atomicAdd(changed, 1u);
+    if (lane == 0) {
+      const uint32_t old = assign[v];
+      if (old != best_idx) {
+        assign[v] = best_idx;
+        atomicAdd(changed, 1u);
+      }
     }
   }
 }
@@ -502,15 +603,11 @@ __global__ void __launch_bounds__(256)
   for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < src.n_local;
        v += (unsigned long long)gridDim.x * blockDim.x) {
     const int a = (KT == 1 || assign == nullptr) ? 0 : (int)assign[v];
-    unsigned long long base, img;
-    vec_base(src, v, base, img);
     int L[DIM];
     int q = 0;
+    gather_lattice<DIM>(src, v, L);
 #pragma unroll
-    for (int e = 0; e < DIM; e++) {
-      L[e] = load_lattice(src, img, base, e);
-      q += L[e] * L[e];
-    }
+    for (int e = 0; e < DIM; e++) q += L[e] * L[e];
 #pragma unroll
     for (int k = 0; k < KT; k++) {
       const bool hit = (a == k);
@@ -546,11 +643,12 @@ __global__ void __launch_bounds__(256)
 // so codebooks whose table exceeds shared memory are handled by blockIdx.y slices that each re-read
 // the 4 + dim bytes per vector), shared-memory atomics while streaming, 64-bit global atomics of
 // the non-zero entries at the end.
+template <int DIMT>
 __global__ void __launch_bounds__(256)
     accumulate_smem_kernel(const VecSource src, const uint32_t *__restrict__ assign, const int K,
                            const int k_slice, unsigned long long *__restrict__ stats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int dim = src.dim;
+  const int dim = DIMT ? DIMT : src.dim;
   const int k_base = blockIdx.y * k_slice;
   const int k_count = min(k_slice, K - k_base);
   unsigned long long *s_q = reinterpret_cast<unsigned long long *>(smem_raw);  // [k_slice]
@@ -566,14 +664,24 @@ __global__ void __launch_bounds__(256)
        v += (unsigned long long)gridDim.x * blockDim.x) {
     const int a = (assign ? (int)assign[v] : 0) - k_base;
     if (a < 0 || a >= k_count) continue;
-    unsigned long long base, img;
-    vec_base(src, v, base, img);
     int q = 0;
     int *row = s_s + a * dim;
-    for (int e = 0; e < dim; e++) {
-      const int L = load_lattice(src, img, base, e);
-      q += L * L;
-      if (L != 0) atomicAdd(row + e, L);
+    if constexpr (DIMT != 0) {
+      int Lv[DIMT ? DIMT : 1];
+      gather_lattice<DIMT>(src, v, Lv);
+#pragma unroll
+      for (int e = 0; e < DIMT; e++) {
+        q += Lv[e] * Lv[e];
+        if (Lv[e] != 0) atomicAdd(row + e, Lv[e]);
+      }
+    } else {
+      unsigned long long base, img;
+      vec_base(src, v, base, img);
+      for (int e = 0; e < dim; e++) {
+        const int L = load_lattice(src, img, base, e);
+        q += L * L;
+        if (L != 0) atomicAdd(row + e, L);
+      }
     }
     atomicAdd(s_n + a, 1);
     atomicAdd(s_q + a, (unsigned long long)q);
@@ -655,6 +763,7 @@ __global__ void __launch_bounds__(256)
 //            of 256 rows, per limb, per 16-wide K block: 8-row x 16-byte core matrices, the two core matrices
 //            of a K block 128 B apart, 8-row groups 256 B apart.  Limbs of v: bf16(v), bf16(v - hi),
 //            bf16(v - hi - mid) - together 24 mantissa bits.
+//   cb_t     the FP64 codebook transposed ([dim][K]) for the brute-force resolver
 //   c_max    max_k |C_k| (slightly rounded up), as float bits via atomicMax (non-negative floats order as ints)
 __device__ __forceinline__ unsigned short bf16_rn_bits(float f) {
   unsigned int u = __float_as_uint(f);
@@ -664,7 +773,8 @@ __device__ __forceinline__ unsigned short bf16_rn_bits(float f) {
 __global__ void __launch_bounds__(128)
     stage_codebook_kernel(const double *__restrict__ cb, const int K, const int k_rows32, const int k_rows_tc,
                           const int dim, const int scaled, float *__restrict__ rows32, const int row32,
-                          unsigned char *__restrict__ tc_out, const int kblocks, unsigned int *__restrict__ c_max_bits) {
+                          unsigned char *__restrict__ tc_out, const int kblocks, unsigned int *__restrict__ c_max_bits,
+                          double *__restrict__ cb_t) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_rows = k_rows32 > k_rows_tc ? k_rows32 : k_rows_tc;
   if (k >= n_rows) return;
@@ -688,6 +798,7 @@ __global__ void __launch_bounds__(128)
     float Cf = 0.f;
     if (k < K) {
       const double c = cb[(size_t)k * dim + e];
+      cb_t[(size_t)e * K + k] = c;  // transposed FP64 copy for the brute-force resolver
       Cf = (float)(scaled ? __dsub_rn(__dmul_rn(255.0, c), 128.0) : c);
       n2 = __dadd_rn(n2, __dmul_rn((double)Cf, (double)Cf));
     }
@@ -788,18 +899,19 @@ cudaError_t launch_assign(const AssignLaunch &a) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, int K, const KdDevice &tree,
+cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const double *cbt, int K,
+                           const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed, int sm_count,
                            cudaStream_t stream) {
   // phase A: brute force, one warp per flagged query (the count is only known on the device)
   const unsigned int blocks_a = (unsigned int)sm_count * 8;
   if (src.dim <= 16)
-    resolve_bruteforce_kernel<16><<<blocks_a, 128, 0, stream>>>(src, scaled, cb, K, flag_list, flag_count, assign, tie_list, tie_count, changed);
+    resolve_bruteforce_kernel<16><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed);
   else if (src.dim <= 48)
-    resolve_bruteforce_kernel<48><<<blocks_a, 128, 0, stream>>>(src, scaled, cb, K, flag_list, flag_count, assign, tie_list, tie_count, changed);
+    resolve_bruteforce_kernel<48><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed);
   else
-    resolve_bruteforce_kernel<kMaxDim><<<blocks_a, 128, 0, stream>>>(src, scaled, cb, K, flag_list, flag_count, assign, tie_list, tie_count, changed);
+    resolve_bruteforce_kernel<kMaxDim><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -875,14 +987,25 @@ cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int 
   if ((size_t)k_slice * per_cell > smem_cap) k_slice = (int)(smem_cap / per_cell);
   const int slices = (K + k_slice - 1) / k_slice;
   const size_t smem = (size_t)k_slice * per_cell;
-  err = cudaFuncSetAttribute(accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+  auto kernel = accumulate_smem_kernel<0>;
+  switch (dim) {
+    case 3: kernel = accumulate_smem_kernel<3>; break;
+    case 6: kernel = accumulate_smem_kernel<6>; break;
+    case 9: kernel = accumulate_smem_kernel<9>; break;
+    case 12: kernel = accumulate_smem_kernel<12>; break;
+    case 24: kernel = accumulate_smem_kernel<24>; break;
+    case 27: kernel = accumulate_smem_kernel<27>; break;
+    case 48: kernel = accumulate_smem_kernel<48>; break;
+    default: break;
+  }
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
   if (err != cudaSuccess) return err;
   unsigned long long blocks = (src.n_local + 255) / 256;
   unsigned long long cap = (unsigned long long)sm_count * (smem > 100 * 1024 ? 1 : 2);
   if (blocks > cap) blocks = cap;
   if (blocks == 0) return cudaSuccess;
   dim3 grid((unsigned int)blocks, (unsigned int)slices);
-  accumulate_smem_kernel<<<grid, 256, smem, stream>>>(src, assign, K, k_slice, stats);
+  kernel<<<grid, 256, smem, stream>>>(src, assign, K, k_slice, stats);
   g_launch_count++;
   return cudaGetLastError();
 }
@@ -900,12 +1023,13 @@ cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32
 }
 
 cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_rows_tc, int dim, int scaled,
-                                  float *rows32, unsigned char *tc_out, float *c_max, cudaStream_t stream) {
+                                  float *rows32, unsigned char *tc_out, float *c_max, double *cb_t,
+                                  cudaStream_t stream) {
   const int n_rows = k_rows32 > k_rows_tc ? k_rows32 : k_rows_tc;
   if (n_rows == 0) return cudaSuccess;
   stage_codebook_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(cb, K, k_rows32, k_rows_tc, dim, scaled, rows32,
                                                                    assign_row_floats(dim), tc_out, tc_kblocks(dim),
-                                                                   reinterpret_cast<unsigned int *>(c_max));
+                                                                   reinterpret_cast<unsigned int *>(c_max), cb_t);
   g_launch_count++;
   return cudaGetLastError();
 }

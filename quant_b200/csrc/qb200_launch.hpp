@@ -24,11 +24,13 @@ struct AssignLaunch {
 int assign_row_floats(int dim);
 // FP64 codebook (device) -> FP32 rows (+ bf16 limb tiles when tc_out != null) + max codevector norm; c_max must be zeroed.
 cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_rows_tc, int dim, int scaled,
-                                  float *rows32, unsigned char *tc_out, float *c_max, cudaStream_t stream);
+                                  float *rows32, unsigned char *tc_out, float *c_max, double *cb_t,
+                                  cudaStream_t stream);
 cudaError_t launch_assign(const AssignLaunch &a);
 // Exact re-solve of the flagged queries: brute-force FP64 phase, then the reference's KD walk for
 // the (near-)exact ties it leaves in tie_list (capacity: n_local).  Counters are device words.
-cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, int K, const KdDevice &tree,
+cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const double *cbt, int K,
+                           const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed, int sm_count,
                            cudaStream_t stream);
