@@ -417,6 +417,74 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Same job with the FP32 rows staged in SHARED memory (used whenever the padded table fits): one thread per
+// query, the eight candidate rows are read with LDS.128.  Row r keeps its float4 number q at slot
+// (q + (r >> 1)) & 3 (16-float rows) so that 32 lanes reading the same q of 32 unrelated rows spread over all
+// eight 16-byte bank groups; odd row lengths spread by themselves.
+template <int DIM>
+__global__ void __launch_bounds__(1024, 1)
+    tc_finalize_smem_kernel(const VecSource src, const float *__restrict__ rows32, const int k_rows,
+                            const float *__restrict__ state, const float margin_coef,
+                            const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
+                            uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count) {
+  constexpr int ROW32 = TcCfg<DIM>::ROW32, NF4 = ROW32 / 4;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float4 *s_rows = reinterpret_cast<float4 *>(smem_raw);
+  auto slot = [](int r, int q) { return NF4 == 4 ? ((q + (r >> 1)) & 3) : (NF4 == 2 ? ((q + (r >> 2)) & 1) : q); };
+  for (int i = threadIdx.x; i < k_rows * NF4; i += blockDim.x) {
+    const int r = i / NF4, q = i - r * NF4;
+    s_rows[r * NF4 + slot(r, q)] = __ldg(reinterpret_cast<const float4 *>(rows32) + i);
+  }
+  __syncthreads();
+  const float c_max_norm = *c_max_ptr;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long n_round = (src.n_local + 31ull) & ~31ull;  // whole warps stay in the loop for the ballot
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_round;
+       v += (unsigned long long)gridDim.x * blockDim.x) {
+    bool flag = false;
+    if (v < src.n_local) {
+      const float best = state[v * 3 + 0], second = state[v * 3 + 1];
+      const int chunk = __float_as_int(state[v * 3 + 2]);
+      float x[DIM], xn = 0.f;
+      gather_lattice<DIM>(src, v, x);
+#pragma unroll
+      for (int e = 0; e < DIM; e++) xn = fmaf(x[e], x[e], xn);
+      const float rr = sqrtf(xn) + c_max_norm;
+      flag = !((second - best) > margin_coef * rr * rr);
+      int bidx = chunk * 8;
+      if (!flag) {
+        float sb = FLT_MAX;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int r = chunk * 8 + c;
+          float cr[ROW32];
+#pragma unroll
+          for (int q = 0; q < NF4; q++) {
+            const float4 t = s_rows[r * NF4 + slot(r, q)];
+            cr[4 * q] = t.x; cr[4 * q + 1] = t.y; cr[4 * q + 2] = t.z; cr[4 * q + 3] = t.w;
+          }
+          float sc = cr[DIM];
+#pragma unroll
+          for (int e = 0; e < DIM; e++) sc = fmaf(x[e], cr[e], sc);
+          if (sc < sb) {
+            sb = sc;
+            bidx = r;
+          }
+        }
+      }
+      assign[v] = (uint32_t)bidx;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, flag);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned int basepos = 0;
+      if (lane == leader) basepos = atomicAdd(flag_count, (unsigned int)__popc(m));
+      basepos = __shfl_sync(0xffffffffu, basepos, leader);
+      if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+    }
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -456,6 +524,17 @@ static cudaError_t launch_tc_t(const AssignTcLaunch &a) {
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+  }
+  const size_t table = (size_t)kp * Cfg::ROW32 * 4;
+  if (table <= 200 * 1024 && Cfg::ROW32 != 16) {  // FP32 rows fit in shared memory: one thread per query, LDS gathers
+    e = cudaFuncSetAttribute(tc_finalize_smem_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    unsigned long long fb = (a.src.n_local + 1023) / 1024;
+    if (fb > (unsigned long long)a.sm_count) fb = (unsigned long long)a.sm_count;
+    tc_finalize_smem_kernel<DIM><<<(unsigned int)fb, 1024, table, a.stream>>>(a.src, a.rows32, kp, a.state, a.margin_coef,
+                                                                             a.c_max_ptr, a.assign, a.flag_list, a.flag_count);
+    count_launch();
+    return cudaGetLastError();
   }
   const unsigned long long per_block = Cfg::ROW32 == 16 ? 32 : 256;  // queries per 256-thread block per round
   unsigned long long blocks = (a.src.n_local + per_block - 1) / per_block;

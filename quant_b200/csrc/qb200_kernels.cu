@@ -584,62 +584,79 @@ __global__ void __launch_bounds__(128)
 // ------------------------------------------------------------------------------------------------
 // accumulate: per-cell integer statistics  {n_k, S_k[d] = sum L, Q_k = sum_d sum L^2}
 // ------------------------------------------------------------------------------------------------
-// Small codebooks (KT*(DIM+2) accumulators fit in registers): every thread keeps all cells'
-// partial sums, predicated adds, one shuffle tree per accumulator at the end - no atomics while
-// streaming, so K = 1, 2, 4, 8 (where every vector lands in a handful of cells) run at HBM speed.
-template <int DIM, int KT>
-__global__ void __launch_bounds__(256)
-    accumulate_reg_kernel(const VecSource src, const uint32_t *__restrict__ assign,
-                          unsigned long long *__restrict__ stats) {
-  int n[KT], S[KT][DIM];
-  unsigned long long Qs[KT];
-#pragma unroll
-  for (int k = 0; k < KT; k++) {
-    n[k] = 0;
-    Qs[k] = 0;
-#pragma unroll
-    for (int e = 0; e < DIM; e++) S[k][e] = 0;
+// Known dimensions: per-CTA privatised table in shared memory, but the lanes of a warp that hit the SAME
+// cell are combined first - __match_any_sync groups them, __reduce_add_sync (REDUX) sums each coordinate
+// inside every group at once, and only the group leaders issue shared-memory atomics.  Early split
+// levels (K = 1, 2, 4, ... where a warp's 32 vectors fall into a handful of cells) need ~1 atomic per
+// vector instead of dim + 2.  MATCH costs one step per distinct value, so this kernel is used for K <= 8 only.
+// Cells [k_base, k_base + k_count) only: codebooks whose table exceeds shared memory take blockIdx.y slices.
+template <int DIM>
+__global__ void __launch_bounds__(1024, 1)
+    accumulate_match_kernel(const VecSource src, const uint32_t *__restrict__ assign, const int K, const int k_slice,
+                            unsigned long long *__restrict__ stats) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int k_base = blockIdx.y * k_slice;
+  const int k_count = min(k_slice, K - k_base);
+  unsigned long long *s_q = reinterpret_cast<unsigned long long *>(smem_raw);  // [k_slice]
+  int *s_n = reinterpret_cast<int *>(s_q + k_slice);                           // [k_slice]
+  int *s_s = s_n + k_slice;                                                    // [k_slice][DIM]
+  for (int i = threadIdx.x; i < k_slice; i += blockDim.x) {
+    s_q[i] = 0;
+    s_n[i] = 0;
   }
-  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < src.n_local;
+  for (int i = threadIdx.x; i < k_slice * DIM; i += blockDim.x) s_s[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned long long n_round = (src.n_local + 31ull) & ~31ull;  // whole warps stay in the loop
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_round;
        v += (unsigned long long)gridDim.x * blockDim.x) {
-    const int a = (KT == 1 || assign == nullptr) ? 0 : (int)assign[v];
+    int a = -1;
     int L[DIM];
     int q = 0;
-    gather_lattice<DIM>(src, v, L);
+    if (v < src.n_local) {
+      a = (assign ? (int)assign[v] : 0) - k_base;
+      if (a < 0 || a >= k_count) a = -1;
+    }
+    if (a >= 0) {
+      gather_lattice<DIM>(src, v, L);
 #pragma unroll
-    for (int e = 0; e < DIM; e++) q += L[e] * L[e];
+      for (int e = 0; e < DIM; e++) q += L[e] * L[e];
+    } else {
 #pragma unroll
-    for (int k = 0; k < KT; k++) {
-      const bool hit = (a == k);
-      n[k] += hit ? 1 : 0;
-      Qs[k] += hit ? (unsigned long long)q : 0ull;
+      for (int e = 0; e < DIM; e++) L[e] = 0;
+    }
+    const unsigned int group = __match_any_sync(0xffffffffu, a);
+    const bool leader = a >= 0 && lane == __ffs(group) - 1;
+    int *row = s_s + (a >= 0 ? a : 0) * DIM;
 #pragma unroll
-      for (int e = 0; e < DIM; e++) S[k][e] += hit ? L[e] : 0;
+    for (int e = 0; e < DIM; e++) {
+      const int sv = __reduce_add_sync(group, L[e]);
+      if (leader && sv != 0) atomicAdd(row + e, sv);
+    }
+    const unsigned int qs = __reduce_add_sync(group, (unsigned int)q);  // <= 32 * DIM * 128^2: fits
+    if (leader) {
+      atomicAdd(s_n + a, __popc(group));
+      atomicAdd(s_q + a, (unsigned long long)qs);
     }
   }
-  // warp tree, then one 64-bit global atomic per accumulator per warp
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int k = 0; k < KT; k++) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      n[k] += __shfl_xor_sync(0xffffffffu, n[k], o);
-      Qs[k] += __shfl_xor_sync(0xffffffffu, Qs[k], o);
-#pragma unroll
-      for (int e = 0; e < DIM; e++) S[k][e] += __shfl_xor_sync(0xffffffffu, S[k][e], o);
+  __syncthreads();
+  for (int i = threadIdx.x; i < k_count; i += blockDim.x) {
+    if (s_n[i] != 0) {
+      unsigned long long *row = stats + (size_t)(k_base + i) * (DIM + 2);
+      atomicAdd(row, (unsigned long long)s_n[i]);
+      atomicAdd(row + DIM + 1, s_q[i]);
     }
-    if (lane == 0 && n[k] != 0) {
-      unsigned long long *row = stats + (size_t)k * (DIM + 2);
-      atomicAdd(row, (unsigned long long)n[k]);
-#pragma unroll
-      for (int e = 0; e < DIM; e++)
-        if (S[k][e] != 0) atomicAdd(row + 1 + e, (unsigned long long)(long long)S[k][e]);
-      atomicAdd(row + DIM + 1, Qs[k]);
+  }
+  for (int i = threadIdx.x; i < k_count * DIM; i += blockDim.x) {
+    const int sv = s_s[i];
+    if (sv != 0) {
+      const int k = i / DIM, e = i - k * DIM;
+      atomicAdd(stats + (size_t)(k_base + k) * (DIM + 2) + 1 + e, (unsigned long long)(long long)sv);
     }
   }
 }
 
-// General case: per-CTA privatised table in shared memory (cells [k_base, k_base + k_count) only,
+// Any dimension: per-CTA privatised table in shared memory (cells [k_base, k_base + k_count) only,
 // so codebooks whose table exceeds shared memory are handled by blockIdx.y slices that each re-read
 // the 4 + dim bytes per vector), shared-memory atomics while streaming, 64-bit global atomics of
 // the non-zero entries at the end.
@@ -938,47 +955,22 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
   return cudaGetLastError();
 }
 
-template <int DIM, int KT>
-static cudaError_t launch_acc_reg(const VecSource &src, const uint32_t *assign, unsigned long long *stats,
-                                  int sm_count, cudaStream_t stream) {
-  unsigned long long blocks = (src.n_local + 255) / 256;
-  const unsigned long long cap = (unsigned long long)sm_count * 8;
-  if (blocks > cap) blocks = cap;
+template <int DIM>
+static cudaError_t launch_acc_match(const VecSource &src, const uint32_t *assign, int K, int k_slice, int slices,
+                                    size_t smem, unsigned long long *stats, int sm_count, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(accumulate_match_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (err != cudaSuccess) return err;
+  unsigned long long blocks = (src.n_local + 1023) / 1024;
+  if (blocks > (unsigned long long)sm_count) blocks = (unsigned long long)sm_count;
   if (blocks == 0) return cudaSuccess;
-  accumulate_reg_kernel<DIM, KT><<<(unsigned int)blocks, 256, 0, stream>>>(src, assign, stats);
+  dim3 grid((unsigned int)blocks, (unsigned int)slices);
+  accumulate_match_kernel<DIM><<<grid, 1024, smem, stream>>>(src, assign, K, k_slice, stats);
   g_launch_count++;
   return cudaGetLastError();
 }
 
-template <int DIM>
-static bool try_acc_reg(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats, int sm_count,
-                        cudaStream_t stream, cudaError_t &err) {
-  if (K == 1) { err = launch_acc_reg<DIM, 1>(src, assign, stats, sm_count, stream); return true; }
-  if (K == 2) { err = launch_acc_reg<DIM, 2>(src, assign, stats, sm_count, stream); return true; }
-  if constexpr (DIM <= 12) {
-    if (K == 4) { err = launch_acc_reg<DIM, 4>(src, assign, stats, sm_count, stream); return true; }
-    if (K == 8) { err = launch_acc_reg<DIM, 8>(src, assign, stats, sm_count, stream); return true; }
-  }
-  return false;
-}
-
 cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats,
                               int sm_count, cudaStream_t stream) {
-  cudaError_t err = cudaSuccess;
-  bool done = false;
-  if (K <= 8) {
-    switch (src.dim) {
-      case 3: done = try_acc_reg<3>(src, assign, K, stats, sm_count, stream, err); break;
-      case 6: done = try_acc_reg<6>(src, assign, K, stats, sm_count, stream, err); break;
-      case 9: done = try_acc_reg<9>(src, assign, K, stats, sm_count, stream, err); break;
-      case 12: done = try_acc_reg<12>(src, assign, K, stats, sm_count, stream, err); break;
-      case 24: done = try_acc_reg<24>(src, assign, K, stats, sm_count, stream, err); break;
-      case 27: done = try_acc_reg<27>(src, assign, K, stats, sm_count, stream, err); break;
-      case 48: done = try_acc_reg<48>(src, assign, K, stats, sm_count, stream, err); break;
-      default: break;
-    }
-  }
-  if (done) return err;
   if (assign == nullptr && K != 1) return cudaErrorInvalidValue;
   const int dim = src.dim;
   const size_t per_cell = 8 + 4 + 4 * (size_t)dim;
@@ -987,6 +979,18 @@ cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int 
   if ((size_t)k_slice * per_cell > smem_cap) k_slice = (int)(smem_cap / per_cell);
   const int slices = (K + k_slice - 1) / k_slice;
   const size_t smem = (size_t)k_slice * per_cell;
+  if (K <= 8) {  // few cells: combine equal cells inside each warp first (match + redux), see accumulate_match_kernel
+    switch (dim) {
+      case 3: return launch_acc_match<3>(src, assign, K, k_slice, slices, smem, stats, sm_count, stream);
+      case 6: return launch_acc_match<6>(src, assign, K, k_slice, slices, smem, stats, sm_count, stream);
+      case 9: return launch_acc_match<9>(src, assign, K, k_slice, slices, smem, stats, sm_count, stream);
+      case 12: return launch_acc_match<12>(src, assign, K, k_slice, slices, smem, stats, sm_count, stream);
+      case 24: return launch_acc_match<24>(src, assign, K, k_slice, slices, smem, stats, sm_count, stream);
+      case 27: return launch_acc_match<27>(src, assign, K, k_slice, slices, smem, stats, sm_count, stream);
+      case 48: return launch_acc_match<48>(src, assign, K, k_slice, slices, smem, stats, sm_count, stream);
+      default: break;
+    }
+  }
   auto kernel = accumulate_smem_kernel<0>;
   switch (dim) {
     case 3: kernel = accumulate_smem_kernel<3>; break;
@@ -998,10 +1002,12 @@ cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int 
     case 48: kernel = accumulate_smem_kernel<48>; break;
     default: break;
   }
-  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
   if (err != cudaSuccess) return err;
   unsigned long long blocks = (src.n_local + 255) / 256;
-  unsigned long long cap = (unsigned long long)sm_count * (smem > 100 * 1024 ? 1 : 2);
+  unsigned long long per_sm = (200 * 1024) / (smem + 1024);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  unsigned long long cap = (unsigned long long)sm_count * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) return cudaSuccess;
   dim3 grid((unsigned int)blocks, (unsigned int)slices);
