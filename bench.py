@@ -318,7 +318,11 @@ def run_gpu_arm(args):
                     "note": "the GEMM is 3-limb bf16 with a 13-of-16 used K dimension; by design the kernel is bound by the "
                             "top-2 selection over the accumulator columns on the alu pipe (2.75 min/max ops per distance "
                             "evaluation, ncu: profiles/), not by the tensor pipe",
-                    "ms_per_launch": ms_assign, "traffic": None}
+                    "ms_per_launch": ms_assign,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the K=1024 assign_tc_kernel launch on this workload,
+                    # one `ncu --set full` capture (profiles/r1_assign_tc_k1024_ncu_summary.txt): 50.5 MB + 11.5 MB
+                    "traffic": 62.0e6 if (wl == "c2" and world == 1) else None,
+                    "traffic_algorithmic": float(n_local) * dim}
         else:
             roof = {"bound": "fp32", "kernel": f"assign_kernel<{dim}> at K={K}, last split level", "achieved": fp32_equiv,
                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_equiv / fp32_peak,
