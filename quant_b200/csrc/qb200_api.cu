@@ -197,6 +197,8 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   const float *c_max_ptr = reinterpret_cast<const float *>(cnt + 4);
   if (L.use_tc && (rc = ensure(ctx, ctx->d_rows_tc, L.tc_bytes))) return rc;
   if (L.use_tc && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 12))) return rc;
+  if (want_stats) CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(K, dim) * 8, st));
+  bool fused = false;  // did the filter kernel accumulate the per-cell statistics of the queries it decided?
   if (timed) CU(cudaEventRecord(ctx->ev[0], st));
   CU(launch_stage_codebook((const double *)ctx->d_cb64.p, (int)K, (int)L.K_rows, L.use_tc ? (int)L.K_rows : 0, dim,
                            ctx->colorspace == QB200_CS_SCALED, (float *)ctx->d_rows.p,
@@ -232,6 +234,9 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
     a.flag_count = cnt;
     a.sm_count = ctx->sm_count;
     a.stream = st;
+    a.stats = want_stats ? (unsigned long long *)ctx->d_stats.p : nullptr;
+    a.k_real = (int)K;
+    a.fused_out = &fused;
     CU(launch_assign(a));
   }
   if (timed) CU(cudaEventRecord(ctx->ev[1], st));
@@ -269,10 +274,9 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p,
                     (const double *)ctx->d_cb64.p + (size_t)K * dim, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
-                    cnt + 2, cnt + 1, ctx->sm_count, st));
+                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, ctx->sm_count, st));
   if (timed) CU(cudaEventRecord(ctx->ev[2], st));
-  if (want_stats) {
-    CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(K, dim) * 8, st));
+  if (want_stats && !fused) {
     CU(launch_accumulate(ctx->src, (const uint32_t *)ctx->d_assign.p, (int)K, (unsigned long long *)ctx->d_stats.p,
                          ctx->sm_count, st));
   }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
     assign_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int k_chunk,
                   const float margin_coef, const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
                   uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count,
-                  const unsigned long long tiles) {
+                  const unsigned long long tiles, unsigned long long *__restrict__ stats, const int k_real) {
   using Cfg = AssignCfg<DIM>;
   const float c_max_norm = *c_max_ptr;
   constexpr int ROW = Cfg::ROW, Q = Cfg::Q, THREADS = Cfg::THREADS;
@@ -62,6 +62,18 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *s_cb = reinterpret_cast<float *>(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
+  // Fused per-cell statistics (stats != null): the queries this kernel DECIDES are accumulated here into a
+  // per-CTA table behind the codebook chunk; flagged queries are added by the resolver once it has decided them.
+  unsigned long long *s_q = reinterpret_cast<unsigned long long *>(smem_raw + (((size_t)k_chunk * ROW * 4 + 127) & ~(size_t)127));
+  int *s_n = reinterpret_cast<int *>(s_q + k_real);
+  int *s_s = s_n + k_real;
+  if (stats) {
+    for (int i = threadIdx.x; i < k_real; i += THREADS) {
+      s_q[i] = 0;
+      s_n[i] = 0;
+    }
+    for (int i = threadIdx.x; i < k_real * DIM; i += THREADS) s_s[i] = 0;
+  }  // made visible by the __syncthreads() that follows the barrier initialisation below
 
   const int tid = threadIdx.x;
   const int n_chunks = (K + k_chunk - 1) / k_chunk;
@@ -212,6 +224,55 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
         basepos = __shfl_sync(0xffffffffu, basepos, leader);
         if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
       }
+      if (stats) {
+        const int a = (live[q] && !flag) ? bidx : -1;
+        int L[DIM], qs = 0;
+#pragma unroll
+        for (int e = 0; e < DIM; e++) {
+          float lo_, hi_;
+          unpack2(xp[q / 2][e], lo_, hi_);
+          L[e] = a >= 0 ? (int)((q & 1) ? hi_ : lo_) : 0;
+          qs += L[e] * L[e];
+        }
+        int *row = s_s + (a >= 0 ? a : 0) * DIM;
+        if (k_real <= 8) {  // few cells: combine the lanes that hit the same cell first (see accumulate_match_kernel)
+          const unsigned int group = __match_any_sync(0xffffffffu, a);
+          const bool leader = a >= 0 && (tid & 31) == __ffs(group) - 1;
+#pragma unroll
+          for (int e = 0; e < DIM; e++) {
+            const int sv = __reduce_add_sync(group, L[e]);
+            if (leader && sv != 0) atomicAdd(row + e, sv);
+          }
+          const unsigned int qsum = __reduce_add_sync(group, (unsigned int)qs);
+          if (leader) {
+            atomicAdd(s_n + a, __popc(group));
+            atomicAdd(s_q + a, (unsigned long long)qsum);
+          }
+        } else if (a >= 0) {
+#pragma unroll
+          for (int e = 0; e < DIM; e++)
+            if (L[e] != 0) atomicAdd(row + e, L[e]);
+          atomicAdd(s_n + a, 1);
+          atomicAdd(s_q + a, (unsigned long long)qs);
+        }
+      }
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < k_real; i += THREADS) {
+      if (s_n[i] != 0) {
+        unsigned long long *row = stats + (size_t)i * (DIM + 2);
+        atomicAdd(row, (unsigned long long)s_n[i]);
+        atomicAdd(row + DIM + 1, s_q[i]);
+      }
+    }
+    for (int i = threadIdx.x; i < k_real * DIM; i += THREADS) {
+      const int sv = s_s[i];
+      if (sv != 0) {
+        const int k = i / DIM, e = i - k * DIM;
+        atomicAdd(stats + (size_t)k * (DIM + 2) + 1 + e, (unsigned long long)(long long)sv);
+      }
     }
   }
 }
@@ -273,6 +334,21 @@ __global__ void __launch_bounds__(128, 1)
 // ------------------------------------------------------------------------------------------------
 // Phase B: one warp per query phase A (below) could not decide.  Arithmetic is spelled with the round-to-nearest intrinsics so
 // that nvcc cannot contract a*b+c into an FMA: the reference's x86-64 build has none.
+// Adds one query to its cell's statistics row {n, S[dim], Q} (used by the resolver when the filter kernel
+// accumulates the queries it decided itself).
+__device__ __forceinline__ void add_query_stats(const VecSource &src, unsigned long long img, unsigned long long base,
+                                                unsigned long long *row) {
+  const int dim = src.dim;
+  unsigned long long q = 0;
+  for (int e = 0; e < dim; e++) {
+    const int L = load_lattice(src, img, base, e);
+    q += (unsigned long long)(L * L);
+    if (L != 0) atomicAdd(row + 1 + e, (unsigned long long)(long long)L);
+  }
+  atomicAdd(row, 1ull);
+  atomicAdd(row + dim + 1, q);
+}
+
 __device__ __forceinline__ double sq_diff(double a, double b) {
   const double d = __dsub_rn(a, b);
   return __dmul_rn(d, d);
@@ -327,7 +403,7 @@ __global__ void __launch_bounds__(128)
                               const KdDevice tree, const uint32_t *__restrict__ flag_list,
                               const unsigned int *__restrict__ flag_count, uint32_t *__restrict__ assign,
                               uint32_t *__restrict__ tie_list, unsigned int *__restrict__ tie_count,
-                              unsigned int *__restrict__ changed) {
+                              unsigned int *__restrict__ changed, unsigned long long *__restrict__ stats) {
   const int dim = src.dim;
   const unsigned int total = *flag_count;
   const int lane = threadIdx.x & 31;
@@ -439,6 +515,7 @@ __global__ void __launch_bounds__(128)
           assign[v] = (uint32_t)win;
           atomicAdd(changed, 1u);
         }
+        if (stats) add_query_stats(src, img, base, stats + (size_t)win * (dim + 2));
       }
     } else if (lane == 0) {
       tie_list[atomicAdd(tie_count, 1u)] = (uint32_t)v;
@@ -455,7 +532,8 @@ template <int DIMCAP, int DEPTHCAP>
 __global__ void __launch_bounds__(128)
     resolve_kernel(const VecSource src, const int scaled, const double *__restrict__ cb, const KdDevice tree,
                    const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
-                   uint32_t *__restrict__ assign, unsigned int *__restrict__ changed) {
+                   uint32_t *__restrict__ assign, unsigned int *__restrict__ changed,
+                   unsigned long long *__restrict__ stats) {
   // One WARP per query: every lane runs the same (sequential) tree walk; at a leaf the lanes compute the
   // distances of its <= 10 points in parallel.  nanoflann's leaf loop (read worstDist once, add points in
   // order, strict comparisons) keeps the first point that attains the leaf minimum, and only if that
@@ -577,6 +655,7 @@ __global__ void __launch_bounds__(128)
         assign[v] = best_idx;
         atomicAdd(changed, 1u);
       }
+      if (stats) add_query_stats(src, img, base, stats + (size_t)best_idx * (dim + 2));
     }
   }
 }
@@ -871,10 +950,17 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
   const size_t smem_cap = 200 * 1024;
   int k_chunk = a.K;
   if ((size_t)k_chunk * row_bytes > smem_cap) k_chunk = (int)(smem_cap / row_bytes) & ~7;  // even
-  const size_t smem = (size_t)k_chunk * row_bytes;
+  size_t smem = (size_t)k_chunk * row_bytes;
+  // fused statistics only when the whole codebook is one chunk and the table fits behind it
+  const size_t table = ((smem + 127) & ~(size_t)127) - smem + (size_t)a.k_real * (12 + 4 * (size_t)DIM);
+  // (measured: below 32 cells the in-kernel atomics of this one-CTA-per-SM kernel cost more than the separate,
+  //  high-occupancy accumulate pass)
+  const bool fuse = a.stats != nullptr && a.k_real >= 32 && k_chunk == a.K && smem + table <= smem_cap + 16 * 1024;
+  if (fuse) smem += table;
+  if (a.fused_out) *a.fused_out = fuse;
   {
     cudaError_t e = cudaFuncSetAttribute(assign_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_cap);
+                                         (int)(smem_cap + 16 * 1024));
     if (e != cudaSuccess) return e;
   }
   const unsigned long long per_tile = (unsigned long long)Cfg::THREADS * Cfg::Q;
@@ -882,12 +968,14 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
   unsigned long long grid = tiles < (unsigned long long)a.sm_count ? tiles : (unsigned long long)a.sm_count;
   if (grid == 0) return cudaSuccess;
   assign_kernel<DIM><<<(unsigned int)grid, Cfg::THREADS, smem, a.stream>>>(
-      a.src, a.cb_rows, a.K, k_chunk, a.margin_coef, a.c_max_ptr, a.assign, a.flag_list, a.flag_count, tiles);
+      a.src, a.cb_rows, a.K, k_chunk, a.margin_coef, a.c_max_ptr, a.assign, a.flag_list, a.flag_count, tiles,
+      fuse ? a.stats : nullptr, a.k_real);
   g_launch_count++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_assign(const AssignLaunch &a) {
+  if (a.fused_out) *a.fused_out = false;
   switch (a.src.dim) {
     case 3: return launch_assign_t<3>(a);
     case 6: return launch_assign_t<6>(a);
@@ -919,16 +1007,16 @@ cudaError_t launch_assign(const AssignLaunch &a) {
 cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const double *cbt, int K,
                            const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
-                           uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed, int sm_count,
-                           cudaStream_t stream) {
+                           uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
+                           unsigned long long *stats, int sm_count, cudaStream_t stream) {
   // phase A: brute force, one warp per flagged query (the count is only known on the device)
   const unsigned int blocks_a = (unsigned int)sm_count * 8;
   if (src.dim <= 16)
-    resolve_bruteforce_kernel<16><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed);
+    resolve_bruteforce_kernel<16><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed, stats);
   else if (src.dim <= 48)
-    resolve_bruteforce_kernel<48><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed);
+    resolve_bruteforce_kernel<48><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed, stats);
   else
-    resolve_bruteforce_kernel<kMaxDim><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed);
+    resolve_bruteforce_kernel<kMaxDim><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed, stats);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -937,19 +1025,19 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
   const bool deep = tree.depth > 92;
   if (src.dim <= 16) {
     if (!deep)
-      resolve_kernel<16, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
+      resolve_kernel<16, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
     else
-      resolve_kernel<16, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
+      resolve_kernel<16, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
   } else if (src.dim <= 48) {
     if (!deep)
-      resolve_kernel<48, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
+      resolve_kernel<48, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
     else
-      resolve_kernel<48, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
+      resolve_kernel<48, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
   } else {
     if (!deep)
-      resolve_kernel<kMaxDim, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
+      resolve_kernel<kMaxDim, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
     else
-      resolve_kernel<kMaxDim, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed);
+      resolve_kernel<kMaxDim, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
   }
   g_launch_count++;
   return cudaGetLastError();

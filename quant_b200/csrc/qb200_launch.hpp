@@ -19,6 +19,10 @@ struct AssignLaunch {
   unsigned int *flag_count;  // device counter, zeroed by the caller
   int sm_count;
   cudaStream_t stream;
+  // optional fusion of the per-cell statistics of the DECIDED queries (flagged ones are left to the resolver):
+  unsigned long long *stats;  // K*(dim+2) words, zeroed by the caller; null = no fusion
+  int k_real;                 // codevectors without padding rows
+  bool *fused_out;            // set to whether the kernel really accumulated (the table must fit in shared memory)
 };
 
 int assign_row_floats(int dim);
@@ -32,7 +36,8 @@ cudaError_t launch_assign(const AssignLaunch &a);
 cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const double *cbt, int K,
                            const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
-                           uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed, int sm_count,
+                           uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
+                           unsigned long long *stats /* null unless the filter fused the statistics */, int sm_count,
                            cudaStream_t stream);
 // stats must be zeroed by the caller; assign may be null only for K == 1.
 cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats,
