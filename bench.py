@@ -181,7 +181,7 @@ def run_reference_arm(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -357,7 +357,7 @@ def run_gpu_arm(args):
             kind, eng = cpu_engine()
             base, _, _, _ = cpu_sample(kind, eng, wl, args.cpu_budget, 1, 1)
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.barrier()
@@ -365,7 +365,30 @@ def run_gpu_arm(args):
     return 0
 
 
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner from C) write to
+    file descriptor 1 as well, so fd 1 is pointed at stderr for the whole run and the line goes out through
+    a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
+_JSON_FD = None
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--steps", type=int, default=10)

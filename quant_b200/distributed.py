@@ -45,8 +45,11 @@ def make_allreduce(group=None):
 
     def allreduce(dev_ptr: int, count: int, stream: int) -> int:
         t = _wrap_device_int64(dev_ptr, count)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.current_stream().synchronize()
+        # enqueue on the library's stream: torch orders the collective after the work already on it and makes
+        # the stream wait for the result, which is all qb200_allreduce_fn asks for (no host synchronisation)
+        ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+        with torch.cuda.stream(ext):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         return 0
 
     return allreduce
