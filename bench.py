@@ -208,7 +208,11 @@ def run_gpu_arm(args):
     wl = args.workload
     bx, ys, w, h, nbits, desc = WORKLOADS[wl]
     K, dim = 1 << nbits, 3 * w * h
-    xs_total = bx * world                      # weak scaling: one band per rank
+    if args.strong:                            # strong scaling: the named image is split into `world` bands
+        if bx % (w * world):
+            raise SystemExit("--strong needs the image's pixel lines to divide by block width x ranks")
+        bx = bx // world
+    xs_total = bx * world                      # weak scaling (default): one workload-sized band per rank
     wB_band = bx // w
     row_begin, row_end = rank * wB_band, (rank + 1) * wB_band
     n_local = wB_band * (ys // h)
@@ -337,10 +341,11 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "bf16x3 tensor-core / f32 filter + f64 exact re-check; i64 sums",
             "data": "synthetic",
-            "config": {"workload": desc + (f"; weak scaling: {world} such bands, one per rank" if world > 1 else ""),
+            "config": {"workload": desc + ((f"; strong scaling: split into {world} bands" if args.strong else
+                                            f"; weak scaling: {world} such bands, one per rank") if world > 1 else ""),
                        "block": [w, h], "nbits": nbits, "colorspace": "SCALED", "vectors_per_rank": n_local,
                        "schedule": "reference HEAD: one assignment pass per split level, no empty-cell repair",
                        "l2": "512 MiB flush (memset) before every timed step, outside the timed events"},
@@ -397,6 +402,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=None, help="seconds of CPU work for the CPU arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: split the workload image across the ranks (default: weak, one image-sized band per rank)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.cpu_budget is None:

@@ -47,6 +47,12 @@ extern "C" {
 /* Training schedule. */
 #define QB200_MODE_PARITY 0 /* the reference's HEAD schedule: ONE assignment per split level,
                                no empty-cell repair (src/Quantizer.cpp:98-108). */
+/* Extensions - what README.md:29-31 describes but HEAD does not do; there is no reference behaviour
+ * to match beyond that text, so PARITY IS UNPINNED for both:          */
+#define QB200_MODE_FULL 1        /* per split level re-assign and re-fix until the relative change of the
+                                    distortion is <= eps (at most 100 iterations, src/Quantizer.cpp:101) */
+#define QB200_MODE_FULL_REPAIR 2 /* FULL + empty-cell repair: an empty cell takes a pseudo-random member of
+                                    the cell with the largest distortion (qb200_set_seed)                 */
 
 typedef struct qb200_ctx qb200_ctx;
 
@@ -58,6 +64,8 @@ typedef struct qb200_level_report {
   uint32_t ties;          /* of those, how many had (near-)exact FP64 ties and took the KD-tree walk */
   uint32_t dead_cells;    /* cells with no member after the (global) reduction */
   uint32_t kd_depth;      /* depth of the nanoflann-order KD tree built for the resolver */
+  uint32_t iterations;    /* assignment passes of this level (1 in QB200_MODE_PARITY) */
+  uint32_t repaired;      /* empty cells re-seeded at this level (QB200_MODE_FULL_REPAIR) */
   float ms_assign;        /* device time of the FP32 assignment kernel */
   float ms_resolve;       /* device time of the exact resolver kernels (brute force + tree walk) */
   float ms_accumulate;    /* device time of the per-cell statistics kernel */
@@ -88,6 +96,12 @@ int qb200_set_stream(qb200_ctx *ctx, void *cuda_stream);
 int qb200_set_tensor_cores(qb200_ctx *ctx, int enable);
 int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                       size_t *total_mem);
+
+/* Seed of the empty-cell repair's member choice (default 0x5eed).  QB200_MODE_FULL_REPAIR only. */
+int qb200_set_seed(qb200_ctx *ctx, uint64_t seed);
+/* This context's rank among `world` contexts that train one sharded set together.  Needed only by
+ * QB200_MODE_FULL_REPAIR (the ranks agree on the chosen members through the sum all-reduce). */
+int qb200_set_rank(qb200_ctx *ctx, int rank, int world);
 
 /* ---- training set ------------------------------------------------------------------------
  * Replaces getBlocksAsVectorsFromImage (src/Compressor.cpp:31-62).  The N x dim double vectors

@@ -14,12 +14,13 @@ LIB_PATH = os.path.join(HERE, "libqb200.so")
 
 OK, ERR_ARG, ERR_NODEV, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
 CS_NORMAL, CS_SCALED = 0, 1
-MODE_PARITY = 0
+MODE_PARITY, MODE_FULL, MODE_FULL_REPAIR = 0, 1, 2
 
 
 class LevelReport(C.Structure):
     _fields_ = [("K", C.c_uint32), ("flagged", C.c_uint32), ("changed", C.c_uint32),
-                ("ties", C.c_uint32), ("dead_cells", C.c_uint32), ("kd_depth", C.c_uint32), ("ms_assign", C.c_float),
+                ("ties", C.c_uint32), ("dead_cells", C.c_uint32), ("kd_depth", C.c_uint32), ("iterations", C.c_uint32), ("repaired", C.c_uint32),
+                ("ms_assign", C.c_float),
                 ("ms_resolve", C.c_float), ("ms_accumulate", C.c_float),
                 ("distortion_pre", C.c_double), ("distortion_post", C.c_double)]
 
@@ -33,6 +34,8 @@ SIGNATURES = {
     "qb200_destroy": (None, [C.c_void_p]),
     "qb200_last_error": (C.c_char_p, [C.c_void_p]),
     "qb200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qb200_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "qb200_set_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "qb200_set_tensor_cores": (C.c_int, [C.c_void_p, C.c_int]),
     "qb200_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),

@@ -7,7 +7,8 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import ALLREDUCE_FN, CS_NORMAL, CS_SCALED, LevelReport, MODE_PARITY, Qb200Error
+from ._lib import (ALLREDUCE_FN, CS_NORMAL, CS_SCALED, LevelReport, MODE_FULL, MODE_FULL_REPAIR, MODE_PARITY,
+                   Qb200Error)
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -114,8 +115,15 @@ class Context:
         return int(self.lib.qb200_dim(self.h))
 
     # -- hot path ---------------------------------------------------------------------------
+    def set_seed(self, seed: int):
+        self._check(self.lib.qb200_set_seed(self.h, seed))
+
+    def set_rank(self, rank: int, world: int):
+        self._check(self.lib.qb200_set_rank(self.h, rank, world))
+
     def train(self, nbits: int, eps: float = float(np.float32(1e-6)), n_total: int = 0,
-              allreduce: Optional[Callable[[int, int, int], int]] = None, reports: bool = True):
+              allreduce: Optional[Callable[[int, int, int], int]] = None, reports: bool = True,
+              mode: int = MODE_PARITY):
         """LBGQuantizer::quantize. Returns (codebook[K,dim] f64, distortion, [LevelReport...])."""
         K, dim = 1 << nbits, self.dim
         cb = np.empty((K, dim), np.float64)
@@ -131,7 +139,7 @@ class Context:
                     traceback.print_exc()
                     return 1
             cb_fn = ALLREDUCE_FN(tramp)
-        self._check(self.lib.qb200_train(self.h, nbits, eps, MODE_PARITY, n_total,
+        self._check(self.lib.qb200_train(self.h, nbits, eps, mode, n_total,
                                          C.cast(cb_fn, C.c_void_p) if cb_fn else None, None,
                                          _ptr(cb), C.byref(dist),
                                          C.cast(rep, C.c_void_p) if rep is not None else None))

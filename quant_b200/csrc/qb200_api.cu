@@ -5,6 +5,7 @@
 // (assign -> resolve -> accumulate) and an O(K*dim) FP64 finalisation on the host.
 #include "../../include/qb200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -56,6 +57,10 @@ struct qb200_ctx {
   size_t h_pin_cap = 0;
   bool assign_valid = false;
   bool use_tc = true;  // tensor-core filter where it applies (qb200_set_tensor_cores)
+  // empty-cell repair (QB200_MODE_FULL_REPAIR)
+  uint64_t seed = 0x5eed, repair_round = 0;
+  int rank = 0, world = 1;
+  DevBuf d_repair;
 };
 
 namespace {
@@ -347,6 +352,94 @@ void finish_source(VecSource &s, unsigned long long n_images, bool no_padding) {
   s.origin32 = (unsigned int)s.origin;
 }
 
+// Empty-cell repair (extension; parity unpinned - see include/qb200.h).  After the fix step of an iteration:
+// every empty cell, in index order, takes a member of a donor cell - donors are the cells with the largest
+// distortion sum_members |x - c|^2 = Q - |S|^2/n (at least two members, each donor used once per round, largest
+// first).  The member is the vector with the smallest hash of its global index (pick_members_kernel), so every
+// rank - whatever the sharding - arrives at the same vector: ranks exchange their local minima and the chosen
+// bytes through the sum all-reduce (each rank fills its own slot / only the owner contributes).
+int repair_empty_cells(qb200_ctx *ctx, uint32_t K, const std::vector<uint64_t> &n, const std::vector<int64_t> &S,
+                       const std::vector<uint64_t> &Q, qb200_allreduce_fn ar, void *ar_user, double *post,
+                       uint32_t *repaired_out) {
+  const int dim = ctx->src.dim;
+  *repaired_out = 0;
+  std::vector<uint32_t> empty;
+  for (uint32_t k = 0; k < K; k++)
+    if (n[k] == 0) empty.push_back(k);
+  if (empty.empty()) return QB200_OK;
+  std::vector<std::pair<long double, uint32_t>> donors;  // (distortion, cell)
+  for (uint32_t k = 0; k < K; k++) {
+    if (n[k] < 2) continue;
+    long double s2 = 0;
+    for (int e = 0; e < dim; e++) s2 += (long double)S[(size_t)k * dim + e] * (long double)S[(size_t)k * dim + e];
+    const long double d = (long double)Q[k] - s2 / (long double)n[k];
+    if (d > 0) donors.emplace_back(d, k);
+  }
+  std::sort(donors.begin(), donors.end(), [](const std::pair<long double, uint32_t> &a, const std::pair<long double, uint32_t> &b) {
+    return a.first > b.first || (a.first == b.first && a.second < b.second);
+  });
+  const size_t E = std::min(empty.size(), donors.size());
+  if (E == 0) return QB200_OK;
+  const int world = ctx->world, rank = ctx->rank;
+  if (ar && world <= 1) return fail(ctx, QB200_ERR_STATE, "QB200_MODE_FULL_REPAIR on several ranks needs qb200_set_rank");
+  // device scratch: [slot_of_cell int[K] | keys u64[world*E] | local idx i64[E] | member words u64[E*dim]]
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t off_keys = up((size_t)K * 4), off_idx = up(off_keys + (size_t)world * E * 8);
+  const size_t off_mem = up(off_idx + E * 8), total = off_mem + E * (size_t)dim * 8;
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_repair, total))) return rc;
+  char *d = (char *)ctx->d_repair.p;
+  cudaStream_t st = ctx->stream;
+  std::vector<int> slot((size_t)K, -1);
+  for (size_t i = 0; i < E; i++) slot[donors[i].second] = (int)i;
+  std::vector<unsigned long long> keys((size_t)world * E, 0ull);
+  CU(cudaMemcpyAsync(d, slot.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(d + off_keys, 0, (size_t)world * E * 8, st));
+  unsigned long long *my_keys = (unsigned long long *)(d + off_keys) + (size_t)rank * E;
+  CU(cudaMemsetAsync(my_keys, 0xff, E * 8, st));
+  const unsigned long long round_seed = ctx->seed * 0x9E3779B97F4A7C15ull + (++ctx->repair_round);
+  CU(launch_pick_members(ctx->src, (const uint32_t *)ctx->d_assign.p, (const int *)d, round_seed, my_keys, ctx->sm_count, st));
+  if (ar) {
+    // a rank without a member of some donor cell keeps all-ones there; store key+1 so that "none" becomes 0 and sums stay exact
+    CU(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> mine(E);
+    CU(cudaMemcpy(mine.data(), my_keys, E * 8, cudaMemcpyDeviceToHost));
+    for (auto &k : mine) k += 1;  // 0xffff.. -> 0
+    CU(cudaMemcpy(my_keys, mine.data(), E * 8, cudaMemcpyHostToDevice));
+    if (ar(d + off_keys, (size_t)world * E, (void *)st, ar_user) != 0) return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (repair keys)");
+    CU(cudaMemcpyAsync(keys.data(), d + off_keys, (size_t)world * E * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (auto &k : keys) k -= 1;  // back: 0 -> all-ones ("none")
+  } else {
+    CU(cudaMemcpyAsync(keys.data(), my_keys, E * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  std::vector<long long> local_idx(E, -1);
+  for (size_t i = 0; i < E; i++) {
+    unsigned long long best = ~0ull;
+    for (int r = 0; r < world; r++) best = std::min(best, keys[(size_t)r * E + i]);
+    if (best == ~0ull) return fail(ctx, QB200_ERR_STATE, "repair: donor cell %u has no member", donors[i].second);
+    const unsigned long long gv = best & 0xffffffffull;
+    if (gv >= ctx->src.first_vec && gv < ctx->src.first_vec + ctx->src.n_local) local_idx[i] = (long long)(gv - ctx->src.first_vec);
+  }
+  CU(cudaMemcpyAsync(d + off_idx, local_idx.data(), E * 8, cudaMemcpyHostToDevice, st));
+  CU(launch_fetch_members(ctx->src, (const long long *)(d + off_idx), (int)E, (unsigned long long *)(d + off_mem), st));
+  if (ar) {
+    CU(cudaStreamSynchronize(st));
+    if (ar(d + off_mem, E * (size_t)dim, (void *)st, ar_user) != 0) return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (repair members)");
+  }
+  std::vector<unsigned long long> words(E * (size_t)dim);
+  CU(cudaMemcpyAsync(words.data(), d + off_mem, words.size() * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < E; i++)
+    for (int e = 0; e < dim; e++) {
+      const double t = (double)words[i * dim + e];  // lattice value + 128
+      post[(size_t)empty[i] * dim + e] = ctx->colorspace == QB200_CS_SCALED ? t / 255.0 : t - 128.0;
+    }
+  *repaired_out = (uint32_t)E;
+  return QB200_OK;
+}
+
 int set_common(qb200_ctx *ctx, size_t n_local) {
   int rc;
   if ((rc = ensure(ctx, ctx->d_assign, (n_local ? n_local : 1) * 4))) return rc;
@@ -405,7 +498,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_ties, &ctx->d_rows, &ctx->d_rows_tc, &ctx->d_state, &ctx->d_cb64, &ctx->d_nodes,
-                    &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc})
+                    &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc, &ctx->d_repair})
     free_buf(*b);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto &ev : ctx->ev)
@@ -425,6 +518,21 @@ int qb200_set_stream(qb200_ctx *ctx, void *cuda_stream) {
 int qb200_set_tensor_cores(qb200_ctx *ctx, int enable) {
   if (!ctx) return QB200_ERR_ARG;
   ctx->use_tc = enable != 0;
+  return QB200_OK;
+}
+
+int qb200_set_seed(qb200_ctx *ctx, uint64_t seed) {
+  if (!ctx) return QB200_ERR_ARG;
+  ctx->seed = seed;
+  ctx->repair_round = 0;
+  return QB200_OK;
+}
+
+int qb200_set_rank(qb200_ctx *ctx, int rank, int world) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, QB200_ERR_ARG, "qb200_set_rank: rank %d of %d", rank, world);
+  ctx->rank = rank;
+  ctx->world = world;
   return QB200_OK;
 }
 
@@ -638,10 +746,11 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
                 void *allreduce_user, double *codebook_out, double *distortion_out, qb200_level_report *reports) {
   if (!ctx) return QB200_ERR_ARG;
   if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_train: no training set (call qb200_set_image first)");
-  if (mode != QB200_MODE_PARITY) return fail(ctx, QB200_ERR_ARG, "qb200_train: unknown mode %d", mode);
+  if (mode != QB200_MODE_PARITY && mode != QB200_MODE_FULL && mode != QB200_MODE_FULL_REPAIR)
+    return fail(ctx, QB200_ERR_ARG, "qb200_train: unknown mode %d", mode);
   if (nbits < 0 || nbits > 16) return fail(ctx, QB200_ERR_ARG, "qb200_train: nbits %d outside [0,16]", nbits);
   if (!codebook_out) return fail(ctx, QB200_ERR_ARG, "qb200_train: codebook_out == NULL");
-  (void)eps;  // HEAD schedule: the eps test only decides between one and two identical fix rounds
+  // QB200_MODE_PARITY ignores eps: in HEAD the test only decides between one and two identical fix rounds
   const uint64_t N = n_total ? n_total : (uint64_t)ctx->src.n_local;
   // Solution's constructor does trainingSet.at(0) (src/Quantizer.cpp:91): empty input is an error.
   if (N == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
@@ -677,27 +786,28 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
     }
     K *= 2;
     LevelOut lo;
-    if ((rc = run_level(ctx, cb.data(), K, true, reports != nullptr, &lo))) return rc;
-    if ((rc = fetch_stats(ctx, K, allreduce, allreduce_user, words))) return rc;
-    if ((rc = collect_level(ctx, K, reports != nullptr, &lo))) return rc;
-    split_stats(words, K, dim, n, S, Q);
-    qb200_finalize_level(ctx->colorspace, K, dim, N, n.data(), S.data(), Q.data(), cb.data(), post.data(), &dpre,
-                         &dpost);
-    if (reports) {
-      qb200_level_report &r = reports[level];
-      r.K = K;
-      r.flagged = lo.flagged;
-      r.changed = lo.changed;
-      r.ties = lo.ties;
-      r.kd_depth = (uint32_t)lo.kd_depth;
-      r.ms_assign = lo.ms_assign;
-      r.ms_resolve = lo.ms_resolve;
-      r.ms_accumulate = lo.ms_accumulate;
-      r.distortion_pre = dpre;
-      r.distortion_post = dpost;
-      uint32_t dead = 0;
-      for (uint32_t k = 0; k < K; k++) dead += n[k] == 0;
-      r.dead_cells = dead;
+    uint32_t iterations = 0, repaired_total = 0;
+    double d_prev = 0;
+    for (;;) {
+      if ((rc = run_level(ctx, cb.data(), K, true, reports != nullptr, &lo))) return rc;
+      if ((rc = fetch_stats(ctx, K, allreduce, allreduce_user, words))) return rc;
+      if ((rc = collect_level(ctx, K, reports != nullptr, &lo))) return rc;
+      split_stats(words, K, dim, n, S, Q);
+      qb200_finalize_level(ctx->colorspace, K, dim, N, n.data(), S.data(), Q.data(), cb.data(), post.data(), &dpre,
+                           &dpost);
+      iterations++;
+      if (mode == QB200_MODE_PARITY) break;  // HEAD: one assignment per level (src/Quantizer.cpp:98-108)
+      // README.md:29-31 schedule: assign, fix, compare the distortion with the previous round's
+      uint32_t repaired = 0;
+      if (mode == QB200_MODE_FULL_REPAIR &&
+          (rc = repair_empty_cells(ctx, K, n, S, Q, allreduce, allreduce_user, post.data(), &repaired)))
+        return rc;
+      repaired_total += repaired;
+      const double old = iterations == 1 ? dpre : d_prev;
+      d_prev = dpost;
+      const bool converged = old == 0 || std::fabs(old - dpost) / old <= eps;
+      if ((converged && repaired == 0) || iterations >= 100) break;
+      std::memcpy(cb.data(), post.data(), (size_t)K * dim * 8);
     }
     std::memcpy(cb.data(), post.data(), (size_t)K * dim * 8);
     level++;

@@ -912,6 +912,48 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------------------
+// empty-cell repair (extension, QB200_MODE_FULL_REPAIR): pick one member of each donor cell
+// ------------------------------------------------------------------------------------------------
+// The README's repair step ("random vector from the area of biggest distortion", README.md:31; the dead helper
+// getDistortionInArea, src/Quantizer.cpp:34-44) is not implemented in the reference, so there is no RNG to
+// match: the member is the one with the smallest 32-bit hash of (global vector index, seed, round) - a uniform
+// choice that does not depend on how the vectors are sharded.  key = hash << 32 | global index, one atomicMin.
+__device__ __forceinline__ unsigned int mix_hash(unsigned long long x) {  // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return (unsigned int)(x >> 32);
+}
+__global__ void __launch_bounds__(256)
+    pick_members_kernel(const VecSource src, const uint32_t *__restrict__ assign, const int *__restrict__ slot_of_cell,
+                        const unsigned long long seed, unsigned long long *__restrict__ keys) {
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < src.n_local;
+       v += (unsigned long long)gridDim.x * blockDim.x) {
+    const int slot = slot_of_cell[assign[v]];
+    if (slot < 0) continue;
+    const unsigned long long gv = src.first_vec + v;  // index inside the whole (unsharded) training set
+    const unsigned long long key = ((unsigned long long)mix_hash(gv * 0x9E3779B97F4A7C15ull + seed) << 32) | (gv & 0xffffffffull);
+    atomicMin(keys + slot, key);
+  }
+}
+// out[i*dim + e] = lattice value + 128 of local vector local_idx[i] (or 0 when local_idx[i] is not on this rank)
+__global__ void fetch_members_kernel(const VecSource src, const long long *__restrict__ local_idx, const int count,
+                                     unsigned long long *__restrict__ out) {
+  const int i = blockIdx.x;
+  if (i >= count) return;
+  const long long v = local_idx[i];
+  for (int e = threadIdx.x; e < src.dim; e += blockDim.x) {
+    unsigned long long w = 0;
+    if (v >= 0) {
+      unsigned long long base, img;
+      vec_base(src, (unsigned long long)v, base, img);
+      w = (unsigned long long)(load_lattice(src, img, base, e) + 128);
+    }
+    out[(size_t)i * src.dim + e] = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP32 FMA peak probe (roofline denominator measured in the same run)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) ffma_probe_kernel(float *out, int iters, const float m, const float c) {
@@ -1124,6 +1166,25 @@ cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_r
   stage_codebook_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(cb, K, k_rows32, k_rows_tc, dim, scaled, rows32,
                                                                    assign_row_floats(dim), tc_out, tc_kblocks(dim),
                                                                    reinterpret_cast<unsigned int *>(c_max), cb_t);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, const int *slot_of_cell,
+                                unsigned long long seed, unsigned long long *keys, int sm_count, cudaStream_t stream) {
+  unsigned long long blocks = (src.n_local + 255) / 256;
+  const unsigned long long cap = (unsigned long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return cudaSuccess;
+  pick_members_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(src, assign, slot_of_cell, seed, keys);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fetch_members(const VecSource &src, const long long *local_idx, int count, unsigned long long *out,
+                                 cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  fetch_members_kernel<<<count, 64, 0, stream>>>(src, local_idx, count, out);
   g_launch_count++;
   return cudaGetLastError();
 }

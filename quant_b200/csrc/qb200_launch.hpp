@@ -76,6 +76,11 @@ struct DecodeGeom {
 };
 cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32_t *assign, const uint8_t *cb_bytes,
                           uint8_t *out, unsigned long long *sq_err, int sm_count, cudaStream_t stream);
+// Empty-cell repair (QB200_MODE_FULL_REPAIR): smallest (hash, global index) key per donor cell; member bytes.
+cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, const int *slot_of_cell,
+                                unsigned long long seed, unsigned long long *keys, int sm_count, cudaStream_t stream);
+cudaError_t launch_fetch_members(const VecSource &src, const long long *local_idx, int count, unsigned long long *out,
+                                 cudaStream_t stream);
 cudaError_t launch_ffma_probe(float *out, int blocks, int iters, float m, float c, cudaStream_t stream);
 
 constexpr int kResolveDepthCap = 512;
