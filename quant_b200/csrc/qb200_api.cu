@@ -809,6 +809,24 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
       if ((converged && repaired == 0) || iterations >= 100) break;
       std::memcpy(cb.data(), post.data(), (size_t)K * dim * 8);
     }
+    if (reports) {
+      qb200_level_report &r = reports[level];
+      r.K = K;
+      r.flagged = lo.flagged;
+      r.changed = lo.changed;
+      r.ties = lo.ties;
+      r.kd_depth = (uint32_t)lo.kd_depth;
+      r.iterations = iterations;
+      r.repaired = repaired_total;
+      r.ms_assign = lo.ms_assign;
+      r.ms_resolve = lo.ms_resolve;
+      r.ms_accumulate = lo.ms_accumulate;
+      r.distortion_pre = dpre;
+      r.distortion_post = dpost;
+      uint32_t dead = 0;
+      for (uint32_t k = 0; k < K; k++) dead += n[k] == 0;
+      r.dead_cells = dead;
+    }
     std::memcpy(cb.data(), post.data(), (size_t)K * dim * 8);
     level++;
   }

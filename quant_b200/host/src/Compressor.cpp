@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <sstream>
@@ -51,6 +52,14 @@ std::string pretty_bytes(size_t bytes) {
   else  // the remainder is printed in bytes, as the reference does
     s << bytes / (1024 * 1024) << "," << bytes % (1024 * 1024) << "Mb";
   return s.str();
+}
+
+// Training schedule: the reference's HEAD schedule unless QB200_MODE selects an extension
+// (1 = re-assign until convergence, 2 = that + empty-cell repair; include/qb200.h - parity unpinned).
+int training_mode() {
+  const char *e = std::getenv("QB200_MODE");
+  const int m = e ? std::atoi(e) : QB200_MODE_PARITY;
+  return (m == QB200_MODE_FULL || m == QB200_MODE_FULL_REPAIR) ? m : QB200_MODE_PARITY;
 }
 
 int checked_colorspace(ColorSpaces cs) {
@@ -121,7 +130,7 @@ std::pair<CompressedImage, CompressionRaport> CompressedImage::compress(const RG
   qbhost::check(qb200_set_image(ctx, reinterpret_cast<const uint8_t *>(image.img.data()), image.xSize, image.ySize,
                                 blockWidth, blockHeight, cs, 1, 0),
                 "qb200_set_image");
-  qbhost::check(qb200_train(ctx, N, eps, QB200_MODE_PARITY, 0, nullptr, nullptr, cb.data(), &lbg_distortion, nullptr),
+  qbhost::check(qb200_train(ctx, N, eps, training_mode(), 0, nullptr, nullptr, cb.data(), &lbg_distortion, nullptr),
                 "qb200_train");
   res.assignedCodeVector.resize(qb200_num_vectors(ctx));
   qbhost::check(qb200_get_assign_u64(ctx, reinterpret_cast<uint64_t *>(res.assignedCodeVector.data())),
