@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       unsigned int it = 0, tile_seq = 0;
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
         const int ab = tile_seq % kAStages;
-        mbar_wait_bounded<true>(&sh.a_full[ab], (tile_seq / kAStages) & 1, 2);
+        mbar_wait_bounded<200>(&sh.a_full[ab], (tile_seq / kAStages) & 1, 2);
         tc_fence_after();
         for (int jt = 0; jt < n_tiles_n; jt++, it++) {
           const int buf = it & 1;
-          mbar_wait_bounded<true>(&sh.tmem_empty[buf], ((it >> 1) & 1) ^ 1, 3);
+          mbar_wait_bounded<100>(&sh.tmem_empty[buf], ((it >> 1) & 1) ^ 1, 3);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       const int ab = tile_seq % kAStages;
       const unsigned int use = tile_seq / kAStages;
-      if (use >= 1) mbar_wait_bounded<true>(&sh.a_empty[ab], (use - 1) & 1, 4);
+      if (use >= 1) mbar_wait_bounded<1000>(&sh.a_empty[ab], (use - 1) & 1, 4);
       unsigned char *a_tile = s_a + ab * Cfg::A_BYTES;
 #pragma unroll
       for (int kb = 0; kb < KB; kb++) {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
       const unsigned long long v = tile * kTileQ + r;
       const int rb = tile_seq % kResStages;
-      mbar_wait_bounded<true>(&sh.res_full[rb], (tile_seq / kResStages) & 1, 5);
+      mbar_wait_bounded<1000>(&sh.res_full[rb], (tile_seq / kResStages) & 1, 5);
       const float b0 = sh.res_best[rb][0][r], b1 = sh.res_best[rb][1][r];
       const float s0 = sh.res_second[rb][0][r], s1 = sh.res_second[rb][1][r];
       const int c0 = sh.res_chunk[rb][0][r], c1 = sh.res_chunk[rb][1][r];

@@ -530,19 +530,39 @@ struct Frame {
 
 template <int DIMCAP, int DEPTHCAP>
 __global__ void __launch_bounds__(128)
-    resolve_kernel(const VecSource src, const int scaled, const double *__restrict__ cb, const KdDevice tree,
+    resolve_kernel(const VecSource src, const int scaled, const double *cb, const int K, const KdDevice tree,
                    const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
                    uint32_t *__restrict__ assign, unsigned int *__restrict__ changed,
-                   unsigned long long *__restrict__ stats) {
+                   unsigned long long *__restrict__ stats, const unsigned int stage_bytes) {
   // One WARP per query: every lane runs the same (sequential) tree walk; at a leaf the lanes compute the
   // distances of its <= 10 points in parallel.  nanoflann's leaf loop (read worstDist once, add points in
   // order, strict comparisons) keeps the first point that attains the leaf minimum, and only if that
   // minimum is strictly below the best so far - which is what the lane-ordered reduction below returns.
+  // The walk is a chain of dependent loads (node -> vind -> codevector), so a block that has work first
+  // copies tree and codebook into shared memory when they fit (stage_bytes != 0).
   const int dim = src.dim;
   const unsigned int total = *flag_count;
   const int lane = threadIdx.x & 31;
   const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+  if (((blockIdx.x * blockDim.x) >> 5) >= total) return;  // no query for any warp of this block
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const KdNode *nodes = tree.nodes;
+  const unsigned int *vind = tree.vind;
+  if (stage_bytes) {
+    const size_t nb_nodes = (size_t)tree.n_nodes * sizeof(KdNode), nb_cb = (size_t)K * dim * 8, nb_vind = (size_t)K * 4;
+    uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+    const uint4 *s0 = reinterpret_cast<const uint4 *>(cb), *s1 = reinterpret_cast<const uint4 *>(tree.nodes),
+                *s2 = reinterpret_cast<const uint4 *>(tree.vind);
+    const size_t q0 = nb_cb / 16, q1 = nb_nodes / 16, q2 = (nb_vind + 15) / 16;  // cb and nodes are multiples of 16 bytes
+    for (size_t i = threadIdx.x; i < q0; i += blockDim.x) dst[i] = s0[i];
+    for (size_t i = threadIdx.x; i < q1; i += blockDim.x) dst[q0 + i] = s1[i];
+    for (size_t i = threadIdx.x; i < q2; i += blockDim.x) dst[q0 + q1 + i] = s2[i];
+    __syncthreads();
+    cb = reinterpret_cast<const double *>(smem_raw);
+    nodes = reinterpret_cast<const KdNode *>(smem_raw + nb_cb);
+    vind = reinterpret_cast<const unsigned int *>(smem_raw + nb_cb + nb_nodes);
+  }
   double x[DIMCAP], dists[DIMCAP];
   Frame stack[DEPTHCAP];
   for (unsigned int f = warp; f < total; f += n_warps) {
@@ -579,14 +599,14 @@ __global__ void __launch_bounds__(128)
     stack[0].phase = 0;
     while (sp >= 0) {
       Frame &fr = stack[sp];
-      const KdNode nd = tree.nodes[fr.node];
+      const KdNode nd = nodes[fr.node];
       if (fr.phase == 0) {
         if (nd.child1 < 0 && nd.child2 < 0) {
           const int p = nd.a + lane;
           double dist = DBL_MAX;
           unsigned int index = 0;
           if (p < nd.b) {
-            index = tree.vind[p];
+            index = vind[p];
             dist = nanoflann_l2(x, cb + (size_t)index * dim, dim);
           }
           // leaf minimum, first position on ties (lanes are in vind order)
@@ -1065,24 +1085,26 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
   // phase B: the reference's tree walk for the queries phase A left undecided
   const unsigned int blocks = (unsigned int)sm_count * 4;
   const bool deep = tree.depth > 92;
-  if (src.dim <= 16) {
-    if (!deep)
-      resolve_kernel<16, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
-    else
-      resolve_kernel<16, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
-  } else if (src.dim <= 48) {
-    if (!deep)
-      resolve_kernel<48, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
-    else
-      resolve_kernel<48, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
-  } else {
-    if (!deep)
-      resolve_kernel<kMaxDim, 96><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
-    else
-      resolve_kernel<kMaxDim, kResolveDepthCap><<<blocks, 128, 0, stream>>>(src, scaled, cb, tree, tie_list, tie_count, assign, changed, stats);
-  }
+  // tree + codebook in shared memory when they fit (the walk is latency-bound on dependent loads)
+  size_t stage = (size_t)K * src.dim * 8 + (size_t)tree.n_nodes * sizeof(KdNode) + (((size_t)K * 4 + 15) & ~(size_t)15);
+  if (stage > 160 * 1024 || ((size_t)K * src.dim * 8) % 16 != 0) stage = 0;
+  auto go = [&](auto kernel) -> cudaError_t {
+    if (stage) {
+      cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e2 != cudaSuccess) return e2;
+    }
+    kernel<<<blocks, 128, stage, stream>>>(src, scaled, cb, K, tree, tie_list, tie_count, assign, changed, stats,
+                                           (unsigned int)stage);
+    return cudaGetLastError();
+  };
+  if (src.dim <= 16)
+    e = deep ? go(resolve_kernel<16, kResolveDepthCap>) : go(resolve_kernel<16, 96>);
+  else if (src.dim <= 48)
+    e = deep ? go(resolve_kernel<48, kResolveDepthCap>) : go(resolve_kernel<48, 96>);
+  else
+    e = deep ? go(resolve_kernel<kMaxDim, kResolveDepthCap>) : go(resolve_kernel<kMaxDim, 96>);
   g_launch_count++;
-  return cudaGetLastError();
+  return e;
 }
 
 template <int DIM>

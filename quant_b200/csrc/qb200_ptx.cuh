@@ -68,10 +68,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug must end the kernel with an error, never hang the GPU.
-// RELAXED waiters (roles that run far ahead of the role they wait for) sleep between polls so that
+// RELAXED waiters (roles that run far ahead of the role they wait for) sleep RELAXED_NS between polls so that
 // their spinning does not take issue slots from the warps doing the work on the same sub-partition.
-template <bool RELAXED = false>
+template <int RELAXED_NS = 0>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, int tag) {
+  constexpr bool RELAXED = RELAXED_NS > 0;
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
   for (unsigned int spin = 0; spin < (RELAXED ? (1u << 22) : (1u << 26)); spin++) {
@@ -86,7 +87,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
-    if (RELAXED) __nanosleep(128);
+    if (RELAXED) __nanosleep(RELAXED_NS);
   }
   printf("libqb200: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, (int)blockIdx.x, (int)threadIdx.x);
   __trap();
