@@ -277,6 +277,113 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
   }
 }
 
+// Early split levels (K <= 8; the kernel itself handles up to 16): filter + per-cell statistics in ONE high-occupancy pass.  With a handful of
+// codevectors the work per vector is tiny, so the persistent one-CTA-per-SM kernel above and a separate
+// accumulate pass are both dominated by their fixed costs; here every thread takes one vector per iteration,
+// scores it against the K rows (shared memory, broadcast reads), applies the same margin rule, and the
+// vectors it DECIDES are accumulated at once: lanes that chose the same cell are combined with
+// __match_any_sync + __reduce_add_sync and only group leaders touch the per-CTA table (flagged vectors are
+// added by the resolver).  stats may be null (assignment only).
+template <int DIM>
+__global__ void __launch_bounds__(256)
+    small_k_fused_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const float margin_coef,
+                         const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
+                         uint32_t *__restrict__ flag_list, unsigned int *__restrict__ flag_count,
+                         unsigned long long *__restrict__ stats) {
+  constexpr int ROW = AssignCfg<DIM>::ROW, KMAX = 16;
+  __shared__ __align__(16) float s_rows[KMAX * ROW];
+  __shared__ unsigned long long s_q[KMAX];
+  __shared__ int s_n[KMAX];
+  __shared__ int s_s[KMAX * DIM];
+  for (int i = threadIdx.x; i < K * ROW; i += blockDim.x) s_rows[i] = cb_rows[i];
+  for (int i = threadIdx.x; i < KMAX; i += blockDim.x) {
+    s_q[i] = 0;
+    s_n[i] = 0;
+  }
+  for (int i = threadIdx.x; i < KMAX * DIM; i += blockDim.x) s_s[i] = 0;
+  __syncthreads();
+  const float c_max_norm = *c_max_ptr;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long n_round = (src.n_local + 31ull) & ~31ull;  // whole warps stay in the loop
+  for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_round;
+       v += (unsigned long long)gridDim.x * blockDim.x) {
+    const bool live = v < src.n_local;
+    float x[DIM], xn = 0.f;
+    if (live) {
+      gather_lattice<DIM>(src, v, x);
+    } else {
+#pragma unroll
+      for (int e = 0; e < DIM; e++) x[e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < DIM; e++) xn = fmaf(x[e], x[e], xn);
+    float best = FLT_MAX, second = FLT_MAX;
+    int bidx = 0;
+    for (int k = 0; k < K; k++) {
+      const float4 *r4 = reinterpret_cast<const float4 *>(s_rows + k * ROW);
+      float c[ROW];
+#pragma unroll
+      for (int q = 0; q < ROW / 4; q++) {
+        const float4 t = r4[q];
+        c[4 * q] = t.x; c[4 * q + 1] = t.y; c[4 * q + 2] = t.z; c[4 * q + 3] = t.w;
+      }
+      float sc = c[DIM];
+#pragma unroll
+      for (int e = 0; e < DIM; e++) sc = fmaf(x[e], c[e], sc);
+      second = fminf(second, fmaxf(sc, best));
+      bidx = sc < best ? k : bidx;
+      best = fminf(best, sc);
+    }
+    const float rr = sqrtf(xn) + c_max_norm;
+    const bool flag = live && !((second - best) > margin_coef * rr * rr);
+    if (live) assign[v] = (uint32_t)bidx;
+    const unsigned int m = __ballot_sync(0xffffffffu, flag);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned int basepos = 0;
+      if (lane == leader) basepos = atomicAdd(flag_count, (unsigned int)__popc(m));
+      basepos = __shfl_sync(0xffffffffu, basepos, leader);
+      if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+    }
+    if (stats) {
+      const int a = (live && !flag) ? bidx : -1;
+      const unsigned int group = __match_any_sync(0xffffffffu, a);
+      const bool lead = a >= 0 && lane == __ffs(group) - 1;
+      int *row = s_s + (a >= 0 ? a : 0) * DIM;
+      int qs = 0;
+#pragma unroll
+      for (int e = 0; e < DIM; e++) {
+        const int L = a >= 0 ? (int)x[e] : 0;
+        qs += L * L;
+        const int sv = __reduce_add_sync(group, L);
+        if (lead && sv != 0) atomicAdd(row + e, sv);
+      }
+      const unsigned int qsum = __reduce_add_sync(group, (unsigned int)qs);
+      if (lead) {
+        atomicAdd(s_n + a, __popc(group));
+        atomicAdd(s_q + a, (unsigned long long)qsum);
+      }
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      if (s_n[i] != 0) {
+        unsigned long long *row = stats + (size_t)i * (DIM + 2);
+        atomicAdd(row, (unsigned long long)s_n[i]);
+        atomicAdd(row + DIM + 1, s_q[i]);
+      }
+    }
+    for (int i = threadIdx.x; i < K * DIM; i += blockDim.x) {
+      const int sv = s_s[i];
+      if (sv != 0) {
+        const int k = i / DIM, e = i - k * DIM;
+        atomicAdd(stats + (size_t)k * (DIM + 2) + 1 + e, (unsigned long long)(long long)sv);
+      }
+    }
+  }
+}
+
 // Generic-dimension filter (any dim <= kMaxDim that has no template instance): one query per
 // thread, the query lives in shared memory (column per thread), codebook rows streamed from L2.
 // Same score, same margin rule; slower, only there so that every block shape works.
@@ -1008,6 +1115,18 @@ int assign_row_floats(int dim) { return ((dim + 1 + 3) / 4) * 4; }
 template <int DIM>
 static cudaError_t launch_assign_t(const AssignLaunch &a) {
   using Cfg = AssignCfg<DIM>;
+  if (a.k_real <= 8) {  // early split levels: one fused high-occupancy pass (measured: slower than two passes at 16)
+    unsigned long long blocks = (a.src.n_local + 255) / 256;
+    const unsigned long long cap = (unsigned long long)a.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (a.fused_out) *a.fused_out = a.stats != nullptr;
+    if (blocks == 0) return cudaSuccess;
+    small_k_fused_kernel<DIM><<<(unsigned int)blocks, 256, 0, a.stream>>>(a.src, a.cb_rows, a.k_real, a.margin_coef,
+                                                                           a.c_max_ptr, a.assign, a.flag_list,
+                                                                           a.flag_count, a.stats);
+    g_launch_count++;
+    return cudaGetLastError();
+  }
   const size_t row_bytes = (size_t)Cfg::ROW * 4;
   const size_t smem_cap = 200 * 1024;
   int k_chunk = a.K;
