@@ -74,9 +74,12 @@ typedef struct qb200_level_report {
 } qb200_level_report;
 
 /* In-place sum all-reduce over `count` unsigned 64-bit integers at device address `dev_u64`.
- * On entry the data is complete (the library has synchronised its stream); on return the reduced
- * values must be visible to later work on `cuda_stream`.  Two's-complement wrap-around makes the
- * same call correct for the signed sums.  Return 0 on success. */
+ * STREAM-ORDERED: when it is called the work that produces the data has been enqueued on
+ * `cuda_stream` but has not necessarily run; the callback must enqueue the reduction on that stream
+ * (ncclAllReduce(..., (cudaStream_t)cuda_stream) does exactly this) - or synchronise the stream, reduce
+ * by other means and return - so that later work on `cuda_stream` sees the reduced values.  The library
+ * does not synchronise around the call (the train has no host round trip between split levels).
+ * Two's-complement wrap-around makes the same call correct for the signed sums.  Return 0 on success. */
 typedef int (*qb200_allreduce_fn)(void *dev_u64, size_t count, void *cuda_stream, void *user);
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

@@ -37,6 +37,10 @@ struct qb200_ctx {
   size_t total_mem = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> pipe_ev;  // pipelined train: 4 timing events per level + 2 codebook-ready events
+  void *h_pipe = nullptr;            // pinned slots of the pipelined train
+  size_t h_pipe_cap = 0;
+  DevBuf d_cbnext[2], d_post, d_summary;
   std::string err;
 
   // training set
@@ -147,6 +151,15 @@ bool tc_enabled() {
   }();
   return on;
 }
+// The HEAD-schedule train runs without host round trips between levels unless QB200_NO_PIPELINE=1 (the
+// level-by-level path, which the extension modes always use, stays available for comparison).
+bool pipeline_enabled() {
+  static const bool on = [] {
+    const char *e = std::getenv("QB200_NO_PIPELINE");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 // Smallest codebook the tensor-core filter is used for; below it the per-tile pipeline overhead outweighs
 // the saved FMAs and the CUDA-core kernel is faster (measured crossover; QB200_TC_MIN_K overrides).
 int tc_min_k() {
@@ -177,13 +190,16 @@ LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
   return L;
 }
 
-// Runs assign (+ resolve) (+ accumulate) for one codebook.  Leaves the assignment in d_assign and,
-// when want_stats, the K*(dim+2) statistics words in d_stats (NOT yet all-reduced / copied).
-int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, bool timed, LevelOut *out) {
+// One level = level_begin (upload / stage the codebook, launch the filter) + level_finish (KD tree, resolver,
+// statistics).  Between the two the host builds the tree while the filter runs.  Leaves the assignment in
+// d_assign and, when want_stats, the K*(dim+2) statistics words in d_stats (NOT yet all-reduced / copied).
+//   cb_host  the codebook on the host (used for the upload when cb_dev == null)
+//   cb_dev   the codebook already on the device (pipelined train), copied device-to-device
+int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uint32_t K, bool want_stats,
+                cudaEvent_t ev0, cudaEvent_t ev1, bool *fused_out) {
   const int dim = ctx->src.dim;
   const LevelLayout L = level_layout(ctx, K, dim);
-  const size_t rows_bytes = L.rows_bytes, cb_bytes = L.cb_bytes, max_nodes = L.max_nodes;
-  const size_t off_nodes = L.off_nodes, off_vind = L.off_vind, off_bbox = L.off_bbox, off_cnt = L.off_cnt;
+  const size_t rows_bytes = L.rows_bytes, cb_bytes = L.cb_bytes;
   int rc;
   if ((rc = ensure(ctx, ctx->d_rows, rows_bytes))) return rc;
   if ((rc = ensure(ctx, ctx->d_cb64, 2 * cb_bytes))) return rc;  // row-major | transposed
@@ -191,12 +207,15 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   if (want_stats && (rc = ensure(ctx, ctx->d_stats, stats_words(K, dim) * 8))) return rc;
   if ((rc = ensure_pinned(ctx, L.total))) return rc;
   char *pin = (char *)ctx->h_pin;
-  double *h_cb = (double *)(pin + L.off_cb);
-
-  // The FP64 codebook is the only thing uploaded; FP32 rows, bf16 limb tiles and max|C| are derived on the device.
-  std::memcpy(h_cb, cb, cb_bytes);
   cudaStream_t st = ctx->stream;
-  CU(cudaMemcpyAsync(ctx->d_cb64.p, h_cb, cb_bytes, cudaMemcpyHostToDevice, st));
+  // The FP64 codebook is the only thing uploaded; FP32 rows, bf16 limb tiles and max|C| are derived on the device.
+  if (cb_dev) {
+    CU(cudaMemcpyAsync(ctx->d_cb64.p, cb_dev, cb_bytes, cudaMemcpyDeviceToDevice, st));
+  } else {
+    double *h_cb = (double *)(pin + L.off_cb);
+    std::memcpy(h_cb, cb_host, cb_bytes);
+    CU(cudaMemcpyAsync(ctx->d_cb64.p, h_cb, cb_bytes, cudaMemcpyHostToDevice, st));
+  }
   CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
   unsigned int *cnt = (unsigned int *)ctx->d_counters.p;  // [0] flagged, [1] changed, [2] ties, [4] max|C| (float)
   const float *c_max_ptr = reinterpret_cast<const float *>(cnt + 4);
@@ -204,7 +223,7 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
   if (L.use_tc && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 12))) return rc;
   if (want_stats) CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(K, dim) * 8, st));
   bool fused = false;  // did the filter kernel accumulate the per-cell statistics of the queries it decided?
-  if (timed) CU(cudaEventRecord(ctx->ev[0], st));
+  if (ev0) CU(cudaEventRecord(ev0, st));
   CU(launch_stage_codebook((const double *)ctx->d_cb64.p, (int)K, (int)L.K_rows, L.use_tc ? (int)L.K_rows : 0, dim,
                            ctx->colorspace == QB200_CS_SCALED, (float *)ctx->d_rows.p,
                            L.use_tc ? (unsigned char *)ctx->d_rows_tc.p : nullptr, reinterpret_cast<float *>(cnt + 4),
@@ -244,9 +263,23 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
     a.fused_out = &fused;
     CU(launch_assign(a));
   }
-  if (timed) CU(cudaEventRecord(ctx->ev[1], st));
+  if (ev1) CU(cudaEventRecord(ev1, st));
+  *fused_out = fused;
+  return QB200_OK;
+}
 
-
+// cb: the level's codebook on the host (for the KD tree).  counters_dst: pinned destination of the three
+// counters {flagged, changed, ties} (12 bytes), valid after the stream has reached this point.
+int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, bool fused, cudaEvent_t ev2,
+                 cudaEvent_t ev3, void *counters_dst, int *kd_depth_out) {
+  const int dim = ctx->src.dim;
+  const LevelLayout L = level_layout(ctx, K, dim);
+  const size_t max_nodes = L.max_nodes;
+  const size_t off_nodes = L.off_nodes, off_vind = L.off_vind, off_bbox = L.off_bbox;
+  char *pin = (char *)ctx->h_pin;
+  cudaStream_t st = ctx->stream;
+  unsigned int *cnt = (unsigned int *)ctx->d_counters.p;
+  int rc;
   // While the filter runs: build the reference's KD tree for this codebook on the host.
   KdHostTree tree;
   build_kd_tree(cb, K, dim, 10 /* src/KDTree.cpp:4 */, tree);
@@ -254,7 +287,7 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
     return fail(ctx, QB200_ERR_ARG, "KD tree depth %d exceeds the resolver's stack (%d)", tree.depth,
                 kResolveDepthCap);
   if (tree.nodes.size() > max_nodes) return fail(ctx, QB200_ERR_STATE, "KD tree larger than expected");
-  if ((rc = ensure(ctx, ctx->d_nodes, tree.nodes.size() * sizeof(KdNode)))) return rc;
+  if ((rc = ensure(ctx, ctx->d_nodes, max_nodes * sizeof(KdNode)))) return rc;
   if ((rc = ensure(ctx, ctx->d_vind, (size_t)K * 8))) return rc;  // vind | inverse
   if ((rc = ensure(ctx, ctx->d_bbox, 2 * (size_t)dim * 8))) return rc;
   std::memcpy(pin + off_nodes, tree.nodes.data(), tree.nodes.size() * sizeof(KdNode));
@@ -280,18 +313,28 @@ int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, boo
                     (const double *)ctx->d_cb64.p + (size_t)K * dim, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
                     cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, ctx->sm_count, st));
-  if (timed) CU(cudaEventRecord(ctx->ev[2], st));
+  if (ev2) CU(cudaEventRecord(ev2, st));
   if (want_stats && !fused) {
     CU(launch_accumulate(ctx->src, (const uint32_t *)ctx->d_assign.p, (int)K, (unsigned long long *)ctx->d_stats.p,
                          ctx->sm_count, st));
   }
-  if (timed) CU(cudaEventRecord(ctx->ev[3], st));
-  CU(cudaMemcpyAsync(pin + off_cnt, ctx->d_counters.p, 12, cudaMemcpyDeviceToHost, st));
+  if (ev3) CU(cudaEventRecord(ev3, st));
+  CU(cudaMemcpyAsync(counters_dst, ctx->d_counters.p, 12, cudaMemcpyDeviceToHost, st));
   ctx->assign_valid = true;
-  if (out) {
-    // the caller synchronises before reading these
-    out->kd_depth = tree.depth;
-  }
+  if (kd_depth_out) *kd_depth_out = tree.depth;
+  return QB200_OK;
+}
+
+int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, bool timed, LevelOut *out) {
+  bool fused = false;
+  int rc = level_begin(ctx, cb, nullptr, K, want_stats, timed ? ctx->ev[0] : nullptr, timed ? ctx->ev[1] : nullptr, &fused);
+  if (rc) return rc;
+  const LevelLayout L = level_layout(ctx, K, ctx->src.dim);
+  int depth = 0;
+  rc = level_finish(ctx, cb, K, want_stats, fused, timed ? ctx->ev[2] : nullptr, timed ? ctx->ev[3] : nullptr,
+                    (char *)ctx->h_pin + L.off_cnt, &depth);
+  if (rc) return rc;
+  if (out) out->kd_depth = depth;  // counters and timings: collect_level after the caller has synchronised
   return QB200_OK;
 }
 
@@ -313,7 +356,6 @@ int collect_level(qb200_ctx *ctx, uint32_t K, bool timed, LevelOut *out) {
 int fetch_stats(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void *ar_user, std::vector<unsigned long long> &host) {
   const size_t words = stats_words(K, ctx->src.dim);
   if (ar) {
-    CU(cudaStreamSynchronize(ctx->stream));
     if (ar(ctx->d_stats.p, words, (void *)ctx->stream, ar_user) != 0)
       return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed at K=%u", K);
   }
@@ -501,6 +543,10 @@ void qb200_destroy(qb200_ctx *ctx) {
                     &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc, &ctx->d_repair})
     free_buf(*b);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
+  for (auto &e2 : ctx->pipe_ev)
+    if (e2) cudaEventDestroy(e2);
+  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary}) free_buf(*b);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -742,6 +788,151 @@ int qb200_codebook_to_bytes(const double *codebook, size_t K, int dim, int color
   return QB200_OK;
 }
 
+namespace {
+
+struct PipeSlot {  // pinned, one per split level
+  unsigned int counters[4];
+  double dist_pre, dist_post;
+  unsigned int dead_cells, pad;
+  unsigned long long n_seen;
+};
+
+// HEAD schedule without host round trips between levels: centroids, distortions and the next split are
+// computed on the device (finalize_split_kernel); the host only builds each level's KD tree, from a codebook
+// copy that arrives while the GPU is already running that level's filter, and reads everything else at the end.
+int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduce_fn ar, void *ar_user,
+                           double *codebook_out, double *distortion_out, qb200_level_report *reports) {
+  const int dim = ctx->src.dim;
+  const uint32_t maxK = 1u << nbits;
+  const size_t cb_max = (size_t)maxK * dim * 8;
+  const int scaled = ctx->colorspace == QB200_CS_SCALED;
+  const double f_up = (double)(1 + 0.2), f_dn = (double)(1 - 0.2);  // src/Quantizer.cpp:136-137
+  cudaStream_t st = ctx->stream;
+  int rc;
+  // everything the levels will need, at its final size: no buffer is reallocated while work is in flight
+  const LevelLayout Lmax = level_layout(ctx, maxK, dim);
+  size_t rows_max = 0, tc_max = 0;
+  for (uint32_t K = 2; K <= maxK && K; K *= 2) {
+    const LevelLayout L = level_layout(ctx, K, dim);
+    rows_max = std::max(rows_max, L.rows_bytes);
+    tc_max = std::max(tc_max, L.tc_bytes);
+  }
+  if ((rc = ensure(ctx, ctx->d_rows, std::max(rows_max, (size_t)256)))) return rc;
+  if ((rc = ensure(ctx, ctx->d_cb64, 2 * cb_max + 256))) return rc;
+  if ((rc = ensure(ctx, ctx->d_counters, 64))) return rc;
+  if ((rc = ensure(ctx, ctx->d_stats, stats_words(maxK, dim) * 8))) return rc;
+  if (tc_max && (rc = ensure(ctx, ctx->d_rows_tc, tc_max))) return rc;
+  if (tc_max && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 12))) return rc;
+  if ((rc = ensure(ctx, ctx->d_nodes, Lmax.max_nodes * sizeof(KdNode)))) return rc;
+  if ((rc = ensure(ctx, ctx->d_vind, (size_t)maxK * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->d_bbox, 2 * (size_t)dim * 8))) return rc;
+  if ((rc = ensure_pinned(ctx, Lmax.total))) return rc;
+  for (int i = 0; i < 2; i++)
+    if ((rc = ensure(ctx, ctx->d_cbnext[i], cb_max + 256))) return rc;
+  if ((rc = ensure(ctx, ctx->d_post, cb_max + 256))) return rc;
+  if ((rc = ensure(ctx, ctx->d_summary, 64 * 32))) return rc;
+  // pinned: [slots | host codebook 0 | host codebook 1 | final codebook]
+  const size_t off_cb0 = (sizeof(PipeSlot) * 20 + 255) & ~(size_t)255, need = off_cb0 + 3 * (cb_max + 256);
+  if (need > ctx->h_pipe_cap) {
+    if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
+    ctx->h_pipe = nullptr;
+    ctx->h_pipe_cap = 0;
+    if (cudaMallocHost(&ctx->h_pipe, need) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, QB200_ERR_OOM, "cudaMallocHost(%zu bytes)", need);
+    }
+    ctx->h_pipe_cap = need;
+  }
+  PipeSlot *slots = (PipeSlot *)ctx->h_pipe;
+  double *h_cb[2] = {(double *)((char *)ctx->h_pipe + off_cb0), (double *)((char *)ctx->h_pipe + off_cb0 + cb_max + 256)};
+  double *h_final = (double *)((char *)ctx->h_pipe + off_cb0 + 2 * (cb_max + 256));
+  const size_t n_ev = 4 * 17 + 2;
+  while (ctx->pipe_ev.size() < n_ev) {
+    cudaEvent_t e;
+    const bool timing = ctx->pipe_ev.size() < 4 * 17;
+    CU(timing ? cudaEventCreate(&e) : cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_ev.push_back(e);
+  }
+  cudaEvent_t *cb_ready = ctx->pipe_ev.data() + 4 * 17;
+  char *summaries = (char *)ctx->d_summary.p;
+
+  // K = 1: mean of the training set (src/Quantizer.cpp:129-130), split into the first two codevectors
+  CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(1, dim) * 8, st));
+  CU(launch_accumulate(ctx->src, nullptr, 1, (unsigned long long *)ctx->d_stats.p, ctx->sm_count, st));
+  if (ar && ar(ctx->d_stats.p, stats_words(1, dim), (void *)st, ar_user) != 0)
+    return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed at K=1");
+  CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, nullptr, 1, dim, scaled, (double)N, f_up, f_dn,
+                           (double *)ctx->d_post.p, nbits ? (double *)ctx->d_cbnext[0].p : nullptr, summaries, st));
+  CU(cudaMemcpyAsync(&slots[0].dist_pre, summaries, 32, cudaMemcpyDeviceToHost, st));
+  if (nbits) {
+    CU(cudaMemcpyAsync(h_cb[0], ctx->d_cbnext[0].p, (size_t)2 * dim * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(cb_ready[0], st));
+  } else {
+    CU(cudaMemcpyAsync(h_final, ctx->d_post.p, (size_t)dim * 8, cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<int> depth((size_t)nbits + 1, 0);
+  uint32_t K = 1;
+  for (int level = 0; level < nbits; level++) {
+    K *= 2;
+    const int cur = level & 1;
+    const bool last = level == nbits - 1;
+    cudaEvent_t *ev = reports ? ctx->pipe_ev.data() + 4 * level : nullptr;
+    bool fused = false;
+    if ((rc = level_begin(ctx, nullptr, (const double *)ctx->d_cbnext[cur].p, K, true, ev ? ev[0] : nullptr,
+                          ev ? ev[1] : nullptr, &fused)))
+      return rc;
+    CU(cudaEventSynchronize(cb_ready[cur]));  // this level's codebook has reached the host (the filter is already running)
+    if ((rc = level_finish(ctx, h_cb[cur], K, true, fused, ev ? ev[2] : nullptr, ev ? ev[3] : nullptr,
+                           slots[level + 1].counters, &depth[level])))
+      return rc;
+    if (ar && ar(ctx->d_stats.p, stats_words(K, dim), (void *)st, ar_user) != 0)
+      return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed at K=%u", K);
+    CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, (const double *)ctx->d_cb64.p, (int)K, dim, scaled,
+                             (double)N, f_up, f_dn, (double *)ctx->d_post.p,
+                             last ? nullptr : (double *)ctx->d_cbnext[cur ^ 1].p, summaries + 32 * (level + 1), st));
+    CU(cudaMemcpyAsync(&slots[level + 1].dist_pre, summaries + 32 * (level + 1), 32, cudaMemcpyDeviceToHost, st));
+    if (!last) {
+      CU(cudaMemcpyAsync(h_cb[cur ^ 1], ctx->d_cbnext[cur ^ 1].p, (size_t)2 * K * dim * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaEventRecord(cb_ready[cur ^ 1], st));
+    } else {
+      CU(cudaMemcpyAsync(h_final, ctx->d_post.p, (size_t)K * dim * 8, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  if (nbits == 0) CU(cudaMemsetAsync(ctx->d_assign.p, 0, (size_t)ctx->src.n_local * 4, st));
+  CU(cudaStreamSynchronize(st));
+  ctx->assign_valid = true;
+  if (slots[0].n_seen != N)
+    return fail(ctx, QB200_ERR_STATE, "vector count mismatch: reduced %llu, expected %llu",
+                (unsigned long long)slots[0].n_seen, (unsigned long long)N);
+  std::memcpy(codebook_out, h_final, (size_t)K * dim * 8);
+  if (distortion_out) *distortion_out = slots[nbits].dist_post;
+  if (reports) {
+    uint32_t Kl = 1;
+    for (int level = 0; level < nbits; level++) {
+      Kl *= 2;
+      qb200_level_report &r = reports[level];
+      const PipeSlot &s = slots[level + 1];
+      cudaEvent_t *ev = ctx->pipe_ev.data() + 4 * level;
+      r.K = Kl;
+      r.flagged = s.counters[0];
+      r.changed = s.counters[1];
+      r.ties = s.counters[2];
+      r.dead_cells = s.dead_cells;
+      r.kd_depth = (uint32_t)depth[level];
+      r.iterations = 1;
+      r.repaired = 0;
+      CU(cudaEventElapsedTime(&r.ms_assign, ev[0], ev[1]));
+      CU(cudaEventElapsedTime(&r.ms_resolve, ev[1], ev[2]));
+      CU(cudaEventElapsedTime(&r.ms_accumulate, ev[2], ev[3]));
+      r.distortion_pre = s.dist_pre;
+      r.distortion_post = s.dist_post;
+    }
+  }
+  return QB200_OK;
+}
+
+}  // namespace
+
 int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_total, qb200_allreduce_fn allreduce,
                 void *allreduce_user, double *codebook_out, double *distortion_out, qb200_level_report *reports) {
   if (!ctx) return QB200_ERR_ARG;
@@ -756,6 +947,8 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
   if (N == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
   if (!allreduce && ctx->src.n_local == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
   CU(cudaSetDevice(ctx->device));
+  if (mode == QB200_MODE_PARITY && pipeline_enabled())
+    return train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);
   const int dim = ctx->src.dim;
   const uint32_t maxK = 1u << nbits;
   std::vector<double> cb((size_t)maxK * dim), post((size_t)maxK * dim);

@@ -1039,6 +1039,84 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------------------
+// finalize_split_kernel: fixCodeVectors + the two updateDistortion values + the next split, on the device
+// ------------------------------------------------------------------------------------------------
+// Device twin of qb200_finalize_level (qb200_api.cu) followed by the split of src/Quantizer.cpp:134-138, so
+// that the HEAD-schedule train needs no host round trip between levels: from the reduced integer statistics
+// it writes the centroids (same IEEE operations as the host version: ((double)S_t / unit) / n, zero vector for
+// an empty cell), the next level's codebook (1.2 c | 0.8 c) and {distortion before fix, after fix, dead cells}.
+// One block; per-thread partial sums in a fixed order + a fixed shared-memory tree: deterministic.
+struct LevelSummary {
+  double dist_pre, dist_post;
+  unsigned int dead_cells, pad;
+  unsigned long long n_total_seen;
+};
+__global__ void __launch_bounds__(1024)
+    finalize_split_kernel(const unsigned long long *__restrict__ stats, const double *__restrict__ cb_pre, const int K,
+                          const int dim, const int scaled, const double n_total, const double f_up, const double f_dn,
+                          double *__restrict__ cb_post, double *__restrict__ cb_next,
+                          LevelSummary *__restrict__ summary) {
+  __shared__ double s_pre[1024], s_post[1024];
+  __shared__ unsigned int s_dead[1024];
+  __shared__ unsigned long long s_n[1024];
+  const double unit = scaled ? 255.0 : 1.0;
+  double acc_pre = 0.0, acc_post = 0.0;
+  unsigned int dead = 0;
+  unsigned long long seen = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const unsigned long long *row = stats + (size_t)k * (dim + 2);
+    const unsigned long long n = row[0];
+    seen += n;
+    dead += n == 0;
+    long long s_all = 0;
+    for (int e = 0; e < dim; e++) s_all += (long long)row[1 + e];
+    // Q in the colour space's lattice t (SCALED: t = L + 128): sum t^2 = Q_L + 256 S_L + 128^2 dim n
+    const double Qt = scaled ? (double)row[dim + 1] + 256.0 * (double)s_all + 16384.0 * (double)dim * (double)n
+                             : (double)row[dim + 1];
+    double st2 = 0.0, cross = 0.0, c2 = 0.0;
+    for (int e = 0; e < dim; e++) {
+      const long long St = (long long)row[1 + e] + (scaled ? (long long)(128ull * n) : 0ll);
+      const double c = n ? __ddiv_rn(__ddiv_rn((double)St, unit), (double)n) : 0.0;
+      cb_post[(size_t)k * dim + e] = c;
+      if (cb_next) {
+        cb_next[(size_t)k * dim + e] = __dmul_rn(c, f_up);
+        cb_next[((size_t)K + k) * dim + e] = __dmul_rn(c, f_dn);
+      }
+      st2 += (double)St * (double)St;
+      if (cb_pre) {
+        const double cp = cb_pre[(size_t)k * dim + e];
+        cross += cp * (double)St;
+        c2 += cp * cp;
+      }
+    }
+    if (n) acc_post += Qt - st2 / (double)n;
+    if (cb_pre) acc_pre += Qt - 2.0 * unit * cross + unit * unit * (double)n * c2;
+  }
+  s_pre[threadIdx.x] = acc_pre;
+  s_post[threadIdx.x] = acc_post;
+  s_dead[threadIdx.x] = dead;
+  s_n[threadIdx.x] = seen;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_pre[threadIdx.x] += s_pre[threadIdx.x + o];
+      s_post[threadIdx.x] += s_post[threadIdx.x + o];
+      s_dead[threadIdx.x] += s_dead[threadIdx.x + o];
+      s_n[threadIdx.x] += s_n[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double denom = unit * unit * n_total * (double)dim;
+    summary->dist_pre = s_pre[0] / denom;
+    summary->dist_post = s_post[0] / denom;
+    summary->dead_cells = s_dead[0];
+    summary->pad = 0;
+    summary->n_total_seen = s_n[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // empty-cell repair (extension, QB200_MODE_FULL_REPAIR): pick one member of each donor cell
 // ------------------------------------------------------------------------------------------------
 // The README's repair step ("random vector from the area of biggest distortion", README.md:31; the dead helper
@@ -1307,6 +1385,15 @@ cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_r
   stage_codebook_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(cb, K, k_rows32, k_rows_tc, dim, scaled, rows32,
                                                                    assign_row_floats(dim), tc_out, tc_kblocks(dim),
                                                                    reinterpret_cast<unsigned int *>(c_max), cb_t);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, int K, int dim, int scaled,
+                                  double n_total, double f_up, double f_dn, double *cb_post, double *cb_next,
+                                  void *summary, cudaStream_t stream) {
+  finalize_split_kernel<<<1, 1024, 0, stream>>>(stats, cb_pre, K, dim, scaled, n_total, f_up, f_dn, cb_post, cb_next,
+                                                reinterpret_cast<LevelSummary *>(summary));
   g_launch_count++;
   return cudaGetLastError();
 }

@@ -76,6 +76,11 @@ struct DecodeGeom {
 };
 cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32_t *assign, const uint8_t *cb_bytes,
                           uint8_t *out, unsigned long long *sq_err, int sm_count, cudaStream_t stream);
+// Device-side fix + distortions + split of one level.  summary: 32 bytes {double dist_pre, dist_post; u32 dead_cells,
+// pad; u64 vectors counted}.  cb_pre / cb_next may be null (K = 1 has no previous codebook; the last level no next).
+cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, int K, int dim, int scaled,
+                                  double n_total, double f_up, double f_dn, double *cb_post, double *cb_next,
+                                  void *summary, cudaStream_t stream);
 // Empty-cell repair (QB200_MODE_FULL_REPAIR): smallest (hash, global index) key per donor cell; member bytes.
 cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, const int *slot_of_cell,
                                 unsigned long long seed, unsigned long long *keys, int sm_count, cudaStream_t stream);
