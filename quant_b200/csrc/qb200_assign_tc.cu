@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       unsigned int it = 0, tile_seq = 0;
       for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
         const int ab = tile_seq % kAStages;
-        mbar_wait_bounded<200>(&sh.a_full[ab], (tile_seq / kAStages) & 1, 2);
+        mbar_wait_bounded<20000>(&sh.a_full[ab], (tile_seq / kAStages) & 1, 2);
         tc_fence_after();
         for (int jt = 0; jt < n_tiles_n; jt++, it++) {
           const int buf = it & 1;
-          mbar_wait_bounded<100>(&sh.tmem_empty[buf], ((it >> 1) & 1) ^ 1, 3);
+          mbar_wait_bounded<20000>(&sh.tmem_empty[buf], ((it >> 1) & 1) ^ 1, 3);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       const int ab = tile_seq % kAStages;
       const unsigned int use = tile_seq / kAStages;
-      if (use >= 1) mbar_wait_bounded<1000>(&sh.a_empty[ab], (use - 1) & 1, 4);
+      if (use >= 1) mbar_wait_bounded<20000>(&sh.a_empty[ab], (use - 1) & 1, 4);
       unsigned char *a_tile = s_a + ab * Cfg::A_BYTES;
 #pragma unroll
       for (int kb = 0; kb < KB; kb++) {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
       const unsigned long long v = tile * kTileQ + r;
       const int rb = tile_seq % kResStages;
-      mbar_wait_bounded<1000>(&sh.res_full[rb], (tile_seq / kResStages) & 1, 5);
+      mbar_wait_bounded<20000>(&sh.res_full[rb], (tile_seq / kResStages) & 1, 5);
       const float b0 = sh.res_best[rb][0][r], b1 = sh.res_best[rb][1][r];
       const float s0 = sh.res_second[rb][0][r], s1 = sh.res_second[rb][1][r];
       const int c0 = sh.res_chunk[rb][0][r], c1 = sh.res_chunk[rb][1][r];
@@ -222,48 +222,52 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           chunk = __float_as_int(state[v * 3 + 2]);
         }
       }
-      // Flat sequence of column chunks (<= 32 columns each) over the N tiles of this query tile, software
-      // pipelined over two register buffers: the tcgen05.ld of chunk g+1 is in flight while chunk g is reduced.
-      constexpr int half_cols = kTileN / 2, ch_shift = 2, ch_mask = 3;  // 4 chunks of 32 columns per N tile and half
+      // Per N tile this warp scans 128 columns as four chunks of 32, software-pipelined over two register
+      // buffers: the tcgen05.ld of the next chunk (the next N tile's first chunk included) is in flight while
+      // the current one is reduced.  Everything but the buffer address and the chunk base is a constant.
+      constexpr int half_cols = kTileN / 2;
       const int col0 = half * half_cols;
-      const int total = n_tiles_n << ch_shift;
-      auto issue = [&](int g, float *v) {
-        const int jt = g >> ch_shift, c = (g & ch_mask) * 32;
-        const unsigned int itg = it + jt;
-        const int buf = itg & 1;
-        if (c == 0) {
-          mbar_wait_bounded(&sh.tmem_full[buf], (itg >> 1) & 1, 6);
-          tc_fence_after();
-        }
-        const uint32_t taddr = lane_addr + (uint32_t)(buf * 256 + col0 + c);
+      auto load32 = [&](uint32_t taddr, float *v) {
 #pragma unroll
         for (int q = 0; q < 4; q++) tmem_ld8(taddr + q * 8, v + q * 8);
       };
-      auto landed = [&](int g, float *v) {  // after this the chunk is in registers
+      auto landed = [&](float *v) {  // after this the chunk is in registers
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; q++) tmem_ld_pin8(v + q * 8);
-        if ((g & ch_mask) == ch_mask) {  // last chunk of its N tile: hand the buffer back to the MMA
-          tc_fence_before();
-          mbar_arrive(&sh.tmem_empty[(it + (g >> ch_shift)) & 1]);
-        }
       };
-      auto reduce = [&](int g, const float *v) {
-        const int cid = (k_base + (g >> ch_shift) * kTileN + col0 + (g & ch_mask) * 32) >> 3;
+      auto reduce = [&](int cid, const float *v) {
 #pragma unroll
         for (int q = 0; q < 4; q++) top2_update8(v + q * 8, cid + q, best, second, chunk);
       };
+      auto acquire = [&](unsigned int itg) -> uint32_t {  // wait for N tile `itg`, return its first column address
+        const int buf = itg & 1;
+        mbar_wait_bounded(&sh.tmem_full[buf], (itg >> 1) & 1, 6);
+        tc_fence_after();
+        return lane_addr + (uint32_t)(buf * 256 + col0);
+      };
       float va[32], vb[32];
-      issue(0, va);
-      for (int g = 0; g < total; g += 2) {
-        landed(g, va);
-        if (g + 1 < total) issue(g + 1, vb);
-        reduce(g, va);
-        if (g + 1 < total) {
-          landed(g + 1, vb);
-          if (g + 2 < total) issue(g + 2, va);
-          reduce(g + 1, vb);
+      uint32_t taddr = acquire(it);
+      load32(taddr, va);
+      int cid = (k_base + col0) >> 3;
+      for (int jt = 0; jt < n_tiles_n; jt++, cid += kTileN / 8) {
+        landed(va);
+        load32(taddr + 32, vb);
+        reduce(cid, va);
+        landed(vb);
+        load32(taddr + 64, va);
+        reduce(cid + 4, vb);
+        landed(va);
+        load32(taddr + 96, vb);
+        reduce(cid + 8, va);
+        landed(vb);  // the whole N tile is in registers: hand the buffer back to the MMA
+        tc_fence_before();
+        mbar_arrive(&sh.tmem_empty[(it + jt) & 1]);
+        if (jt + 1 < n_tiles_n) {
+          taddr = acquire(it + jt + 1);
+          load32(taddr, va);
         }
+        reduce(cid + 12, vb);
       }
       it += n_tiles_n;
       const int rb = tile_seq % kResStages;

@@ -68,26 +68,39 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug must end the kernel with an error, never hang the GPU.
-// RELAXED waiters (roles that run far ahead of the role they wait for) sleep RELAXED_NS between polls so that
-// their spinning does not take issue slots from the warps doing the work on the same sub-partition.
+// RELAXED waiters (roles that run far ahead of the role they wait for) give try_wait a suspend-time hint of
+// RELAXED_NS so that their waiting does not take issue slots from the warps doing the work.
 template <int RELAXED_NS = 0>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, int tag) {
   constexpr bool RELAXED = RELAXED_NS > 0;
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
-  for (unsigned int spin = 0; spin < (RELAXED ? (1u << 22) : (1u << 26)); spin++) {
+  for (unsigned int spin = 0; spin < (RELAXED ? (1u << 20) : (1u << 26)); spin++) {
     uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
+    if (RELAXED) {
+      // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint
+      // expires) instead of the thread polling - no issue slots taken from the working warps, no wake-up skew
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(ok)
+          : "r"(addr), "r"(parity), "r"((uint32_t)RELAXED_NS)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(ok)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    }
     if (ok) return;
-    if (RELAXED) __nanosleep(RELAXED_NS);
   }
   printf("libqb200: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, (int)blockIdx.x, (int)threadIdx.x);
   __trap();
