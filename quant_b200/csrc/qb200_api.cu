@@ -220,7 +220,7 @@ int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uin
   unsigned int *cnt = (unsigned int *)ctx->d_counters.p;  // [0] flagged, [1] changed, [2] ties, [4] max|C| (float)
   const float *c_max_ptr = reinterpret_cast<const float *>(cnt + 4);
   if (L.use_tc && (rc = ensure(ctx, ctx->d_rows_tc, L.tc_bytes))) return rc;
-  if (L.use_tc && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 12))) return rc;
+  if (L.use_tc && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 16))) return rc;
   if (want_stats) CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(K, dim) * 8, st));
   bool fused = false;  // did the filter kernel accumulate the per-cell statistics of the queries it decided?
   if (ev0) CU(cudaEventRecord(ev0, st));
@@ -822,7 +822,7 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
   if ((rc = ensure(ctx, ctx->d_counters, 64))) return rc;
   if ((rc = ensure(ctx, ctx->d_stats, stats_words(maxK, dim) * 8))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_rows_tc, tc_max))) return rc;
-  if (tc_max && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 12))) return rc;
+  if (tc_max && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 16))) return rc;
   if ((rc = ensure(ctx, ctx->d_nodes, Lmax.max_nodes * sizeof(KdNode)))) return rc;
   if ((rc = ensure(ctx, ctx->d_vind, (size_t)maxK * 8))) return rc;
   if ((rc = ensure(ctx, ctx->d_bbox, 2 * (size_t)dim * 8))) return rc;

@@ -199,9 +199,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int c0 = sh.res_chunk[rb][0][r], c1 = sh.res_chunk[rb][1][r];
       mbar_arrive(&sh.res_empty[rb]);
       if (v < src.n_local) {
-        state[v * 3 + 0] = fminf(b0, b1);
-        state[v * 3 + 1] = fmin3(fmaxf(b0, b1), s0, s1);
-        state[v * 3 + 2] = __int_as_float(b1 < b0 ? c1 : c0);
+        reinterpret_cast<float4 *>(state)[v] =
+            make_float4(fminf(b0, b1), fmin3(fmaxf(b0, b1), s0, s1), __int_as_float(b1 < b0 ? c1 : c0), 0.f);
       }
     }
   } else {
@@ -217,9 +216,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (!first_pass && half == 0) {
         const unsigned long long v = tile * kTileQ + r;
         if (v < src.n_local) {
-          best = state[v * 3 + 0];
-          second = state[v * 3 + 1];
-          chunk = __float_as_int(state[v * 3 + 2]);
+          const float4 rec = reinterpret_cast<const float4 *>(state)[v];
+          best = rec.x;
+          second = rec.y;
+          chunk = __float_as_int(rec.z);
         }
       }
       // Per N tile this warp scans 128 columns as four chunks of 32, software-pipelined over two register
@@ -312,8 +312,9 @@ __global__ void __launch_bounds__(256)
       const bool live = v < src.n_local;
       bool flag = false;
       if (live) {
-        const float best = state[v * 3 + 0], second = state[v * 3 + 1];
-        const int chunk = __float_as_int(state[v * 3 + 2]);
+        const float4 rec = __ldcs(reinterpret_cast<const float4 *>(state) + v);  // streamed: keep the rows in L1
+        const float best = rec.x, second = rec.y;
+        const int chunk = __float_as_int(rec.z);
         // this lane's four extended coordinates [x, 1, 0, 0][4*cb .. 4*cb+3], and |x|^2 via the group
         float xe[4], part = 0.f;
         if (src.fast) {
@@ -378,8 +379,9 @@ __global__ void __launch_bounds__(256)
       const bool live = v < src.n_local;
       bool flag = false;
       if (live) {
-        const float best = state[v * 3 + 0], second = state[v * 3 + 1];
-        const int chunk = __float_as_int(state[v * 3 + 2]);
+        const float4 rec = __ldcs(reinterpret_cast<const float4 *>(state) + v);  // streamed: keep the rows in L1
+        const float best = rec.x, second = rec.y;
+        const int chunk = __float_as_int(rec.z);
         float x[DIM], xn = 0.f;
         gather_lattice<DIM>(src, v, x);
 #pragma unroll
@@ -447,8 +449,9 @@ __global__ void __launch_bounds__(1024, 1)
        v += (unsigned long long)gridDim.x * blockDim.x) {
     bool flag = false;
     if (v < src.n_local) {
-      const float best = state[v * 3 + 0], second = state[v * 3 + 1];
-      const int chunk = __float_as_int(state[v * 3 + 2]);
+      const float4 rec = __ldcs(reinterpret_cast<const float4 *>(state) + v);  // streamed: keep the rows in L1
+      const float best = rec.x, second = rec.y;
+      const int chunk = __float_as_int(rec.z);
       float x[DIM], xn = 0.f;
       gather_lattice<DIM>(src, v, x);
 #pragma unroll

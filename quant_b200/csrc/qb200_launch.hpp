@@ -53,7 +53,7 @@ struct AssignTcLaunch {
   int K;              // real codevectors
   float margin_coef;
   const float *c_max_ptr;  // device
-  float *state;       // n_local * 3 floats: per-query (best, second, chunk) records between the passes and the finalise kernel
+  float *state;       // n_local float4: per-query (best, second, chunk, -) records between the passes and the finalise kernel
   uint32_t *assign, *flag_list;
   unsigned int *flag_count;
   int sm_count;
