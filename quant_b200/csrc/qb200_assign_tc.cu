@@ -290,10 +290,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 //
 // The chunk's 8 rows are contiguous (8 * ROW32 floats).  Gathering them one query per thread touches 32
 // different cache lines per warp-wide load and the L1 tag stage (one line per clock) becomes the bound,
-// so for 16-float rows (dim 12..15) EIGHT LANES SHARE ONE QUERY: at step i lane j reads float4 number
-// 8*i + j of the chunk (8 lanes = one 128-byte line), which is columns 4*(j%4).. of row 2*i + j/4; the four
-// lanes of a row add their partial dot products with two shuffles, each half-group keeps the best of its
-// four rows and one more shuffle merges the halves.  4 lines per warp-wide load instead of 32.
+// so for 16-float rows (dim 12..15) FOUR LANES SHARE ONE QUERY, each owning one 16-byte column block of every
+// row: a warp-wide load then touches 8 half-lines instead of 32 lines, and the per-query bookkeeping is
+// replicated 4 times instead of 32 (measured balance between L1 tag rate and instruction count).
 template <int DIM>
 __global__ void __launch_bounds__(256)
     tc_finalize_kernel(const VecSource src, const float *__restrict__ rows32, const float *__restrict__ state,
@@ -303,25 +302,27 @@ __global__ void __launch_bounds__(256)
   const float c_max_norm = *c_max_ptr;
   const int lane = threadIdx.x & 31;
   if constexpr (ROW32 == 16) {
-    const int j = lane & 7, cb = j & 3;  // lane inside the query group; column block of this lane
-    const unsigned int gmask = 0xFFu << (lane & 24);  // the eight lanes of this group: a dead group skips the shuffles
-    const unsigned long long gthread = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long n_groups = (unsigned long long)gridDim.x * blockDim.x / 8;
-    const unsigned long long n_round = (src.n_local + 3ull) & ~3ull;  // 4 queries per warp per round
-    for (unsigned long long v = gthread >> 3; v < n_round; v += n_groups) {
-      const bool live = v < src.n_local;
+    // FOUR lanes share one query: lane j owns column block j (floats 4j..4j+3 of every row), at step i the
+    // group reads the four float4 of candidate row i (64 contiguous bytes), each lane forms its partial dot
+    // product and two shuffles complete the row's score in all four lanes.
+    const int j = lane & 3;
+    const unsigned int gmask = 0xFu << (lane & 28);  // the four lanes of this group: a dead group skips the shuffles
+    const unsigned int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int n_groups = gridDim.x * blockDim.x / 4;
+    const unsigned int n_local = (unsigned int)src.n_local;  // the fast path implies < 2^32 vectors
+    const unsigned int n_round = (n_local + 7u) & ~7u;       // 8 queries per warp per round
+    for (unsigned int v = gthread >> 2; v < n_round; v += n_groups) {
       bool flag = false;
-      if (live) {
+      if (v < n_local) {
         const float4 rec = __ldcs(reinterpret_cast<const float4 *>(state) + v);  // streamed: keep the rows in L1
-        const float best = rec.x, second = rec.y;
         const int chunk = __float_as_int(rec.z);
-        // this lane's four extended coordinates [x, 1, 0, 0][4*cb .. 4*cb+3], and |x|^2 via the group
-        float xe[4], part = 0.f;
+        // this lane's four extended coordinates [x, 1, 0, 0][4j .. 4j+3]
+        float xe[4];
         if (src.fast) {
           const signed char *p = fast_vec_ptr(src, v);
 #pragma unroll
           for (int t = 0; t < 4; t++) {
-            const int e = 4 * cb + t;
+            const int e = 4 * j + t;
             xe[t] = e < DIM ? (float)(int)__ldg(p + src.elem_off[e < DIM ? e : 0]) : (e == DIM ? 1.f : 0.f);
           }
         } else {
@@ -329,37 +330,34 @@ __global__ void __launch_bounds__(256)
           vec_base(src, v, base, img);
 #pragma unroll
           for (int t = 0; t < 4; t++) {
-            const int e = 4 * cb + t;
+            const int e = 4 * j + t;
             xe[t] = e < DIM ? (float)load_lattice(src, img, base, e < DIM ? e : 0) : (e == DIM ? 1.f : 0.f);
           }
         }
+        float part = 0.f;
 #pragma unroll
-        for (int t = 0; t < 4; t++) part = (4 * cb + t) < DIM ? fmaf(xe[t], xe[t], part) : part;
+        for (int t = 0; t < 4; t++) part = (4 * j + t) < DIM ? fmaf(xe[t], xe[t], part) : part;
         part += __shfl_xor_sync(gmask, part, 1);
         part += __shfl_xor_sync(gmask, part, 2);
         const float rr = sqrtf(part) + c_max_norm;
-        flag = !((second - best) > margin_coef * rr * rr);
-        const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * ROW32);
+        flag = !((rec.y - rec.x) > margin_coef * rr * rr);
+        const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * ROW32) + j;
         float sb = FLT_MAX;
         int rbest = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 c = __ldg(rows + i * 8 + j);
+        for (int i = 0; i < 8; i++) {
+          const float4 c = __ldg(rows + i * 4);
           float p = xe[0] * c.x;
           p = fmaf(xe[1], c.y, p);
           p = fmaf(xe[2], c.z, p);
           p = fmaf(xe[3], c.w, p);
           p += __shfl_xor_sync(gmask, p, 1);
           p += __shfl_xor_sync(gmask, p, 2);
-          const int row = 2 * i + (j >> 2);
           if (p < sb) {
             sb = p;
-            rbest = row;
+            rbest = i;
           }
         }
-        const float so = __shfl_xor_sync(gmask, sb, 4);
-        const int ro = __shfl_xor_sync(gmask, rbest, 4);
-        if (so < sb || (so == sb && ro < rbest)) rbest = ro;
         if (j == 0) assign[v] = (uint32_t)(chunk * 8 + rbest);
         flag = flag && j == 0;
       }
@@ -543,7 +541,7 @@ static cudaError_t launch_tc_t(const AssignTcLaunch &a) {
     count_launch();
     return cudaGetLastError();
   }
-  const unsigned long long per_block = Cfg::ROW32 == 16 ? 32 : 256;  // queries per 256-thread block per round
+  const unsigned long long per_block = Cfg::ROW32 == 16 ? 64 : 256;  // queries per 256-thread block per round
   unsigned long long blocks = (a.src.n_local + per_block - 1) / per_block;
   const unsigned long long cap = (unsigned long long)a.sm_count * 8;
   if (blocks > cap) blocks = cap;
