@@ -196,6 +196,12 @@ class Context:
         self._check(self.lib.qb200_decode(self.h, _ptr(cbb), cbb.shape[0], _ptr(out), C.byref(mse)))
         return out, mse.value
 
+    def filter_records(self) -> np.ndarray:
+        """(num_vectors, 4) float32 records of the last tensor-core filter pass: best, second, chunk bits, 0."""
+        out = np.empty((self.num_vectors, 4), np.float32)
+        self._check(self.lib.qb200_debug_filter_records(self.h, _ptr(out)))
+        return out
+
     def measure_fp32_peak(self) -> float:
         v = C.c_double()
         self._check(self.lib.qb200_measure_fp32_peak(self.h, C.byref(v)))

@@ -234,9 +234,12 @@ int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uin
     a.b_staged = (const unsigned char *)ctx->d_rows_tc.p;
     a.rows32 = (const float *)ctx->d_rows.p;
     a.K = (int)K;
-    // per-score bound: 3*(dim+1) exact products accumulated in FP32 (allowing truncation: 2^-23 each) plus
-    // the limb residual, relative to (|X| + |C|)^2; the margin is three times that (see qb200_assign_tc.cu)
-    a.margin_coef = 3.0f * (float)(3 * (dim + 1) + 2) * 1.1920929e-7f;
+    // Per-score error bound in units of 2^-23 * (|X| + |C|)^2: every MMA (16 exact products + the accumulator) may
+    // lose up to one unit per addend to alignment truncation inside the tensor core - 17 units x 3 limbs x KB K
+    // blocks - plus the limb residual of |C|^2 and the FP32 rounding of C (4 units).  The margin is three times the
+    // bound: a decided query's best score then beats every other one by more than the bound, which is also more than
+    // twice the FP32 bound the finalise kernel's rescoring needs (see qb200_assign_tc.cu).
+    a.margin_coef = 3.0f * (float)(17 * 3 * tc_kblocks(dim) + 4) * 1.1920929e-7f;
     a.c_max_ptr = c_max_ptr;
     a.state = (float *)ctx->d_state.p;
     a.assign = (uint32_t *)ctx->d_assign.p;
@@ -1167,6 +1170,15 @@ int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *orde
     for (size_t i = 0; i < K; i++) order_out[i] = t.order[i];
   if (n_nodes_out) *n_nodes_out = (int)t.nodes.size();
   if (depth_out) *depth_out = t.depth;
+  return QB200_OK;
+}
+
+int qb200_debug_filter_records(qb200_ctx *ctx, float *records_out) {
+  if (!ctx || !records_out) return QB200_ERR_ARG;
+  if (!ctx->have_set || !ctx->d_state.p) return fail(ctx, QB200_ERR_STATE, "no tensor-core filter pass has run");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(records_out, ctx->d_state.p, (size_t)ctx->src.n_local * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return QB200_OK;
 }
 
