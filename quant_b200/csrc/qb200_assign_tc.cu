@@ -12,12 +12,13 @@
 // the three limbs are three accumulating MMAs into the same FP32 accumulator in tensor memory.
 // All products are exact in FP32; the error is limb truncation + FP32 accumulation of 3*(dim+1) terms.
 //
-// Roles inside the one persistent CTA per SM (544 threads):
+// Roles inside the one persistent CTA per SM (544 threads with one producer group):
 //   warp 0        barrier setup, TMEM allocation, one lane issues TMA staging of the codebook and all MMAs
-//   warps 1-4     producers: thread r gathers the bytes of query r of a tile and writes its bf16 A row
-//   warps 5-8     mergers: thread r merges the two column halves of query r and stores its record
+//   warps 1-4     producers (kProdGroups groups of four): thread r gathers the bytes of query r
+//                 of a tile and writes its bf16 A row
+//   next 4 warps  mergers: thread r merges the two column halves of query r and stores its record
 //                 (best, second, chunk) - tc_finalize_kernel turns records into indices and flags
-//   warps 9-16    epilogue: two warps per TMEM lane quarter, each scanning half of the N columns with
+//   last 8 warps  epilogue: two warps per TMEM lane quarter, each scanning half of the N columns with
 //                 tcgen05.ld and tracking (best, second, chunk-of-8 index) in registers with min/max ops:
 //                 2.75 alu operations per distance evaluation - this, not the tensor pipe, is the bound
 // Pipelines: ring of 4 A tiles in shared memory (a_full/a_empty), accumulator double-buffered in
@@ -36,7 +37,8 @@ namespace qb {
 
 namespace {
 
-constexpr int kTcThreads = 32 * 17;  // 1 MMA + 4 producer + 4 finaliser + 8 epilogue warps
+constexpr int kProdGroups = 1;          // producer groups of 4 warps taking alternate tiles (2 measured slower: register cap)
+constexpr int kTcThreads = 32 * (1 + 4 * kProdGroups + 4 + 8);  // MMA + producer + merger + epilogue warps
 constexpr int kAStages = 4;            // A tiles in flight (shared memory ring)
 constexpr int kResStages = 4;          // per-tile result records in flight
 constexpr int kTileQ = 128;  // queries per tile = MMA M = TMEM lanes
@@ -149,12 +151,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         umma_commit(&sh.a_empty[ab]);
       }
     }
-  } else if (warp <= 4) {
+  } else if (warp <= 4 * kProdGroups) {
     // =========================== producers: gather query bytes, write bf16 A rows ===========================
-    const int r = (warp - 1) * 32 + lane;  // query row inside a tile
+    // kProdGroups groups of 128 threads take alternate tiles: a tile costs one global-memory round trip per
+    // thread, two groups keep two tiles in flight.
+    const int group = (warp - 1) >> 2;
+    const int r = ((warp - 1) & 3) * 32 + lane;  // query row inside a tile
     const uint32_t row_off = (uint32_t)(r >> 3) * 256u + (uint32_t)(r & 7) * 16u;
-    unsigned int tile_seq = 0;
-    for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
+    unsigned int tile_seq = group;
+    for (unsigned long long tile = blockIdx.x + (unsigned long long)group * gridDim.x; tile < tiles;
+         tile += (unsigned long long)kProdGroups * gridDim.x, tile_seq += kProdGroups) {
       float x[DIM];
       const unsigned long long v = tile * kTileQ + r;
       if (v < src.n_local) {
@@ -184,11 +190,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&sh.a_full[ab]);
     }
-  } else if (warp <= 8) {
+  } else if (warp <= 4 * kProdGroups + 4) {
     // =========================== mergers: combine the two column halves, store the per-query record ===========================
     // No dependent global loads here (they would serialise one tile per memory round trip); the margin
     // test and the index inside the winning chunk are done by tc_finalize_kernel after the last pass.
-    const int r = (warp - 5) * 32 + lane;
+    const int r = (warp - 1 - 4 * kProdGroups) * 32 + lane;
     unsigned int tile_seq = 0;
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
       const unsigned long long v = tile * kTileQ + r;
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   } else {
     // =========================== epilogue: TMEM -> registers -> running top-2 ===========================
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter + 32) are the ones this warp may read
-    const int half = (warp - 9) >> 2;      // which half of the N columns
+    const int half = (warp - 5 - 4 * kProdGroups) >> 2;  // which half of the N columns
     const int r = quarter * 32 + lane;     // query row = TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     unsigned int it = 0, tile_seq = 0;
