@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
     for (int q = 0; q < Q; q++) {
       const unsigned long long v = v0 + (unsigned long long)q * THREADS + tid;
       // which member of the winning pair: the same FMA sequence on the same operands gives the
-      // same bits as the loop did (rows come from global memory: the chunk may be gone from smem)
+      // same bits as the loop did (rows from global memory / L1: measured faster than divergent shared-memory reads)
       const float *r0 = cb_rows + (size_t)bpair[q] * ROW;
       float t0 = __ldg(r0 + DIM), t1 = __ldg(r0 + ROW + DIM);
 #pragma unroll
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
   }
 }
 
-// Early split levels (K <= 8; the kernel itself handles up to 16): filter + per-cell statistics in ONE high-occupancy pass.  With a handful of
+// Early split levels (K <= 16): filter + per-cell statistics in ONE high-occupancy pass.  With a handful of
 // codevectors the work per vector is tiny, so the persistent one-CTA-per-SM kernel above and a separate
 // accumulate pass are both dominated by their fixed costs; here every thread takes one vector per iteration,
 // scores it against the K rows (shared memory, broadcast reads), applies the same margin rule, and the
@@ -349,14 +349,20 @@ __global__ void __launch_bounds__(256)
       const int a = (live && !flag) ? bidx : -1;
       const unsigned int group = __match_any_sync(0xffffffffu, a);
       const bool lead = a >= 0 && lane == __ffs(group) - 1;
+      // t = L + 128 in [0, 255]: two coordinates per register, 16 bits each (32 lanes x 255 < 2^16), so one REDUX
+      // sums two coordinates; the table holds sums of t and is turned back into sums of L when it is flushed
       int *row = s_s + (a >= 0 ? a : 0) * DIM;
       int qs = 0;
 #pragma unroll
-      for (int e = 0; e < DIM; e++) {
-        const int L = a >= 0 ? (int)x[e] : 0;
-        qs += L * L;
-        const int sv = __reduce_add_sync(group, L);
-        if (lead && sv != 0) atomicAdd(row + e, sv);
+      for (int e = 0; e < DIM; e += 2) {
+        const int L0 = a >= 0 ? (int)x[e] : -128;
+        const int L1 = (e + 1 < DIM && a >= 0) ? (int)x[e + 1 < DIM ? e + 1 : e] : -128;
+        qs += (a >= 0 ? L0 * L0 : 0) + ((e + 1 < DIM && a >= 0) ? L1 * L1 : 0);
+        const unsigned int sv = __reduce_add_sync(group, (unsigned int)(L0 + 128) | ((unsigned int)(L1 + 128) << 16));
+        if (lead) {
+          if (sv & 0xffffu) atomicAdd(row + e, (int)(sv & 0xffffu));
+          if (e + 1 < DIM && (sv >> 16)) atomicAdd(row + e + 1, (int)(sv >> 16));
+        }
       }
       const unsigned int qsum = __reduce_add_sync(group, (unsigned int)qs);
       if (lead) {
@@ -375,11 +381,9 @@ __global__ void __launch_bounds__(256)
       }
     }
     for (int i = threadIdx.x; i < K * DIM; i += blockDim.x) {
-      const int sv = s_s[i];
-      if (sv != 0) {
-        const int k = i / DIM, e = i - k * DIM;
-        atomicAdd(stats + (size_t)k * (DIM + 2) + 1 + e, (unsigned long long)(long long)sv);
-      }
+      const int k = i / DIM, e = i - k * DIM;
+      const int sv = s_s[i] - 128 * s_n[k];  // sum of t -> sum of L
+      if (sv != 0) atomicAdd(stats + (size_t)k * (DIM + 2) + 1 + e, (unsigned long long)(long long)sv);
     }
   }
 }
@@ -834,10 +838,16 @@ __global__ void __launch_bounds__(1024, 1)
     const unsigned int group = __match_any_sync(0xffffffffu, a);
     const bool leader = a >= 0 && lane == __ffs(group) - 1;
     int *row = s_s + (a >= 0 ? a : 0) * DIM;
+    // two coordinates per REDUX: t = L + 128 in [0, 255], 16 bits each (the table holds sums of t, see the flush)
 #pragma unroll
-    for (int e = 0; e < DIM; e++) {
-      const int sv = __reduce_add_sync(group, L[e]);
-      if (leader && sv != 0) atomicAdd(row + e, sv);
+    for (int e = 0; e < DIM; e += 2) {
+      const unsigned int t0 = a >= 0 ? (unsigned int)(L[e] + 128) : 0u;
+      const unsigned int t1 = (e + 1 < DIM && a >= 0) ? (unsigned int)(L[e + 1 < DIM ? e + 1 : e] + 128) : 0u;
+      const unsigned int sv = __reduce_add_sync(group, t0 | (t1 << 16));
+      if (leader) {
+        if (sv & 0xffffu) atomicAdd(row + e, (int)(sv & 0xffffu));
+        if (e + 1 < DIM && (sv >> 16)) atomicAdd(row + e + 1, (int)(sv >> 16));
+      }
     }
     const unsigned int qs = __reduce_add_sync(group, (unsigned int)q);  // <= 32 * DIM * 128^2: fits
     if (leader) {
@@ -854,11 +864,9 @@ __global__ void __launch_bounds__(1024, 1)
     }
   }
   for (int i = threadIdx.x; i < k_count * DIM; i += blockDim.x) {
-    const int sv = s_s[i];
-    if (sv != 0) {
-      const int k = i / DIM, e = i - k * DIM;
-      atomicAdd(stats + (size_t)(k_base + k) * (DIM + 2) + 1 + e, (unsigned long long)(long long)sv);
-    }
+    const int k = i / DIM, e = i - k * DIM;
+    const int sv = s_s[i] - 128 * s_n[k];  // sum of t -> sum of L
+    if (sv != 0) atomicAdd(stats + (size_t)(k_base + k) * (DIM + 2) + 1 + e, (unsigned long long)(long long)sv);
   }
 }
 
@@ -1193,7 +1201,7 @@ int assign_row_floats(int dim) { return ((dim + 1 + 3) / 4) * 4; }
 template <int DIM>
 static cudaError_t launch_assign_t(const AssignLaunch &a) {
   using Cfg = AssignCfg<DIM>;
-  if (a.k_real <= 8) {  // early split levels: one fused high-occupancy pass (measured: slower than two passes at 16)
+  if (a.k_real <= 16) {  // early split levels: one fused high-occupancy pass
     unsigned long long blocks = (a.src.n_local + 255) / 256;
     const unsigned long long cap = (unsigned long long)a.sm_count * 8;
     if (blocks > cap) blocks = cap;
