@@ -74,7 +74,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except OSError:
@@ -281,8 +281,9 @@ def run_gpu_arm(args):
     fp32_peak = ctx.measure_fp32_peak() if rank == 0 else None
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res, reps, launches, (t0, t1), cb_res, d_res = timed("resident", args.steps, args.warmup)
-    clocks = sampler.stop(t0, t1) if sampler else None
-    ms_e2e, _, _, _, cb_e2e, d_e2e = timed("e2e", args.steps, args.warmup)
+    ms_e2e, _, _, (t2, t3), cb_e2e, d_e2e = timed("e2e", args.steps, args.warmup)
+    # clocks over both timed regions (a train lasts milliseconds: the e2e warm-up in between is under load as well)
+    clocks = sampler.stop(t0, t3) if sampler else None
     assert np.array_equal(cb_res, cb_e2e) and d_res == d_e2e, "resident and e2e trains disagree"
 
     if rank == 0:
@@ -324,9 +325,9 @@ def run_gpu_arm(args):
                             "evaluation, ncu: profiles/), not by the tensor pipe",
                     "ms_per_launch": ms_assign,
                     # dram__bytes_read.sum + dram__bytes_write.sum of the K=1024 assign_tc_kernel launch on this workload,
-                    # one `ncu --set full` capture (profiles/r1_assign_tc_k1024_ncu_summary.txt): 50.5 MB + 20.1 MB
+                    # one `ncu --set full` capture (profiles/r1_assign_tc_k1024_ncu_summary.txt): 50.7 MB + 23.1 MB
                     # (image bytes in; 16-byte per-query records out, part of which stays in L2)
-                    "traffic": 70.6e6 if (wl == "c2" and world == 1) else None,
+                    "traffic": 73.8e6 if (wl == "c2" and world == 1) else None,
                     "traffic_algorithmic": float(n_local) * dim}
         else:
             roof = {"bound": "fp32", "kernel": f"assign_kernel<{dim}> at K={K}, last split level", "achieved": fp32_equiv,
