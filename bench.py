@@ -394,6 +394,100 @@ def emit(line):
 _JSON_FD = None
 
 
+def run_encode_arm(args):
+    """BASELINE config 5: encode-only assignment of a batch of Kodak-shaped images against a fixed trained
+    1024-entry codebook (the body of Solution::assignCodeVectors = KDTree + nearestNeighbour per vector).
+    A step is one assignment pass over the batch; value = N*K / time.  No collective: ranks take batches."""
+    import torch
+    import quant_b200 as qb
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    xs, ys, w, h, nbits, n_img = 768, 512, 2, 2, 10, args.images
+    K, dim = 1 << nbits, 12
+    n_local = n_img * (xs // w) * (ys // h)
+    stream = torch.cuda.Stream()
+    ctx = qb.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(1234 + rank)
+    host = torch.empty(n_img * xs * ys * 3, dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = rng.integers(0, 256, host.numel(), dtype=np.uint8)
+    host_assign = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    with torch.cuda.stream(stream):
+        ctx.set_image(host.numpy()[: xs * ys * 3], xs, ys, w, h, qb.CS_SCALED)
+        codebook, _, _ = ctx.train(nbits)                       # the fixed codebook: trained on the first image
+        dev = host.to("cuda", non_blocking=True)
+    stream.synchronize()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def run(n, mode):
+        total, last = 0.0, None
+        for _ in range(n):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                if mode == "resident":
+                    last = ctx.assign_only(codebook)
+                else:
+                    ctx.set_image(host.numpy(), xs, ys, w, h, qb.CS_SCALED, n_images=n_img)
+                    last = ctx.assign_only(codebook)
+                    ctx.get_assign(out=host_assign.numpy().view(np.uint32))
+                e1.record(stream)
+                e1.synchronize()
+                total += e0.elapsed_time(e1)
+        return total, last
+
+    def timed(mode):
+        if mode == "resident":
+            ctx.set_image_device(dev.data_ptr(), xs, ys, w, h, qb.CS_SCALED, n_images=n_img, keep=dev)
+        run(args.warmup, mode)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        qb.launch_count(reset=True)
+        ms, last = run(args.steps, mode)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches = qb.launch_count()
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last, launches
+
+    ms_res, last, launches = timed("resident")
+    ms_e2e, _, _ = timed("e2e")
+    if rank == 0:
+        evals = float(n_local) * world * K
+        line = {"metric": "encode-only Gdist-evals/s (N*K per assignment pass)", "value": evals * args.steps / (ms_res * 1e-3) / 1e9,
+                "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16x3 tensor-core filter + f64 exact re-check", "data": "synthetic",
+                "config": {"workload": f"encode-only: {n_img} synthetic noise 768x512 images per rank, 2x2 block, against a fixed "
+                                       f"trained 1024-entry codebook ({n_local} vectors per rank)",
+                           "l2": "512 MiB flush before every timed step"},
+                "e2e": {"value": evals * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(host.numel()) * world, "d2h_bytes_per_step": n_local * 4 * world},
+                "gpu_launches": launches, "flagged": last["flagged"],
+                "ms_filter": last["ms_assign"], "ms_resolver": last["ms_resolve"]}
+        emit(line)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -401,7 +495,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--images", type=int, default=1024, help="images per rank of the encode-only workload c5")
     ap.add_argument("--cpu-budget", type=float, default=None, help="seconds of CPU work for the CPU arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--strong", action="store_true",
@@ -410,6 +505,10 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.cpu_budget is None:
         args.cpu_budget = 120.0 if args.impl == "reference" else 20.0
+    if args.workload == "c5":
+        if args.impl == "reference":
+            raise SystemExit("--workload c5 has no reference arm (the reference has no encode-only entry point)")
+        sys.exit(run_encode_arm(args))
     sys.exit(run_reference_arm(args) if args.impl == "reference" else run_gpu_arm(args))
 
 

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "Compressor.hpp"
+#include "KDTree.hpp"
 
 static int failures = 0;
 #define EXPECT(cond)                                                        \
@@ -68,6 +69,20 @@ static int test_quantize(const std::string &ppm, int w, int h, int n) {
   EXPECT(chars == res.first.codeVectors);
   EXPECT(std::get<1>(out) == res.first.assignedCodeVector);
   EXPECT(std::get<2>(out) >= 0);
+  // the public nearest-neighbour class against the returned codebook: one more LBG assignment step
+  {
+    KDTree tree(vecs[0].size(), std::get<0>(out));
+    std::vector<size_t> nn = tree.nearestNeighbours(vecs);
+    EXPECT(nn.size() == vecs.size());
+    size_t worse = 0;
+    for (size_t i = 0; i < vecs.size(); i += 97) {
+      const double d_nn = norm(vecs[i] - std::get<0>(out)[nn[i]]);
+      for (size_t k = 0; k < std::get<0>(out).size(); k += 7) worse += norm(vecs[i] - std::get<0>(out)[k]) < d_nn;
+      EXPECT(tree.nearestNeighbour(vecs[i]) == nn[i]);
+      if (i > 97 * 20) break;
+    }
+    EXPECT(worse == 0);
+  }
   bool threw = false;
   try {
     q->quantize(std::vector<Vector>(), n, 1e-6f);
