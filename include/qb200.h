@@ -66,9 +66,9 @@ typedef struct qb200_level_report {
   uint32_t kd_depth;      /* depth of the nanoflann-order KD tree built for the resolver */
   uint32_t iterations;    /* assignment passes of this level (1 in QB200_MODE_PARITY) */
   uint32_t repaired;      /* empty cells re-seeded at this level (QB200_MODE_FULL_REPAIR) */
-  float ms_assign;        /* device time of the FP32 assignment kernel */
+  float ms_assign;        /* device time of the filter (codebook staging + tensor-core or CUDA-core kernel [+ finalise]) */
   float ms_resolve;       /* device time of the exact resolver kernels (brute force + tree walk) */
-  float ms_accumulate;    /* device time of the per-cell statistics kernel */
+  float ms_accumulate;    /* device time of the separate per-cell statistics kernel (~0 when the filter accumulates) */
   double distortion_pre;  /* updateDistortion() before fixCodeVectors (src/Quantizer.cpp:100) */
   double distortion_post; /* updateDistortion() after fixCodeVectors  (src/Quantizer.cpp:104) */
 } qb200_level_report;

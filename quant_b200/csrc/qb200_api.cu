@@ -1,8 +1,9 @@
 // C ABI of libqb200 (include/qb200.h) and the host-side level driver.
 //
 // The driver restates LBGQuantizer::quantize + Solution::LBGIterate
-// (/root/reference/src/Quantizer.cpp:98-143) around three kernels per split level
-// (assign -> resolve -> accumulate) and an O(K*dim) FP64 finalisation on the host.
+// (/root/reference/src/Quantizer.cpp:98-143): per split level stage -> filter -> resolve -> statistics ->
+// centroids/distortion/split.  The HEAD schedule runs without host round trips between levels
+// (train_parity_pipelined); the extension schedules finalise each iteration on the host.
 #include "../../include/qb200.h"
 
 #include <algorithm>
@@ -141,7 +142,7 @@ struct LevelLayout {
   uint32_t K_rows;  // staged FP32 rows
   bool use_tc;
   size_t rows_bytes, tc_bytes, cb_bytes, max_nodes;
-  size_t off_tc, off_cb, off_nodes, off_vind, off_bbox, off_cnt, total;
+  size_t off_cb, off_nodes, off_vind, off_bbox, off_cnt, total;
 };
 
 bool tc_enabled() {
@@ -180,7 +181,6 @@ LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
   L.cb_bytes = (size_t)K * dim * 8;
   L.max_nodes = 2 * (size_t)K + 8;
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  L.off_tc = 0;
   L.off_cb = 0;
   L.off_nodes = up(L.off_cb + L.cb_bytes);
   L.off_vind = L.off_nodes + L.max_nodes * sizeof(KdNode);

@@ -1,19 +1,25 @@
-// Hand-written sm_100a kernels of the LBG hot path and their launchers.
+// Hand-written sm_100a kernels of the LBG hot path and their launchers (the tensor-core filter lives in
+// qb200_assign_tc.cu).
 //
-//   assign_kernel      Solution::assignCodeVectors   (/root/reference/src/Quantizer.cpp:24-32)
-//                      brute-force FP32 nearest-codevector FILTER over raw image bytes
-//   resolve_kernel     KDTree::nearestNeighbour      (/root/reference/src/KDTree.cpp:20-29 ->
-//                      nanoflann.hpp:906-920,1188-1270,320-345) exact FP64 re-solve of the queries
-//                      the filter could not decide
-//   accumulate_*       fixCodeVectors / updateDistortion as integer per-cell statistics
-//                      (/root/reference/src/Quantizer.cpp:9-22,59-87)
-//   decode_kernel      decompress + getImageFromVectors (/root/reference/src/Compressor.cpp:64-92,156-165)
+//   stage_codebook_kernel   FP64 codebook -> FP32 rows, bf16 limb tiles, transposed FP64 copy, max|C|
+//   assign_kernel           Solution::assignCodeVectors   (/root/reference/src/Quantizer.cpp:24-32)
+//                           brute-force FP32 (FFMA2) nearest-codevector FILTER over raw image bytes, K < 256
+//   small_k_fused_kernel    the same filter + per-cell statistics in one pass for the first split levels (K <= 16)
+//   resolve_bruteforce_kernel / resolve_kernel
+//                           KDTree::nearestNeighbour      (/root/reference/src/KDTree.cpp:20-29 ->
+//                           nanoflann.hpp:906-920,1188-1270,320-345) exact FP64 re-solve of the queries
+//                           the filter could not decide: brute force, then the reference's tree walk for ties
+//   accumulate_*            fixCodeVectors / updateDistortion as integer per-cell statistics
+//                           (/root/reference/src/Quantizer.cpp:9-22,59-87)
+//   finalize_split_kernel   centroids, distortions and the next split (src/Quantizer.cpp:81-85,134-138) on the device
+//   pick_members_kernel / fetch_members_kernel   empty-cell repair (extension)
+//   decode_kernel           decompress + getImageFromVectors (/root/reference/src/Compressor.cpp:64-92,156-165)
 //
 // Why a filter + resolver: the reference computes everything in FP64 (include/VectorOperations.hpp:10)
-// and breaks exact ties by KD-tree traversal order.  FP32 cannot reproduce that bit-for-bit, so the
-// FP32 pass only decides queries whose best and second-best scores differ by more than a rigorous
-// bound on its own rounding error; all others are appended to a list and re-solved by walking the
-// reference's tree with the reference's arithmetic.
+// and breaks exact ties by KD-tree traversal order.  Reduced precision cannot reproduce that bit-for-bit, so
+// a filter pass only decides queries whose best and second-best scores differ by more than a rigorous
+// bound on its own rounding error; all others are appended to a list and re-solved with the reference's
+// arithmetic and tie order.
 #include "qb200_launch.hpp"
 #include "qb200_ptx.cuh"
 
