@@ -486,6 +486,22 @@ __device__ __forceinline__ double nanoflann_l2(const double *a, const double *__
   return result;
 }
 
+// Compile-time dimension: fully unrolled (loads issued back to back, the query stays in registers).
+template <int DIM>
+__device__ __forceinline__ double nanoflann_l2_t_fixed(const double *a, const double *__restrict__ bt, size_t stride) {
+  double result = 0.0;
+#pragma unroll
+  for (int d = 0; d + 3 < DIM; d += 4) {
+    const double g = __dadd_rn(__dadd_rn(__dadd_rn(sq_diff(a[d], bt[d * stride]), sq_diff(a[d + 1], bt[(d + 1) * stride])),
+                                         sq_diff(a[d + 2], bt[(d + 2) * stride])),
+                               sq_diff(a[d + 3], bt[(d + 3) * stride]));
+    result = __dadd_rn(result, g);
+  }
+#pragma unroll
+  for (int d = DIM & ~3; d < DIM; d++) result = __dadd_rn(result, sq_diff(a[d], bt[d * stride]));
+  return result;
+}
+
 // Same arithmetic on the TRANSPOSED codebook (element e of codevector k at bt[e * stride + k]): lanes that
 // hold consecutive k read consecutive doubles, so a warp-wide load touches 2 cache lines instead of 32.
 __device__ __forceinline__ double nanoflann_l2_t(const double *a, const double *__restrict__ bt, size_t stride, int dim) {
@@ -514,14 +530,14 @@ __device__ __forceinline__ double nanoflann_l2_t(const double *a, const double *
 // below the FP32 filter's margin).  EXACT ties (all candidates bitwise equal) are decided by the tree's
 // visiting order without a walk (see below); what remains - distinct distances closer than the band, or
 // more than 32 candidates - goes to the tie list and phase B walks the tree.
-template <int DIMCAP>
+template <int DIMCAP, int DIMT>  // DIMT != 0: dimension known at compile time (== DIMCAP)
 __global__ void __launch_bounds__(128)
     resolve_bruteforce_kernel(const VecSource src, const int scaled, const double *__restrict__ cbt, const int K,
                               const KdDevice tree, const uint32_t *__restrict__ flag_list,
                               const unsigned int *__restrict__ flag_count, uint32_t *__restrict__ assign,
                               uint32_t *__restrict__ tie_list, unsigned int *__restrict__ tie_count,
                               unsigned int *__restrict__ changed, unsigned long long *__restrict__ stats) {
-  const int dim = src.dim;
+  const int dim = DIMT ? DIMT : src.dim;
   const unsigned int total = *flag_count;
   const int lane = threadIdx.x & 31;
   const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -531,14 +547,15 @@ __global__ void __launch_bounds__(128)
     const unsigned long long v = flag_list[f];
     unsigned long long base, img;
     vec_base(src, v, base, img);
-    for (int e = 0; e < dim; e++) {
+#pragma unroll
+    for (int e = 0; e < (DIMT ? DIMT : dim); e++) {
       const double L = (double)load_lattice(src, img, base, e);
       x[e] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
     }
     double d1 = DBL_MAX, d2 = DBL_MAX, dmax = 0.0;  // this lane's smallest, second smallest, largest
     int k1 = 0;
     for (int k = lane; k < K; k += 32) {
-      const double d = nanoflann_l2_t(x, cbt + k, (size_t)K, dim);
+      const double d = DIMT ? nanoflann_l2_t_fixed<DIMT ? DIMT : 1>(x, cbt + k, (size_t)K) : nanoflann_l2_t(x, cbt + k, (size_t)K, dim);
       dmax = fmax(dmax, d);
       if (d < d1) {
         d2 = d1;
@@ -575,7 +592,7 @@ __global__ void __launch_bounds__(128)
         const int k = k0 + lane;
         bool cand = false;
         if (k < K) {
-          const double d = nanoflann_l2_t(x, cbt + k, (size_t)K, dim);
+          const double d = DIMT ? nanoflann_l2_t_fixed<DIMT ? DIMT : 1>(x, cbt + k, (size_t)K) : nanoflann_l2_t(x, cbt + k, (size_t)K, dim);
           cand = d <= lim;
           exact = exact && (!cand || d == wmin);
         }
@@ -604,7 +621,9 @@ __global__ void __launch_bounds__(128)
           const bool any1 = __any_sync(0xffffffffu, in1), any2 = __any_sync(0xffffffffu, in2);
           bool go1;
           if (any1 && any2) {
-            const double val = x[nd.a];
+            double val = 0.0;  // x[nd.a] by selection: a dynamic index would push x[] out of registers
+#pragma unroll
+            for (int e = 0; e < (DIMT ? DIMT : DIMCAP); e++) val = (e == nd.a) ? x[e] : val;
             go1 = __dadd_rn(__dsub_rn(val, nd.divlow), __dsub_rn(val, nd.divhigh)) < 0;  // nearer child first
           } else {
             go1 = any1;
@@ -1284,12 +1303,26 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            unsigned long long *stats, int sm_count, cudaStream_t stream) {
   // phase A: brute force, one warp per flagged query (the count is only known on the device)
   const unsigned int blocks_a = (unsigned int)sm_count * 8;
-  if (src.dim <= 16)
-    resolve_bruteforce_kernel<16><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed, stats);
-  else if (src.dim <= 48)
-    resolve_bruteforce_kernel<48><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed, stats);
-  else
-    resolve_bruteforce_kernel<kMaxDim><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, assign, tie_list, tie_count, changed, stats);
+#define QB_RESOLVE_A(CAP, DT)                                                                                        \
+  resolve_bruteforce_kernel<CAP, DT><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, \
+                                                                   assign, tie_list, tie_count, changed, stats)
+  switch (src.dim) {
+    case 3: QB_RESOLVE_A(3, 3); break;
+    case 6: QB_RESOLVE_A(6, 6); break;
+    case 9: QB_RESOLVE_A(9, 9); break;
+    case 12: QB_RESOLVE_A(12, 12); break;
+    case 24: QB_RESOLVE_A(24, 24); break;
+    case 27: QB_RESOLVE_A(27, 27); break;
+    case 48: QB_RESOLVE_A(48, 48); break;
+    default:
+      if (src.dim <= 16)
+        QB_RESOLVE_A(16, 0);
+      else if (src.dim <= 48)
+        QB_RESOLVE_A(48, 0);
+      else
+        QB_RESOLVE_A(kMaxDim, 0);
+  }
+#undef QB_RESOLVE_A
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
