@@ -54,7 +54,7 @@ struct qb200_ctx {
   const uint8_t *borrowed = nullptr;
 
   // per-vector
-  DevBuf d_assign, d_flags, d_ties;
+  DevBuf d_assign, d_flags, d_ties, d_dense;
   // per-level
   DevBuf d_rows, d_rows_tc, d_state, d_cb64, d_nodes, d_vind, d_bbox, d_stats, d_counters, d_misc;
   // pinned staging
@@ -487,6 +487,15 @@ int repair_empty_cells(qb200_ctx *ctx, uint32_t K, const std::vector<uint64_t> &
 
 int set_common(qb200_ctx *ctx, size_t n_local) {
   int rc;
+  // dense byte copy of the training set: every later gather is a few coalesced word loads
+  {
+    VecSource &s = ctx->src;
+    s.dense = nullptr;
+    s.dense_stride = (unsigned int)((s.dim + 3) & ~3);
+    if ((rc = ensure(ctx, ctx->d_dense, (n_local ? n_local : 1) * (size_t)s.dense_stride + 16))) return rc;
+    CU(launch_pack_vectors(s, (uint8_t *)ctx->d_dense.p, (int)s.dense_stride, ctx->sm_count, ctx->stream));
+    s.dense = (const uint8_t *)ctx->d_dense.p;
+  }
   if ((rc = ensure(ctx, ctx->d_assign, (n_local ? n_local : 1) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->d_flags, (n_local ? n_local : 1) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->d_ties, (n_local ? n_local : 1) * 4))) return rc;
@@ -542,7 +551,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_ties, &ctx->d_rows, &ctx->d_rows_tc, &ctx->d_state, &ctx->d_cb64, &ctx->d_nodes,
+  for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_ties, &ctx->d_dense, &ctx->d_rows, &ctx->d_rows_tc, &ctx->d_state, &ctx->d_cb64, &ctx->d_nodes,
                     &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc, &ctx->d_repair})
     free_buf(*b);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);

@@ -34,6 +34,11 @@ struct VecSource {
   unsigned int hb_mul, hb_shift;       // v / hB        (fastdiv)
   unsigned int pi_mul, pi_shift;       // v / per_image (fastdiv)
   unsigned int row_stride32, img_bytes32, first_vec32, per_image32, origin32;
+  // Dense copy of the training set made once per set_image/set_vectors (pack_vectors_kernel): local vector v is
+  // the dense_stride bytes at dense + v * dense_stride (dim rounded up to a multiple of 4, padding bytes 0).
+  // When present, the hot kernels read whole words from it instead of gathering bytes from the image.
+  const uint8_t *dense;
+  unsigned int dense_stride;
 };
 
 // Division of a 32-bit n by an invariant d (Granlund-Montgomery): q = (t + ((n - t) >> 1)) >> (l - 1),
@@ -94,7 +99,23 @@ __device__ __forceinline__ const signed char *fast_vec_ptr(const VecSource &s, u
 // All DIM lattice values of local vector v (template DIM: fully unrolled, values stay in registers).
 template <int DIM, typename T>
 __device__ __forceinline__ void gather_lattice(const VecSource &s, unsigned long long v_local, T *out) {
-  if (s.fast) {
+  if (s.dense) {
+    constexpr int WORDS = (DIM + 3) / 4;
+    const unsigned int *p = reinterpret_cast<const unsigned int *>(s.dense + v_local * (unsigned long long)s.dense_stride);
+    unsigned int w[WORDS];
+    if constexpr (WORDS % 4 == 0) {  // 16-byte rows (dim 48: 3 x 128-bit loads)
+#pragma unroll
+      for (int i = 0; i < WORDS / 4; i++) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+        w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < WORDS; i++) w[i] = __ldg(p + i);
+    }
+#pragma unroll
+    for (int e = 0; e < DIM; e++) out[e] = (T)(int)(signed char)(w[e >> 2] >> (8 * (e & 3)));
+  } else if (s.fast) {
     const signed char *p = fast_vec_ptr(s, v_local);
 #pragma unroll
     for (int e = 0; e < DIM; e++) out[e] = (T)(int)__ldg(p + s.elem_off[e]);

@@ -1011,6 +1011,40 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// pack_vectors_kernel: getBlocksAsVectorsFromImage (/root/reference/src/Compressor.cpp:31-62) as BYTES
+// ------------------------------------------------------------------------------------------------
+// One thread per 4-byte word of the dense N x stride copy of the training set: gathers four block elements
+// with the reference's layout rule (any shape: padding and the y-overflow wrap are resolved here, once) and
+// stores them coalesced.  The reference materialises 240-byte double vectors at this point; this is 12 bytes.
+__global__ void __launch_bounds__(256) pack_vectors_kernel(const VecSource src, uint8_t *__restrict__ dense, const int stride) {
+  const int words = stride >> 2;
+  const unsigned long long total = src.n_local * (unsigned long long)words;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long v = t / (unsigned int)words;
+    const int wd = (int)(t - v * (unsigned int)words);
+    unsigned int packed = 0;
+    if (src.fast) {
+      const signed char *p = fast_vec_ptr(src, v);
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int e = 4 * wd + b;
+        if (e < src.dim) packed |= (unsigned int)(unsigned char)__ldg(p + src.elem_off[e]) << (8 * b);
+      }
+    } else {
+      unsigned long long base, img;
+      vec_base(src, v, base, img);
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int e = 4 * wd + b;
+        if (e < src.dim) packed |= (unsigned int)(unsigned char)load_lattice(src, img, base, e) << (8 * b);
+      }
+    }
+    reinterpret_cast<unsigned int *>(dense)[t] = packed;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stage_codebook_kernel: FP64 codebook -> what the filters consume, on the device (one thread per row)
 // ------------------------------------------------------------------------------------------------
 // Lattice coordinates C = 255*c - 128 (SCALED) or c (NORMAL), rounded once to FP32.
@@ -1420,6 +1454,17 @@ cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32
   if (blocks > cap) blocks = cap;
   if (blocks == 0) return cudaSuccess;
   decode_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(g, orig, assign, cb_bytes, out, sq_err);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_vectors(const VecSource &src, uint8_t *dense, int stride, int sm_count, cudaStream_t stream) {
+  const unsigned long long total = src.n_local * (unsigned long long)(stride / 4);
+  unsigned long long blocks = (total + 255) / 256;
+  const unsigned long long cap = (unsigned long long)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) return cudaSuccess;
+  pack_vectors_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(src, dense, stride);
   g_launch_count++;
   return cudaGetLastError();
 }

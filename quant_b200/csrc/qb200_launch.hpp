@@ -26,6 +26,8 @@ struct AssignLaunch {
 };
 
 int assign_row_floats(int dim);
+// Dense byte copy of the training set (stride = dim rounded up to 4); src.dense must still be null.
+cudaError_t launch_pack_vectors(const VecSource &src, uint8_t *dense, int stride, int sm_count, cudaStream_t stream);
 // FP64 codebook (device) -> FP32 rows (+ bf16 limb tiles when tc_out != null) + max codevector norm; c_max must be zeroed.
 cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_rows_tc, int dim, int scaled,
                                   float *rows32, unsigned char *tc_out, float *c_max, double *cb_t,
