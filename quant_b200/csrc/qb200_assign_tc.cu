@@ -296,9 +296,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 //
 // The chunk's 8 rows are contiguous (8 * ROW32 floats).  Gathering them one query per thread touches 32
 // different cache lines per warp-wide load and the L1 tag stage (one line per clock) becomes the bound,
-// so for 16-float rows (dim 12..15) FOUR LANES SHARE ONE QUERY, each owning one 16-byte column block of every
-// row: a warp-wide load then touches 8 half-lines instead of 32 lines, and the per-query bookkeeping is
-// replicated 4 times instead of 32 (measured balance between L1 tag rate and instruction count).
+// so for 16-float rows (dim 12..15) FOUR LANES SHARE ONE QUERY, each reading 32 bytes (256-bit load) per step:
+// a warp-wide load then touches 8 whole lines for 8 queries, and the per-query bookkeeping is replicated 4
+// times instead of 32 (measured balance between L1 tag rate and instruction count).
 template <int DIM>
 __global__ void __launch_bounds__(256)
     tc_finalize_kernel(const VecSource src, const float *__restrict__ rows32, const float *__restrict__ state,
@@ -308,62 +308,64 @@ __global__ void __launch_bounds__(256)
   const float c_max_norm = *c_max_ptr;
   const int lane = threadIdx.x & 31;
   if constexpr (ROW32 == 16) {
-    // FOUR lanes share one query: lane j owns column block j (floats 4j..4j+3 of every row), at step i the
-    // group reads the four float4 of candidate row i (64 contiguous bytes), each lane forms its partial dot
-    // product and two shuffles complete the row's score in all four lanes.
-    const int j = lane & 3;
-    const unsigned int gmask = 0xFu << (lane & 28);  // the four lanes of this group: a dead group skips the shuffles
+    // FOUR lanes share one query (src.dense is set by the host).  The chunk's 8 rows are 512 contiguous bytes; at
+    // step i the group reads 128 of them with one 256-bit load per lane: lane j gets the column half h = j & 1
+    // (floats 8h..8h+7) of row 2i + (j >> 1).  One shuffle completes a row's score, one more merges the two row
+    // parities.  The query's bytes come as words from the dense copy: lane j loads word j and the two words a
+    // lane needs travel by shuffle.
+    constexpr int WORDS = (DIM + 3) / 4;
+    const int j = lane & 3, h = j & 1;
+    const int gbase = lane & 28;
+    const unsigned int gmask = 0xFu << gbase;  // the four lanes of this group: a dead group skips the shuffles
     const unsigned int gthread = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int n_groups = gridDim.x * blockDim.x / 4;
-    const unsigned int n_local = (unsigned int)src.n_local;  // the fast path implies < 2^32 vectors
-    const unsigned int n_round = (n_local + 7u) & ~7u;       // 8 queries per warp per round
+    const unsigned int n_local = (unsigned int)src.n_local;
+    const unsigned int n_round = (n_local + 7u) & ~7u;  // 8 queries per warp per round
+    const unsigned int *xwords = reinterpret_cast<const unsigned int *>(src.dense);
     for (unsigned int v = gthread >> 2; v < n_round; v += n_groups) {
       bool flag = false;
       if (v < n_local) {
         const float4 rec = __ldcs(reinterpret_cast<const float4 *>(state) + v);  // streamed: keep the rows in L1
         const int chunk = __float_as_int(rec.z);
-        // this lane's four extended coordinates [x, 1, 0, 0][4j .. 4j+3]
-        float xe[4];
-        if (src.fast) {
-          const signed char *p = fast_vec_ptr(src, v);
+        const unsigned int mine = j < WORDS ? __ldg(xwords + (size_t)v * WORDS + j) : 0u;
+        const unsigned int w0 = __shfl_sync(gmask, mine, gbase + 2 * h);
+        const unsigned int w1 = __shfl_sync(gmask, mine, gbase + 2 * h + 1);
+        float xe[8], part = 0.f;
 #pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const int e = 4 * j + t;
-            xe[t] = e < DIM ? (float)(int)__ldg(p + src.elem_off[e < DIM ? e : 0]) : (e == DIM ? 1.f : 0.f);
-          }
-        } else {
-          unsigned long long base, img;
-          vec_base(src, v, base, img);
-#pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const int e = 4 * j + t;
-            xe[t] = e < DIM ? (float)load_lattice(src, img, base, e < DIM ? e : 0) : (e == DIM ? 1.f : 0.f);
-          }
+        for (int t = 0; t < 8; t++) {
+          const unsigned int word = t < 4 ? w0 : w1;
+          const float byte = (float)(int)(signed char)(word >> (8 * (t & 3)));
+          // element index e = 8h + t: coordinates below DIM, then the constant 1 that picks up |C|^2, then zeros
+          const float lo = t < DIM ? byte : (t == DIM ? 1.f : 0.f);              // h == 0
+          const float hi = (8 + t) < DIM ? byte : ((8 + t) == DIM ? 1.f : 0.f);  // h == 1
+          xe[t] = h ? hi : lo;
+          const bool coord = h ? (8 + t) < DIM : t < DIM;
+          part = coord ? fmaf(xe[t], xe[t], part) : part;
         }
-        float part = 0.f;
-#pragma unroll
-        for (int t = 0; t < 4; t++) part = (4 * j + t) < DIM ? fmaf(xe[t], xe[t], part) : part;
         part += __shfl_xor_sync(gmask, part, 1);
-        part += __shfl_xor_sync(gmask, part, 2);
         const float rr = sqrtf(part) + c_max_norm;
         flag = !((rec.y - rec.x) > margin_coef * rr * rr);
-        const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * ROW32) + j;
+        const float *rows = rows32 + (size_t)chunk * 8 * ROW32 + j * 8;
         float sb = FLT_MAX;
         int rbest = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const float4 c = __ldg(rows + i * 4);
-          float p = xe[0] * c.x;
-          p = fmaf(xe[1], c.y, p);
-          p = fmaf(xe[2], c.z, p);
-          p = fmaf(xe[3], c.w, p);
+        for (int i = 0; i < 4; i++) {
+          float c[8];
+          asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+              : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]), "=f"(c[4]), "=f"(c[5]), "=f"(c[6]), "=f"(c[7])
+              : "l"(rows + i * 32));
+          float p = xe[0] * c[0];
+#pragma unroll
+          for (int t = 1; t < 8; t++) p = fmaf(xe[t], c[t], p);
           p += __shfl_xor_sync(gmask, p, 1);
-          p += __shfl_xor_sync(gmask, p, 2);
           if (p < sb) {
             sb = p;
-            rbest = i;
+            rbest = 2 * i + (j >> 1);
           }
         }
+        const float so = __shfl_xor_sync(gmask, sb, 2);
+        const int ro = __shfl_xor_sync(gmask, rbest, 2);
+        if (so < sb || (so == sb && ro < rbest)) rbest = ro;
         if (j == 0) assign[v] = (uint32_t)(chunk * 8 + rbest);
         flag = flag && j == 0;
       }
