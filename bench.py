@@ -310,7 +310,7 @@ def run_gpu_arm(args):
         tc_peak = float(peaks.get("bf16_tflops", 1590.0))
         tc_src = "MEASURED_PEAKS.json bf16_tflops, burst (of measured)" if "bf16_tflops" in peaks else "1590 TFLOP/s (of fallback)"
         acc_gbs = float(n_local) * (dim + 4) / (ms_acc * 1e-3) / 1e9
-        uses_tc = K >= max(int(os.environ.get("QB200_TC_MIN_K", "256") or 256), 64) and os.environ.get("QB200_DISABLE_TC", "0") != "1"
+        uses_tc = K >= max(int(os.environ.get("QB200_TC_MIN_K", "128") or 128), 64) and os.environ.get("QB200_DISABLE_TC", "0") != "1"
         kb = (dim + 1 + 15) // 16
         k_pad = ((K + 255) // 256) * 256
         # executed tensor flops of the filter: 128-query tiles x padded codebook x (3 bf16 limbs x 16*kb) x 2

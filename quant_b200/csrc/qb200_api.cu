@@ -167,7 +167,7 @@ int tc_min_k() {
   static const int k = [] {
     const char *e = std::getenv("QB200_TC_MIN_K");
     const int v = e ? std::atoi(e) : 0;
-    return v >= 16 ? v : 256;
+    return v >= 16 ? v : 128;
   }();
   return k;
 }
