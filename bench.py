@@ -325,9 +325,9 @@ def run_gpu_arm(args):
                             "evaluation, ncu: profiles/), not by the tensor pipe",
                     "ms_per_launch": ms_assign,
                     # dram__bytes_read.sum + dram__bytes_write.sum of the K=1024 assign_tc_kernel launch on this workload,
-                    # one `ncu --set full` capture (profiles/r1_assign_tc_k1024_ncu_summary.txt): 50.7 MB + 23.1 MB
+                    # one `ncu --set full` capture (profiles/r1_assign_tc_k1024_ncu_summary.txt): 50.5 MB + 20.4 MB
                     # (image bytes in; 16-byte per-query records out, part of which stays in L2)
-                    "traffic": 73.8e6 if (wl == "c2" and world == 1) else None,
+                    "traffic": 70.9e6 if (wl == "c2" and world == 1) else None,
                     "traffic_algorithmic": float(n_local) * dim}
         else:
             roof = {"bound": "fp32", "kernel": f"assign_kernel<{dim}> at K={K}, last split level", "achieved": fp32_equiv,

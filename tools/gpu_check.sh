@@ -14,10 +14,10 @@ python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/plain_$TAG.log 2>&1 &
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
-ncu --set full --clock-control none --import-source on -k regex:assign_tc_kernel -s 2 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:assign_tc_kernel -s 3 -c 1 \
     -o gpurun_out/prof_assign_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_assign_$TAG.log 2>&1
 echo "ncu assign exit $?"
-ncu --set full --clock-control none --import-source on -k regex:accumulate_smem -s 6 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:accumulate_smem -s 3 -c 1 \
     -o gpurun_out/prof_acc_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_acc_$TAG.log 2>&1
 echo "ncu acc exit $?"
 fi
