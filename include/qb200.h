@@ -92,7 +92,7 @@ void qb200_destroy(qb200_ctx *ctx);
 const char *qb200_last_error(const qb200_ctx *ctx);
 /* Run all device work on an existing CUDA stream (cudaStream_t); NULL restores the context's own. */
 int qb200_set_stream(qb200_ctx *ctx, void *cuda_stream);
-/* Filter engine for codebooks of 16 or more entries: 1 (default) = tcgen05 tensor-core kernel,
+/* Filter engine for codebooks of 128 or more entries (QB200_TC_MIN_K): 1 (default) = tcgen05 tensor-core kernel,
  * 0 = FP32 CUDA-core kernel.  Results are identical either way (both only filter; flagged queries
  * are re-solved exactly); the switch exists for measurement and for the parity tests.
  * The environment variable QB200_DISABLE_TC=1 forces 0 process-wide. */

@@ -3,7 +3,7 @@
 //
 //   stage_codebook_kernel   FP64 codebook -> FP32 rows, bf16 limb tiles, transposed FP64 copy, max|C|
 //   assign_kernel           Solution::assignCodeVectors   (/root/reference/src/Quantizer.cpp:24-32)
-//                           brute-force FP32 (FFMA2) nearest-codevector FILTER over raw image bytes, K < 256
+//                           brute-force FP32 (FFMA2) nearest-codevector FILTER, 16 < K < 128 (and whenever the tensor-core engine is off)
 //   small_k_fused_kernel    the same filter + per-cell statistics in one pass for the first split levels (K <= 16)
 //   resolve_bruteforce_kernel / resolve_kernel
 //                           KDTree::nearestNeighbour      (/root/reference/src/KDTree.cpp:20-29 ->
