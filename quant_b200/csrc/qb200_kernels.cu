@@ -486,6 +486,21 @@ __device__ __forceinline__ double nanoflann_l2(const double *a, const double *__
   return result;
 }
 
+// Compile-time dimension, row-major codevector: fully unrolled.
+template <int DIM>
+__device__ __forceinline__ double nanoflann_l2_fixed(const double *a, const double *b) {
+  double result = 0.0;
+#pragma unroll
+  for (int d = 0; d + 3 < DIM; d += 4) {
+    const double g = __dadd_rn(__dadd_rn(__dadd_rn(sq_diff(a[d], b[d]), sq_diff(a[d + 1], b[d + 1])), sq_diff(a[d + 2], b[d + 2])),
+                               sq_diff(a[d + 3], b[d + 3]));
+    result = __dadd_rn(result, g);
+  }
+#pragma unroll
+  for (int d = DIM & ~3; d < DIM; d++) result = __dadd_rn(result, sq_diff(a[d], b[d]));
+  return result;
+}
+
 // Compile-time dimension: fully unrolled (loads issued back to back, the query stays in registers).
 template <int DIM>
 __device__ __forceinline__ double nanoflann_l2_t_fixed(const double *a, const double *__restrict__ bt, size_t stride) {
@@ -664,7 +679,7 @@ struct Frame {
   double mind, cut, saved;
 };
 
-template <int DIMCAP, int DEPTHCAP>
+template <int DIMCAP, int DEPTHCAP, int DIMT>  // DIMT != 0: dimension known at compile time (== DIMCAP)
 __global__ void __launch_bounds__(128)
     resolve_kernel(const VecSource src, const int scaled, const double *cb, const int K, const KdDevice tree,
                    const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
@@ -676,7 +691,7 @@ __global__ void __launch_bounds__(128)
   // minimum is strictly below the best so far - which is what the lane-ordered reduction below returns.
   // The walk is a chain of dependent loads (node -> vind -> codevector), so a block that has work first
   // copies tree and codebook into shared memory when they fit (stage_bytes != 0).
-  const int dim = src.dim;
+  const int dim = DIMT ? DIMT : src.dim;
   const unsigned int total = *flag_count;
   const int lane = threadIdx.x & 31;
   const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -705,7 +720,8 @@ __global__ void __launch_bounds__(128)
     const unsigned long long v = flag_list[f];
     unsigned long long base, img;
     vec_base(src, v, base, img);
-    for (int e = 0; e < dim; e++) {
+#pragma unroll
+    for (int e = 0; e < (DIMT ? DIMT : dim); e++) {
       const double L = (double)load_lattice(src, img, base, e);
       // ScaledColor::RGBtoColorSpace: ((double)c + 128.0) / 255 (src/ColorSpace.cpp:16-21);
       // a past-the-end element is the literal 0.0 and (-128 + 128)/255 == 0.0 as well.
@@ -713,7 +729,8 @@ __global__ void __launch_bounds__(128)
     }
     // computeInitialDistances (nanoflann.hpp:1188-1205)
     double distsq = 0.0;
-    for (int e = 0; e < dim; e++) {
+#pragma unroll
+    for (int e = 0; e < (DIMT ? DIMT : dim); e++) {
       dists[e] = 0.0;
       if (x[e] < tree.bbox_low[e]) {
         dists[e] = sq_diff(x[e], tree.bbox_low[e]);
@@ -743,13 +760,13 @@ __global__ void __launch_bounds__(128)
           unsigned int index = 0;
           if (p < nd.b) {
             index = vind[p];
-            dist = nanoflann_l2(x, cb + (size_t)index * dim, dim);
+            dist = DIMT ? nanoflann_l2_fixed<DIMT ? DIMT : 1>(x, cb + (size_t)index * dim) : nanoflann_l2(x, cb + (size_t)index * dim, dim);
           }
           // leaf minimum, first position on ties (lanes are in vind order)
           double m = dist;
           int ml = lane;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
+          for (int o = 16; o > 0; o >>= 1) {  // all 32 lanes must end with the same (m, ml): they share the walk's state
             const double om = __shfl_xor_sync(0xffffffffu, m, o);
             const int ol = __shfl_xor_sync(0xffffffffu, ml, o);
             if (om < m || (om == m && ol < ml)) {
@@ -767,7 +784,14 @@ __global__ void __launch_bounds__(128)
           continue;
         }
         const int feat = nd.a;
-        const double val = x[feat];
+        double val;
+        if (DIMT) {  // by selection: a dynamic index would push x[] out of registers
+          val = 0.0;
+#pragma unroll
+          for (int e = 0; e < (DIMT ? DIMT : 1); e++) val = (e == feat) ? x[e] : val;
+        } else {
+          val = x[feat];
+        }
         const double diff1 = __dsub_rn(val, nd.divlow);
         const double diff2 = __dsub_rn(val, nd.divhigh);
         int first;
@@ -1375,12 +1399,22 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                                            (unsigned int)stage);
     return cudaGetLastError();
   };
-  if (src.dim <= 16)
-    e = deep ? go(resolve_kernel<16, kResolveDepthCap>) : go(resolve_kernel<16, 96>);
-  else if (src.dim <= 48)
-    e = deep ? go(resolve_kernel<48, kResolveDepthCap>) : go(resolve_kernel<48, 96>);
-  else
-    e = deep ? go(resolve_kernel<kMaxDim, kResolveDepthCap>) : go(resolve_kernel<kMaxDim, 96>);
+  switch (src.dim) {
+    case 3: e = deep ? go(resolve_kernel<3, kResolveDepthCap, 3>) : go(resolve_kernel<3, 96, 3>); break;
+    case 6: e = deep ? go(resolve_kernel<6, kResolveDepthCap, 6>) : go(resolve_kernel<6, 96, 6>); break;
+    case 9: e = deep ? go(resolve_kernel<9, kResolveDepthCap, 9>) : go(resolve_kernel<9, 96, 9>); break;
+    case 12: e = deep ? go(resolve_kernel<12, kResolveDepthCap, 12>) : go(resolve_kernel<12, 96, 12>); break;
+    case 24: e = deep ? go(resolve_kernel<24, kResolveDepthCap, 24>) : go(resolve_kernel<24, 96, 24>); break;
+    case 27: e = deep ? go(resolve_kernel<27, kResolveDepthCap, 27>) : go(resolve_kernel<27, 96, 27>); break;
+    case 48: e = deep ? go(resolve_kernel<48, kResolveDepthCap, 48>) : go(resolve_kernel<48, 96, 48>); break;
+    default:
+      if (src.dim <= 16)
+        e = deep ? go(resolve_kernel<16, kResolveDepthCap, 0>) : go(resolve_kernel<16, 96, 0>);
+      else if (src.dim <= 48)
+        e = deep ? go(resolve_kernel<48, kResolveDepthCap, 0>) : go(resolve_kernel<48, 96, 0>);
+      else
+        e = deep ? go(resolve_kernel<kMaxDim, kResolveDepthCap, 0>) : go(resolve_kernel<kMaxDim, 96, 0>);
+  }
   g_launch_count++;
   return e;
 }
