@@ -222,6 +222,10 @@ def run_gpu_arm(args):
     ctx = qb.Context(local)
     ctx.set_stream(stream.cuda_stream)
     allreduce = make_allreduce() if world > 1 else None
+    exact = args.exact or os.environ.get("QB200_EXACT_CENTROIDS") == "1"
+    ctx.set_exact_centroids(exact)
+    if world > 1:
+        ctx.set_rank(rank, world)
 
     band_np = noise_band(bx, ys, 1234 + rank).reshape(-1)
     host_band = torch.empty(band_np.size, dtype=torch.uint8, pin_memory=True)
@@ -350,6 +354,8 @@ def run_gpu_arm(args):
                                             f"; weak scaling: {world} such bands, one per rank") if world > 1 else ""),
                        "block": [w, h], "nbits": nbits, "colorspace": "SCALED", "vectors_per_rank": n_local,
                        "schedule": "reference HEAD: one assignment pass per split level, no empty-cell repair",
+                       "centroids": ("exact: the reference's compensated FP64 member sums, executed in its order"
+                                     if exact else "from integer per-cell sums (<= 4e-16 relative of the reference's)"),
                        "l2": "512 MiB flush (memset) before every timed step, outside the timed events"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(host_band.numel()) * world,
@@ -499,6 +505,8 @@ def main():
     ap.add_argument("--images", type=int, default=1024, help="images per rank of the encode-only workload c5")
     ap.add_argument("--cpu-budget", type=float, default=None, help="seconds of CPU work for the CPU arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exact", action="store_true",
+                    help="bit-exact centroid mode (qb200_set_exact_centroids): slower, identical to the reference on any input")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: split the workload image across the ranks (default: weak, one image-sized band per rank)")
     args = ap.parse_args()

@@ -100,10 +100,23 @@ int qb200_set_tensor_cores(qb200_ctx *ctx, int enable);
 int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                       size_t *total_mem);
 
+/* Bit-exact centroids (default 0 = off; the environment variable QB200_EXACT_CENTROIDS=1 turns it on for every
+ * new context).  Off: a centroid is derived from the cell's integer sum, ((double)S_t / 255) / n, within 4e-16
+ * relative of the reference's compensated FP64 sum (Solution::sumInArea, src/Quantizer.cpp:59-70) but not always
+ * equal in the last bit; on inputs dominated by duplicated vectors (palettes, flat areas) that bit decides exact
+ * ties of the next split level, so the final codebook and indices can differ from the reference's although every
+ * assignment pass, given the same input codebook, is bit-identical.  On: the library runs the reference's
+ * summation itself (stable sort by cell, then the same four FP64 operations per member in ascending vector
+ * order), which makes the whole train bit-identical on any input at the cost of a latency-bound chain of
+ * about 2 N dependent steps per train.  SCALED only (NORMAL sums are integers and always exact).  With an
+ * all-reduce callback the ranks continue each other's chains: qb200_set_rank is required and rank order must
+ * be vector order (rank r owns lower vector indices than rank r+1). */
+int qb200_set_exact_centroids(qb200_ctx *ctx, int enable);
 /* Seed of the empty-cell repair's member choice (default 0x5eed).  QB200_MODE_FULL_REPAIR only. */
 int qb200_set_seed(qb200_ctx *ctx, uint64_t seed);
-/* This context's rank among `world` contexts that train one sharded set together.  Needed only by
- * QB200_MODE_FULL_REPAIR (the ranks agree on the chosen members through the sum all-reduce). */
+/* This context's rank among `world` contexts that train one sharded set together.  Needed by
+ * QB200_MODE_FULL_REPAIR (the ranks agree on the chosen members through the sum all-reduce) and by
+ * qb200_set_exact_centroids. */
 int qb200_set_rank(qb200_ctx *ctx, int rank, int world);
 
 /* ---- training set ------------------------------------------------------------------------

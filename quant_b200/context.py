@@ -115,6 +115,11 @@ class Context:
         return int(self.lib.qb200_dim(self.h))
 
     # -- hot path ---------------------------------------------------------------------------
+    def set_exact_centroids(self, enable: bool):
+        """Bit-exact centroids: run the reference's compensated member sums (src/Quantizer.cpp:59-70) instead of
+        deriving the centroid from integer sums; see include/qb200.h."""
+        self._check(self.lib.qb200_set_exact_centroids(self.h, 1 if enable else 0))
+
     def set_seed(self, seed: int):
         self._check(self.lib.qb200_set_seed(self.h, seed))
 

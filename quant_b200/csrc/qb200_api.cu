@@ -66,6 +66,10 @@ struct qb200_ctx {
   uint64_t seed = 0x5eed, repair_round = 0;
   int rank = 0, world = 1;
   DevBuf d_repair;
+  // bit-exact centroid sums (qb200_set_exact_centroids; qb200_exact.cu)
+  bool exact = false;
+  DevBuf d_exact, d_sort_keys, d_sort_iota, d_sort_order, d_sort_tmp;
+  size_t iota_n = 0;
 };
 
 namespace {
@@ -543,6 +547,7 @@ int qb200_create(int device, qb200_ctx **out) {
   }
   ctx->stream = ctx->own_stream;
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  if (const char *ex = std::getenv("QB200_EXACT_CENTROIDS")) ctx->exact = ex[0] == '1';
   *out = ctx;
   return QB200_OK;
 }
@@ -558,7 +563,9 @@ void qb200_destroy(qb200_ctx *ctx) {
   if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
   for (auto &e2 : ctx->pipe_ev)
     if (e2) cudaEventDestroy(e2);
-  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary}) free_buf(*b);
+  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_exact, &ctx->d_sort_keys,
+                    &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp})
+    free_buf(*b);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -576,6 +583,12 @@ int qb200_set_stream(qb200_ctx *ctx, void *cuda_stream) {
 int qb200_set_tensor_cores(qb200_ctx *ctx, int enable) {
   if (!ctx) return QB200_ERR_ARG;
   ctx->use_tc = enable != 0;
+  return QB200_OK;
+}
+
+int qb200_set_exact_centroids(qb200_ctx *ctx, int enable) {
+  if (!ctx) return QB200_ERR_ARG;
+  ctx->exact = enable != 0;
   return QB200_OK;
 }
 
@@ -802,6 +815,73 @@ int qb200_codebook_to_bytes(const double *codebook, size_t K, int dim, int color
 
 namespace {
 
+// Bit-exact centroid sums (opt-in, SCALED only): leaves in ctx->d_exact the K*dim pairs {sum, c} the reference's
+// compensated loop ends with for the assignment now in d_assign (K == 1: the whole set; src/Quantizer.cpp:46-70).
+// Sharded runs: the loop is sequential in the vector index, so the ranks run their part of every chain one after
+// the other in rank order (= vector order: rank r must own lower indices than rank r+1) and hand the state on
+// through the sum all-reduce - the owner contributes its state, everyone else zeros, so the 64-bit patterns
+// arrive unchanged.  world rounds of 2*K*dim words; all work stays stream-ordered.
+int exact_prepare(qb200_ctx *ctx, uint32_t maxK) {
+  const size_t n = (size_t)ctx->src.n_local;
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_exact, (size_t)maxK * ctx->src.dim * 16 + 256))) return rc;
+  if (maxK > 1 && n) {
+    if ((rc = ensure(ctx, ctx->d_sort_keys, n * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_sort_order, n * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_sort_tmp, exact_sort_temp_bytes(n) + 256))) return rc;
+    if (ctx->d_sort_iota.cap < n * 4 || ctx->iota_n != n) {
+      if ((rc = ensure(ctx, ctx->d_sort_iota, n * 4))) return rc;
+      CU(launch_exact_iota((uint32_t *)ctx->d_sort_iota.p, n, ctx->sm_count, ctx->stream));
+      ctx->iota_n = n;
+    }
+  }
+  return QB200_OK;
+}
+
+int exact_centroid_sums(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void *ar_user) {
+  const int dim = ctx->src.dim;
+  const size_t n = (size_t)ctx->src.n_local, words = (size_t)K * dim * 2;
+  cudaStream_t st = ctx->stream;
+  int rc;
+  if (ar && ctx->world <= 1)
+    return fail(ctx, QB200_ERR_STATE, "exact centroids with an all-reduce callback need qb200_set_rank (rank order = vector order)");
+  if ((rc = exact_prepare(ctx, K))) return rc;
+  CU(cudaMemsetAsync(ctx->d_exact.p, 0, words * 8, st));
+  int key_bits = 0;
+  while ((1u << key_bits) < K) key_bits++;
+  if (K > 1 && n)
+    CU(launch_exact_sort((const uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_sort_keys.p, (const uint32_t *)ctx->d_sort_iota.p,
+                         (uint32_t *)ctx->d_sort_order.p, n, key_bits, ctx->d_sort_tmp.p, ctx->d_sort_tmp.cap, st));
+  const int world = ar ? ctx->world : 1;
+  for (int q = 0; q < world; q++) {
+    if (!ar || q == ctx->rank) {
+      if (n)
+        CU(launch_kahan_sums(ctx->src, K > 1 ? (const uint32_t *)ctx->d_sort_keys.p : nullptr,
+                             K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K, 1, (double *)ctx->d_exact.p, st));
+    } else {
+      CU(cudaMemsetAsync(ctx->d_exact.p, 0, words * 8, st));
+    }
+    if (ar && ar(ctx->d_exact.p, words, (void *)st, ar_user) != 0)
+      return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (exact centroid sums, K=%u, round %d)", K, q);
+  }
+  return QB200_OK;
+}
+
+// Host-loop variant: fetch the sums and overwrite the centroids qb200_finalize_level derived from the integer sums.
+int exact_override_centroids(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void *ar_user, const std::vector<uint64_t> &n,
+                             double *centroids) {
+  const int dim = ctx->src.dim;
+  int rc;
+  if ((rc = exact_centroid_sums(ctx, K, ar, ar_user))) return rc;
+  std::vector<double> state((size_t)K * dim * 2);
+  CU(cudaMemcpyAsync(state.data(), ctx->d_exact.p, state.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t k = 0; k < K; k++)
+    for (int e = 0; e < dim; e++)
+      centroids[(size_t)k * dim + e] = n[k] ? state[((size_t)k * dim + e) * 2] / (double)n[k] : 0.0;
+  return QB200_OK;
+}
+
 struct PipeSlot {  // pinned, one per split level
   unsigned int counters[4];
   double dist_pre, dist_post;
@@ -821,6 +901,8 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
   const double f_up = (double)(1 + 0.2), f_dn = (double)(1 - 0.2);  // src/Quantizer.cpp:136-137
   cudaStream_t st = ctx->stream;
   int rc;
+  const bool exact = ctx->exact && scaled;
+  if (exact && (rc = exact_prepare(ctx, maxK))) return rc;
   // everything the levels will need, at its final size: no buffer is reallocated while work is in flight
   const LevelLayout Lmax = level_layout(ctx, maxK, dim);
   size_t rows_max = 0, tc_max = 0;
@@ -873,7 +955,9 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
   CU(launch_accumulate(ctx->src, nullptr, 1, (unsigned long long *)ctx->d_stats.p, ctx->sm_count, st));
   if (ar && ar(ctx->d_stats.p, stats_words(1, dim), (void *)st, ar_user) != 0)
     return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed at K=1");
-  CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, nullptr, 1, dim, scaled, (double)N, f_up, f_dn,
+  if (exact && (rc = exact_centroid_sums(ctx, 1, ar, ar_user))) return rc;
+  CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, nullptr, exact ? (const double *)ctx->d_exact.p : nullptr,
+                           1, dim, scaled, (double)N, f_up, f_dn,
                            (double *)ctx->d_post.p, nbits ? (double *)ctx->d_cbnext[0].p : nullptr, summaries, st));
   CU(cudaMemcpyAsync(&slots[0].dist_pre, summaries, 32, cudaMemcpyDeviceToHost, st));
   if (nbits) {
@@ -899,7 +983,9 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
       return rc;
     if (ar && ar(ctx->d_stats.p, stats_words(K, dim), (void *)st, ar_user) != 0)
       return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed at K=%u", K);
-    CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, (const double *)ctx->d_cb64.p, (int)K, dim, scaled,
+    if (exact && (rc = exact_centroid_sums(ctx, K, ar, ar_user))) return rc;
+    CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, (const double *)ctx->d_cb64.p,
+                             exact ? (const double *)ctx->d_exact.p : nullptr, (int)K, dim, scaled,
                              (double)N, f_up, f_dn, (double *)ctx->d_post.p,
                              last ? nullptr : (double *)ctx->d_cbnext[cur ^ 1].p, summaries + 32 * (level + 1), st));
     CU(cudaMemcpyAsync(&slots[level + 1].dist_pre, summaries + 32 * (level + 1), 32, cudaMemcpyDeviceToHost, st));
@@ -979,6 +1065,8 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
                              (unsigned long long)n[0], (unsigned long long)N);
   double dpost = 0, dpre = 0;
   qb200_finalize_level(ctx->colorspace, 1, dim, N, n.data(), S.data(), Q.data(), nullptr, cb.data(), nullptr, &dpost);
+  const bool exact = ctx->exact && ctx->colorspace == QB200_CS_SCALED;
+  if (exact && (rc = exact_override_centroids(ctx, 1, allreduce, allreduce_user, n, cb.data()))) return rc;
   uint32_t K = 1;
   int level = 0;
   ctx->assign_valid = false;
@@ -1000,6 +1088,7 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
       split_stats(words, K, dim, n, S, Q);
       qb200_finalize_level(ctx->colorspace, K, dim, N, n.data(), S.data(), Q.data(), cb.data(), post.data(), &dpre,
                            &dpost);
+      if (exact && (rc = exact_override_centroids(ctx, K, allreduce, allreduce_user, n, post.data()))) return rc;
       iterations++;
       if (mode == QB200_MODE_PARITY) break;  // HEAD: one assignment per level (src/Quantizer.cpp:98-108)
       // README.md:29-31 schedule: assign, fix, compare the distortion with the previous round's

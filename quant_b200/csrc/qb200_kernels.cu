@@ -1143,8 +1143,8 @@ struct LevelSummary {
   unsigned long long n_total_seen;
 };
 __global__ void __launch_bounds__(1024)
-    finalize_split_kernel(const unsigned long long *__restrict__ stats, const double *__restrict__ cb_pre, const int K,
-                          const int dim, const int scaled, const double n_total, const double f_up, const double f_dn,
+    finalize_split_kernel(const unsigned long long *__restrict__ stats, const double *__restrict__ cb_pre,
+                          const double *__restrict__ exact_state, const int K, const int dim, const int scaled, const double n_total, const double f_up, const double f_dn,
                           double *__restrict__ cb_post, double *__restrict__ cb_next,
                           LevelSummary *__restrict__ summary) {
   __shared__ double s_pre[1024], s_post[1024];
@@ -1167,7 +1167,10 @@ __global__ void __launch_bounds__(1024)
     double st2 = 0.0, cross = 0.0, c2 = 0.0;
     for (int e = 0; e < dim; e++) {
       const long long St = (long long)row[1 + e] + (scaled ? (long long)(128ull * n) : 0ll);
-      const double c = n ? __ddiv_rn(__ddiv_rn((double)St, unit), (double)n) : 0.0;
+      // exact_state: the reference's compensated sum itself (qb200_exact.cu), divided as in src/Quantizer.cpp:84-85
+      const double c = !n ? 0.0
+                          : exact_state ? __ddiv_rn(exact_state[((size_t)k * dim + e) * 2], (double)n)
+                                        : __ddiv_rn(__ddiv_rn((double)St, unit), (double)n);
       cb_post[(size_t)k * dim + e] = c;
       if (cb_next) {
         cb_next[(size_t)k * dim + e] = __dmul_rn(c, f_up);
@@ -1515,11 +1518,11 @@ cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_r
   return cudaGetLastError();
 }
 
-cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, int K, int dim, int scaled,
-                                  double n_total, double f_up, double f_dn, double *cb_post, double *cb_next,
-                                  void *summary, cudaStream_t stream) {
-  finalize_split_kernel<<<1, 1024, 0, stream>>>(stats, cb_pre, K, dim, scaled, n_total, f_up, f_dn, cb_post, cb_next,
-                                                reinterpret_cast<LevelSummary *>(summary));
+cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, const double *exact_state, int K,
+                                  int dim, int scaled, double n_total, double f_up, double f_dn, double *cb_post,
+                                  double *cb_next, void *summary, cudaStream_t stream) {
+  finalize_split_kernel<<<1, 1024, 0, stream>>>(stats, cb_pre, exact_state, K, dim, scaled, n_total, f_up, f_dn, cb_post,
+                                                cb_next, reinterpret_cast<LevelSummary *>(summary));
   g_launch_count++;
   return cudaGetLastError();
 }

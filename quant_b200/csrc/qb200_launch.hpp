@@ -80,9 +80,19 @@ cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32
                           uint8_t *out, unsigned long long *sq_err, int sm_count, cudaStream_t stream);
 // Device-side fix + distortions + split of one level.  summary: 32 bytes {double dist_pre, dist_post; u32 dead_cells,
 // pad; u64 vectors counted}.  cb_pre / cb_next may be null (K = 1 has no previous codebook; the last level no next).
-cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, int K, int dim, int scaled,
-                                  double n_total, double f_up, double f_dn, double *cb_post, double *cb_next,
-                                  void *summary, cudaStream_t stream);
+// exact_state (null = centroids from the integer sums): K*dim pairs {sum, c} left by launch_kahan_sums; the
+// centroid is then sum / n, the reference's own operation.
+cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, const double *exact_state, int K,
+                                  int dim, int scaled, double n_total, double f_up, double f_dn, double *cb_post,
+                                  double *cb_next, void *summary, cudaStream_t stream);
+// Bit-exact centroid sums (qb200_exact.cu): stable sort of the members by cell, then the reference's compensated
+// summation in ascending vector order, one warp per cell.
+size_t exact_sort_temp_bytes(size_t n);
+cudaError_t launch_exact_iota(uint32_t *iota, size_t n, int sm_count, cudaStream_t stream);
+cudaError_t launch_exact_sort(const uint32_t *assign, uint32_t *keys_out, const uint32_t *iota, uint32_t *order, size_t n,
+                              int key_bits, void *tmp, size_t tmp_bytes, cudaStream_t stream);
+cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, int scaled,
+                              double *state, cudaStream_t stream);
 // Empty-cell repair (QB200_MODE_FULL_REPAIR): smallest (hash, global index) key per donor cell; member bytes.
 cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, const int *slot_of_cell,
                                 unsigned long long seed, unsigned long long *keys, int sm_count, cudaStream_t stream);
