@@ -101,3 +101,22 @@ def test_plugin_quantize_entry_agrees_with_compress(host_built, tmp_path):
     write_ppm(p, g.rgb, g.xs, g.ys)
     r = subprocess.run([HOST_TEST, "quantize", p, str(g.w), str(g.h), str(g.nbits)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_exact_centroid_mode_on_a_palette_image(host_built, port, tmp_path):
+    """QB200_EXACT_CENTROIDS=1 reaches the C++ layer through the environment: on a five-colour image (exact ties
+    at every split) the CLI's .quant file must be the oracle's byte for byte."""
+    xs, ys, w, h, nbits = 141, 138, 2, 2, 8
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (5, 3))[rng.integers(0, 5, (ys, xs))].astype(np.uint8)
+    X = port.blocks(rgb, xs, ys, w, h, 1)
+    cb_o, a_o, _ = port.quantize(X, nbits)
+    want = port.quant_serialize(port.codebook_to_bytes(cb_o, 1), a_o, xs, ys, w, h, 1)
+    p, q = str(tmp_path / "i.ppm"), str(tmp_path / "o.quant")
+    write_ppm(p, rgb, xs, ys)
+    env = dict(os.environ, QB200_EXACT_CENTROIDS="1")
+    r = subprocess.run([QUANT, p, "-o", q, "-n", str(nbits), "-w", str(w), "-h", str(h), "--c", "1"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert open(q, "rb").read() == want
