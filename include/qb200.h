@@ -43,6 +43,7 @@ extern "C" {
  * (/root/reference/include/ColorSpace.hpp:6).  CIE1931 (2) is rejected with QB200_ERR_ARG. */
 #define QB200_CS_NORMAL 0 /* value = (double)(int8)byte        src/ColorSpace.cpp:4-6   */
 #define QB200_CS_SCALED 1 /* value = ((int8)byte + 128.0)/255  src/ColorSpace.cpp:16-21 */
+#define QB200_CS_CIE1931 2 /* 3x3 matrix / 0.17697 per pixel     src/ColorSpace.cpp:31-48; FP64 vectors, see below */
 
 /* Training schedule. */
 #define QB200_MODE_PARITY 0 /* the reference's HEAD schedule: ONE assignment per split level,
@@ -144,6 +145,16 @@ int qb200_set_image_band(qb200_ctx *ctx, const uint8_t *band, size_t band_len, i
  * AbstractQuantizer::quantize(vector<Vector>) entry (include/Quantizer.hpp:12-14). */
 int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors, int dim,
                          int colorspace, int bytes_is_device);
+/* Training set given as an N x dim matrix of doubles (row-major): the fully general form of
+ * AbstractQuantizer::quantize(vector<Vector>) (include/Quantizer.hpp:12-14).  x_is_device != 0: a device pointer
+ * that stays valid until the next set call (no copy).
+ * General FP64 vectors - this call, and images in QB200_CS_CIE1931 (qb200_set_image converts them to doubles on
+ * the device) - have no integer statistics: the assignment keeps the filter + exact re-check (the filter works on
+ * the values rounded to FP32, its margin covers that), centroids are the reference's compensated FP64 sums executed
+ * in vector order (as with qb200_set_exact_centroids, so codebooks are bit-identical to the reference's) and the
+ * distortions are FP64 sums (reference: OpenMP reduction, order unspecified; 1e-6 relative).  Single GPU only
+ * (qb200_train rejects an all-reduce callback), QB200_MODE_PARITY and QB200_MODE_FULL. */
+int qb200_set_vectors_f64(qb200_ctx *ctx, const double *x, size_t n_vectors, int dim, int x_is_device);
 /* Number of vectors this context holds / their dimension. */
 size_t qb200_num_vectors(const qb200_ctx *ctx);
 int qb200_dim(const qb200_ctx *ctx);

@@ -21,6 +21,7 @@
 
 #define ORC_NORMAL 0
 #define ORC_SCALED 1
+#define ORC_CIE1931 2
 #define ORC_LEAF_MAX 10 /* src/KDTree.cpp:4 KD_LEAF_MAX_SIZE; KDTreeVectorOfVectorsAdaptor.hpp:59 */
 
 /* ------------------------------------------------------------------------------------------
@@ -33,6 +34,15 @@ static double orc_color(uint8_t u, int cs) {
   double s = (double)(int8_t)u;
   if (cs == ORC_SCALED) return (s + 128.0) / 255;
   return s;
+}
+
+/* src/ColorSpace.cpp:35-39 Cie1931::RGBtoColorSpace: c[i] are SIGNED chars promoted to double; the sums are
+ * evaluated left to right and divided by 0.17697 (plain x86-64 build: no fused multiply-add). */
+static void orc_cie_forward(const uint8_t *px, double *out) {
+  const double c0 = (double)(int8_t)px[0], c1 = (double)(int8_t)px[1], c2 = (double)(int8_t)px[2];
+  out[0] = (c0 * 0.490 + c1 * 0.310 + c2 * 0.200) / 0.17697;
+  out[1] = (c0 * 0.17697 + c1 * 0.81240 + c2 * 0.01063) / 0.17697;
+  out[2] = (c0 * 0 + c1 * 0.01 + c2 * 0.99) / 0.17697;
 }
 
 /* Integer lattice value of a byte: SCALED value == t/255.0 with t = u ^ 0x80 in [0,255];
@@ -57,7 +67,10 @@ void orc_blocks(const uint8_t *rgb, int xSize, int ySize, int w, int h, int cs, 
         for (size_t y = j * h; y < j * h + h; y++) {
           size_t img = x * ySize + y;
           size_t e = ((x - i * w) * h + (y - j * h)) * 3;
-          for (int ch = 0; ch < 3; ch++) v[e + ch] = img < npix ? orc_color(rgb[img * 3 + ch], cs) : 0.0;
+          if (cs == ORC_CIE1931 && img < npix)
+            orc_cie_forward(rgb + img * 3, v + e);
+          else
+            for (int ch = 0; ch < 3; ch++) v[e + ch] = img < npix ? orc_color(rgb[img * 3 + ch], cs) : 0.0;
         }
     }
 }
@@ -84,6 +97,18 @@ void orc_blocks_lattice(const uint8_t *rgb, int xSize, int ySize, int w, int h, 
  * SCALED: (char)std::round((c - 128.0) * 255) - only right through int8 wrap-around; the x86
  * build converts through a 32-bit integer, stated explicitly here. */
 void orc_codebook_to_bytes(const double *cb, size_t K, int dim, int cs, uint8_t *out) {
+  if (cs == ORC_CIE1931) { /* src/ColorSpace.cpp:41-48 Cie1931::colorSpaceToRGB, one pixel (3 elements) at a time */
+    for (size_t i = 0; i + 2 < K * (size_t)dim; i += 3) {
+      const double *c = cb + i;
+      double t0 = (c[0] * 0.418 + c[1] * (-0.15866) + c[2] * (-0.082835));
+      double t1 = (c[0] * (-0.091169) + c[1] * 0.25243 + c[2] * 0.015708);
+      double t2 = (c[0] * 0.0009209 + c[1] * (-0.0025498) + c[2] * 0.17860);
+      out[i] = (uint8_t)(int8_t)(int)round(t0);
+      out[i + 1] = (uint8_t)(int8_t)(int)round(t1);
+      out[i + 2] = (uint8_t)(int8_t)(int)round(t2);
+    }
+    return;
+  }
   for (size_t i = 0; i < K * (size_t)dim; i++) {
     double r = cs == ORC_SCALED ? round((cb[i] - 128.0) * 255) : round(cb[i]);
     out[i] = (uint8_t)(int8_t)(int)r;

@@ -2,7 +2,7 @@
 Quantizer / Compressor interface.  The compute path is libqb200.so (hand-written sm_100a CUDA,
 C ABI in include/qb200.h); this package is the host-side mirror of the reference's API.
 """
-from ._lib import (CS_NORMAL, CS_SCALED, LIB_PATH, MODE_FULL, MODE_FULL_REPAIR, MODE_PARITY, Qb200Error, load)
+from ._lib import (CS_CIE1931, CS_NORMAL, CS_SCALED, LIB_PATH, MODE_FULL, MODE_FULL_REPAIR, MODE_PARITY, Qb200Error, load)
 from . import distributed
 from .context import Context, codebook_to_bytes, finalize_level, launch_count
 from .rgbimage import RGBImage

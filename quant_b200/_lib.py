@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libqb200.so")
 
 OK, ERR_ARG, ERR_NODEV, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
-CS_NORMAL, CS_SCALED = 0, 1
+CS_NORMAL, CS_SCALED, CS_CIE1931 = 0, 1, 2
 MODE_PARITY, MODE_FULL, MODE_FULL_REPAIR = 0, 1, 2
 
 
@@ -46,6 +46,7 @@ SIGNATURES = {
                                         C.c_int, C.c_size_t, C.c_size_t]),
     "qb200_set_image_band": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t]),
+    "qb200_set_vectors_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "qb200_set_vectors_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                        C.c_int]),
     "qb200_num_vectors": (C.c_size_t, [C.c_void_p]),

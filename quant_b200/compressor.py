@@ -14,7 +14,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from ._lib import CS_NORMAL, CS_SCALED
+from ._lib import CS_CIE1931, CS_NORMAL, CS_SCALED
 from .context import codebook_to_bytes
 from .quantizer import Quantizers, getQuantizer
 from .rgbimage import RGBImage
@@ -28,8 +28,8 @@ class ColorSpaces(enum.IntEnum):
 
 def _check_cs(cs) -> int:
     cs = int(cs)
-    if cs not in (CS_NORMAL, CS_SCALED):
-        raise NotImplementedError("CIE1931 is outside the accelerated path (SURVEY.md 8f row 3)")
+    if cs not in (CS_NORMAL, CS_SCALED, CS_CIE1931):
+        raise ValueError(f"unknown colour space {cs}")
     return cs
 
 
@@ -53,6 +53,11 @@ def getBlocksAsVectorsFromImage(image: RGBImage, w: int, h: int, cs) -> np.ndarr
     px = image.img[np.where(valid, idx, 0)].astype(np.int8).astype(np.float64)  # signed char
     if cs == CS_SCALED:
         px = (px + 128.0) / 255
+    elif cs == CS_CIE1931:   # Cie1931::RGBtoColorSpace (src/ColorSpace.cpp:35-39), sums left to right
+        c0, c1, c2 = px[..., 0], px[..., 1], px[..., 2]
+        px = np.stack([(c0 * 0.490 + c1 * 0.310 + c2 * 0.200) / 0.17697,
+                       (c0 * 0.17697 + c1 * 0.81240 + c2 * 0.01063) / 0.17697,
+                       (0.0 + c1 * 0.01 + c2 * 0.99) / 0.17697], -1)
     px = np.where(valid[..., None], px, 0.0)
     return px.reshape(idx.shape[0], -1)
 

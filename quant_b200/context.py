@@ -106,6 +106,13 @@ class Context:
         self._keep = mat
         self._check(self.lib.qb200_set_vectors_u8(self.h, _ptr(mat), n, dim, colorspace, 0))
 
+    def set_vectors_f64(self, mat: np.ndarray):
+        """General FP64 training vectors (no byte lattice): qb200_set_vectors_f64."""
+        mat = np.ascontiguousarray(mat, np.float64)
+        n, dim = mat.shape
+        self._keep = mat
+        self._check(self.lib.qb200_set_vectors_f64(self.h, _ptr(mat), n, dim, 0))
+
     @property
     def num_vectors(self) -> int:
         return int(self.lib.qb200_num_vectors(self.h))

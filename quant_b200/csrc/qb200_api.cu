@@ -70,6 +70,8 @@ struct qb200_ctx {
   bool exact = false;
   DevBuf d_exact, d_sort_keys, d_sort_iota, d_sort_order, d_sort_tmp;
   size_t iota_n = 0;
+  // general FP64 vectors (qb200_set_vectors_f64, CIE1931 images; qb200_generic.cu)
+  DevBuf d_f64, d_partials, d_counts;
 };
 
 namespace {
@@ -178,7 +180,7 @@ int tc_min_k() {
 
 LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
   LevelLayout L;
-  L.use_tc = ctx->use_tc && tc_enabled() && (int)K >= tc_min_k() && tc_supported(dim, (int)K);
+  L.use_tc = ctx->use_tc && tc_enabled() && (int)K >= tc_min_k() && tc_supported(dim, (int)K) && !ctx->src.f64;
   L.K_rows = L.use_tc ? (uint32_t)tc_padded_rows((int)K) : K + (K & 1u);
   L.rows_bytes = (size_t)L.K_rows * assign_row_floats(dim) * 4;
   L.tc_bytes = L.use_tc ? (size_t)L.K_rows * tc_row_bytes(dim) : 0;
@@ -258,7 +260,8 @@ int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uin
     a.cb_rows = (const float *)ctx->d_rows.p;
     a.K = (int)L.K_rows;
     // 2 scores * (dim+3) * 2^-24 * (|X|+|C|)^2, with 25% head-room (see qb200_kernels.cu)
-    a.margin_coef = 2.5f * (float)(dim + 3) * 5.9604645e-8f;
+    // FP64 vectors reach the filter rounded to FP32: 2 <x - fl(x), C> <= 2^-24 (|X|+|C|)^2 / 2 more per score
+    a.margin_coef = 2.5f * (float)(dim + (ctx->src.f64 ? 5 : 3)) * 5.9604645e-8f;
     a.c_max_ptr = c_max_ptr;
     a.assign = (uint32_t *)ctx->d_assign.p;
     a.flag_list = (uint32_t *)ctx->d_flags.p;
@@ -489,10 +492,10 @@ int repair_empty_cells(qb200_ctx *ctx, uint32_t K, const std::vector<uint64_t> &
   return QB200_OK;
 }
 
-int set_common(qb200_ctx *ctx, size_t n_local) {
+int set_common(qb200_ctx *ctx, size_t n_local, bool pack = true) {
   int rc;
   // dense byte copy of the training set: every later gather is a few coalesced word loads
-  {
+  if (pack) {
     VecSource &s = ctx->src;
     s.dense = nullptr;
     s.dense_stride = (unsigned int)((s.dim + 3) & ~3);
@@ -564,7 +567,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   for (auto &e2 : ctx->pipe_ev)
     if (e2) cudaEventDestroy(e2);
   for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_exact, &ctx->d_sort_keys,
-                    &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp})
+                    &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp, &ctx->d_f64, &ctx->d_partials, &ctx->d_counts})
     free_buf(*b);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -626,8 +629,10 @@ static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySi
   if (xSize <= 0 || ySize <= 0 || w <= 0 || h <= 0 || n_images <= 0)
     return fail(ctx, QB200_ERR_ARG, "set_image: sizes must be positive (x=%d y=%d w=%d h=%d n=%d)", xSize, ySize, w,
                 h, n_images);
-  if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED)
-    return fail(ctx, QB200_ERR_ARG, "set_image: colour space %d is not supported (NORMAL=0, SCALED=1)", colorspace);
+  if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED && colorspace != QB200_CS_CIE1931)
+    return fail(ctx, QB200_ERR_ARG, "set_image: colour space %d is not supported (NORMAL=0, SCALED=1, CIE1931=2)", colorspace);
+  if (colorspace == QB200_CS_CIE1931 && shard)
+    return fail(ctx, QB200_ERR_ARG, "set_image_shard: CIE1931 vectors are not on the byte lattice; the FP64 path is single-GPU");
   const long long dim = 3LL * w * h;
   if (dim > kMaxDim) return fail(ctx, QB200_ERR_ARG, "set_image: block %dx%d gives dim %lld > %d", w, h, dim, kMaxDim);
   CU(cudaSetDevice(ctx->device));
@@ -697,7 +702,13 @@ static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySi
   ctx->geom.hB = (unsigned int)hB;
   ctx->geom.n_pixels = (unsigned long long)xSize * ySize;
   ctx->geom.n_images = n_images;
-  return set_common(ctx, (size_t)s.n_local);
+  int rc = set_common(ctx, (size_t)s.n_local, colorspace != QB200_CS_CIE1931);
+  if (rc || colorspace != QB200_CS_CIE1931) return rc;
+  // CIE1931: the block vectors as doubles (Cie1931::RGBtoColorSpace per pixel), once, on the device
+  if ((rc = ensure(ctx, ctx->d_f64, (size_t)(s.n_local ? s.n_local : 1) * (size_t)dim * 8))) return rc;
+  CU(launch_cie_vectors(ctx->src, (double *)ctx->d_f64.p, ctx->sm_count, ctx->stream));
+  ctx->src.f64 = (const double *)ctx->d_f64.p;
+  return QB200_OK;
 }
 
 int qb200_set_image(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth, int blockHeight,
@@ -757,6 +768,33 @@ int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors,
   return set_common(ctx, n_vectors);
 }
 
+int qb200_set_vectors_f64(qb200_ctx *ctx, const double *x, size_t n_vectors, int dim, int x_is_device) {
+  if (!ctx) return QB200_ERR_ARG;
+  if (!x && n_vectors) return fail(ctx, QB200_ERR_ARG, "set_vectors_f64: x == NULL");
+  if (dim <= 0 || dim > kMaxDim) return fail(ctx, QB200_ERR_ARG, "set_vectors_f64: dim %d outside [1,%d]", dim, kMaxDim);
+  if (n_vectors > 0xffffffffull) return fail(ctx, QB200_ERR_ARG, "set_vectors_f64: more than 2^32 vectors");
+  CU(cudaSetDevice(ctx->device));
+  VecSource s{};
+  s.per_image = n_vectors ? n_vectors : 1;
+  s.n_local = n_vectors;
+  s.hB = 1;
+  s.dim = dim;
+  ctx->borrowed = nullptr;
+  if (x_is_device) {
+    s.f64 = x;
+  } else {
+    int rc = ensure(ctx, ctx->d_f64, (n_vectors ? n_vectors : 1) * (size_t)dim * 8);
+    if (rc) return rc;
+    if (n_vectors) CU(cudaMemcpyAsync(ctx->d_f64.p, x, n_vectors * (size_t)dim * 8, cudaMemcpyHostToDevice, ctx->stream));
+    s.f64 = (const double *)ctx->d_f64.p;
+  }
+  ctx->src = s;
+  ctx->colorspace = QB200_CS_NORMAL;  // values are used as they are
+  ctx->is_image = false;
+  ctx->is_shard = false;
+  return set_common(ctx, n_vectors, false);
+}
+
 size_t qb200_num_vectors(const qb200_ctx *ctx) { return ctx && ctx->have_set ? (size_t)ctx->src.n_local : 0; }
 int qb200_dim(const qb200_ctx *ctx) { return ctx && ctx->have_set ? ctx->src.dim : 0; }
 
@@ -804,6 +842,19 @@ int qb200_finalize_level(int colorspace, uint32_t K, int dim, uint64_t n_total, 
 
 int qb200_codebook_to_bytes(const double *codebook, size_t K, int dim, int colorspace, uint8_t *bytes_out) {
   if (!codebook || !bytes_out || dim <= 0) return QB200_ERR_ARG;
+  if (colorspace == QB200_CS_CIE1931) {  // Cie1931::colorSpaceToRGB (src/ColorSpace.cpp:41-48), pixel by pixel
+    if (dim % 3) return QB200_ERR_ARG;
+    for (size_t i = 0; i < K * (size_t)dim; i += 3) {
+      const double *c = codebook + i;
+      const double t0 = (c[0] * 0.418 + c[1] * (-0.15866) + c[2] * (-0.082835));
+      const double t1 = (c[0] * (-0.091169) + c[1] * 0.25243 + c[2] * 0.015708);
+      const double t2 = (c[0] * 0.0009209 + c[1] * (-0.0025498) + c[2] * 0.17860);
+      bytes_out[i] = (uint8_t)(int8_t)(int)std::round(t0);
+      bytes_out[i + 1] = (uint8_t)(int8_t)(int)std::round(t1);
+      bytes_out[i + 2] = (uint8_t)(int8_t)(int)std::round(t2);
+    }
+    return QB200_OK;
+  }
   if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED) return QB200_ERR_ARG;
   for (size_t i = 0; i < K * (size_t)dim; i++) {
     // ScaledColor::colorSpaceToRGB: (char)std::round((c - 128.0) * 255); ColorSpace: (char)std::round(c)
@@ -857,7 +908,8 @@ int exact_centroid_sums(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void 
     if (!ar || q == ctx->rank) {
       if (n)
         CU(launch_kahan_sums(ctx->src, K > 1 ? (const uint32_t *)ctx->d_sort_keys.p : nullptr,
-                             K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K, 1, (double *)ctx->d_exact.p, st));
+                             K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K, 1, (double *)ctx->d_exact.p,
+                             nullptr, st));
     } else {
       CU(cudaMemsetAsync(ctx->d_exact.p, 0, words * 8, st));
     }
@@ -879,6 +931,114 @@ int exact_override_centroids(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, 
   for (uint32_t k = 0; k < K; k++)
     for (int e = 0; e < dim; e++)
       centroids[(size_t)k * dim + e] = n[k] ? state[((size_t)k * dim + e) * 2] / (double)n[k] : 0.0;
+  return QB200_OK;
+}
+
+// LBGQuantizer::quantize on general FP64 vectors (qb200_set_vectors_f64, CIE1931 images): level by level on the
+// host loop.  Assignment = filter (vectors rounded to FP32) + exact resolver; centroids = the reference's compensated
+// sums in vector order divided by the member count (src/Quantizer.cpp:46-87); distortions = FP64 sums over the
+// vectors (src/Quantizer.cpp:9-22).  Single GPU.
+int train_generic(qb200_ctx *ctx, int nbits, double eps, int mode, double *codebook_out, double *distortion_out,
+                  qb200_level_report *reports) {
+  const int dim = ctx->src.dim;
+  const size_t n = (size_t)ctx->src.n_local;
+  const uint32_t maxK = 1u << nbits;
+  cudaStream_t st = ctx->stream;
+  int rc;
+  if ((rc = exact_prepare(ctx, maxK))) return rc;
+  const int nb = distortion_blocks(ctx->sm_count);
+  if ((rc = ensure(ctx, ctx->d_counts, (size_t)maxK * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_partials, (size_t)nb * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->d_post, (size_t)maxK * dim * 8 + 256))) return rc;
+  std::vector<double> cb((size_t)maxK * dim), post((size_t)maxK * dim), state((size_t)maxK * dim * 2), partials(nb);
+  std::vector<unsigned int> counts(maxK);
+  auto sums = [&](uint32_t K) -> int {  // member sums (+ counts) of the assignment in d_assign -> state, counts
+    CU(cudaMemsetAsync(ctx->d_exact.p, 0, (size_t)K * dim * 16, st));
+    int key_bits = 0;
+    while ((1u << key_bits) < K) key_bits++;
+    if (K > 1)
+      CU(launch_exact_sort((const uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_sort_keys.p, (const uint32_t *)ctx->d_sort_iota.p,
+                           (uint32_t *)ctx->d_sort_order.p, n, key_bits, ctx->d_sort_tmp.p, ctx->d_sort_tmp.cap, st));
+    CU(launch_kahan_sums(ctx->src, K > 1 ? (const uint32_t *)ctx->d_sort_keys.p : nullptr,
+                         K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K, 0, (double *)ctx->d_exact.p,
+                         K > 1 ? (unsigned int *)ctx->d_counts.p : nullptr, st));
+    CU(cudaMemcpyAsync(state.data(), ctx->d_exact.p, (size_t)K * dim * 16, cudaMemcpyDeviceToHost, st));
+    if (K > 1) CU(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
+    return QB200_OK;
+  };
+  auto distortion = [&](const double *cb_dev, double *out) -> int {  // updateDistortion against a device codebook
+    CU(launch_distortion_f64(ctx->src, (const uint32_t *)ctx->d_assign.p, cb_dev, (double *)ctx->d_partials.p, ctx->sm_count, st));
+    CU(cudaMemcpyAsync(partials.data(), ctx->d_partials.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    double acc = 0.0;
+    for (int b = 0; b < nb; b++) acc += partials[b];
+    *out = acc / ((double)n * (double)dim);
+    return QB200_OK;
+  };
+  // initial codevector = mean of the training set (src/Quantizer.cpp:129-130)
+  if ((rc = sums(1))) return rc;
+  CU(cudaStreamSynchronize(st));
+  for (int e = 0; e < dim; e++) cb[e] = state[2 * (size_t)e] / (double)n;
+  uint32_t K = 1;
+  int level = 0;
+  double dpre = 0, dpost = 0;
+  ctx->assign_valid = false;
+  while (K < maxK) {
+    for (size_t i = 0; i < (size_t)K * dim; i++) {  // split (src/Quantizer.cpp:134-138)
+      const double v = cb[i];
+      cb[i] = v * (double)(1 + 0.2);
+      cb[(size_t)K * dim + i] = v * (double)(1 - 0.2);
+    }
+    K *= 2;
+    LevelOut lo;
+    uint32_t iterations = 0, dead = 0;
+    double d_prev = 0;
+    for (;;) {
+      if ((rc = run_level(ctx, cb.data(), K, false, reports != nullptr, &lo))) return rc;
+      if ((rc = sums(K))) return rc;
+      if ((rc = distortion((const double *)ctx->d_cb64.p, &dpre))) return rc;  // synchronises
+      if ((rc = collect_level(ctx, K, reports != nullptr, &lo))) return rc;
+      dead = 0;
+      for (uint32_t k = 0; k < K; k++) {
+        dead += counts[k] == 0;
+        for (int e = 0; e < dim; e++)  // fixCodeVectors: sum / count, an empty cell keeps the zero sum (:81-85)
+          post[(size_t)k * dim + e] = counts[k] ? state[((size_t)k * dim + e) * 2] / (double)counts[k] : 0.0;
+      }
+      CU(cudaMemcpyAsync(ctx->d_post.p, post.data(), (size_t)K * dim * 8, cudaMemcpyHostToDevice, st));
+      if ((rc = distortion((const double *)ctx->d_post.p, &dpost))) return rc;
+      iterations++;
+      if (mode == QB200_MODE_PARITY) break;  // HEAD: one assignment per level
+      const double old = iterations == 1 ? dpre : d_prev;
+      d_prev = dpost;
+      if (old == 0 || std::fabs(old - dpost) / old <= eps || iterations >= 100) break;
+      std::memcpy(cb.data(), post.data(), (size_t)K * dim * 8);
+    }
+    if (reports) {
+      qb200_level_report &r = reports[level];
+      r.K = K;
+      r.flagged = lo.flagged;
+      r.changed = lo.changed;
+      r.ties = lo.ties;
+      r.kd_depth = (uint32_t)lo.kd_depth;
+      r.iterations = iterations;
+      r.repaired = 0;
+      r.ms_assign = lo.ms_assign;
+      r.ms_resolve = lo.ms_resolve;
+      r.ms_accumulate = lo.ms_accumulate;
+      r.distortion_pre = dpre;
+      r.distortion_post = dpost;
+      r.dead_cells = dead;
+    }
+    std::memcpy(cb.data(), post.data(), (size_t)K * dim * 8);
+    level++;
+  }
+  std::memcpy(codebook_out, cb.data(), (size_t)K * dim * 8);
+  if (distortion_out) *distortion_out = dpost;
+  if (nbits == 0) {
+    CU(cudaMemsetAsync(ctx->d_assign.p, 0, (n ? n : 1) * 4, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->assign_valid = true;
+  }
   return QB200_OK;
 }
 
@@ -1045,6 +1205,11 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
   if (N == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
   if (!allreduce && ctx->src.n_local == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
   CU(cudaSetDevice(ctx->device));
+  if (ctx->src.f64) {
+    if (allreduce) return fail(ctx, QB200_ERR_ARG, "qb200_train: FP64 vectors (CIE1931 / set_vectors_f64) train on a single GPU; no all-reduce");
+    if (mode == QB200_MODE_FULL_REPAIR) return fail(ctx, QB200_ERR_ARG, "qb200_train: QB200_MODE_FULL_REPAIR is not available for FP64 vectors");
+    return train_generic(ctx, nbits, eps, mode, codebook_out, distortion_out, reports);
+  }
   if (mode == QB200_MODE_PARITY && pipeline_enabled())
     return train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);
   const int dim = ctx->src.dim;
@@ -1169,6 +1334,28 @@ int qb200_assign_accumulate(qb200_ctx *ctx, const double *codebook, uint32_t K, 
   if (!codebook || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_assign_accumulate: empty codebook");
   if (K > (1u << 24)) return fail(ctx, QB200_ERR_ARG, "qb200_assign_accumulate: K too large");
   CU(cudaSetDevice(ctx->device));
+  if (ctx->src.f64) {  // general FP64 vectors have no integer statistics: indices (and counts, from them) only
+    if (sum_out || sqsum_out)
+      return fail(ctx, QB200_ERR_ARG, "qb200_assign_accumulate: FP64 vectors have no integer sums (pass NULL)");
+    LevelOut lo;
+    int rc = run_level(ctx, codebook, K, false, false, &lo);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if ((rc = collect_level(ctx, K, false, &lo))) return rc;
+    if (flagged_out) *flagged_out = lo.flagged;
+    std::vector<uint32_t> tmp;
+    uint32_t *a = assign_out;
+    if (!a && count_out) {
+      tmp.resize((size_t)ctx->src.n_local);
+      a = tmp.data();
+    }
+    if (a && (rc = qb200_get_assign(ctx, a))) return rc;
+    if (count_out) {
+      std::fill(count_out, count_out + K, 0);
+      for (size_t i = 0; i < (size_t)ctx->src.n_local; i++) count_out[a[i]]++;
+    }
+    return QB200_OK;
+  }
   const bool want_stats = count_out || sum_out || sqsum_out;
   LevelOut lo;
   int rc = run_level(ctx, codebook, K, want_stats, false, &lo);

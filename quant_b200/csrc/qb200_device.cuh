@@ -39,6 +39,10 @@ struct VecSource {
   // When present, the hot kernels read whole words from it instead of gathering bytes from the image.
   const uint8_t *dense;
   unsigned int dense_stride;
+  // General FP64 training vectors (qb200_set_vectors_f64, CIE1931 images): n_local x dim doubles, row-major.
+  // When set, the byte fields above are not used by the training kernels: the filter runs on the values
+  // rounded to FP32, the resolver and the centroid sums on the doubles themselves (qb200_generic.cu).
+  const double *f64;
 };
 
 // Division of a 32-bit n by an invariant d (Granlund-Montgomery): q = (t + ((n - t) >> 1)) >> (l - 1),

@@ -35,29 +35,36 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kBatch = 32;  // members staged per batch (one per lane)
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 
-// One warp per cell.  The members' dense rows are copied to shared memory with cp.async one batch ahead and their
-// indices are loaded two batches ahead, so the only thing the warp ever waits for is its own FP64 chain.
-// DCH = dimensions per lane (lane handles e = lane + 32 m).  The code is kept small on purpose: the loop streams
-// through the instruction cache once per batch.
-template <int DCH>
+// One warp per cell.  The members' rows (dense bytes, or doubles for general FP64 vectors) are copied to shared
+// memory with cp.async one batch ahead and their indices are loaded two batches ahead, so the only thing the warp
+// ever waits for is its own FP64 chain.  DCH = dimensions per lane (lane handles e = lane + 32 m); `batch` members
+// are staged at a time (one per lane, <= 32).  The code is kept small on purpose: the loop streams through the
+// instruction cache once per batch.
+template <int DCH, bool F64>
 __global__ void __launch_bounds__(128)
     kahan_sums_kernel(const VecSource src, const uint32_t *__restrict__ keys_sorted, const uint32_t *__restrict__ order,
-                      const int K, const int scaled, double *__restrict__ state) {
+                      const int K, const int scaled, const int batch, double *__restrict__ state,
+                      unsigned int *__restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *s_val = reinterpret_cast<double *>(smem_raw);  // colour-space value of a raw byte (src/ColorSpace.cpp:16-21)
-  for (int u = threadIdx.x; u < 256; u += blockDim.x) {
-    const double L = (double)(int)(signed char)u;
-    s_val[u] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+  if (!F64) {
+    for (int u = threadIdx.x; u < 256; u += blockDim.x) {
+      const double L = (double)(int)(signed char)u;
+      s_val[u] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * (blockDim.x >> 5) + warp;
   if (k >= K) return;
   const int dim = src.dim;
-  const unsigned int stride = src.dense_stride, words = stride >> 2;
-  unsigned char *buf = smem_raw + 2048 + (size_t)warp * 2 * kBatch * stride;  // [2][kBatch][stride]
+  const unsigned int stride = F64 ? (unsigned int)dim * 8u : src.dense_stride;  // bytes per staged row
+  const unsigned int words = F64 ? (unsigned int)dim : stride >> 2;             // cp.async transfers per row
+  unsigned char *buf = smem_raw + 2048 + (size_t)warp * 2 * batch * stride;     // [2][batch][stride]
   const unsigned int n = (unsigned int)src.n_local;
   // members of cell k: positions [beg, end) of the sorted list (K == 1: the whole set in its own order)
   unsigned int beg = 0, end = n;
@@ -72,6 +79,7 @@ __global__ void __launch_bounds__(128)
     beg = __shfl_sync(0xffffffffu, lo, 0);
     end = __shfl_sync(0xffffffffu, lo, 1);
   }
+  if (counts && lane == 0) counts[k] = end - beg;
   double sum[DCH], c[DCH];
 #pragma unroll
   for (int m = 0; m < DCH; m++) {
@@ -80,20 +88,26 @@ __global__ void __launch_bounds__(128)
     c[m] = e < dim ? state[((size_t)k * dim + e) * 2 + 1] : 0.0;
   }
   auto member = [&](unsigned int j) -> unsigned int {  // this lane's member of the batch starting at j
-    if (j >= end || lane >= end - j) return 0xffffffffu;
+    if (lane >= batch || j >= end || (unsigned int)lane >= end - j) return 0xffffffffu;
     return order ? __ldg(order + j + lane) : j + lane;
   };
   auto stage = [&](unsigned int mine, int slot) {       // every lane copies its own member's row, asynchronously
-    unsigned char *dst = buf + ((size_t)slot * kBatch + lane) * stride;
+    unsigned char *dst = buf + ((size_t)slot * batch + lane) * stride;
     if (mine != 0xffffffffu) {
-      const unsigned char *row = src.dense + (unsigned long long)mine * stride;
-      for (unsigned int w = 0; w < words; w++) cp_async_4(dst + 4 * w, row + 4 * w);
+      if (F64) {
+        const double *row = src.f64 + (unsigned long long)mine * dim;
+        for (unsigned int w = 0; w < words; w++) cp_async_8(dst + 8 * w, row + w);
+      } else {
+        const unsigned char *row = src.dense + (unsigned long long)mine * stride;
+        for (unsigned int w = 0; w < words; w++) cp_async_4(dst + 4 * w, row + 4 * w);
+      }
     }
     cp_async_commit();
   };
   // value of element (lane + 32 m) of staged member s
   auto value = [&](const unsigned char *rows, unsigned int s, int m) -> double {
     const int e = lane + 32 * m;
+    if (F64) return reinterpret_cast<const double *>(rows + s * stride)[e < dim ? e : 0];
     return s_val[rows[s * stride + (e < (int)stride ? e : 0)]];
   };
   // src/Quantizer.cpp:64-67:  y = x - c;  t = sum + y;  c = (t - sum) - y;  sum = t
@@ -106,15 +120,15 @@ __global__ void __launch_bounds__(128)
   constexpr int G = DCH == 1 ? 8 : DCH == 2 ? 4 : 2;  // members whose values are fetched ahead of the chain
   unsigned int idx_next = member(beg);
   stage(idx_next, 0);
-  idx_next = member(beg + kBatch);
+  idx_next = member(beg + batch);
   int slot = 0;
-  for (unsigned int j0 = beg; j0 < end; j0 += kBatch, slot ^= 1) {
-    const unsigned int cnt = min((unsigned int)kBatch, end - j0);
-    stage(idx_next, slot ^ 1);                       // batch j0 + kBatch (an empty group past the end)
-    idx_next = member(j0 + 2 * kBatch);              // consumed one iteration later
+  for (unsigned int j0 = beg; j0 < end; j0 += batch, slot ^= 1) {
+    const unsigned int cnt = min((unsigned int)batch, end - j0);
+    stage(idx_next, slot ^ 1);                       // batch j0 + batch (an empty group past the end)
+    idx_next = member(j0 + 2 * batch);               // consumed one iteration later
     cp_async_wait<1>();                              // batch j0 has landed
     __syncwarp();
-    const unsigned char *rows = buf + (size_t)slot * kBatch * stride;
+    const unsigned char *rows = buf + (size_t)slot * batch * stride;
     unsigned int s = 0;
     if (cnt >= (unsigned int)G) {
       double xa[G][DCH], xb[G][DCH];
@@ -185,20 +199,34 @@ cudaError_t launch_exact_sort(const uint32_t *assign, uint32_t *keys_out, const 
 }
 
 // state: K*dim pairs {sum, c}, read as the chain's initial state and overwritten with its final one.
-// Needs the dense copy of the training set (always made by set_image / set_vectors).
+// counts (may be null): members of every cell on this context.  Reads the dense byte copy of the training set
+// (always made by set_image / set_vectors_u8) or, for general FP64 vectors, the doubles themselves.
 cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, int scaled,
-                              double *state, cudaStream_t stream) {
-  if (!src.dense) return cudaErrorInvalidValue;
-  const int dim = src.dim, warps = src.dense_stride <= 48 ? 4 : 1, blocks = (K + warps - 1) / warps;
-  const size_t smem = 2048 + (size_t)warps * 2 * kBatch * src.dense_stride;
+                              double *state, unsigned int *counts, cudaStream_t stream) {
+  const bool f64 = src.f64 != nullptr;
+  if (!f64 && !src.dense) return cudaErrorInvalidValue;
+  const int dim = src.dim;
+  const size_t row = f64 ? (size_t)dim * 8 : src.dense_stride;
+  int batch = 32;
+  while (batch > 4 && 2 * (size_t)batch * row > 40 * 1024) batch >>= 1;
+  int warps = (int)((40 * 1024) / (2 * (size_t)batch * row));
+  warps = warps < 1 ? 1 : warps > 4 ? 4 : warps;
+  const int blocks = (K + warps - 1) / warps;
+  const size_t smem = 2048 + (size_t)warps * 2 * batch * row;
+#define QB_KAHAN(DCH)                                                                                                    \
+  (f64 ? kahan_sums_kernel<DCH, true><<<blocks, 32 * warps, smem, stream>>>(src, keys_sorted, order, K, scaled, batch,  \
+                                                                            state, counts)                              \
+       : kahan_sums_kernel<DCH, false><<<blocks, 32 * warps, smem, stream>>>(src, keys_sorted, order, K, scaled, batch, \
+                                                                             state, counts))
   if (dim <= 32)
-    kahan_sums_kernel<1><<<blocks, 32 * warps, smem, stream>>>(src, keys_sorted, order, K, scaled, state);
+    QB_KAHAN(1);
   else if (dim <= 64)
-    kahan_sums_kernel<2><<<blocks, 32 * warps, smem, stream>>>(src, keys_sorted, order, K, scaled, state);
+    QB_KAHAN(2);
   else if (dim <= 96)
-    kahan_sums_kernel<3><<<blocks, 32 * warps, smem, stream>>>(src, keys_sorted, order, K, scaled, state);
+    QB_KAHAN(3);
   else
-    kahan_sums_kernel<6><<<blocks, 32 * warps, smem, stream>>>(src, keys_sorted, order, K, scaled, state);
+    QB_KAHAN(6);
+#undef QB_KAHAN
   count_launch();
   return cudaGetLastError();
 }

@@ -410,7 +410,14 @@ __global__ void __launch_bounds__(128, 1)
     const unsigned long long v = v0 + tid;
     const bool live = v < src.n_local;
     float xn = 0.f;
-    if (live) {
+    if (live && src.f64) {  // general FP64 vectors: the filter sees them rounded to FP32 (the margin covers it)
+      const double *xv = src.f64 + v * (unsigned long long)dim;
+      for (int e = 0; e < dim; e++) {
+        const float f = (float)xv[e];
+        s_x[e * 128 + tid] = f;
+        xn = fmaf(f, f, xn);
+      }
+    } else if (live) {
       unsigned long long base, img;
       vec_base(src, v, base, img);
       for (int e = 0; e < dim; e++) {
@@ -560,12 +567,17 @@ __global__ void __launch_bounds__(128)
   double x[DIMCAP];
   for (unsigned int f = warp; f < total; f += n_warps) {
     const unsigned long long v = flag_list[f];
-    unsigned long long base, img;
-    vec_base(src, v, base, img);
+    unsigned long long base = 0, img = 0;
+    const double *xv = src.f64 ? src.f64 + v * (unsigned long long)dim : nullptr;  // general FP64 vectors: as they are
+    if (!xv) vec_base(src, v, base, img);
 #pragma unroll
     for (int e = 0; e < (DIMT ? DIMT : dim); e++) {
-      const double L = (double)load_lattice(src, img, base, e);
-      x[e] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+      if (xv) {
+        x[e] = xv[e];
+      } else {
+        const double L = (double)load_lattice(src, img, base, e);
+        x[e] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+      }
     }
     double d1 = DBL_MAX, d2 = DBL_MAX, dmax = 0.0;  // this lane's smallest, second smallest, largest
     int k1 = 0;
@@ -718,14 +730,19 @@ __global__ void __launch_bounds__(128)
   Frame stack[DEPTHCAP];
   for (unsigned int f = warp; f < total; f += n_warps) {
     const unsigned long long v = flag_list[f];
-    unsigned long long base, img;
-    vec_base(src, v, base, img);
+    unsigned long long base = 0, img = 0;
+    const double *xv = src.f64 ? src.f64 + v * (unsigned long long)dim : nullptr;
+    if (!xv) vec_base(src, v, base, img);
 #pragma unroll
     for (int e = 0; e < (DIMT ? DIMT : dim); e++) {
-      const double L = (double)load_lattice(src, img, base, e);
-      // ScaledColor::RGBtoColorSpace: ((double)c + 128.0) / 255 (src/ColorSpace.cpp:16-21);
-      // a past-the-end element is the literal 0.0 and (-128 + 128)/255 == 0.0 as well.
-      x[e] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+      if (xv) {
+        x[e] = xv[e];
+      } else {
+        const double L = (double)load_lattice(src, img, base, e);
+        // ScaledColor::RGBtoColorSpace: ((double)c + 128.0) / 255 (src/ColorSpace.cpp:16-21);
+        // a past-the-end element is the literal 0.0 and (-128 + 128)/255 == 0.0 as well.
+        x[e] = scaled ? __ddiv_rn(__dadd_rn(L, 128.0), 255.0) : L;
+      }
     }
     // computeInitialDistances (nanoflann.hpp:1188-1205)
     double distsq = 0.0;
@@ -1329,7 +1346,7 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
 
 cudaError_t launch_assign(const AssignLaunch &a) {
   if (a.fused_out) *a.fused_out = false;
-  switch (a.src.dim) {
+  switch (a.src.f64 ? -1 : a.src.dim) {  // FP64 vectors: the generic kernel, whatever the dimension
     case 3: return launch_assign_t<3>(a);
     case 6: return launch_assign_t<6>(a);
     case 9: return launch_assign_t<9>(a);

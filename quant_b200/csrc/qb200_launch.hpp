@@ -92,7 +92,15 @@ cudaError_t launch_exact_iota(uint32_t *iota, size_t n, int sm_count, cudaStream
 cudaError_t launch_exact_sort(const uint32_t *assign, uint32_t *keys_out, const uint32_t *iota, uint32_t *order, size_t n,
                               int key_bits, void *tmp, size_t tmp_bytes, cudaStream_t stream);
 cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, int scaled,
-                              double *state, cudaStream_t stream);
+                              double *state, unsigned int *counts, cudaStream_t stream);
+// General FP64 training vectors (qb200_generic.cu).
+// CIE1931 colour space (src/ColorSpace.cpp:31-39): the image's block vectors as doubles, n_local x dim.
+cudaError_t launch_cie_vectors(const VecSource &src, double *out, int sm_count, cudaStream_t stream);
+// updateDistortion (src/Quantizer.cpp:9-22) for FP64 vectors: partials[b] = sum over block b's vectors of
+// |x - cb[assign]|^2; the caller adds the `blocks` partials in order and divides by N*dim.  Returns blocks.
+int distortion_blocks(int sm_count);
+cudaError_t launch_distortion_f64(const VecSource &src, const uint32_t *assign, const double *cb, double *partials,
+                                  int sm_count, cudaStream_t stream);
 // Empty-cell repair (QB200_MODE_FULL_REPAIR): smallest (hash, global index) key per donor cell; member bytes.
 cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, const int *slot_of_cell,
                                 unsigned long long seed, unsigned long long *keys, int sm_count, cudaStream_t stream);

@@ -65,7 +65,8 @@ int training_mode() {
 int checked_colorspace(ColorSpaces cs) {
   if (cs == ColorSpaces::NORMAL) return QB200_CS_NORMAL;
   if (cs == ColorSpaces::SCALED) return QB200_CS_SCALED;
-  throw std::runtime_error("compress: colour space CIE1931 is outside the B200 path");
+  if (cs == ColorSpaces::CIE1931) return QB200_CS_CIE1931;  // FP64 vectors on the device (include/qb200.h)
+  throw std::runtime_error("compress: unknown colour space");
 }
 
 }  // namespace

@@ -15,7 +15,8 @@ class KDTree::KDTreeImpl {
 };
 
 namespace {
-// same lattice rule as Quantizer.cpp: NORMAL = integers in [-128, 127], SCALED = t/255.0 with t in [0, 255]
+// same lattice rule as Quantizer.cpp: NORMAL = integers in [-128, 127], SCALED = t/255.0 with t in [0, 255];
+// -1: neither (the queries then go to the library as FP64 vectors)
 int lattice_of(const std::vector<Vector> &pts, size_t dim, std::vector<uint8_t> &bytes) {
   bool normal = true, scaled = true;
   for (const Vector &p : pts) {
@@ -26,7 +27,7 @@ int lattice_of(const std::vector<Vector> &pts, size_t dim, std::vector<uint8_t> 
       if (scaled && !(t >= 0 && t <= 255 && t / 255.0 == x)) scaled = false;
     }
   }
-  if (!normal && !scaled) throw std::runtime_error("KDTree: queries are not on the NORMAL or SCALED byte lattice");
+  if (!normal && !scaled) return -1;
   bytes.resize(pts.size() * dim);
   for (size_t i = 0; i < pts.size(); i++)
     for (size_t d = 0; d < dim; d++)
@@ -54,7 +55,14 @@ std::vector<size_t> KDTree::nearestNeighbours(const std::vector<Vector> &pts) co
   std::vector<uint8_t> bytes;
   const int cs = lattice_of(pts, impl->dim, bytes);
   qb200_ctx *ctx = qbhost::context();
-  qbhost::check(qb200_set_vectors_u8(ctx, bytes.data(), pts.size(), (int)impl->dim, cs, 0), "qb200_set_vectors_u8");
+  if (cs >= 0) {
+    qbhost::check(qb200_set_vectors_u8(ctx, bytes.data(), pts.size(), (int)impl->dim, cs, 0), "qb200_set_vectors_u8");
+  } else {
+    std::vector<double> flat;
+    flat.reserve(pts.size() * impl->dim);
+    for (const Vector &p : pts) flat.insert(flat.end(), p.begin(), p.end());
+    qbhost::check(qb200_set_vectors_f64(ctx, flat.data(), pts.size(), (int)impl->dim, 0), "qb200_set_vectors_f64");
+  }
   std::vector<uint32_t> idx(pts.size());
   qbhost::check(qb200_assign_accumulate(ctx, impl->codebook.data(), (uint32_t)K, idx.data(), nullptr, nullptr, nullptr, nullptr),
                 "qb200_assign_accumulate");

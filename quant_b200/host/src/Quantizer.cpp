@@ -3,8 +3,9 @@
 // The reference's LBGQuantizer::quantize (src/Quantizer.cpp:121-143) and everything under it
 // (assignCodeVectors :24-32, updateDistortion :9-22, fixCodeVectors :72-87, the split :134-138)
 // run on the GPU behind qb200_train.  This file only marshals the generic vector<Vector>
-// signature: the GPU path works on the byte lattice image data lives on, so the doubles are mapped
-// back to bytes - exactly, or the call fails (general FP64 inputs are a "next" row).
+// signature: the fast GPU path works on the byte lattice image data lives on, so the doubles are mapped
+// back to bytes when that is exact; any other input goes to the library as FP64 vectors
+// (qb200_set_vectors_f64).
 #include "Quantizer.hpp"
 
 #include <cmath>
@@ -18,6 +19,7 @@ namespace {
 
 // NORMAL lattice: every element is an integer in [-128, 127] (byte = value mod 256).
 // SCALED lattice: every element equals t/255.0 for an integer t in [0, 255] (byte = t xor 0x80).
+// Returns the colour space of the lattice, or -1 when the vectors are on neither.
 int to_lattice_bytes(const std::vector<Vector> &set, size_t dim, std::vector<uint8_t> &bytes) {
   bytes.resize(set.size() * dim);
   bool normal = true, scaled = true;
@@ -32,9 +34,7 @@ int to_lattice_bytes(const std::vector<Vector> &set, size_t dim, std::vector<uin
       }
     }
   }
-  if (!normal && !scaled)
-    throw std::runtime_error("quantize: training vectors are not on the NORMAL or SCALED byte lattice; "
-                             "the B200 path has no general FP64-input kernel and no CPU fallback");
+  if (!normal && !scaled) return -1;
   const int cs = normal ? QB200_CS_NORMAL : QB200_CS_SCALED;
   for (size_t i = 0; i < set.size(); i++)
     for (size_t d = 0; d < dim; d++) {
@@ -52,7 +52,16 @@ class LBGQuantizer : public AbstractQuantizer {
     std::vector<uint8_t> bytes;
     const int cs = to_lattice_bytes(trainingSet, dim, bytes);
     qb200_ctx *ctx = qbhost::context();
-    qbhost::check(qb200_set_vectors_u8(ctx, bytes.data(), trainingSet.size(), (int)dim, cs, 0), "qb200_set_vectors_u8");
+    if (cs >= 0) {
+      qbhost::check(qb200_set_vectors_u8(ctx, bytes.data(), trainingSet.size(), (int)dim, cs, 0), "qb200_set_vectors_u8");
+    } else {  // arbitrary doubles
+      std::vector<double> flat(trainingSet.size() * dim);
+      for (size_t i = 0; i < trainingSet.size(); i++) {
+        if (trainingSet[i].size() != dim) throw std::runtime_error("quantize: vectors of unequal dimension");
+        for (size_t d = 0; d < dim; d++) flat[i * dim + d] = trainingSet[i][d];
+      }
+      qbhost::check(qb200_set_vectors_f64(ctx, flat.data(), trainingSet.size(), (int)dim, 0), "qb200_set_vectors_f64");
+    }
     const size_t K = (size_t)1 << n;
     std::vector<double> cb(K * dim);
     double distortion = 0;

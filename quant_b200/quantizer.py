@@ -4,11 +4,11 @@
     q = getQuantizer(Quantizers.LBG)
     codeVectors, assignedCodeVector, distortion = q.quantize(trainingSet, n, eps)
 
-``trainingSet`` is an (N, dim) float64 array: what getBlocksAsVectorsFromImage returns.  The GPU
-path works on the integer lattice the image bytes live on, so the generic entry first maps the
-doubles back to bytes (exactly - it refuses inputs that are not on a supported lattice; the
-general FP64-input path is SURVEY.md 8f row 3).  ``CompressedImage.compress`` skips this and hands
-the raw image bytes to the library.
+``trainingSet`` is an (N, dim) float64 array: what getBlocksAsVectorsFromImage returns.  The fast GPU
+path works on the integer lattice the image bytes live on, so the generic entry first tries to map the
+doubles back to bytes (exactly); inputs that are not on a supported lattice take the library's general
+FP64-vector path (qb200_set_vectors_f64).  ``CompressedImage.compress`` skips this
+and hands the raw image bytes to the library.
 """
 from __future__ import annotations
 
@@ -44,8 +44,7 @@ def vectors_to_lattice_bytes(X: np.ndarray) -> Tuple[np.ndarray, int]:
     ok = (t >= 0) & (t <= 255)
     if ok.all() and np.array_equal(t / 255.0, X):
         return (t.astype(np.int64) ^ 0x80).astype(np.uint8), CS_SCALED
-    raise ValueError("trainingSet is not on the NORMAL or SCALED byte lattice; the general FP64 "
-                     "input path is not implemented on the GPU (and there is no CPU fallback)")
+    raise ValueError("trainingSet is not on the NORMAL or SCALED byte lattice")
 
 
 class AbstractQuantizer:
@@ -72,9 +71,14 @@ class LBGQuantizer(AbstractQuantizer):
         if X.ndim != 2 or X.shape[0] == 0:
             # Solution's constructor calls trainingSet.at(0) (src/Quantizer.cpp:91)
             raise IndexError("trainingSet is empty")
-        mat, cs = vectors_to_lattice_bytes(X)
         ctx = self.context
-        ctx.set_vectors_u8(mat, cs)
+        try:
+            mat, cs = vectors_to_lattice_bytes(X)
+            ctx.set_vectors_u8(mat, cs)
+        except ValueError:          # arbitrary doubles: the general FP64-vector path of the library
+            if X.shape[1] > 192:
+                raise
+            ctx.set_vectors_f64(X)
         cb, dist, self.last_reports = ctx.train(int(n), float(eps))
         return cb, ctx.get_assign_u64(), dist
 

@@ -1,7 +1,7 @@
 // C++ checks of the drop-in host layer, written like the reference's only unit test
 // (/root/reference/src/test.cpp:5-62, compressor_test.something) plus the plugin entry on a GPU.
 //   host_test layout                CPU only: block -> vector -> char vector -> image round trips
-//   host_test quantize <in.ppm> w h n  needs a B200: getQuantizer(LBG)->quantize(vectors) must agree with
+//   host_test quantize <in.ppm> w h n [cs]  needs a B200: getQuantizer(LBG)->quantize(vectors) must agree with
 //                                   CompressedImage::compress(image) (codebook bytes, indices)
 #include <cstdio>
 #include <cstring>
@@ -58,10 +58,10 @@ static int test_layout() {
   return failures;
 }
 
-static int test_quantize(const std::string &ppm, int w, int h, int n) {
+static int test_quantize(const std::string &ppm, int w, int h, int n, ColorSpaces space) {
   RGBImage img(ppm);
-  auto res = CompressedImage::compress(img, Quantizers::LBG, ColorSpaces::SCALED, w, h, 1e-6f, n);
-  ColorSpacePtr cs = getColorSpace(ColorSpaces::SCALED);
+  auto res = CompressedImage::compress(img, Quantizers::LBG, space, w, h, 1e-6f, n);
+  ColorSpacePtr cs = getColorSpace(space);  // CIE1931: the vectors below are not on a byte lattice (FP64 path)
   auto vecs = getBlocksAsVectorsFromImage(img, w, h, cs);
   auto q = getQuantizer(Quantizers::LBG);
   auto out = q->quantize(vecs, n, 1e-6f);
@@ -98,12 +98,13 @@ int main(int argc, char **argv) {
   try {
     if (argc >= 2 && std::strcmp(argv[1], "layout") == 0) return test_layout() ? 1 : (std::puts("layout ok"), 0);
     if (argc >= 6 && std::strcmp(argv[1], "quantize") == 0)
-      return test_quantize(argv[2], std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5])) ? 1
+      return test_quantize(argv[2], std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]),
+                           argc >= 7 ? (ColorSpaces)std::atoi(argv[6]) : ColorSpaces::SCALED) ? 1
                                                                                               : (std::puts("quantize ok"), 0);
   } catch (const std::exception &e) {
     std::printf("exception: %s\n", e.what());
     return 3;
   }
-  std::puts("usage: host_test layout | quantize <in.ppm> w h n");
+  std::puts("usage: host_test layout | quantize <in.ppm> w h n [colourspace]");
   return 2;
 }

@@ -119,5 +119,38 @@ def main():
     print("encode-only fixture:", idx.shape)
 
 
+def main_fp64():
+    """Fixtures of the general FP64-vector path: CIE1931 images and arbitrary double vectors.
+    Written by `python tests/golden/make_golden.py fp64` without touching the other fixtures."""
+    R, Rrel = RefLib("strict"), RefLib("release")
+    k1, _, _ = load_png(os.path.join(KODIM, "kodim01.png"))
+    k5, _, _ = load_png(os.path.join(KODIM, "kodim05.png"))
+    crop = np.ascontiguousarray(k1[128:256, 192:384])  # 192 x 128
+    make_case(R, Rrel, "kodim01_small_2x2_n8_cie", crop, 192, 128, 2, 2, 8, 2)
+    odd = np.ascontiguousarray(k5[200:267, 100:201])
+    make_case(R, Rrel, "odd_101x67_3x2_n5_cie", odd, 101, 67, 3, 2, 5, 2)
+    two = np.full((32, 32, 3), 10, np.uint8)
+    two[:, 16:] = 240
+    make_case(R, Rrel, "twotone_32x32_2x2_n5_cie", two, 32, 32, 2, 2, 5, 2)
+    rng = np.random.default_rng(77)
+    sets = {"generic_gauss_d7_n6": (rng.normal(size=(6000, 7)) * np.array([1, 10, 0.1, 5, 2, 3, 1e-3]), 6),
+            "generic_clusters_d12_n7": (rng.normal(size=(40, 12))[rng.integers(0, 40, 9000)] * 50
+                                        + rng.normal(size=(9000, 12)) * 0.01, 7),
+            "generic_dups_d5_n6": (np.round(rng.normal(size=(4000, 5)) * 2) / 3.0, 6),   # heavy duplicates, exact ties
+            "generic_big_d40_n5": (rng.normal(size=(3000, 40)) * 1e6 + 3e6, 5)}
+    for name, (X, nbits) in sets.items():
+        X = np.ascontiguousarray(X, np.float64)
+        cb0, lv = R.levels(X, nbits)
+        cb, a, dist = R.quantize(X, nbits)
+        d = dict(X=X, nbits=np.int64(nbits), cb0=cb0, codebook=cb, assign=a.astype(np.uint32), distortion=np.float64(dist))
+        for i, l in enumerate(lv):
+            d[f"L{i}_pre"] = l["cb_pre"]
+            d[f"L{i}_post"] = l["cb_post"]
+            d[f"L{i}_assign"] = l["assign"].astype(np.uint16)
+            d[f"L{i}_d"] = np.array([l["d0"], l["d1"]])
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+        print(f"{name}: N={X.shape[0]} dim={X.shape[1]} K={1 << nbits} used={len(np.unique(a))} dist={dist:.6g}")
+
+
 if __name__ == "__main__":
-    main()
+    main_fp64() if sys.argv[1:] == ["fp64"] else main()

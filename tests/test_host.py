@@ -97,6 +97,13 @@ def test_vectors_to_lattice_bytes(port):
         qb.LBGQuantizer().quantize(np.zeros((0, 12)), 4, 1e-6)  # trainingSet.at(0) throws
 
 
-def test_cie1931_is_declared_out_of_scope():
-    with pytest.raises(NotImplementedError):
-        getBlocksAsVectorsFromImage(letters_image(), 1, 1, ColorSpaces.CIE1931)
+def test_cie1931_block_vectors_match_the_oracle(port):
+    """Cie1931::RGBtoColorSpace through the host mirror == the C port (itself pinned to the real reference)."""
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (7, 9, 3), dtype=np.uint8)
+    img = qb.RGBImage.from_array(rgb, 9, 7)
+    for (w, h) in [(1, 1), (2, 2), (4, 3)]:
+        got = getBlocksAsVectorsFromImage(img, w, h, ColorSpaces.CIE1931)
+        assert got.tobytes() == port.blocks(rgb, 9, 7, w, h, 2).tobytes()
+    with pytest.raises(ValueError):
+        getBlocksAsVectorsFromImage(img, 1, 1, 3)

@@ -76,8 +76,11 @@ def test_cli_rejects_bad_arguments(host_built, tmp_path):
     assert subprocess.run([QUANT, "--help"], capture_output=True).returncode == 0
 
 
+CIE_GOLDENS = ["kodim01_small_2x2_n8_cie", "odd_101x67_3x2_n5_cie"]   # --c 2: FP64 vectors on the device
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names() + CIE_GOLDENS)
 def test_cli_compress_writes_the_reference_quant_file(host_built, tmp_path, name):
     g = load_golden(name)
     p, q, d = str(tmp_path / "i.ppm"), str(tmp_path / "o.quant"), str(tmp_path / "o.ppm")
@@ -100,6 +103,9 @@ def test_plugin_quantize_entry_agrees_with_compress(host_built, tmp_path):
     p = str(tmp_path / "i.ppm")
     write_ppm(p, g.rgb, g.xs, g.ys)
     r = subprocess.run([HOST_TEST, "quantize", p, str(g.w), str(g.h), str(g.nbits)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # CIE1931: the generic entry sees vectors off the byte lattice and takes the FP64 path; same result as compress()
+    r = subprocess.run([HOST_TEST, "quantize", p, str(g.w), str(g.h), str(g.nbits), "2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
 
 
