@@ -39,12 +39,44 @@ def make_image(xs, ys, kind):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
+def make_vectors():
+    """General FP64 training vectors: odd dimensions, wild scales, duplicates (exact ties)."""
+    n, dim = int(rng.integers(2, 4000)), int(rng.choice([1, 2, 3, 5, 7, 12, 13, 31, 32, 33, 48, 64, 65, 100, 192]))
+    kind = int(rng.integers(0, 4))
+    scale = 10.0 ** rng.integers(-8, 9)
+    if kind == 0:
+        X = rng.normal(size=(n, dim)) * rng.uniform(0.01, 100, dim)
+    elif kind == 1:      # a few centres, tiny spread
+        X = rng.normal(size=(7, dim))[rng.integers(0, 7, n)] + rng.normal(size=(n, dim)) * 1e-6
+    elif kind == 2:      # coarse grid: duplicates and exact ties everywhere
+        X = np.round(rng.normal(size=(n, dim)) * 2) / 3.0
+    else:                # one value repeated, a few outliers
+        X = np.tile(rng.normal(size=(1, dim)), (n, 1))
+        X[rng.integers(0, n, min(n, 5))] = rng.normal(size=(min(n, 5), dim)) * 10
+    return np.ascontiguousarray(X * scale), kind
+
+
 while time.time() < t_end:
+    if rng.random() < 0.25:
+        X, kind = make_vectors()
+        N, dim = X.shape
+        nbits = int(rng.integers(1, 9))
+        cb_o, a_o, d_o = P.quantize(X, nbits)
+        ctx.set_vectors_f64(X)
+        cb, d, _ = ctx.train(nbits)
+        a = ctx.get_assign().astype(np.uint64)
+        if not (np.array_equal(a, a_o) and cb.tobytes() == np.ascontiguousarray(cb_o).tobytes()):
+            bad += 1
+            print(f"MISMATCH f64 train kind={kind} N={N} dim={dim} nbits={nbits}: {int((a != a_o).sum())} indices", flush=True)
+        cases += 1
+        continue
     w, h = int(rng.integers(1, 5)), int(rng.integers(1, 5))
-    if 3 * w * h not in (3, 6, 9, 12, 24, 27, 48) and rng.random() < 0.7:
+    if rng.random() < 0.05:
+        w, h = int(rng.integers(5, 9)), int(rng.integers(5, 9))      # generic-dimension kernels (dim up to 192)
+    elif 3 * w * h not in (3, 6, 9, 12, 24, 27, 48) and rng.random() < 0.7:
         continue
     xs, ys = int(rng.integers(w, 200)), int(rng.integers(h, 160))
-    cs = int(rng.integers(0, 2))
+    cs = int(rng.integers(0, 3))
     kind = int(rng.integers(0, 4))
     rgb = make_image(xs, ys, kind)
     X = P.blocks(rgb, xs, ys, w, h, cs)
@@ -74,7 +106,7 @@ while time.time() < t_end:
         cb, d, _ = ctx.train(nbits)
         a = ctx.get_assign().astype(np.uint64)
         ok = np.array_equal(a, a_o) and np.array_equal(qb.codebook_to_bytes(cb, cs), P.codebook_to_bytes(cb_o, cs))
-        if exact or cs == 0:
+        if exact or cs != 1:
             ok = ok and cb.tobytes() == np.ascontiguousarray(cb_o).tobytes()
         if not ok and not exact and cs == 1:
             # allowed only if every level, fed the oracle's own codebook, is bit-identical (indices, counts, sums)
