@@ -817,12 +817,29 @@ int qb200_finalize_level(int colorspace, uint32_t K, int dim, uint64_t n_total, 
     const long double Qt = scaled ? (long double)sqsum[k] + 256.0L * (long double)s_all +
                                         16384.0L * (long double)dim * (long double)n
                                   : (long double)sqsum[k];
+    // A cell whose members are all the SAME vector (n * Q == sum_d S_d^2, tested without overflow as: every S_d
+    // divisible by n and Q == n * sum_d (S_d/n)^2): the reference's compensated sum of n equal terms v is exactly
+    // fl(n * v) - every step of the loop is exact - so its centroid fl(fl(n*v)/n) is reproduced bit for bit.  It
+    // matters: such a cell has c == x, and x is then equidistant from the children 1.2c / 0.8c at the next split.
+    bool same = scaled && n > 0;
+    if (same) {
+      uint64_t q = 0;
+      for (int e = 0; e < dim && same; e++) {
+        const int64_t S = sum[(size_t)k * dim + e];
+        same = S % (int64_t)n == 0;
+        q += (uint64_t)((S / (int64_t)n) * (S / (int64_t)n));
+      }
+      same = same && sqsum[k] == n * q;
+    }
     for (int e = 0; e < dim; e++) {
       const int64_t St = sum[(size_t)k * dim + e] + (scaled ? (int64_t)(128 * n) : 0);
       // centroid: the reference divides the Kahan sum of the members by their count
       // (src/Quantizer.cpp:81-85); an empty cell keeps the zero vector.
       double c = 0.0;
-      if (n) c = ((double)St / unit) / (double)n;
+      if (same)
+        c = ((double)n * ((double)(St / (int64_t)n) / unit)) / (double)n;
+      else if (n)
+        c = ((double)St / unit) / (double)n;
       if (codebook_post) codebook_post[(size_t)k * dim + e] = c;
       st2 += (long double)St * (long double)St;
       if (codebook_pre) {

@@ -1181,13 +1181,26 @@ __global__ void __launch_bounds__(1024)
     // Q in the colour space's lattice t (SCALED: t = L + 128): sum t^2 = Q_L + 256 S_L + 128^2 dim n
     const double Qt = scaled ? (double)row[dim + 1] + 256.0 * (double)s_all + 16384.0 * (double)dim * (double)n
                              : (double)row[dim + 1];
+    // all members the same vector (see qb200_finalize_level): the reference's sum of n equal terms is fl(n * v)
+    bool same = scaled && n > 0 && !exact_state;
+    if (same) {
+      unsigned long long q = 0;
+      for (int e = 0; e < dim && same; e++) {
+        const long long S = (long long)row[1 + e];
+        const long long m = S / (long long)n;
+        same = m * (long long)n == S;
+        q += (unsigned long long)(m * m);
+      }
+      same = same && row[dim + 1] == n * q;
+    }
     double st2 = 0.0, cross = 0.0, c2 = 0.0;
     for (int e = 0; e < dim; e++) {
       const long long St = (long long)row[1 + e] + (scaled ? (long long)(128ull * n) : 0ll);
       // exact_state: the reference's compensated sum itself (qb200_exact.cu), divided as in src/Quantizer.cpp:84-85
       const double c = !n ? 0.0
                           : exact_state ? __ddiv_rn(exact_state[((size_t)k * dim + e) * 2], (double)n)
-                                        : __ddiv_rn(__ddiv_rn((double)St, unit), (double)n);
+                          : same ? __ddiv_rn(__dmul_rn((double)n, __ddiv_rn((double)(St / (long long)n), unit)), (double)n)
+                                 : __ddiv_rn(__ddiv_rn((double)St, unit), (double)n);
       cb_post[(size_t)k * dim + e] = c;
       if (cb_next) {
         cb_next[(size_t)k * dim + e] = __dmul_rn(c, f_up);

@@ -107,3 +107,25 @@ def test_cie1931_block_vectors_match_the_oracle(port):
         assert got.tobytes() == port.blocks(rgb, 9, 7, w, h, 2).tobytes()
     with pytest.raises(ValueError):
         getBlocksAsVectorsFromImage(img, 1, 1, 3)
+
+
+def test_finalize_level_reproduces_the_compensated_sum_of_equal_members(port):
+    """A cell whose members are all the same vector: the reference's Kahan sum of n equal terms v is fl(n*v), and
+    qb200_finalize_level must return fl(fl(n*v)/n) - bit for bit what Solution::fixCodeVectors computes."""
+    rng = np.random.default_rng(9)
+    dim = 6
+    for n in [1, 2, 3, 7, 10, 66, 255, 1000, 4099, 65537]:
+        t = rng.integers(0, 256, (4, dim))                      # four cells, each n copies of one lattice vector
+        X = np.repeat(t / 255.0, n, axis=0)
+        assign = np.repeat(np.arange(4, dtype=np.uint64), n)
+        want = port.fix(X, assign, 4)
+        L = (t - 128).astype(np.int64)
+        count = np.full(4, n, np.uint64)
+        post, _, _ = qb.finalize_level(qb.CS_SCALED, 4 * n, count, L * n, ((L * L).sum(1) * n).astype(np.uint64))
+        assert post.tobytes() == want.tobytes(), n
+    # two different members: the plain integer-sum formula, within a few ulp
+    X = np.array([[10, 20, 30, 40, 50, 60], [11, 20, 30, 40, 50, 61]]) / 255.0
+    L = np.array([[10, 20, 30, 40, 50, 60], [11, 20, 30, 40, 50, 61]]) - 128
+    post, _, _ = qb.finalize_level(qb.CS_SCALED, 2, np.array([2], np.uint64), L.sum(0, keepdims=True),
+                                   np.array([(L * L).sum()], np.uint64))
+    assert np.allclose(post, port.fix(X, np.zeros(2, np.uint64), 1), rtol=1e-15, atol=0)
