@@ -42,7 +42,7 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 // One warp per cell.  The members' rows (dense bytes, or doubles for general FP64 vectors) are copied to shared
 // memory with cp.async one batch ahead and their indices are loaded two batches ahead, so the only thing the warp
 // ever waits for is its own FP64 chain.  DCH = dimensions per lane (lane handles e = lane + 32 m); `batch` members
-// are staged at a time (one per lane, <= 32).  The code is kept small on purpose: the loop streams through the
+// (<= 128, up to four per lane) are staged at a time.  The code is kept small on purpose: the loop streams through the
 // instruction cache once per batch.
 template <int DCH, bool F64>
 __global__ void __launch_bounds__(128)
@@ -87,18 +87,26 @@ __global__ void __launch_bounds__(128)
     sum[m] = e < dim ? state[((size_t)k * dim + e) * 2] : 0.0;
     c[m] = e < dim ? state[((size_t)k * dim + e) * 2 + 1] : 0.0;
   }
-  auto member = [&](unsigned int j) -> unsigned int {  // this lane's member of the batch starting at j
-    if (lane >= batch || j >= end || (unsigned int)lane >= end - j) return 0xffffffffu;
-    return order ? __ldg(order + j + lane) : j + lane;
+  // lane's members of the batch starting at j: positions j + lane + 32 r (r < kRows) inside [j, j + batch) and [beg, end)
+  constexpr int kRows = 4;
+  auto member = [&](unsigned int j, unsigned int (&out)[kRows]) {
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+      const unsigned int o = lane + 32 * r;
+      const bool ok = (int)o < batch && j < end && o < end - j;
+      out[r] = !ok ? 0xffffffffu : order ? __ldg(order + j + o) : j + o;
+    }
   };
-  auto stage = [&](unsigned int mine, int slot) {       // every lane copies its own member's row, asynchronously
-    unsigned char *dst = buf + ((size_t)slot * batch + lane) * stride;
-    if (mine != 0xffffffffu) {
+  auto stage = [&](const unsigned int (&mine)[kRows], int slot) {  // every lane copies its own members' rows, asynchronously
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+      if (mine[r] == 0xffffffffu) continue;
+      unsigned char *dst = buf + ((size_t)slot * batch + lane + 32 * r) * stride;
       if (F64) {
-        const double *row = src.f64 + (unsigned long long)mine * dim;
+        const double *row = src.f64 + (unsigned long long)mine[r] * dim;
         for (unsigned int w = 0; w < words; w++) cp_async_8(dst + 8 * w, row + w);
       } else {
-        const unsigned char *row = src.dense + (unsigned long long)mine * stride;
+        const unsigned char *row = src.dense + (unsigned long long)mine[r] * stride;
         for (unsigned int w = 0; w < words; w++) cp_async_4(dst + 4 * w, row + 4 * w);
       }
     }
@@ -118,14 +126,15 @@ __global__ void __launch_bounds__(128)
     sum[m] = t;
   };
   constexpr int G = DCH == 1 ? 8 : DCH == 2 ? 4 : 2;  // members whose values are fetched ahead of the chain
-  unsigned int idx_next = member(beg);
+  unsigned int idx_next[kRows];
+  member(beg, idx_next);
   stage(idx_next, 0);
-  idx_next = member(beg + batch);
+  member(beg + batch, idx_next);
   int slot = 0;
   for (unsigned int j0 = beg; j0 < end; j0 += batch, slot ^= 1) {
     const unsigned int cnt = min((unsigned int)batch, end - j0);
     stage(idx_next, slot ^ 1);                       // batch j0 + batch (an empty group past the end)
-    idx_next = member(j0 + 2 * batch);               // consumed one iteration later
+    member(j0 + 2 * batch, idx_next);                // consumed one iteration later
     cp_async_wait<1>();                              // batch j0 has landed
     __syncwarp();
     const unsigned char *rows = buf + (size_t)slot * batch * stride;
@@ -207,7 +216,7 @@ cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted,
   if (!f64 && !src.dense) return cudaErrorInvalidValue;
   const int dim = src.dim;
   const size_t row = f64 ? (size_t)dim * 8 : src.dense_stride;
-  int batch = 32;
+  int batch = 128;  // long batches amortise the per-batch bookkeeping of the latency-bound chain
   while (batch > 4 && 2 * (size_t)batch * row > 40 * 1024) batch >>= 1;
   int warps = (int)((40 * 1024) / (2 * (size_t)batch * row));
   warps = warps < 1 ? 1 : warps > 4 ? 4 : warps;
