@@ -176,6 +176,12 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
 int qb200_get_assign(qb200_ctx *ctx, uint32_t *assign_out);
 /* Same, widened to the reference's std::vector<size_t> element type. */
 int qb200_get_assign_u64(qb200_ctx *ctx, uint64_t *assign_out);
+/* The assignment as a bit stream, `bits` bits per index (1..32; every index must fit), index i in stream bits
+ * [i*bits, (i+1)*bits), bit p of the stream = bit p%8 of byte p/8 (LSB first): the packed form the reference's
+ * sizeInBits() counts (src/Compressor.cpp:174-182) but its file never stores (README "possible improvements").
+ * Packed on the device, so only ceil(n*bits/8) bytes cross PCIe.  out_bytes must be at least that.  Extension:
+ * the packed .quant container of quant_b200/host (CompressedImage::saveToFilePacked) uses it. */
+int qb200_get_assign_packed(qb200_ctx *ctx, int bits, uint8_t *out, size_t out_bytes);
 /* Device address of the assignment array (uint32[num_vectors]); valid until the next call that
  * changes the training set. */
 int qb200_assign_device_ptr(qb200_ctx *ctx, void **dev_ptr);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "qb200_last_error": (C.c_char_p, [C.c_void_p]),
     "qb200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qb200_set_exact_centroids": (C.c_int, [C.c_void_p, C.c_int]),
+    "qb200_get_assign_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "qb200_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "qb200_set_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "qb200_set_tensor_cores": (C.c_int, [C.c_void_p, C.c_int]),

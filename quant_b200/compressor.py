@@ -33,6 +33,18 @@ def _check_cs(cs) -> int:
     return cs
 
 
+def pack_indices(indices, bits: int) -> np.ndarray:
+    """Index i -> stream bits [i*bits, (i+1)*bits), bit p of the stream = bit p%8 of byte p/8 (LSB first)."""
+    a = np.asarray(indices, np.uint64)
+    b = ((a[:, None] >> np.arange(bits, dtype=np.uint64)[None, :]) & 1).astype(np.uint8).reshape(-1)
+    return np.packbits(b, bitorder="little")
+
+
+def unpack_indices(stream, n: int, bits: int) -> np.ndarray:
+    b = np.unpackbits(np.asarray(stream, np.uint8), bitorder="little")[:n * bits].reshape(n, bits).astype(np.uint64)
+    return (b << np.arange(bits, dtype=np.uint64)[None, :]).sum(1).astype(np.uint64)
+
+
 def _block_index_map(xSize: int, ySize: int, w: int, h: int):
     """img index of every (vector, pixel-in-block) pair: (N, w*h) int64, per src/Compressor.cpp:44-50."""
     wB, hB = (xSize + w - 1) // w, (ySize + h - 1) // h
@@ -176,15 +188,31 @@ class CompressedImage:
         idx = a.view(np.uint8).reshape(-1, 8)[:, :bpi]  # low bytes of a little-endian size_t
         return hdr + np.ascontiguousarray(self.codeVectors, np.uint8).tobytes() + idx.tobytes()
 
+    def to_bytes_packed(self) -> bytes:
+        """Extension (README "possible improvements"; `quant --pack`): header "QP1 ..." and the indices as one
+        LSB-first bit stream of `bits` bits each - the size sizeInBits() has always reported."""
+        bits = _smallest_pow2(len(self.codeVectors))
+        hdr = b"QP1 %d %d %d %d %d %d %d\n" % (bits, int(self.colorSpace), len(self.assignedCodeVector),
+                                               self.xSize, self.ySize, self.blockWidth, self.blockHeight)
+        return hdr + np.ascontiguousarray(self.codeVectors, np.uint8).tobytes() + pack_indices(self.assignedCodeVector, bits).tobytes()
+
     def saveToFile(self, path: str):
         with open(path, "wb") as f:
             f.write(self.to_bytes())
+
+    def saveToFilePacked(self, path: str):
+        with open(path, "wb") as f:
+            f.write(self.to_bytes_packed())
 
     def loadFromFile(self, path: str):
         with open(path, "rb") as f:
             data = f.read()
         nl = data.index(b"\n")
-        bits, cs, n, xs, ys, bw, bh = (int(t) for t in data[:nl].split())
+        fields = data[:nl].split()
+        packed = fields[0] == b"QP1"
+        if packed:
+            fields = fields[1:]
+        bits, cs, n, xs, ys, bw, bh = (int(t) for t in fields)
         self.xSize, self.ySize, self.blockWidth, self.blockHeight = xs, ys, bw, bh
         try:
             self.colorSpace = ColorSpaces(cs)
@@ -194,6 +222,10 @@ class CompressedImage:
         pos = nl + 1
         self.codeVectors = np.frombuffer(data, np.uint8, K * dim, pos).reshape(K, dim).copy()
         pos += K * dim
+        if packed:
+            stream = np.frombuffer(data, np.uint8, (n * bits + 7) // 8, pos)
+            self.assignedCodeVector = unpack_indices(stream, n, bits)
+            return
         bpi = (bits + 7) // 8
         raw = np.frombuffer(data, np.uint8, n * bpi, pos).reshape(n, bpi)
         a = np.zeros((n, 8), np.uint8)

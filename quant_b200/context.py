@@ -175,6 +175,12 @@ class Context:
         self._check(self.lib.qb200_get_assign_u64(self.h, _ptr(a)))
         return a
 
+    def get_assign_packed(self, bits: int) -> np.ndarray:
+        """The assignment as an LSB-first bit stream, `bits` per index, packed on the device (qb200_get_assign_packed)."""
+        out = np.empty((self.num_vectors * bits + 7) // 8, np.uint8)
+        self._check(self.lib.qb200_get_assign_packed(self.h, bits, _ptr(out), out.size))
+        return out
+
     def assign_device_ptr(self) -> int:
         p = C.c_void_p()
         self._check(self.lib.qb200_assign_device_ptr(self.h, C.byref(p)))

@@ -1337,6 +1337,22 @@ int qb200_get_assign_u64(qb200_ctx *ctx, uint64_t *assign_out) {
   return QB200_OK;
 }
 
+int qb200_get_assign_packed(qb200_ctx *ctx, int bits, uint8_t *out, size_t out_bytes) {
+  if (!ctx || !out) return QB200_ERR_ARG;
+  if (!ctx->have_set || !ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_get_assign_packed: no assignment yet");
+  if (bits < 1 || bits > 32) return fail(ctx, QB200_ERR_ARG, "qb200_get_assign_packed: bits %d outside [1,32]", bits);
+  const unsigned long long n = ctx->src.n_local, need = (n * (unsigned long long)bits + 7) / 8, words = (need + 3) / 4;
+  if (out_bytes < need) return fail(ctx, QB200_ERR_ARG, "qb200_get_assign_packed: %zu bytes given, %llu needed", out_bytes, need);
+  if (need == 0) return QB200_OK;
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure(ctx, ctx->d_misc, (size_t)words * 4);
+  if (rc) return rc;
+  CU(launch_pack_indices((const uint32_t *)ctx->d_assign.p, n, bits, (uint32_t *)ctx->d_misc.p, words, ctx->sm_count, ctx->stream));
+  CU(cudaMemcpyAsync(out, ctx->d_misc.p, (size_t)need, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return QB200_OK;
+}
+
 int qb200_assign_device_ptr(qb200_ctx *ctx, void **dev_ptr) {
   if (!ctx || !dev_ptr) return QB200_ERR_ARG;
   if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "no training set");

@@ -1568,6 +1568,32 @@ cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, co
   return cudaGetLastError();
 }
 
+// One thread per 32-bit word of the stream: word w holds stream bits [32w, 32w + 32).
+__global__ void pack_indices_kernel(const uint32_t *__restrict__ assign, const unsigned long long n, const int bits,
+                                    uint32_t *__restrict__ out, const unsigned long long out_words) {
+  for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < out_words;
+       w += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long lo = 32ull * w, hi = lo + 32ull;
+    uint32_t word = 0;
+    for (unsigned long long i = lo / (unsigned)bits; i < n && i * (unsigned)bits < hi; i++) {
+      const unsigned long long pos = i * (unsigned)bits;
+      const uint32_t a = __ldg(assign + i);
+      word |= pos >= lo ? a << (unsigned)(pos - lo) : a >> (unsigned)(lo - pos);
+    }
+    out[w] = word;
+  }
+}
+
+cudaError_t launch_pack_indices(const uint32_t *assign, unsigned long long n, int bits, uint32_t *out,
+                                unsigned long long out_words, int sm_count, cudaStream_t stream) {
+  if (out_words == 0) return cudaSuccess;
+  unsigned long long blocks = (out_words + 255) / 256;
+  if (blocks > (unsigned long long)sm_count * 16) blocks = (unsigned long long)sm_count * 16;
+  pack_indices_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(assign, n, bits, out, out_words);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fetch_members(const VecSource &src, const long long *local_idx, int count, unsigned long long *out,
                                  cudaStream_t stream) {
   if (count == 0) return cudaSuccess;

@@ -106,6 +106,9 @@ cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, co
                                 unsigned long long seed, unsigned long long *keys, int sm_count, cudaStream_t stream);
 cudaError_t launch_fetch_members(const VecSource &src, const long long *local_idx, int count, unsigned long long *out,
                                  cudaStream_t stream);
+// Indices as a bit stream (qb200_get_assign_packed): out_words 32-bit words, zero padded.
+cudaError_t launch_pack_indices(const uint32_t *assign, unsigned long long n, int bits, uint32_t *out,
+                                unsigned long long out_words, int sm_count, cudaStream_t stream);
 cudaError_t launch_ffma_probe(float *out, int blocks, int iters, float m, float c, cudaStream_t stream);
 
 constexpr int kResolveDepthCap = 512;

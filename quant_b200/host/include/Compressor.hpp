@@ -46,7 +46,12 @@ class CompressedImage {
   // ---- the rest: host code ----
   static RGBImage decompress(const CompressedImage &);
   void saveToFile(const std::string &path);    // .quant: ASCII header line, codebook bytes, byte-aligned indices
-  void loadFromFile(const std::string &path);
+  void loadFromFile(const std::string &path);  // reads both containers
+  // Extension (the reference's README lists it under "possible improvements"; `quant --pack`): the same container
+  // with the indices bit-packed, ceil(N * bits / 8) bytes instead of N * ceil(bits / 8), and a header line that
+  // starts with "QP1 " so that the two cannot be confused.  Index i occupies stream bits [i*bits, (i+1)*bits),
+  // LSB first - exactly the size sizeInBits() has always reported.
+  void saveToFilePacked(const std::string &path);
   size_t sizeInBits();                         // bit-packed size estimate the report uses
 };
 

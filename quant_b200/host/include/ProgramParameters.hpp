@@ -18,6 +18,9 @@ struct ProgramParameters {
   int height;          // -h : block height in pixels                                         (default 2)
   int quantizer;       // -q / --quantizer  : enum Quantizers as int                           (default LBG = 0)
   int colorspace;      // --c / --colorspace : enum ColorSpaces as int                         (default SCALED = 1)
+
+  // --- extension, not in the reference ---------------------------------------------------------------------
+  bool pack;           // --pack : write the bit-packed .quant container (Compressor.hpp)      (default false)
 };
 
 // The process-wide instance, and a reset to the defaults listed above.

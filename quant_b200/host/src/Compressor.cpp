@@ -197,11 +197,33 @@ void CompressedImage::saveToFile(const std::string &path) {
   out.write(packed.data(), (std::streamsize)packed.size());
 }
 
+// Packed container (extension): "QP1 <bits> <colorSpace> <N> <xSize> <ySize> <blockW> <blockH>\n", K * dim codebook
+// bytes, then the N indices as one LSB-first bit stream of <bits> bits each, zero padded to a whole byte.
+void CompressedImage::saveToFilePacked(const std::string &path) {
+  std::ofstream out(path, std::ios::binary);
+  if (!out) throw std::runtime_error("cannot write " + path);
+  const size_t bits = index_bits(codeVectors.size()), n = assignedCodeVector.size();
+  out << "QP1 " << bits << " " << (int)colorSpace << " " << n << " " << xSize << " " << ySize << " " << blockWidth << " "
+      << blockHeight << "\n";
+  for (const CharVector &c : codeVectors) out.write(c.data(), (std::streamsize)c.size());
+  std::vector<unsigned char> stream(ceil_div(n * bits, 8), 0);
+  for (size_t i = 0; i < n; i++)
+    for (size_t b = 0; b < bits; b++)
+      if ((assignedCodeVector[i] >> b) & 1) stream[(i * bits + b) >> 3] |= (unsigned char)(1u << ((i * bits + b) & 7));
+  out.write(reinterpret_cast<const char *>(stream.data()), (std::streamsize)stream.size());
+}
+
 void CompressedImage::loadFromFile(const std::string &path) {
   std::ifstream in(path, std::ios::binary);
   if (!in) throw std::runtime_error("cannot open " + path);
   size_t bits = 0, n = 0;
   long long cs = 0;
+  const bool packed = in.peek() == 'Q';
+  if (packed) {
+    std::string magic;
+    in >> magic;
+    if (magic != "QP1") throw std::runtime_error(path + ": unknown container " + magic);
+  }
   in >> bits >> cs >> n >> xSize >> ySize >> blockWidth >> blockHeight;
   if (!in || bits > 24 || blockWidth == 0 || blockHeight == 0) throw std::runtime_error(path + ": bad .quant header");
   in.get();  // '\n'
@@ -210,12 +232,18 @@ void CompressedImage::loadFromFile(const std::string &path) {
   const size_t K = (size_t)1 << bits, dim = blockWidth * blockHeight * 3, bpi = ceil_div(bits, 8);
   codeVectors.assign(K, CharVector(dim));
   for (CharVector &c : codeVectors) in.read(c.data(), (std::streamsize)dim);
-  std::vector<unsigned char> packed(n * bpi);
-  in.read(reinterpret_cast<char *>(packed.data()), (std::streamsize)packed.size());
+  std::vector<unsigned char> raw(packed ? ceil_div(n * bits, 8) : n * bpi);
+  in.read(reinterpret_cast<char *>(raw.data()), (std::streamsize)raw.size());
   if (!in) throw std::runtime_error(path + ": truncated .quant file");
   assignedCodeVector.assign(n, 0);
+  if (packed) {
+    for (size_t i = 0; i < n; i++)
+      for (size_t b = 0; b < bits; b++)
+        assignedCodeVector[i] |= (size_t)((raw[(i * bits + b) >> 3] >> ((i * bits + b) & 7)) & 1) << b;
+    return;
+  }
   for (size_t i = 0; i < n; i++)
-    for (size_t b = 0; b < bpi; b++) assignedCodeVector[i] |= (size_t)packed[i * bpi + b] << (8 * b);
+    for (size_t b = 0; b < bpi; b++) assignedCodeVector[i] |= (size_t)raw[i * bpi + b] << (8 * b);
 }
 
 std::ostream &operator<<(std::ostream &s, const CompressionRaport &r) {

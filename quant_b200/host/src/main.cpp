@@ -1,6 +1,7 @@
 // quant - command-line front end with the reference's flags (/root/reference/src/main.cpp:45-112),
 // parsed without boost::program_options:
 //   quant <file> -o <saveto> [-n bits] [-e eps] [-w W] [-h H] [-r 1] [-q quantizer] [--c colorspace] [--help]
+//   plus one extension: --pack writes the bit-packed .quant container (reading detects either container).
 // Mode by file extension: .ppm -> .quant compresses, .quant -> .ppm decompresses, .ppm -> .ppm does both.
 #include <cstdlib>
 #include <iostream>
@@ -35,7 +36,8 @@ void usage() {
                "  -o [ --saveto ] arg    Save to\n"
                "  -r arg (=0)            Print raport to std::out\n"
                "  -q [ --quantizer ] arg (=0)  Pick quantizer\n"
-               "  --c [ --colorspace ] arg (=1) Pick ColorSpace\n";
+               "  --c [ --colorspace ] arg (=1) Pick ColorSpace\n"
+               "  --pack                 (extension) bit-packed indices in the .quant file\n";
 }
 
 bool parse_bool(const std::string &v) { return v == "1" || v == "true" || v == "yes" || v == "on"; }
@@ -62,6 +64,7 @@ int main(int argc, char **argv) {
       else if (a == "-r") par->raport = (i + 1 < argc && argv[i + 1][0] != '-') ? parse_bool(value()) : true;
       else if (a == "-q" || a == "--quantizer") par->quantizer = std::stoi(value());
       else if (a == "--c" || a == "--colorspace") par->colorspace = std::stoi(value());
+      else if (a == "--pack") par->pack = true;
       else if (!a.empty() && a[0] == '-') throw std::runtime_error("unrecognised option '" + a + "'");
       else par->file = a;  // positional: the input file
     }
@@ -85,7 +88,8 @@ int main(int argc, char **argv) {
       c.loadFromFile(par->file);
       CompressedImage::decompress(c).saveToFile(par->saveto);
     } else if (from == FileType::PPM && to == FileType::QUANT) {
-      run_compression().saveToFile(par->saveto);
+      CompressedImage c = run_compression();
+      if (par->pack) c.saveToFilePacked(par->saveto); else c.saveToFile(par->saveto);
     } else {
       std::cerr << "File type not supported" << std::endl;
       return 1;

@@ -126,3 +126,58 @@ def test_cli_exact_centroid_mode_on_a_palette_image(host_built, port, tmp_path):
                        capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     assert open(q, "rb").read() == want
+
+
+def test_packed_container_roundtrip_and_cross_reading(host_built, tmp_path):
+    """Extension: the bit-packed .quant container.  The Python mirror and the C++ CLI must read each
+    other's packed files, decode them to the same image as the byte-aligned container, and the payload must have the
+    size CompressedImage::sizeInBits() has always reported."""
+    import quant_b200 as qb
+    g = load_golden("kodim01_crop_2x2_n10")       # 10 bits per index: 2 bytes each in the reference's container
+    ci = qb.CompressedImage()
+    ci.codeVectors, ci.assignedCodeVector = g.z["codebook_bytes"], g.z["assign"].astype(np.uint64)
+    ci.xSize, ci.ySize, ci.blockWidth, ci.blockHeight, ci.colorSpace = g.xs, g.ys, g.w, g.h, qb.ColorSpaces.SCALED
+    plain, packed = ci.to_bytes(), ci.to_bytes_packed()
+    assert hashlib.sha256(plain).hexdigest() == str(g.z["quant_sha"])          # the reference's container is untouched
+    hdr = packed.index(b"\n") + 1
+    assert packed.startswith(b"QP1 10 ") and (len(packed) - hdr) * 8 == ci.sizeInBits()
+    assert len(packed) < 0.75 * len(plain)
+    pq, out = str(tmp_path / "p.quant"), str(tmp_path / "p.ppm")
+    ci.saveToFilePacked(pq)
+    back = qb.CompressedImage()
+    back.loadFromFile(pq)
+    assert np.array_equal(back.assignedCodeVector, ci.assignedCodeVector) and np.array_equal(back.codeVectors, ci.codeVectors)
+    r = subprocess.run([QUANT, pq, "-o", out], capture_output=True, text=True)     # C++ reads the Python-written file
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(ppm_payload(out, g.xs, g.ys)).hexdigest() == str(g.z["decoded_sha"])
+    for bits in (1, 3, 8, 13, 24):
+        rng = np.random.default_rng(bits)
+        a = rng.integers(0, 1 << bits, 1001).astype(np.uint64)
+        s = qb.pack_indices(a, bits)
+        assert s.size == (1001 * bits + 7) // 8 and np.array_equal(qb.unpack_indices(s, 1001, bits), a)
+
+
+@pytest.mark.gpu
+def test_cli_pack_flag_and_device_side_packing(host_built, tmp_path):
+    import quant_b200 as qb
+    g = load_golden("odd_101x67_3x2_n5")
+    p, q, q2, d = str(tmp_path / "i.ppm"), str(tmp_path / "o.quant"), str(tmp_path / "o2.quant"), str(tmp_path / "o.ppm")
+    write_ppm(p, g.rgb, g.xs, g.ys)
+    args = ["-n", str(g.nbits), "-w", str(g.w), "-h", str(g.h), "--c", str(g.cs)]
+    assert subprocess.run([QUANT, p, "-o", q, "--pack"] + args, capture_output=True).returncode == 0
+    back = qb.CompressedImage()
+    back.loadFromFile(q)                                   # Python reads the C++-written packed file
+    assert np.array_equal(back.assignedCodeVector, g.z["assign"].astype(np.uint64))
+    assert np.array_equal(back.codeVectors, g.z["codebook_bytes"])
+    back.saveToFile(q2)                                    # ... and rewrites the reference's container from it
+    assert hashlib.sha256(open(q2, "rb").read()).hexdigest() == str(g.z["quant_sha"])
+    assert subprocess.run([QUANT, q, "-o", d], capture_output=True).returncode == 0
+    assert hashlib.sha256(ppm_payload(d, g.xs, g.ys)).hexdigest() == str(g.z["decoded_sha"])
+    ctx = qb.Context(0)
+    ctx.set_image(g.rgb, g.xs, g.ys, g.w, g.h, g.cs)
+    ctx.train(g.nbits)
+    for bits in (g.nbits, g.nbits + 3, 17, 32):            # packed on the device == packed on the host
+        assert np.array_equal(ctx.get_assign_packed(bits), qb.pack_indices(ctx.get_assign(), bits))
+    with pytest.raises(qb.Qb200Error):
+        ctx.get_assign_packed(0)
+    ctx.close()
