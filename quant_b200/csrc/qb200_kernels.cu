@@ -55,7 +55,7 @@ struct AssignCfg {
 // two scores with the identical FMA sequence (bit-identical), so the loop carries no per-codevector
 // index bookkeeping.  The staged codebook always holds an even number of rows (the host pads an odd
 // K with a row that can never win).
-template <int DIM>
+template <int DIM, bool F64 = false>  // F64: general FP64 vectors, scored after rounding to FP32 (qb200_generic.cu)
 __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
     assign_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int k_chunk,
                   const float margin_coef, const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
@@ -130,7 +130,13 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
         live[q] = v < src.n_local;
         xn[q] = 0.f;
         if (live[q]) {
-          gather_lattice<DIM>(src, v, x[h]);
+          if constexpr (F64) {
+            const double *xv = src.f64 + v * DIM;
+#pragma unroll
+            for (int e = 0; e < DIM; e++) x[h][e] = (float)xv[e];
+          } else {
+            gather_lattice<DIM>(src, v, x[h]);
+          }
 #pragma unroll
           for (int e = 0; e < DIM; e++) xn[q] = fmaf(x[h][e], x[h][e], xn[q]);
         } else {
@@ -1341,16 +1347,16 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
   const bool fuse = a.stats != nullptr && a.k_real >= 32 && k_chunk == a.K && smem + table <= smem_cap + 16 * 1024;
   if (fuse) smem += table;
   if (a.fused_out) *a.fused_out = fuse;
+  auto kernel = a.src.f64 ? assign_kernel<DIM, true> : assign_kernel<DIM, false>;
   {
-    cudaError_t e = cudaFuncSetAttribute(assign_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(smem_cap + 16 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap + 16 * 1024));
     if (e != cudaSuccess) return e;
   }
   const unsigned long long per_tile = (unsigned long long)Cfg::THREADS * Cfg::Q;
   const unsigned long long tiles = (a.src.n_local + per_tile - 1) / per_tile;
   unsigned long long grid = tiles < (unsigned long long)a.sm_count ? tiles : (unsigned long long)a.sm_count;
   if (grid == 0) return cudaSuccess;
-  assign_kernel<DIM><<<(unsigned int)grid, Cfg::THREADS, smem, a.stream>>>(
+  kernel<<<(unsigned int)grid, Cfg::THREADS, smem, a.stream>>>(
       a.src, a.cb_rows, a.K, k_chunk, a.margin_coef, a.c_max_ptr, a.assign, a.flag_list, a.flag_count, tiles,
       fuse ? a.stats : nullptr, a.k_real);
   g_launch_count++;
@@ -1359,7 +1365,9 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
 
 cudaError_t launch_assign(const AssignLaunch &a) {
   if (a.fused_out) *a.fused_out = false;
-  switch (a.src.f64 ? -1 : a.src.dim) {  // FP64 vectors: the generic kernel, whatever the dimension
+  // FP64 vectors: the tiled kernel where the dimension has an instance and the codebook is past the fused
+  // small-K pass (which accumulates integer statistics), else the generic kernel
+  switch (a.src.f64 && a.k_real <= 16 ? -1 : a.src.dim) {
     case 3: return launch_assign_t<3>(a);
     case 6: return launch_assign_t<6>(a);
     case 9: return launch_assign_t<9>(a);
