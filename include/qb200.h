@@ -40,7 +40,9 @@ extern "C" {
 #define QB200_ERR_COMM (-6)   /* the all-reduce callback reported failure */
 
 /* Colour spaces: same integer values as the reference's `enum class ColorSpaces`
- * (/root/reference/include/ColorSpace.hpp:6).  CIE1931 (2) is rejected with QB200_ERR_ARG. */
+ * (/root/reference/include/ColorSpace.hpp:6).  NORMAL and SCALED vectors live on the byte lattice (integer
+ * statistics, tensor-core filter, multi-GPU); CIE1931 vectors do not and take the FP64-vector path
+ * (qb200_set_vectors_f64 below). */
 #define QB200_CS_NORMAL 0 /* value = (double)(int8)byte        src/ColorSpace.cpp:4-6   */
 #define QB200_CS_SCALED 1 /* value = ((int8)byte + 128.0)/255  src/ColorSpace.cpp:16-21 */
 #define QB200_CS_CIE1931 2 /* 3x3 matrix / 0.17697 per pixel     src/ColorSpace.cpp:31-48; FP64 vectors, see below */

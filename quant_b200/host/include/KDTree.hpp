@@ -4,8 +4,9 @@
 // exact - the index the reference's tree returns, its tie order included.
 //
 // One query per call wastes the GPU: nearestNeighbours() (an extension) takes a batch, which is what
-// encode-only use against a fixed trained codebook (BASELINE config 5) should call.  Points and queries must
-// lie on the NORMAL or SCALED byte lattice; anything else raises std::runtime_error.
+// encode-only use against a fixed trained codebook (BASELINE config 5) should call.  Queries on the NORMAL or
+// SCALED byte lattice (everything that came from an image) take the fast path; any other doubles are searched
+// as FP64 vectors, with the same exact result.
 #pragma once
 #include <memory>
 #include <vector>

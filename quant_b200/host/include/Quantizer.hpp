@@ -8,8 +8,9 @@
 // trainingSet: N vectors of equal dimension; n: bits, K = 2^n codevectors; eps: the reference's
 // convergence threshold (it has no effect on the HEAD schedule).
 // Errors: std::out_of_range for an empty training set (the reference's trainingSet.at(0));
-// std::runtime_error if no B200 is usable or the vectors are not on a byte lattice - there is no
-// CPU fallback.
+// std::runtime_error if no B200 is usable - there is no CPU fallback.  Vectors on the NORMAL / SCALED
+// byte lattice (what getBlocksAsVectorsFromImage produces) train on the fast integer path, any other
+// doubles (CIE1931, arbitrary data; dimension <= 192) as FP64 vectors - same results, slower.
 #pragma once
 #include <memory>
 #include <tuple>
