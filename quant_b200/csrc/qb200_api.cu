@@ -297,9 +297,9 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
     return fail(ctx, QB200_ERR_ARG, "KD tree depth %d exceeds the resolver's stack (%d)", tree.depth,
                 kResolveDepthCap);
   if (tree.nodes.size() > max_nodes) return fail(ctx, QB200_ERR_STATE, "KD tree larger than expected");
-  if ((rc = ensure(ctx, ctx->d_nodes, max_nodes * sizeof(KdNode)))) return rc;
-  if ((rc = ensure(ctx, ctx->d_vind, (size_t)K * 8))) return rc;  // vind | inverse
-  if ((rc = ensure(ctx, ctx->d_bbox, 2 * (size_t)dim * 8))) return rc;
+  // nodes | vind | inverse | bounding box: contiguous in the pinned block, so one copy into one device block
+  const size_t tree_bytes = L.off_cnt - off_nodes;
+  if ((rc = ensure(ctx, ctx->d_nodes, tree_bytes))) return rc;
   std::memcpy(pin + off_nodes, tree.nodes.data(), tree.nodes.size() * sizeof(KdNode));
   std::memcpy(pin + off_vind, tree.order.data(), (size_t)K * 4);
   {
@@ -308,14 +308,13 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
   }
   std::memcpy(pin + off_bbox, tree.box_low.data(), (size_t)dim * 8);
   std::memcpy(pin + off_bbox + (size_t)dim * 8, tree.box_high.data(), (size_t)dim * 8);
-  CU(cudaMemcpyAsync(ctx->d_nodes.p, pin + off_nodes, tree.nodes.size() * sizeof(KdNode), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_vind.p, pin + off_vind, (size_t)K * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_bbox.p, pin + off_bbox, 2 * (size_t)dim * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_nodes.p, pin + off_nodes, tree_bytes, cudaMemcpyHostToDevice, st));
+  const char *tree_dev = (const char *)ctx->d_nodes.p;
   KdDevice kd{};
-  kd.nodes = (const KdNode *)ctx->d_nodes.p;
-  kd.vind = (const unsigned int *)ctx->d_vind.p;
+  kd.nodes = (const KdNode *)tree_dev;
+  kd.vind = (const unsigned int *)(tree_dev + (off_vind - off_nodes));
   kd.inv = kd.vind + K;
-  kd.bbox_low = (const double *)ctx->d_bbox.p;
+  kd.bbox_low = (const double *)(tree_dev + (off_bbox - off_nodes));
   kd.bbox_high = kd.bbox_low + dim;
   kd.n_nodes = (int)tree.nodes.size();
   kd.depth = tree.depth;
@@ -1094,9 +1093,7 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
   if ((rc = ensure(ctx, ctx->d_stats, stats_words(maxK, dim) * 8))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_rows_tc, tc_max))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 16))) return rc;
-  if ((rc = ensure(ctx, ctx->d_nodes, Lmax.max_nodes * sizeof(KdNode)))) return rc;
-  if ((rc = ensure(ctx, ctx->d_vind, (size_t)maxK * 8))) return rc;
-  if ((rc = ensure(ctx, ctx->d_bbox, 2 * (size_t)dim * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->d_nodes, Lmax.off_cnt - Lmax.off_nodes))) return rc;
   if ((rc = ensure_pinned(ctx, Lmax.total))) return rc;
   for (int i = 0; i < 2; i++)
     if ((rc = ensure(ctx, ctx->d_cbnext[i], cb_max + 256))) return rc;

@@ -296,7 +296,14 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
 // vectors it DECIDES are accumulated at once: lanes that chose the same cell are combined with
 // __match_any_sync + __reduce_add_sync and only group leaders touch the per-CTA table (flagged vectors are
 // added by the resolver).  stats may be null (assignment only).
-template <int DIM>
+//
+// Statistics, KCAP > 0 (K <= KCAP): every thread keeps its OWN partial sums for all KCAP cells in registers - per cell
+// (DIM+1)/2 words of two 16-bit lattice sums (t = L + 128 <= 255, so 256 vectors fit), a count and a sum of squares -
+// and adds a vector to its cell with predicated integer adds: no shuffles, no atomics in the loop.  Every 256
+// vectors (and at the end) the registers are summed across the warp (REDUX) into the per-CTA table.
+// KCAP == 0: the register file cannot hold KCAP cells of this dimension; lanes that chose the same cell are combined
+// per vector with __match_any_sync + __reduce_add_sync instead.
+template <int DIM, int KCAP>
 __global__ void __launch_bounds__(256)
     small_k_fused_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const float margin_coef,
                          const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
@@ -316,6 +323,45 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   const float c_max_norm = *c_max_ptr;
   const int lane = threadIdx.x & 31;
+  constexpr int P = (DIM + 1) / 2, KC = KCAP > 0 ? KCAP : 1;
+  unsigned int acc_s[KC][P], acc_n[KC], acc_q[KC];
+  int pending = 0;  // vectors in the register accumulators since the last flush
+#pragma unroll
+  for (int k = 0; k < KC; k++) {
+    acc_n[k] = 0;
+    acc_q[k] = 0;
+#pragma unroll
+    for (int j = 0; j < P; j++) acc_s[k][j] = 0;
+  }
+  auto flush_registers = [&]() {  // warp-wide sums of the register accumulators -> per-CTA table, lane 0 adds
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+      if (k < K) {
+        const unsigned int n = __reduce_add_sync(0xffffffffu, acc_n[k]);
+        if (n) {  // warp-uniform
+          const unsigned int q = __reduce_add_sync(0xffffffffu, acc_q[k]);
+          if (lane == 0) {
+            atomicAdd(s_n + k, (int)n);
+            atomicAdd(s_q + k, (unsigned long long)q);
+          }
+#pragma unroll
+          for (int j = 0; j < P; j++) {
+            const unsigned int lo = __reduce_add_sync(0xffffffffu, acc_s[k][j] & 0xffffu);
+            const unsigned int hi = __reduce_add_sync(0xffffffffu, acc_s[k][j] >> 16);
+            if (lane == 0) {
+              if (lo) atomicAdd(s_s + k * DIM + 2 * j, (int)lo);
+              if (2 * j + 1 < DIM && hi) atomicAdd(s_s + k * DIM + 2 * j + 1, (int)hi);
+            }
+          }
+        }
+      }
+      acc_n[k] = 0;
+      acc_q[k] = 0;
+#pragma unroll
+      for (int j = 0; j < P; j++) acc_s[k][j] = 0;
+    }
+    pending = 0;
+  };
   const unsigned long long n_round = (src.n_local + 31ull) & ~31ull;  // whole warps stay in the loop
   for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_round;
        v += (unsigned long long)gridDim.x * blockDim.x) {
@@ -357,7 +403,25 @@ __global__ void __launch_bounds__(256)
       basepos = __shfl_sync(0xffffffffu, basepos, leader);
       if (flag) flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
     }
-    if (stats) {
+    if (stats && KCAP > 0) {
+      const int a = (live && !flag) ? bidx : -1;
+      unsigned int px[P], qs = 0;
+#pragma unroll
+      for (int j = 0; j < P; j++) {
+        const int L0 = (int)x[2 * j], L1 = 2 * j + 1 < DIM ? (int)x[2 * j + 1 < DIM ? 2 * j + 1 : 2 * j] : -128;
+        qs += (unsigned int)(L0 * L0) + (2 * j + 1 < DIM ? (unsigned int)(L1 * L1) : 0u);
+        px[j] = (unsigned int)(L0 + 128) | ((unsigned int)(L1 + 128) << 16);
+      }
+#pragma unroll
+      for (int k = 0; k < KC; k++) {
+        const bool hit = a == k;
+        acc_n[k] += hit ? 1u : 0u;
+        acc_q[k] += hit ? qs : 0u;
+#pragma unroll
+        for (int j = 0; j < P; j++) acc_s[k][j] += hit ? px[j] : 0u;
+      }
+      if (++pending == 256) flush_registers();  // 256 * 255 < 2^16: the packed 16-bit sums cannot overflow
+    } else if (stats) {
       const int a = (live && !flag) ? bidx : -1;
       const unsigned int group = __match_any_sync(0xffffffffu, a);
       const bool lead = a >= 0 && lane == __ffs(group) - 1;
@@ -384,6 +448,7 @@ __global__ void __launch_bounds__(256)
     }
   }
   if (stats) {
+    if (KCAP > 0) flush_registers();
     __syncthreads();
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
       if (s_n[i] != 0) {
@@ -1329,9 +1394,23 @@ static cudaError_t launch_assign_t(const AssignLaunch &a) {
     if (blocks > cap) blocks = cap;
     if (a.fused_out) *a.fused_out = a.stats != nullptr;
     if (blocks == 0) return cudaSuccess;
-    small_k_fused_kernel<DIM><<<(unsigned int)blocks, 256, 0, a.stream>>>(a.src, a.cb_rows, a.k_real, a.margin_coef,
-                                                                           a.c_max_ptr, a.assign, a.flag_list,
-                                                                           a.flag_count, a.stats);
+    // register accumulators for as many cells as ~128 registers hold ((DIM+1)/2 + 2 words per cell)
+    constexpr int kFit = 128 / ((DIM + 1) / 2 + 2);
+    // (measured, dim 12: K = 16 needs 173 registers, one CTA per SM, and is slower than the REDUX path: stop at 8)
+    constexpr int kCap = kFit >= 8 ? 8 : kFit >= 4 ? 4 : kFit >= 2 ? 2 : 0;
+#define QB_SMALLK(KC)                                                                                              \
+  small_k_fused_kernel<DIM, KC><<<(unsigned int)blocks, 256, 0, a.stream>>>(a.src, a.cb_rows, a.k_real, a.margin_coef, \
+                                                                            a.c_max_ptr, a.assign, a.flag_list,      \
+                                                                            a.flag_count, a.stats)
+    if (a.stats == nullptr || a.k_real > kCap)
+      QB_SMALLK(0);
+    else if (a.k_real <= 2 && kCap >= 2)
+      QB_SMALLK(kCap >= 2 ? 2 : 0);
+    else if (a.k_real <= 4 && kCap >= 4)
+      QB_SMALLK(kCap >= 4 ? 4 : 0);
+    else
+      QB_SMALLK(kCap >= 8 ? 8 : 0);
+#undef QB_SMALLK
     g_launch_count++;
     return cudaGetLastError();
   }
