@@ -154,8 +154,11 @@ int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors,
  * the device) - have no integer statistics: the assignment keeps the filter + exact re-check (the filter works on
  * the values rounded to FP32, its margin covers that), centroids are the reference's compensated FP64 sums executed
  * in vector order (as with qb200_set_exact_centroids, so codebooks are bit-identical to the reference's) and the
- * distortions are FP64 sums (reference: OpenMP reduction, order unspecified; 1e-6 relative).  Single GPU only
- * (qb200_train rejects an all-reduce callback), QB200_MODE_PARITY and QB200_MODE_FULL. */
+ * distortions are FP64 sums (reference: OpenMP reduction, order unspecified; 1e-6 relative).  Modes
+ * QB200_MODE_PARITY and QB200_MODE_FULL.  Sharded over several contexts (each holding a contiguous range of the
+ * vectors, or qb200_set_image_shard / _band for CIE1931) it needs qb200_set_rank with rank order = vector order:
+ * the ranks continue each other's sums in turn and exchange their distortion partials as one slot per rank
+ * through the same u64 sum all-reduce, so every rank gets the single-GPU bits. */
 int qb200_set_vectors_f64(qb200_ctx *ctx, const double *x, size_t n_vectors, int dim, int x_is_device);
 /* Number of vectors this context holds / their dimension. */
 size_t qb200_num_vectors(const qb200_ctx *ctx);

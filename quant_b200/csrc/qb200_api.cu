@@ -630,8 +630,6 @@ static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySi
                 h, n_images);
   if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED && colorspace != QB200_CS_CIE1931)
     return fail(ctx, QB200_ERR_ARG, "set_image: colour space %d is not supported (NORMAL=0, SCALED=1, CIE1931=2)", colorspace);
-  if (colorspace == QB200_CS_CIE1931 && shard)
-    return fail(ctx, QB200_ERR_ARG, "set_image_shard: CIE1931 vectors are not on the byte lattice; the FP64 path is single-GPU");
   const long long dim = 3LL * w * h;
   if (dim > kMaxDim) return fail(ctx, QB200_ERR_ARG, "set_image: block %dx%d gives dim %lld > %d", w, h, dim, kMaxDim);
   CU(cudaSetDevice(ctx->device));
@@ -905,15 +903,18 @@ int exact_prepare(qb200_ctx *ctx, uint32_t maxK) {
   return QB200_OK;
 }
 
-int exact_centroid_sums(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void *ar_user) {
+// counts (device, K words, may be null): members per cell, summed over the ranks.
+int exact_centroid_sums(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void *ar_user,
+                        unsigned long long *counts = nullptr) {
   const int dim = ctx->src.dim;
   const size_t n = (size_t)ctx->src.n_local, words = (size_t)K * dim * 2;
   cudaStream_t st = ctx->stream;
   int rc;
   if (ar && ctx->world <= 1)
-    return fail(ctx, QB200_ERR_STATE, "exact centroids with an all-reduce callback need qb200_set_rank (rank order = vector order)");
+    return fail(ctx, QB200_ERR_STATE, "compensated member sums with an all-reduce callback need qb200_set_rank (rank order = vector order)");
   if ((rc = exact_prepare(ctx, K))) return rc;
   CU(cudaMemsetAsync(ctx->d_exact.p, 0, words * 8, st));
+  if (counts) CU(cudaMemsetAsync(counts, 0, (size_t)K * 8, st));
   int key_bits = 0;
   while ((1u << key_bits) < K) key_bits++;
   if (K > 1 && n)
@@ -924,14 +925,16 @@ int exact_centroid_sums(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void 
     if (!ar || q == ctx->rank) {
       if (n)
         CU(launch_kahan_sums(ctx->src, K > 1 ? (const uint32_t *)ctx->d_sort_keys.p : nullptr,
-                             K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K, 1, (double *)ctx->d_exact.p,
-                             nullptr, st));
+                             K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K,
+                             ctx->colorspace == QB200_CS_SCALED, (double *)ctx->d_exact.p, K > 1 ? counts : nullptr, st));
     } else {
       CU(cudaMemsetAsync(ctx->d_exact.p, 0, words * 8, st));
     }
     if (ar && ar(ctx->d_exact.p, words, (void *)st, ar_user) != 0)
       return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (exact centroid sums, K=%u, round %d)", K, q);
   }
+  if (counts && K > 1 && ar && ar(counts, K, (void *)st, ar_user) != 0)
+    return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (member counts, K=%u)", K);
   return QB200_OK;
 }
 
@@ -954,47 +957,50 @@ int exact_override_centroids(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, 
 // host loop.  Assignment = filter (vectors rounded to FP32) + exact resolver; centroids = the reference's compensated
 // sums in vector order divided by the member count (src/Quantizer.cpp:46-87); distortions = FP64 sums over the
 // vectors (src/Quantizer.cpp:9-22).  Single GPU.
-int train_generic(qb200_ctx *ctx, int nbits, double eps, int mode, double *codebook_out, double *distortion_out,
-                  qb200_level_report *reports) {
+int train_generic(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t N, qb200_allreduce_fn ar, void *ar_user,
+                  double *codebook_out, double *distortion_out, qb200_level_report *reports) {
   const int dim = ctx->src.dim;
   const size_t n = (size_t)ctx->src.n_local;
   const uint32_t maxK = 1u << nbits;
+  const int world = ar ? ctx->world : 1, rank = ar ? ctx->rank : 0;
   cudaStream_t st = ctx->stream;
   int rc;
+  if (ar && ctx->world <= 1)
+    return fail(ctx, QB200_ERR_STATE, "FP64 vectors with an all-reduce callback need qb200_set_rank (rank order = vector order)");
   if ((rc = exact_prepare(ctx, maxK))) return rc;
   const int nb = distortion_blocks(ctx->sm_count);
-  if ((rc = ensure(ctx, ctx->d_counts, (size_t)maxK * 4))) return rc;
-  if ((rc = ensure(ctx, ctx->d_partials, (size_t)nb * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->d_counts, (size_t)maxK * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->d_partials, ((size_t)nb + world) * 8))) return rc;
   if ((rc = ensure(ctx, ctx->d_post, (size_t)maxK * dim * 8 + 256))) return rc;
-  std::vector<double> cb((size_t)maxK * dim), post((size_t)maxK * dim), state((size_t)maxK * dim * 2), partials(nb);
-  std::vector<unsigned int> counts(maxK);
-  auto sums = [&](uint32_t K) -> int {  // member sums (+ counts) of the assignment in d_assign -> state, counts
-    CU(cudaMemsetAsync(ctx->d_exact.p, 0, (size_t)K * dim * 16, st));
-    int key_bits = 0;
-    while ((1u << key_bits) < K) key_bits++;
-    if (K > 1)
-      CU(launch_exact_sort((const uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_sort_keys.p, (const uint32_t *)ctx->d_sort_iota.p,
-                           (uint32_t *)ctx->d_sort_order.p, n, key_bits, ctx->d_sort_tmp.p, ctx->d_sort_tmp.cap, st));
-    CU(launch_kahan_sums(ctx->src, K > 1 ? (const uint32_t *)ctx->d_sort_keys.p : nullptr,
-                         K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K, 0, (double *)ctx->d_exact.p,
-                         K > 1 ? (unsigned int *)ctx->d_counts.p : nullptr, st));
+  std::vector<double> cb((size_t)maxK * dim), post((size_t)maxK * dim), state((size_t)maxK * dim * 2), slots(world);
+  std::vector<unsigned long long> counts(maxK);
+  // member sums (+ counts) of the assignment in d_assign, over all ranks in rank order -> state, counts (host, after a sync)
+  auto sums = [&](uint32_t K) -> int {
+    int r2 = exact_centroid_sums(ctx, K, ar, ar_user, (unsigned long long *)ctx->d_counts.p);
+    if (r2) return r2;
     CU(cudaMemcpyAsync(state.data(), ctx->d_exact.p, (size_t)K * dim * 16, cudaMemcpyDeviceToHost, st));
-    if (K > 1) CU(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
+    if (K > 1) CU(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, (size_t)K * 8, cudaMemcpyDeviceToHost, st));
     return QB200_OK;
   };
-  auto distortion = [&](const double *cb_dev, double *out) -> int {  // updateDistortion against a device codebook
-    CU(launch_distortion_f64(ctx->src, (const uint32_t *)ctx->d_assign.p, cb_dev, (double *)ctx->d_partials.p, ctx->sm_count, st));
-    CU(cudaMemcpyAsync(partials.data(), ctx->d_partials.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+  // updateDistortion against a device codebook: per-rank sums in a fixed order, exchanged as one slot per rank
+  // and added in rank order, so every rank (and any re-run) gets the same bits
+  auto distortion = [&](const double *cb_dev, double *out) -> int {
+    double *partials = (double *)ctx->d_partials.p, *dslots = partials + nb;
+    CU(launch_distortion_f64(ctx->src, (const uint32_t *)ctx->d_assign.p, cb_dev, partials, ctx->sm_count, st));
+    CU(launch_sum_partials(partials, nb, dslots, rank, world, st));
+    if (ar && ar(dslots, (size_t)world, (void *)st, ar_user) != 0)
+      return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (distortion)");
+    CU(cudaMemcpyAsync(slots.data(), dslots, (size_t)world * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     double acc = 0.0;
-    for (int b = 0; b < nb; b++) acc += partials[b];
-    *out = acc / ((double)n * (double)dim);
+    for (int r = 0; r < world; r++) acc += slots[r];
+    *out = acc / ((double)N * (double)dim);
     return QB200_OK;
   };
   // initial codevector = mean of the training set (src/Quantizer.cpp:129-130)
   if ((rc = sums(1))) return rc;
   CU(cudaStreamSynchronize(st));
-  for (int e = 0; e < dim; e++) cb[e] = state[2 * (size_t)e] / (double)n;
+  for (int e = 0; e < dim; e++) cb[e] = state[2 * (size_t)e] / (double)N;
   uint32_t K = 1;
   int level = 0;
   double dpre = 0, dpost = 0;
@@ -1220,9 +1226,8 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
   if (!allreduce && ctx->src.n_local == 0) return fail(ctx, QB200_ERR_ARG, "qb200_train: empty training set");
   CU(cudaSetDevice(ctx->device));
   if (ctx->src.f64) {
-    if (allreduce) return fail(ctx, QB200_ERR_ARG, "qb200_train: FP64 vectors (CIE1931 / set_vectors_f64) train on a single GPU; no all-reduce");
     if (mode == QB200_MODE_FULL_REPAIR) return fail(ctx, QB200_ERR_ARG, "qb200_train: QB200_MODE_FULL_REPAIR is not available for FP64 vectors");
-    return train_generic(ctx, nbits, eps, mode, codebook_out, distortion_out, reports);
+    return train_generic(ctx, nbits, eps, mode, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);
   }
   if (mode == QB200_MODE_PARITY && pipeline_enabled())
     return train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);

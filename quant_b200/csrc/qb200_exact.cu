@@ -48,7 +48,7 @@ template <int DCH, bool F64>
 __global__ void __launch_bounds__(128)
     kahan_sums_kernel(const VecSource src, const uint32_t *__restrict__ keys_sorted, const uint32_t *__restrict__ order,
                       const int K, const int scaled, const int batch, double *__restrict__ state,
-                      unsigned int *__restrict__ counts) {
+                      unsigned long long *__restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *s_val = reinterpret_cast<double *>(smem_raw);  // colour-space value of a raw byte (src/ColorSpace.cpp:16-21)
   if (!F64) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128)
     beg = __shfl_sync(0xffffffffu, lo, 0);
     end = __shfl_sync(0xffffffffu, lo, 1);
   }
-  if (counts && lane == 0) counts[k] = end - beg;
+  if (counts && lane == 0) counts[k] = (unsigned long long)(end - beg);
   double sum[DCH], c[DCH];
 #pragma unroll
   for (int m = 0; m < DCH; m++) {
@@ -211,7 +211,7 @@ cudaError_t launch_exact_sort(const uint32_t *assign, uint32_t *keys_out, const 
 // counts (may be null): members of every cell on this context.  Reads the dense byte copy of the training set
 // (always made by set_image / set_vectors_u8) or, for general FP64 vectors, the doubles themselves.
 cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, int scaled,
-                              double *state, unsigned int *counts, cudaStream_t stream) {
+                              double *state, unsigned long long *counts, cudaStream_t stream) {
   const bool f64 = src.f64 != nullptr;
   if (!f64 && !src.dense) return cudaErrorInvalidValue;
   const int dim = src.dim;

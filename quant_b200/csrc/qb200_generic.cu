@@ -64,7 +64,22 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) partials[blockIdx.x] = s_acc[0];
 }
 
+__global__ void sum_partials_kernel(const double *__restrict__ partials, const int n, double *__restrict__ slots,
+                                    const int rank, const int world) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double acc = 0.0;
+  for (int i = 0; i < n; i++) acc = __dadd_rn(acc, partials[i]);
+  for (int r = 0; r < world; r++) slots[r] = r == rank ? acc : 0.0;
+}
+
 }  // namespace
+
+cudaError_t launch_sum_partials(const double *partials, int n_partials, double *slots, int rank, int world,
+                                cudaStream_t stream) {
+  sum_partials_kernel<<<1, 32, 0, stream>>>(partials, n_partials, slots, rank, world);
+  count_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t launch_cie_vectors(const VecSource &src, double *out, int sm_count, cudaStream_t stream) {
   const unsigned long long total = src.n_local * (unsigned long long)(src.dim / 3);

@@ -92,7 +92,7 @@ cudaError_t launch_exact_iota(uint32_t *iota, size_t n, int sm_count, cudaStream
 cudaError_t launch_exact_sort(const uint32_t *assign, uint32_t *keys_out, const uint32_t *iota, uint32_t *order, size_t n,
                               int key_bits, void *tmp, size_t tmp_bytes, cudaStream_t stream);
 cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, int scaled,
-                              double *state, unsigned int *counts, cudaStream_t stream);
+                              double *state, unsigned long long *counts, cudaStream_t stream);
 // General FP64 training vectors (qb200_generic.cu).
 // CIE1931 colour space (src/ColorSpace.cpp:31-39): the image's block vectors as doubles, n_local x dim.
 cudaError_t launch_cie_vectors(const VecSource &src, double *out, int sm_count, cudaStream_t stream);
@@ -101,6 +101,10 @@ cudaError_t launch_cie_vectors(const VecSource &src, double *out, int sm_count, 
 int distortion_blocks(int sm_count);
 cudaError_t launch_distortion_f64(const VecSource &src, const uint32_t *assign, const double *cb, double *partials,
                                   int sm_count, cudaStream_t stream);
+// slots[0..world) = 0 except slots[rank] = partials[0] + partials[1] + ... (in that order): what a rank contributes
+// to the sum all-reduce so that every rank ends up with every rank's partial sum, bit patterns intact.
+cudaError_t launch_sum_partials(const double *partials, int n_partials, double *slots, int rank, int world,
+                                cudaStream_t stream);
 // Empty-cell repair (QB200_MODE_FULL_REPAIR): smallest (hash, global index) key per donor cell; member bytes.
 cudaError_t launch_pick_members(const VecSource &src, const uint32_t *assign, const int *slot_of_cell,
                                 unsigned long long seed, unsigned long long *keys, int sm_count, cudaStream_t stream);
