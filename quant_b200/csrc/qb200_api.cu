@@ -37,8 +37,14 @@ struct qb200_ctx {
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   size_t total_mem = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // Tensor-core levels run the statistics pass on side_stream next to the exact resolver (level_begin / level_finish)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_pending = false;
+  bool side_used = false;                       // the level just run had its statistics pass on the side stream
+  cudaEvent_t ev_side[2] = {nullptr, nullptr};  // ... bracketed by these (level-by-level driver)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  std::vector<cudaEvent_t> pipe_ev;  // pipelined train: 4 timing events per level + 2 codebook-ready events
+  std::vector<cudaEvent_t> pipe_ev;  // pipelined train: 6 timing events per level + 2 codebook-ready events
   void *h_pipe = nullptr;            // pinned slots of the pipelined train
   size_t h_pipe_cap = 0;
   DevBuf d_cbnext[2], d_post, d_summary;
@@ -167,6 +173,14 @@ bool pipeline_enabled() {
   }();
   return on;
 }
+// QB200_NO_OVERLAP=1: statistics after the resolver on the main stream, as on the CUDA-core levels.
+bool side_overlap_enabled() {
+  static const bool on = [] {
+    const char *e = std::getenv("QB200_NO_OVERLAP");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 // Smallest codebook the tensor-core filter is used for; below it the per-tile pipeline overhead outweighs
 // the saved FMAs and the CUDA-core kernel is faster (measured crossover; QB200_TC_MIN_K overrides).
 int tc_min_k() {
@@ -202,7 +216,9 @@ LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
 //   cb_host  the codebook on the host (used for the upload when cb_dev == null)
 //   cb_dev   the codebook already on the device (pipelined train), copied device-to-device
 int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uint32_t K, bool want_stats,
-                cudaEvent_t ev0, cudaEvent_t ev1, bool *fused_out) {
+                cudaEvent_t ev0, cudaEvent_t ev1, bool *fused_out, cudaEvent_t ev_s0 = nullptr, cudaEvent_t ev_s1 = nullptr) {
+  ctx->side_pending = false;
+  ctx->side_used = false;
   const int dim = ctx->src.dim;
   const LevelLayout L = level_layout(ctx, K, dim);
   const size_t rows_bytes = L.rows_bytes, cb_bytes = L.cb_bytes;
@@ -254,6 +270,21 @@ int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uin
     a.sm_count = ctx->sm_count;
     a.stream = st;
     CU(launch_assign_tc(a));
+    // The statistics of the queries the filter decided do not depend on the resolver: run them on the side stream
+    // while the main stream uploads the KD tree and re-solves the flagged queries (whose entries carry the
+    // "undecided" mark and are skipped; the resolver adds them itself).  level_finish joins the two.
+    if (want_stats && ctx->side_stream && side_overlap_enabled()) {
+      CU(cudaEventRecord(ctx->ev_fork, st));
+      CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+      if (ev_s0) CU(cudaEventRecord(ev_s0, ctx->side_stream));
+      CU(launch_accumulate(ctx->src, (const uint32_t *)ctx->d_assign.p, (int)K, (unsigned long long *)ctx->d_stats.p,
+                           ctx->sm_count, ctx->side_stream));
+      if (ev_s1) CU(cudaEventRecord(ev_s1, ctx->side_stream));
+      CU(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+      ctx->side_pending = true;
+      ctx->side_used = true;
+      fused = true;  // the resolver adds the flagged queries' statistics
+    }
   } else {
     AssignLaunch a{};
     a.src = ctx->src;
@@ -318,10 +349,18 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
   kd.bbox_high = kd.bbox_low + dim;
   kd.n_nodes = (int)tree.nodes.size();
   kd.depth = tree.depth;
+  // with the statistics pass reading d_assign on the side stream, exact indices go to a side array first (the
+  // filter's per-query records in d_state are dead by now) and are committed after the join
+  uint32_t *result = ctx->side_pending ? (uint32_t *)ctx->d_state.p : nullptr;
   CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p,
                     (const double *)ctx->d_cb64.p + (size_t)K * dim, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
-                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, ctx->sm_count, st));
+                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, result, ctx->sm_count, st));
+  if (ctx->side_pending) {
+    CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    CU(launch_commit_resolved((const uint32_t *)ctx->d_flags.p, cnt, result, (uint32_t *)ctx->d_assign.p, ctx->sm_count, st));
+    ctx->side_pending = false;
+  }
   if (ev2) CU(cudaEventRecord(ev2, st));
   if (want_stats && !fused) {
     CU(launch_accumulate(ctx->src, (const uint32_t *)ctx->d_assign.p, (int)K, (unsigned long long *)ctx->d_stats.p,
@@ -336,7 +375,8 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
 
 int run_level(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, bool timed, LevelOut *out) {
   bool fused = false;
-  int rc = level_begin(ctx, cb, nullptr, K, want_stats, timed ? ctx->ev[0] : nullptr, timed ? ctx->ev[1] : nullptr, &fused);
+  int rc = level_begin(ctx, cb, nullptr, K, want_stats, timed ? ctx->ev[0] : nullptr, timed ? ctx->ev[1] : nullptr, &fused,
+                       timed ? ctx->ev_side[0] : nullptr, timed ? ctx->ev_side[1] : nullptr);
   if (rc) return rc;
   const LevelLayout L = level_layout(ctx, K, ctx->src.dim);
   int depth = 0;
@@ -357,7 +397,10 @@ int collect_level(qb200_ctx *ctx, uint32_t K, bool timed, LevelOut *out) {
   if (timed) {
     CU(cudaEventElapsedTime(&out->ms_assign, ctx->ev[0], ctx->ev[1]));
     CU(cudaEventElapsedTime(&out->ms_resolve, ctx->ev[1], ctx->ev[2]));
-    CU(cudaEventElapsedTime(&out->ms_accumulate, ctx->ev[2], ctx->ev[3]));
+    if (ctx->side_used)  // the statistics pass ran next to the resolver: its own duration
+      CU(cudaEventElapsedTime(&out->ms_accumulate, ctx->ev_side[0], ctx->ev_side[1]));
+    else
+      CU(cudaEventElapsedTime(&out->ms_accumulate, ctx->ev[2], ctx->ev[3]));
   }
   return QB200_OK;
 }
@@ -548,7 +591,11 @@ int qb200_create(int device, qb200_ctx **out) {
     return fail(nullptr, QB200_ERR_CUDA, "stream creation: %s", msg.c_str());
   }
   ctx->stream = ctx->own_stream;
+  cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  for (auto &ev : ctx->ev_side) cudaEventCreate(&ev);
   if (const char *ex = std::getenv("QB200_EXACT_CENTROIDS")) ctx->exact = ex[0] == '1';
   *out = ctx;
   return QB200_OK;
@@ -570,6 +617,11 @@ void qb200_destroy(qb200_ctx *ctx) {
     free_buf(*b);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->ev_side)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1120,14 +1172,14 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
   PipeSlot *slots = (PipeSlot *)ctx->h_pipe;
   double *h_cb[2] = {(double *)((char *)ctx->h_pipe + off_cb0), (double *)((char *)ctx->h_pipe + off_cb0 + cb_max + 256)};
   double *h_final = (double *)((char *)ctx->h_pipe + off_cb0 + 2 * (cb_max + 256));
-  const size_t n_ev = 4 * 17 + 2;
+  const size_t n_ev = 6 * 17 + 2;
   while (ctx->pipe_ev.size() < n_ev) {
     cudaEvent_t e;
-    const bool timing = ctx->pipe_ev.size() < 4 * 17;
+    const bool timing = ctx->pipe_ev.size() < 6 * 17;
     CU(timing ? cudaEventCreate(&e) : cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->pipe_ev.push_back(e);
   }
-  cudaEvent_t *cb_ready = ctx->pipe_ev.data() + 4 * 17;
+  cudaEvent_t *cb_ready = ctx->pipe_ev.data() + 6 * 17;
   char *summaries = (char *)ctx->d_summary.p;
 
   // K = 1: mean of the training set (src/Quantizer.cpp:129-130), split into the first two codevectors
@@ -1147,16 +1199,18 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
     CU(cudaMemcpyAsync(h_final, ctx->d_post.p, (size_t)dim * 8, cudaMemcpyDeviceToHost, st));
   }
   std::vector<int> depth((size_t)nbits + 1, 0);
+  std::vector<char> side_used((size_t)nbits + 1, 0);
   uint32_t K = 1;
   for (int level = 0; level < nbits; level++) {
     K *= 2;
     const int cur = level & 1;
     const bool last = level == nbits - 1;
-    cudaEvent_t *ev = reports ? ctx->pipe_ev.data() + 4 * level : nullptr;
+    cudaEvent_t *ev = reports ? ctx->pipe_ev.data() + 6 * level : nullptr;
     bool fused = false;
     if ((rc = level_begin(ctx, nullptr, (const double *)ctx->d_cbnext[cur].p, K, true, ev ? ev[0] : nullptr,
-                          ev ? ev[1] : nullptr, &fused)))
+                          ev ? ev[1] : nullptr, &fused, ev ? ev[4] : nullptr, ev ? ev[5] : nullptr)))
       return rc;
+    side_used[level] = ctx->side_used;
     CU(cudaEventSynchronize(cb_ready[cur]));  // this level's codebook has reached the host (the filter is already running)
     if ((rc = level_finish(ctx, h_cb[cur], K, true, fused, ev ? ev[2] : nullptr, ev ? ev[3] : nullptr,
                            slots[level + 1].counters, &depth[level])))
@@ -1190,7 +1244,7 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
       Kl *= 2;
       qb200_level_report &r = reports[level];
       const PipeSlot &s = slots[level + 1];
-      cudaEvent_t *ev = ctx->pipe_ev.data() + 4 * level;
+      cudaEvent_t *ev = ctx->pipe_ev.data() + 6 * level;
       r.K = Kl;
       r.flagged = s.counters[0];
       r.changed = s.counters[1];
@@ -1201,7 +1255,10 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
       r.repaired = 0;
       CU(cudaEventElapsedTime(&r.ms_assign, ev[0], ev[1]));
       CU(cudaEventElapsedTime(&r.ms_resolve, ev[1], ev[2]));
-      CU(cudaEventElapsedTime(&r.ms_accumulate, ev[2], ev[3]));
+      if (side_used[level])
+        CU(cudaEventElapsedTime(&r.ms_accumulate, ev[4], ev[5]));
+      else
+        CU(cudaEventElapsedTime(&r.ms_accumulate, ev[2], ev[3]));
       r.distortion_pre = s.dist_pre;
       r.distortion_post = s.dist_post;
     }

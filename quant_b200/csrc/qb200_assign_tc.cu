@@ -41,6 +41,9 @@ constexpr int kProdGroups = 1;          // producer groups of 4 warps taking alt
 constexpr int kTcThreads = 32 * (1 + 4 * kProdGroups + 4 + 8);  // MMA + producer + merger + epilogue warps
 constexpr int kAStages = 4;            // A tiles in flight (shared memory ring)
 constexpr int kResStages = 4;          // per-tile result records in flight
+// Bit 31 of a provisional index: the query is on the flag list.  The exact resolver always rewrites such entries;
+// until then the statistics pass, which may run concurrently with it, skips them (its cell test fails).
+constexpr uint32_t kUndecided = 0x80000000u;
 constexpr int kTileQ = 128;  // queries per tile = MMA M = TMEM lanes
 constexpr int kTileN = 256;  // codevectors per MMA = accumulator columns per TMEM buffer
 
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(256)
         const float so = __shfl_xor_sync(gmask, sb, 2);
         const int ro = __shfl_xor_sync(gmask, rbest, 2);
         if (so < sb || (so == sb && ro < rbest)) rbest = ro;
-        if (j == 0) assign[v] = (uint32_t)(chunk * 8 + rbest);
+        if (j == 0) assign[v] = (uint32_t)(chunk * 8 + rbest) | (flag ? kUndecided : 0u);
         flag = flag && j == 0;
       }
       const unsigned int m = __ballot_sync(0xffffffffu, flag);
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(256)
             }
           }
         }
-        assign[v] = (uint32_t)bidx;
+        assign[v] = (uint32_t)bidx | (flag ? kUndecided : 0u);
       }
       const unsigned int m = __ballot_sync(0xffffffffu, flag);
       if (m) {
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(1024, 1)
           }
         }
       }
-      assign[v] = (uint32_t)bidx;
+      assign[v] = (uint32_t)bidx | (flag ? kUndecided : 0u);
     }
     const unsigned int m = __ballot_sync(0xffffffffu, flag);
     if (m) {

@@ -629,7 +629,11 @@ __global__ void __launch_bounds__(128)
                               const KdDevice tree, const uint32_t *__restrict__ flag_list,
                               const unsigned int *__restrict__ flag_count, uint32_t *__restrict__ assign,
                               uint32_t *__restrict__ tie_list, unsigned int *__restrict__ tie_count,
-                              unsigned int *__restrict__ changed, unsigned long long *__restrict__ stats) {
+                              unsigned int *__restrict__ changed, unsigned long long *__restrict__ stats,
+                              uint32_t *__restrict__ result) {
+  // The filter's guess for a flagged query may carry the "undecided" mark in bit 31 (tensor-core finalise kernels: the
+  // statistics pass that runs next to this kernel skips marked entries).  Every flagged query gets its exact index
+  // written here or in phase B - to `result` when given (committed to `assign` once that pass is done), else in place.
   const int dim = DIMT ? DIMT : src.dim;
   const unsigned int total = *flag_count;
   const int lane = threadIdx.x & 31;
@@ -744,11 +748,9 @@ __global__ void __launch_bounds__(128)
     }
     if (win >= 0) {
       if (lane == 0) {
-        const uint32_t old = assign[v];
-        if (old != (uint32_t)win) {
-          assign[v] = (uint32_t)win;
-          atomicAdd(changed, 1u);
-        }
+        const uint32_t old = assign[v] & 0x7fffffffu;
+        (result ? result : assign)[v] = (uint32_t)win;
+        if (old != (uint32_t)win) atomicAdd(changed, 1u);
         if (stats) add_query_stats(src, img, base, stats + (size_t)win * (dim + 2));
       }
     } else if (lane == 0) {
@@ -767,7 +769,7 @@ __global__ void __launch_bounds__(128)
     resolve_kernel(const VecSource src, const int scaled, const double *cb, const int K, const KdDevice tree,
                    const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
                    uint32_t *__restrict__ assign, unsigned int *__restrict__ changed,
-                   unsigned long long *__restrict__ stats, const unsigned int stage_bytes) {
+                   unsigned long long *__restrict__ stats, const unsigned int stage_bytes, uint32_t *__restrict__ result) {
   // One WARP per query: every lane runs the same (sequential) tree walk; at a leaf the lanes compute the
   // distances of its <= 10 points in parallel.  nanoflann's leaf loop (read worstDist once, add points in
   // order, strict comparisons) keeps the first point that attains the leaf minimum, and only if that
@@ -918,11 +920,9 @@ __global__ void __launch_bounds__(128)
       }
     }
     if (lane == 0) {
-      const uint32_t old = assign[v];
-      if (old != best_idx) {
-        assign[v] = best_idx;
-        atomicAdd(changed, 1u);
-      }
+      const uint32_t old = assign[v] & 0x7fffffffu;
+      (result ? result : assign)[v] = best_idx;
+      if (old != best_idx) atomicAdd(changed, 1u);
       if (stats) add_query_stats(src, img, base, stats + (size_t)best_idx * (dim + 2));
     }
   }
@@ -1474,16 +1474,33 @@ cudaError_t launch_assign(const AssignLaunch &a) {
   return cudaGetLastError();
 }
 
+// assign[v] = result[v] for every flagged query (see resolve_bruteforce_kernel)
+__global__ void commit_resolved_kernel(const uint32_t *__restrict__ flag_list, const unsigned int *__restrict__ flag_count,
+                                       const uint32_t *__restrict__ result, uint32_t *__restrict__ assign) {
+  const unsigned int total = *flag_count;
+  for (unsigned int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    const uint32_t v = flag_list[f];
+    assign[v] = result[v];
+  }
+}
+
+cudaError_t launch_commit_resolved(const uint32_t *flag_list, const unsigned int *flag_count, const uint32_t *result,
+                                   uint32_t *assign, int sm_count, cudaStream_t stream) {
+  commit_resolved_kernel<<<(unsigned int)sm_count, 256, 0, stream>>>(flag_list, flag_count, result, assign);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const double *cbt, int K,
                            const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
-                           unsigned long long *stats, int sm_count, cudaStream_t stream) {
+                           unsigned long long *stats, uint32_t *result, int sm_count, cudaStream_t stream) {
   // phase A: brute force, one warp per flagged query (the count is only known on the device)
   const unsigned int blocks_a = (unsigned int)sm_count * 8;
 #define QB_RESOLVE_A(CAP, DT)                                                                                        \
   resolve_bruteforce_kernel<CAP, DT><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, \
-                                                                   assign, tie_list, tie_count, changed, stats)
+                                                                   assign, tie_list, tie_count, changed, stats, result)
   switch (src.dim) {
     case 3: QB_RESOLVE_A(3, 3); break;
     case 6: QB_RESOLVE_A(6, 6); break;
@@ -1516,7 +1533,7 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
       if (e2 != cudaSuccess) return e2;
     }
     kernel<<<blocks, 128, stage, stream>>>(src, scaled, cb, K, tree, tie_list, tie_count, assign, changed, stats,
-                                           (unsigned int)stage);
+                                           (unsigned int)stage, result);
     return cudaGetLastError();
   };
   switch (src.dim) {

@@ -39,8 +39,12 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
-                           unsigned long long *stats /* null unless the filter fused the statistics */, int sm_count,
-                           cudaStream_t stream);
+                           unsigned long long *stats /* null unless the flagged queries' statistics are added here */,
+                           uint32_t *result /* null: exact indices go straight to assign; else to result[v], see below */,
+                           int sm_count, cudaStream_t stream);
+// assign[v] = result[v] for the flagged queries: used when a statistics pass read `assign` while the resolver ran.
+cudaError_t launch_commit_resolved(const uint32_t *flag_list, const unsigned int *flag_count, const uint32_t *result,
+                                   uint32_t *assign, int sm_count, cudaStream_t stream);
 // stats must be zeroed by the caller; assign may be null only for K == 1.
 cudaError_t launch_accumulate(const VecSource &src, const uint32_t *assign, int K, unsigned long long *stats,
                               int sm_count, cudaStream_t stream);
