@@ -617,10 +617,11 @@ __device__ __forceinline__ double nanoflann_l2_t(const double *a, const double *
 // other one the tree walk must return that codevector and no walk is needed: the only FP64 roundings
 // that differ between the walk and this loop are in the walk's pruning bound (mindistsq + cut_dist -
 // dists[feat], nanoflann.hpp:1254-1262), whose intermediates are distances from the query to actual
-// codevector coordinates, i.e. bounded by dmax = max_k dist_k; their accumulated error is below
-// ~4*dim*2^-53*dmax.  A query is decided here when it has exactly one candidate within
-// band = 2^-30 * dmax of the minimum (orders of magnitude above that error, orders of magnitude
-// below the FP32 filter's margin).  EXACT ties (all candidates bitwise equal) are decided by the tree's
+// codevector coordinates, i.e. bounded by dmax = max_k dist_k: two roundings of at most 2^-53 * dmax per tree level
+// (depth <= kResolveDepthCap = 512: 2^-43 * dmax) plus the (dim + 2) * 2^-53 relative error of a distance - so a
+// subtree holding a codevector more than ~2^-42.6 * dmax closer than the running best is never pruned.  A query is
+// decided here when it has exactly one candidate within band = 2^-36 * dmax of the minimum (two orders of magnitude
+// above that bound, many below the FP32 filter's margin; a wider band only sends more queries to the walk).  EXACT ties (all candidates bitwise equal) are decided by the tree's
 // visiting order without a walk (see below); what remains - distinct distances closer than the band, or
 // more than 32 candidates - goes to the tie list and phase B walks the tree.
 template <int DIMCAP, int DIMT>  // DIMT != 0: dimension known at compile time (== DIMCAP)
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(128)
       wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
       wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     }
-    const double lim = wmin + wmax * 9.313225746154785e-10;  // 2^-30
+    const double lim = wmin + wmax * 1.4551915228366852e-11;  // 2^-36
     const int mine = (d1 <= lim ? 1 : 0) + (d2 <= lim ? 1 : 0);
     const unsigned int holders = __ballot_sync(0xffffffffu, mine > 0);
     const unsigned int multi = __ballot_sync(0xffffffffu, mine > 1);
@@ -787,14 +788,26 @@ __global__ void __launch_bounds__(128)
   const unsigned int *vind = tree.vind;
   if (stage_bytes) {
     const size_t nb_nodes = (size_t)tree.n_nodes * sizeof(KdNode), nb_cb = (size_t)K * dim * 8, nb_vind = (size_t)K * 4;
-    uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
-    const uint4 *s0 = reinterpret_cast<const uint4 *>(cb), *s1 = reinterpret_cast<const uint4 *>(tree.nodes),
-                *s2 = reinterpret_cast<const uint4 *>(tree.vind);
-    const size_t q0 = nb_cb / 16, q1 = nb_nodes / 16, q2 = (nb_vind + 15) / 16;  // cb and nodes are multiples of 16 bytes
-    for (size_t i = threadIdx.x; i < q0; i += blockDim.x) dst[i] = s0[i];
-    for (size_t i = threadIdx.x; i < q1; i += blockDim.x) dst[q0 + i] = s1[i];
-    for (size_t i = threadIdx.x; i < q2; i += blockDim.x) dst[q0 + q1 + i] = s2[i];
+    // bulk copies by the TMA unit (one thread issues, everyone waits on the mbarrier): ~130 KB at K = 1024 arrive in
+    // a few microseconds, where a copy loop of this 128-thread block took ~100 us - longer than the walks themselves
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t b0 = (uint32_t)nb_cb, b1 = (uint32_t)nb_nodes, b2 = (uint32_t)((nb_vind + 15) & ~(size_t)15);
+      mbar_expect_tx(&s_bar, b0 + b1 + b2);  // cb and nodes are multiples of 16 bytes; vind is followed by its inverse
+      auto bulk = [&](unsigned char *d, const void *g, uint32_t bytes) {
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+          tma_load_1d(d + off, reinterpret_cast<const char *>(g) + off, min(32768u, bytes - off), &s_bar);
+      };
+      bulk(smem_raw, cb, b0);
+      bulk(smem_raw + b0, tree.nodes, b1);
+      bulk(smem_raw + b0 + b1, tree.vind, b2);
+    }
+    mbar_wait_bounded(&s_bar, 0, 9);
     cb = reinterpret_cast<const double *>(smem_raw);
     nodes = reinterpret_cast<const KdNode *>(smem_raw + nb_cb);
     vind = reinterpret_cast<const unsigned int *>(smem_raw + nb_cb + nb_nodes);
