@@ -30,3 +30,8 @@ def test_chunked_evaluation_is_exact():
         got, _ = kc.chained(ts[k:], A0, 128)
         assert got == ka.to_A(s_fp, c_fp)
         assert ka.rn53(got)[0] * 2.0 ** -ka.G == s_fp
+
+
+def test_anchored_four_branch_segments_are_exact():
+    import kahan_segments as ks
+    assert ks.check(seed=9, trials=8) == 0
