@@ -10,7 +10,7 @@ from __future__ import annotations
 import enum
 import time
 from dataclasses import dataclass
-from typing import List, Tuple
+from typing import Tuple
 
 import numpy as np
 

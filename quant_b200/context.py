@@ -7,7 +7,7 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (ALLREDUCE_FN, CS_NORMAL, CS_SCALED, LevelReport, MODE_FULL, MODE_FULL_REPAIR, MODE_PARITY,
+from ._lib import (ALLREDUCE_FN, CS_SCALED, LevelReport, MODE_PARITY,
                    Qb200Error)
 
 

@@ -10,7 +10,7 @@ the rare segment whose margin does not cover the true start.  Chains (or stretch
 stay sequential.  This file checks the scheme against the plain integer model."""
 import numpy as np
 
-from kahan_automaton import G, X_T, kahan_fp, kahan_int, rn53, step_int, to_A
+from kahan_automaton import X_T, kahan_fp, kahan_int, step_int, to_A
 from kahan_chunks import M, centered, decision_margin
 
 RESIDUES = (0, 128, 256, 384)
