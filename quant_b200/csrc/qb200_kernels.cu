@@ -623,11 +623,12 @@ __device__ __forceinline__ double nanoflann_l2_t(const double *a, const double *
 // other one the tree walk must return that codevector and no walk is needed: the only FP64 roundings
 // that differ between the walk and this loop are in the walk's pruning bound (mindistsq + cut_dist -
 // dists[feat], nanoflann.hpp:1254-1262), whose intermediates are distances from the query to actual
-// codevector coordinates, i.e. bounded by dmax = max_k dist_k: two roundings of at most 2^-53 * dmax per tree level
-// (depth <= kResolveDepthCap = 512: 2^-43 * dmax) plus the (dim + 2) * 2^-53 relative error of a distance - so a
-// subtree holding a codevector more than ~2^-42.6 * dmax closer than the running best is never pruned.  A query is
-// decided here when it has exactly one candidate within band = 2^-36 * dmax of the minimum (two orders of magnitude
-// above that bound, many below the FP32 filter's margin; a wider band only sends more queries to the walk).  EXACT ties (all candidates bitwise equal) are decided by the tree's
+// codevector coordinates, i.e. bounded by dmax = max_k dist_k: an add and a subtract per tree level on values of at
+// most 2 * dmax, each rounding <= 2^-52 * dmax (depth <= kResolveDepthCap = 512: 2^-42 * dmax in all, 2^-46 at the
+// depths that occur), plus the (dim + 1) * 2^-53 relative error of a distance (<= 2^-45.4 at dim 192) - so a subtree
+// holding a codevector more than ~2^-41.5 * dmax closer than the running best is never pruned.  A query is decided
+// here when it has exactly one candidate within band = 2^-36 * dmax of the minimum (45x above that worst case, many
+// orders below the FP32 filter's margin; a wider band only sends more queries to the walk).  EXACT ties (all candidates bitwise equal) are decided by the tree's
 // visiting order without a walk (see below); what remains - distinct distances closer than the band, or
 // more than 32 candidates - goes to the tie list and phase B walks the tree.
 template <int DIMCAP, int DIMT>  // DIMT != 0: dimension known at compile time (== DIMCAP)
