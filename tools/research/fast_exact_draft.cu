@@ -1,4 +1,5 @@
-// DRAFT - NOT PART OF libqb200, NOT RUN ON HARDWARE YET (round-1 GPU budget was spent).  Compiles with
+// DRAFT - NOT PART OF libqb200.  Checked once on a B200 by fast_exact_test.cu (bit-identical to the floating-point loop,
+// profiles/r1_fast_exact_draft_check.txt); untuned.  Compiles with
 //   nvcc -gencode arch=compute_100a,code=sm_100a -c tools/research/fast_exact_draft.cu -o /dev/null
 // Kernel-level restatement of tools/research/kahan_segments.c (validated on the CPU): the reference's compensated
 // member sums (Solution::sumInArea, /root/reference/src/Quantizer.cpp:59-70) of SCALED lattice vectors, bit for bit,
