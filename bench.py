@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """bench.py - LBG codebook-training throughput on B200 (the metric BASELINE.json names).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c1|c5] [--weak] [--impl reference]
+
+Default workload: BASELINE config 3 (16384 x 16384, 2x2 blocks, K = 4096, 67 M vectors) - north_star's scaling target -
+STRONG scaling: the one image is split into `--gpus` bands of block rows (N = 1 trains the whole image on one GPU).
 
 A STEP is one complete LBG codebook train (LBGQuantizer::quantize, /root/reference/src/Quantizer.cpp:
 121-143: mean -> nbits x {split, assign, accumulate, fix}) over one synthetic image.  Per step the
@@ -21,9 +24,9 @@ SURVEY.md D2); `value` = that / device time, in Gdist-evals/s, whole job over al
              flags, driven through CompressedImage::compress) on the box's host cores, on a bounded
              band of the same image; else the plain-C oracle port (1 thread)
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling - every rank owns one workload-sized band of a
-`world` times taller image; the only exchange is one NCCL all-reduce of K*(dim+2) 64-bit integers
-per split level.
+Multi-GPU (torchrun, one rank per GPU): every rank owns one band of block rows (strong scaling, default: the named
+image split `world` ways; --weak: one workload-sized band per rank of a `world` times taller image); the only
+exchange is one sum all-reduce of K*(dim+2) 64-bit integers per split level.
 """
 from __future__ import annotations
 
@@ -55,6 +58,31 @@ EPS = float(np.float32(1e-6))
 def noise_band(xs, ys, seed):
     """`xs` pixel lines of `ys` pixels (the reference addresses pixel (x, y) at x*ySize + y)."""
     return np.random.default_rng(seed).integers(0, 256, (xs, ys, 3), dtype=np.uint8)
+
+
+_KODAK = None
+
+
+def natural_band(xs, ys, first_line):
+    """`xs` pixel lines of `ys` pixels cut from an endless tiling of kodim01 (768 x 512, tests/golden): natural
+    statistics - flat areas, duplicated blocks, dead cells - instead of noise."""
+    global _KODAK
+    if _KODAK is None:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "kodim01_full_2x2_n10.npz"))
+        kx, ky = int(z["params"][0]), int(z["params"][1])
+        _KODAK = np.ascontiguousarray(z["rgb"], np.uint8).reshape(ky, kx, 3)
+    ky, kx = _KODAK.shape[:2]
+    lines = (first_line + np.arange(xs)) % ky
+    cols = np.arange(ys) % kx
+    return np.ascontiguousarray(_KODAK[lines][:, cols])
+
+
+def make_band(kind, xs, ys, seed, first_line=0):
+    return natural_band(xs, ys, first_line) if kind == "natural" else noise_band(xs, ys, seed)
+
+
+def desc_of(desc, data):
+    return desc if data == "noise" else desc.replace("synthetic noise", "synthetic (kodim01 tiled: natural statistics)")
 
 
 def evals_per_train(n_vectors, nbits):
@@ -137,21 +165,26 @@ def cpu_train_seconds(kind, eng, band, xs, ys, w, h, nbits):
     return time.perf_counter() - t
 
 
-def cpu_sample(kind, eng, wl, budget_s, steps, warmup):
+def cpu_sample(kind, eng, wl, budget_s, steps, warmup, data="noise"):
     """Times `steps` trains (after `warmup`) on a band of the workload image sized to fit budget_s."""
     bx, ys, w, h, nbits, _ = WORKLOADS[wl]
-    cores = eng.max_threads() if kind == "reference" else 1
+    cores = 1
+    if kind == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every host core explicitly
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        eng.set_threads(cores)
+        cores = eng.max_threads()
     # calibrate t(lines) = a + b*lines on two small bands (the first call also warms the OpenMP pool)
     p1 = max(w * 8, min(bx, 64 if kind == "reference" else 16))
     p2 = min(bx, 4 * p1)
-    cpu_train_seconds(kind, eng, noise_band(p1, ys, 1234), p1, ys, w, h, nbits)
-    t1 = cpu_train_seconds(kind, eng, noise_band(p1, ys, 1234), p1, ys, w, h, nbits)
-    t2 = cpu_train_seconds(kind, eng, noise_band(p2, ys, 1234), p2, ys, w, h, nbits) if p2 > p1 else t1
+    cpu_train_seconds(kind, eng, make_band(data, p1, ys, 1234), p1, ys, w, h, nbits)
+    t1 = cpu_train_seconds(kind, eng, make_band(data, p1, ys, 1234), p1, ys, w, h, nbits)
+    t2 = cpu_train_seconds(kind, eng, make_band(data, p2, ys, 1234), p2, ys, w, h, nbits) if p2 > p1 else t1
     b = max((t2 - t1) / max(p2 - p1, 1), 1e-9)
     a = max(t1 - b * p1, 0.0)
     xs = int((budget_s / (steps + warmup) - a) / b)
     xs = max(p1, min(bx, (xs // (8 * w)) * 8 * w))
-    band = noise_band(xs, ys, 1234)
+    band = make_band(data, xs, ys, 1234)
     n_vec = ((xs + w - 1) // w) * ((ys + h - 1) // h)
     for _ in range(warmup):
         cpu_train_seconds(kind, eng, band, xs, ys, w, h, nbits)
@@ -170,17 +203,21 @@ def run_reference_arm(args):
     kind, eng = cpu_engine()
     wl = args.workload
     bx, ys, w, h, nbits, desc = WORKLOADS[wl]
-    base, sec, xs, n_vec = cpu_sample(kind, eng, wl, args.cpu_budget, args.steps, max(args.warmup, 1))
+    base, sec, xs, n_vec = cpu_sample(kind, eng, wl, args.cpu_budget, args.steps, max(args.warmup, 1), args.data)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "bounded_sample": base["sample"], "block": [w, h], "nbits": nbits,
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc_of(desc, args.data), "bounded_sample": base["sample"], "block": [w, h], "nbits": nbits,
                    "colorspace": "SCALED", "cpu_threads": base["cores"]},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.data == "noise" and not args.no_natural:          # the same shape on natural data, bounded the same way
+        nat, nsec, _, _ = cpu_sample(kind, eng, wl, 0.4 * args.cpu_budget, 1, 1, "natural")
+        line["natural"] = {"data": "kodim01 (tests/golden) tiled to the workload's shape", "value": nat["value"], "unit": UNIT,
+                           "ms_per_step": nsec * 1e3, "bounded_sample": nat["sample"], "cpu_threads": nat["cores"]}
     emit(line)
     return 0
 
@@ -188,6 +225,39 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def cpp_compress_leg(band, xs, ys, w, h, nbits, steps, n_total, cb_expect):
+    import ctypes as C
+    so = os.path.join(ROOT, "quant_b200", "host", "libquantsrc.so")
+    if not os.path.exists(so):
+        return {"unavailable": "quant_b200/host/libquantsrc.so not built"}
+    L = C.CDLL(so)
+    L.quantsrc_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float),
+                                    C.POINTER(C.c_double)]
+    L.quantsrc_last_error.restype = C.c_char_p
+    K, dim = 1 << nbits, 3 * w * h
+    pix = np.array(band, np.uint8, copy=True)                 # plain pageable memory
+    cbb = np.empty((K, dim), np.uint8)
+    a = np.empty(n_total, np.uint64)
+    d, bpp, sec = C.c_double(), C.c_float(), C.c_double()
+    times = []
+    for i in range(steps + 1):                                # first call: context creation + allocations (warm-up)
+        rc = L.quantsrc_compress(pix.ctypes.data, xs, ys, 1, w, h, EPS, nbits, cbb.ctypes.data, a.ctypes.data,
+                                 C.byref(d), C.byref(bpp), C.byref(sec))
+        if rc < 0:
+            return {"unavailable": (L.quantsrc_last_error() or b"").decode()}
+        if i:
+            times.append(sec.value)
+    import quant_b200 as qb
+    same = bool(np.array_equal(cbb, qb.codebook_to_bytes(cb_expect, qb.CS_SCALED)))
+    t = float(np.mean(times))
+    return {"value": evals_per_train(n_total, nbits) / t / 1e9, "unit": UNIT, "seconds_per_train": t, "steps": steps,
+            "through": "libquantsrc.so CompressedImage::compress (C++ drop-in API): pageable std::vector<RGB> in, "
+                       "std::vector<size_t> indices out; the report's own 'Compression time' (host clock)",
+            "h2d_bytes_per_step": int(pix.size), "d2h_bytes_per_step": int(n_total) * 4,
+            "codebook_bytes_equal_c_abi_run": same, "report_mse": d.value, "bits_per_pixel": bpp.value}
+
+
 def run_gpu_arm(args):
     import torch
     import quant_b200 as qb
@@ -208,11 +278,11 @@ def run_gpu_arm(args):
     wl = args.workload
     bx, ys, w, h, nbits, desc = WORKLOADS[wl]
     K, dim = 1 << nbits, 3 * w * h
-    if args.strong:                            # strong scaling: the named image is split into `world` bands
+    if args.strong:                            # strong scaling (default): the named image is split into `world` bands
         if bx % (w * world):
-            raise SystemExit("--strong needs the image's pixel lines to divide by block width x ranks")
+            raise SystemExit("strong scaling needs the image's pixel lines to divide by block width x ranks")
         bx = bx // world
-    xs_total = bx * world                      # weak scaling (default): one workload-sized band per rank
+    xs_total = bx * world                      # --weak: one workload-sized band per rank
     wB_band = bx // w
     row_begin, row_end = rank * wB_band, (rank + 1) * wB_band
     n_local = wB_band * (ys // h)
@@ -227,7 +297,7 @@ def run_gpu_arm(args):
     if world > 1:
         ctx.set_rank(rank, world)
 
-    band_np = noise_band(bx, ys, 1234 + rank).reshape(-1)
+    band_np = make_band(args.data, bx, ys, 1234 + rank, rank * bx).reshape(-1)
     host_band = torch.empty(band_np.size, dtype=torch.uint8, pin_memory=True)
     host_band.numpy()[:] = band_np
     host_assign = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
@@ -290,6 +360,34 @@ def run_gpu_arm(args):
     clocks = sampler.stop(t0, t3) if sampler else None
     assert np.array_equal(cb_res, cb_e2e) and d_res == d_e2e, "resident and e2e trains disagree"
 
+    # The same shape on NATURAL data (kodim01 tiled): flat areas, duplicated blocks and dead cells push far more
+    # queries through the exact FP64 resolver and its tree walk than noise does (and the reference's KD search is
+    # faster there), so the noise headline alone would flatter the comparison.  Reported next to it.
+    natural = None
+    if args.data == "noise" and not args.no_natural:
+        host_band.numpy()[:] = natural_band(bx, ys, rank * bx).reshape(-1)
+        n_steps = min(args.steps, 3)
+        ms_nr, reps_n, _, _, _, d_nat = timed("resident", n_steps, 3)
+        ms_ne, _, _, _, _, _ = timed("e2e", n_steps, 3)
+        if rank == 0:
+            ev = evals_per_train(n_total, nbits)
+            natural = {"data": "kodim01 (tests/golden) tiled to the workload's shape",
+                       "value": ev * n_steps / (ms_nr * 1e-3) / 1e9, "ms_per_step": ms_nr / n_steps,
+                       "e2e": {"value": ev * n_steps / (ms_ne * 1e-3) / 1e9, "ms_per_step": ms_ne / n_steps}, "unit": UNIT,
+                       "steps": n_steps, "distortion": d_nat,
+                       "flagged_per_level": {str(r["K"]): int(r["flagged"]) for r in reps_n[-1]},
+                       "kd_walk_ties_per_level": {str(r["K"]): int(r["ties"]) for r in reps_n[-1]},
+                       "dead_cells_last_level": int(reps_n[-1][-1]["dead_cells"]),
+                       "ms_resolve_per_train": float(np.mean([sum(r["ms_resolve"] for r in rep) for rep in reps_n]))}
+        host_band.numpy()[:] = band_np
+
+    # Second end-to-end leg: the reference-facing C++ call itself - CompressedImage::compress of libquantsrc.so
+    # (quant_b200/host), PAGEABLE std::vector<RGB> pixels in, std::vector<size_t> indices out, timed by the C++
+    # layer's own host clock over the reference's scope (src/Compressor.cpp:118-123).  One process, one GPU.
+    e2e_cpp = None
+    if rank == 0 and world == 1 and not args.no_cpp:
+        e2e_cpp = cpp_compress_leg(band_np, xs_total, ys, w, h, nbits, min(args.steps, 5), n_total, cb_res)
+
     if rank == 0:
         evals = evals_per_train(n_total, nbits)
         value = evals * args.steps / (ms_res * 1e-3) / 1e9
@@ -302,8 +400,8 @@ def run_gpu_arm(args):
                      for i, r in enumerate(reps[0])}
         flagged_last = int(last[-1]["flagged"])
         ties_last = int(last[-1]["ties"])
-        flops = float(n_local) * K * 3.0 * dim            # algorithmic: sub, mul, add per dimension and evaluation
-        fp32_equiv = flops / (ms_assign * 1e-3) / 1e12
+        flops = float(n_local) * K * 3.0 * dim            # algorithmic (SURVEY 8d): sub, mul, add per dimension and evaluation
+        alg_tflops = flops / (ms_assign * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -313,44 +411,49 @@ def run_gpu_arm(args):
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         tc_peak = float(peaks.get("bf16_tflops", 1590.0))
         tc_src = "MEASURED_PEAKS.json bf16_tflops, burst (of measured)" if "bf16_tflops" in peaks else "1590 TFLOP/s (of fallback)"
-        acc_gbs = float(n_local) * (dim + 4) / (ms_acc * 1e-3) / 1e9
+        acc_gbs = float(n_local) * (dim + 4) / (ms_acc * 1e-3) / 1e9 if ms_acc > 0 else None
         uses_tc = K >= max(int(os.environ.get("QB200_TC_MIN_K", "128") or 128), 64) and os.environ.get("QB200_DISABLE_TC", "0") != "1"
         kb = (dim + 1 + 15) // 16
         k_pad = ((K + 255) // 256) * 256
         # executed tensor flops of the filter: 128-query tiles x padded codebook x (3 bf16 limbs x 16*kb) x 2
         tc_flops = float(((n_local + 127) // 128) * 128) * k_pad * (3 * 16 * kb) * 2.0
-        tc_ach = tc_flops / (ms_assign * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch, from the committed ncu capture
+        # of this workload (profiles/traffic.json, written by tools/ncu_summary.py); null when there is none
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = f"{wl}/n{world}/{'tc' if uses_tc else 'cc'}"
+            traffic = tj.get(key, {}).get("bytes")
+        except (OSError, ValueError):
+            pass
         if uses_tc:
             roof = {"bound": "tensor", "kernel": f"assign_tc_kernel<{dim}> (+ its finalise kernel) at K={K}, last split level",
-                    "achieved": tc_ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": tc_ach / tc_peak, "peak_source": tc_src,
-                    "algorithmic": "executed bf16 MMA flops: ceil(N/128)*128 x K padded to 256 x 3 limbs x 16*ceil((dim+1)/16) x 2",
-                    "note": "the GEMM is 3-limb bf16 with a 13-of-16 used K dimension; by design the kernel is bound by the "
-                            "top-2 selection over the accumulator columns on the alu pipe (2.75 min/max ops per distance "
-                            "evaluation, ncu: profiles/), not by the tensor pipe",
-                    "ms_per_launch": ms_assign,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of the K=1024 assign_tc_kernel launch on this workload,
-                    # one `ncu --set full` capture (profiles/r1_assign_tc_k1024_ncu_summary.txt): 50.5 MB + 20.4 MB
-                    # (image bytes in; 16-byte per-query records out, part of which stays in L2)
-                    "traffic": 70.9e6 if (wl == "c2" and world == 1) else None,
-                    "traffic_algorithmic": float(n_local) * dim}
+                    "achieved": alg_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": alg_tflops / tc_peak, "peak_source": tc_src,
+                    "algorithmic": "SURVEY 8d: 3*dim flop per distance evaluation x N*K evaluations of the launch",
+                    "executed": {"achieved": tc_flops / (ms_assign * 1e-3) / 1e12, "frac": tc_flops / (ms_assign * 1e-3) / 1e12 / tc_peak,
+                                 "what": "bf16 MMA flops really issued: ceil(N/128)*128 x K padded to 256 x 3 limbs x 16*ceil((dim+1)/16) x 2"},
+                    "note": "the contraction runs on the tensor pipe (3 bf16 limbs = 24 mantissa bits); the kernel's own limiter is the "
+                            "min-selection over the accumulator columns on the alu pipe (1.125 min/max ops per evaluation, ncu: profiles/)",
+                    "ms_per_launch": ms_assign, "traffic": traffic, "traffic_algorithmic": float(n_local) * dim}
         else:
-            roof = {"bound": "fp32", "kernel": f"assign_kernel<{dim}> at K={K}, last split level", "achieved": fp32_equiv,
-                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_equiv / fp32_peak,
-                    "peak_source": "FP32 FFMA probe in this run (FMA = 2 flop)", "ms_per_launch": ms_assign, "traffic": None}
+            roof = {"bound": "fp32", "kernel": f"assign_kernel<{dim}> at K={K}, last split level", "achieved": alg_tflops,
+                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": alg_tflops / fp32_peak,
+                    "peak_source": "FP32 FFMA probe in this run (FMA = 2 flop)", "ms_per_launch": ms_assign, "traffic": traffic}
         roof["gdist_evals_per_s"] = float(n_local) * K / (ms_assign * 1e-3) / 1e9
-        roof["fp32_equivalent"] = {"achieved": fp32_equiv, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_equiv / fp32_peak,
+        roof["fp32_equivalent"] = {"achieved": alg_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": alg_tflops / fp32_peak,
                                    "algorithmic": "3*dim flop per distance evaluation x N*K evaluations (the reference's sub, mul, add)",
                                    "peak_source": "FP32 FFMA probe in this run (FMA = 2 flop); MEASURED_PEAKS.json has no FP32 figure"}
-        roof["hbm"] = {"kernel": "accumulate (per-cell integer statistics), same level", "achieved": acc_gbs, "peak": hbm_peak,
-                       "unit": "GB/s", "frac": acc_gbs / hbm_peak, "peak_source": hbm_src, "ms_per_launch": ms_acc,
-                       "algorithmic": "(dim + 4) bytes per vector"}
+        if acc_gbs:
+            roof["hbm"] = {"kernel": "per-cell integer statistics pass, same level", "achieved": acc_gbs, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": acc_gbs / hbm_peak, "peak_source": hbm_src, "ms_per_launch": ms_acc,
+                           "algorithmic": "(dim + 4) bytes per vector"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "bf16x3 tensor-core / f32 filter + f64 exact re-check; i64 sums",
             "data": "synthetic",
-            "config": {"workload": desc + ((f"; strong scaling: split into {world} bands" if args.strong else
+            "config": {"workload": desc_of(desc, args.data) + ((f"; strong scaling: split into {world} bands" if args.strong else
                                             f"; weak scaling: {world} such bands, one per rank") if world > 1 else ""),
                        "block": [w, h], "nbits": nbits, "colorspace": "SCALED", "vectors_per_rank": n_local,
                        "schedule": "reference HEAD: one assignment pass per split level, no empty-cell repair",
@@ -361,6 +464,7 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": int(host_band.numel()) * world,
                     "d2h_bytes_per_step": (n_local * 4) * world,
                     "seconds_per_train": ms_e2e / args.steps / 1e3},
+            "e2e_cpp": e2e_cpp, "natural": natural,
             "gpu_launches": launches,
             "roofline": roof,
             "per_level_ms": per_level, "flagged_last_level": flagged_last, "kd_walk_ties_last_level": ties_last,
@@ -368,7 +472,7 @@ def run_gpu_arm(args):
         }
         if world == 1 and not args.no_cpu:
             kind, eng = cpu_engine()
-            base, _, _, _ = cpu_sample(kind, eng, wl, args.cpu_budget, 1, 1)
+            base, _, _, _ = cpu_sample(kind, eng, wl, args.cpu_budget, 1, 1, args.data)
             line["cpu_baseline"] = base
         emit(line)
     ctx.close()
@@ -501,15 +605,22 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--images", type=int, default=1024, help="images per rank of the encode-only workload c5")
     ap.add_argument("--cpu-budget", type=float, default=None, help="seconds of CPU work for the CPU arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpp", action="store_true", help="skip the C++ CompressedImage::compress end-to-end leg")
+    ap.add_argument("--no-natural", action="store_true", help="skip the natural-image leg")
     ap.add_argument("--exact", action="store_true",
                     help="bit-exact centroid mode (qb200_set_exact_centroids): slower, identical to the reference on any input")
-    ap.add_argument("--strong", action="store_true",
-                    help="strong scaling: split the workload image across the ranks (default: weak, one image-sized band per rank)")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: one workload-sized band per rank (default: strong, the workload image is split across the ranks)")
+    ap.add_argument("--strong", action="store_true", help="(default; kept for compatibility)")
+    ap.add_argument("--data", default="noise", choices=["noise", "natural"],
+                    help="noise: uniform random bytes (worst case for the reference's KD tree, few ties); natural: the Kodak "
+                         "image of tests/golden tiled to the workload's shape (flat areas, duplicates, dead cells)")
     args = ap.parse_args()
+    args.strong = not args.weak
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.cpu_budget is None:
         args.cpu_budget = 120.0 if args.impl == "reference" else 20.0

@@ -209,9 +209,11 @@ class Context:
 
     def decode(self, codebook_bytes: np.ndarray, want_image=True):
         cbb = np.ascontiguousarray(codebook_bytes, np.uint8)
+        if cbb.size % self.dim:
+            raise ValueError(f"codebook bytes ({cbb.size}) are not a multiple of the dimension {self.dim}")
         out = np.empty(len(self._keep) if self._keep is not None else 0, np.uint8) if want_image else None
         mse = C.c_double()
-        self._check(self.lib.qb200_decode(self.h, _ptr(cbb), cbb.shape[0], _ptr(out), C.byref(mse)))
+        self._check(self.lib.qb200_decode(self.h, _ptr(cbb), cbb.size // self.dim, _ptr(out), C.byref(mse)))
         return out, mse.value
 
     def filter_records(self) -> np.ndarray:

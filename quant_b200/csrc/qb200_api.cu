@@ -67,6 +67,7 @@ struct qb200_ctx {
   void *h_pin = nullptr;
   size_t h_pin_cap = 0;
   bool assign_valid = false;
+  uint32_t assign_K = 0;  // codebook size the assignment in d_assign refers to (qb200_decode checks it)
   bool use_tc = true;  // tensor-core filter where it applies (qb200_set_tensor_cores)
   // empty-cell repair (QB200_MODE_FULL_REPAIR)
   uint64_t seed = 0x5eed, repair_round = 0;
@@ -369,6 +370,7 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
   if (ev3) CU(cudaEventRecord(ev3, st));
   CU(cudaMemcpyAsync(counters_dst, ctx->d_counters.p, 12, cudaMemcpyDeviceToHost, st));
   ctx->assign_valid = true;
+  ctx->assign_K = K;
   if (kd_depth_out) *kd_depth_out = tree.depth;
   return QB200_OK;
 }
@@ -536,6 +538,12 @@ int repair_empty_cells(qb200_ctx *ctx, uint32_t K, const std::vector<uint64_t> &
 
 int set_common(qb200_ctx *ctx, size_t n_local, bool pack = true) {
   int rc;
+  // The statistics kernels keep per-CTA partial sums of lattice values (t = L + 128 <= 255) in 32-bit shared-memory
+  // words and run at least one CTA per SM: with every vector in one cell (the K = 1 mean pass, flat images) a CTA's
+  // share n_local / sm_count must stay below 2^31 / 256 = 2^23 vectors.
+  if (pack && n_local > ((size_t)ctx->sm_count << 23))
+    return fail(ctx, QB200_ERR_ARG, "training set of %zu vectors exceeds this device's bound of %zu (sm_count * 2^23)",
+                n_local, (size_t)ctx->sm_count << 23);
   // dense byte copy of the training set: every later gather is a few coalesced word loads
   if (pack) {
     VecSource &s = ctx->src;
@@ -1112,6 +1120,7 @@ int train_generic(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t N, q
     CU(cudaMemsetAsync(ctx->d_assign.p, 0, (n ? n : 1) * 4, st));
     CU(cudaStreamSynchronize(st));
     ctx->assign_valid = true;
+    ctx->assign_K = 1;
   }
   return QB200_OK;
 }
@@ -1126,8 +1135,8 @@ struct PipeSlot {  // pinned, one per split level
 // HEAD schedule without host round trips between levels: centroids, distortions and the next split are
 // computed on the device (finalize_split_kernel); the host only builds each level's KD tree, from a codebook
 // copy that arrives while the GPU is already running that level's filter, and reads everything else at the end.
-int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduce_fn ar, void *ar_user,
-                           double *codebook_out, double *distortion_out, qb200_level_report *reports) {
+int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduce_fn ar, void *ar_user,
+                                double *codebook_out, double *distortion_out, qb200_level_report *reports) {
   const int dim = ctx->src.dim;
   const uint32_t maxK = 1u << nbits;
   const size_t cb_max = (size_t)maxK * dim * 8;
@@ -1232,10 +1241,11 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
   }
   if (nbits == 0) CU(cudaMemsetAsync(ctx->d_assign.p, 0, (size_t)ctx->src.n_local * 4, st));
   CU(cudaStreamSynchronize(st));
-  ctx->assign_valid = true;
   if (slots[0].n_seen != N)
     return fail(ctx, QB200_ERR_STATE, "vector count mismatch: reduced %llu, expected %llu",
                 (unsigned long long)slots[0].n_seen, (unsigned long long)N);
+  ctx->assign_valid = true;
+  ctx->assign_K = K;
   std::memcpy(codebook_out, h_final, (size_t)K * dim * 8);
   if (distortion_out) *distortion_out = slots[nbits].dist_post;
   if (reports) {
@@ -1264,6 +1274,22 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
     }
   }
   return QB200_OK;
+}
+
+// Error exits of the body leave kernels and asynchronous copies into the pinned slots in flight: drain both streams
+// before the caller can retry (and reallocate those buffers), and never serve a partial assignment.
+int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduce_fn ar, void *ar_user,
+                           double *codebook_out, double *distortion_out, qb200_level_report *reports) {
+  ctx->assign_valid = false;
+  const int rc = train_parity_pipelined_body(ctx, nbits, N, ar, ar_user, codebook_out, distortion_out, reports);
+  if (rc != QB200_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+    cudaGetLastError();
+    ctx->side_pending = false;
+    ctx->assign_valid = false;
+  }
+  return rc;
 }
 
 }  // namespace
@@ -1372,6 +1398,7 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
     CU(cudaMemsetAsync(ctx->d_assign.p, 0, (size_t)ctx->src.n_local * 4, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->assign_valid = true;
+    ctx->assign_K = 1;
   }
   return QB200_OK;
 }
@@ -1477,6 +1504,7 @@ int qb200_assign_only(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32
   if (!ctx) return QB200_ERR_ARG;
   if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_assign_only: no training set");
   if (!codebook || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_assign_only: empty codebook");
+  if (K > (1u << 24)) return fail(ctx, QB200_ERR_ARG, "qb200_assign_only: K too large");
   CU(cudaSetDevice(ctx->device));
   LevelOut lo;
   int rc = run_level(ctx, codebook, K, false, true, &lo);
@@ -1495,6 +1523,10 @@ int qb200_decode(qb200_ctx *ctx, const uint8_t *codebook_bytes, uint32_t K, uint
   if (ctx->is_shard) return fail(ctx, QB200_ERR_STATE, "qb200_decode: not available on a sharded context");
   if (!ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_decode: no assignment computed yet");
   if (!codebook_bytes || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_decode: empty codebook");
+  // decode_kernel indexes the codebook with the stored indices: a smaller codebook would be read out of bounds
+  if (K < ctx->assign_K)
+    return fail(ctx, QB200_ERR_ARG, "qb200_decode: codebook of %u entries, but the current assignment indexes %u", K,
+                ctx->assign_K);
   CU(cudaSetDevice(ctx->device));
   const int dim = ctx->src.dim;
   const size_t cbb = (size_t)K * dim;

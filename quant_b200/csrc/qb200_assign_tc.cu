@@ -19,15 +19,22 @@
 //   next 4 warps  mergers: thread r merges the two column halves of query r and stores its record
 //                 (best, second, chunk) - tc_finalize_kernel turns records into indices and flags
 //   last 8 warps  epilogue: two warps per TMEM lane quarter, each scanning half of the N columns with
-//                 tcgen05.ld and tracking (best, second, chunk-of-8 index) in registers with min/max ops:
-//                 2.75 alu operations per distance evaluation - this, not the tensor pipe, is the bound
+//                 tcgen05.ld.  Only CHUNK MINIMA are tracked: every 8 scores are reduced to their minimum m
+//                 (3 FMNMX3 + 1 FMNMX) and (best, runner-up, chunk index) run over the chunk minima
+//                 (runner = min(runner, max(best, m)); chunk = m < best ? id : chunk; best = min(best, m)):
+//                 9 alu operations per 8 distance evaluations (1.125 each; the round-1 kernel tracked the true
+//                 second-best score at 2.75 each and was bound by exactly that).  The true second-best score is
+//                 either the runner-up chunk minimum or the second-best score INSIDE the winning chunk; the
+//                 latter is found by the finalise kernel, which rescans the winning chunk in FP32 anyway.
 // Pipelines: ring of 4 A tiles in shared memory (a_full/a_empty), accumulator double-buffered in
 // TMEM (2 x 256 columns; tmem_full/tmem_empty), ring of 4 per-tile result records (res_full/res_empty).
 //
 // The member of the winning chunk of 8 is identified by tc_finalize_kernel with eight FP32 scores
-// from the FP32 rows (the same rows the CUDA-core kernel uses): a query that passes the margin test has
-// its best score separated from every other score of the chunk by more than the tensor-core bound, which
-// is itself more than twice the FP32 bound, so the FP32 argmin over the chunk is the same codevector.
+// from the FP32 rows (the same rows the CUDA-core kernel uses).  A query is DECIDED when both gaps exceed the
+// tensor-core margin: (runner-up chunk minimum - best chunk minimum), tensor-core scores, and (second - best)
+// of the eight FP32 scores of the winning chunk.  The margin is three times the tensor-core error bound, which
+// is itself more than twice the FP32 bound, so in both comparisons the winner beats everything else by more
+// than the rounding error of either side: the FP32 argmin over the chunk is the exact nearest codevector.
 #include <cfloat>
 
 #include "qb200_launch.hpp"
@@ -64,18 +71,13 @@ struct TcShared {
   int res_chunk[kResStages][2][kTileQ];
 };
 
-// top-2 of eight scores merged into the running (best, second); `chunk` remembers which group of 8 held the best
-__device__ __forceinline__ void top2_update8(const float *a, int cid, float &best, float &second, int &chunk) {
-  const float l01 = fminf(a[0], a[1]), h01 = fmaxf(a[0], a[1]);
-  const float l23 = fminf(a[2], a[3]), h23 = fmaxf(a[2], a[3]);
-  const float l45 = fminf(a[4], a[5]), h45 = fmaxf(a[4], a[5]);
-  const float l67 = fminf(a[6], a[7]), h67 = fmaxf(a[6], a[7]);
-  const float m1a = fminf(l01, l23), m2a = fmin3(fmaxf(l01, l23), h01, h23);
-  const float m1b = fminf(l45, l67), m2b = fmin3(fmaxf(l45, l67), h45, h67);
-  const float m1 = fminf(m1a, m1b), m2 = fmin3(fmaxf(m1a, m1b), m2a, m2b);
-  second = fmin3(second, m2, fmaxf(best, m1));
-  chunk = m1 < best ? cid : chunk;
-  best = fminf(best, m1);
+// minimum of eight scores merged into the running (best, runner-up) over CHUNK MINIMA; `chunk` remembers which group
+// of 8 held the best.  9 alu-pipe operations per 8 scores.
+__device__ __forceinline__ void chunkmin_update8(const float *a, int cid, float &best, float &runner, int &chunk) {
+  const float m = fminf(fmin3(a[0], a[1], a[2]), fmin3(fmin3(a[3], a[4], a[5]), a[6], a[7]));
+  runner = fminf(runner, fmaxf(best, m));
+  chunk = m < best ? cid : chunk;
+  best = fminf(best, m);
 }
 
 template <int DIM>
@@ -161,17 +163,40 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int group = (warp - 1) >> 2;
     const int r = ((warp - 1) & 3) * 32 + lane;  // query row inside a tile
     const uint32_t row_off = (uint32_t)(r >> 3) * 256u + (uint32_t)(r & 7) * 16u;
-    unsigned int tile_seq = group;
-    for (unsigned long long tile = blockIdx.x + (unsigned long long)group * gridDim.x; tile < tiles;
-         tile += (unsigned long long)kProdGroups * gridDim.x, tile_seq += kProdGroups) {
-      float x[DIM];
+    // The query's bytes come as whole words from the dense copy of the training set (the host only selects this
+    // kernel for lattice sources, which always have one).  The loads of the NEXT tile are issued before the
+    // current one is converted and stored, so a tile does not cost a full global-memory round trip.
+    constexpr int WORDS = (DIM + 3) / 4;
+    auto load_words = [&](unsigned long long tile, uint32_t (&w)[WORDS]) {
       const unsigned long long v = tile * kTileQ + r;
-      if (v < src.n_local) {
-        gather_lattice<DIM>(src, v, x);
-      } else {
 #pragma unroll
-        for (int e = 0; e < DIM; e++) x[e] = 0.f;
+      for (int i = 0; i < WORDS; i++) w[i] = 0u;
+      if (tile < tiles && v < src.n_local) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(src.dense + v * (unsigned long long)src.dense_stride);
+        if constexpr (WORDS % 4 == 0) {
+#pragma unroll
+          for (int i = 0; i < WORDS / 4; i++) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < WORDS; i++) w[i] = __ldg(p + i);
+        }
       }
+    };
+    // bf16 bit pattern of element e of the A row: the lattice value (exact in bf16), then the constant 1, then zeros
+    auto a_elem = [&](const uint32_t (&w)[WORDS], int e) -> uint32_t {
+      if (e < DIM) return __float_as_uint((float)(int)(signed char)(w[(e < DIM ? e : 0) >> 2] >> (8 * (e & 3)))) >> 16;
+      return e == DIM ? 0x3F80u : 0u;
+    };
+    const unsigned long long step = (unsigned long long)kProdGroups * gridDim.x;
+    unsigned int tile_seq = group;
+    unsigned long long tile = blockIdx.x + (unsigned long long)group * gridDim.x;
+    uint32_t cur[WORDS], nxt[WORDS];
+    load_words(tile, cur);
+    for (; tile < tiles; tile += step, tile_seq += kProdGroups) {
+      load_words(tile + step, nxt);
       const int ab = tile_seq % kAStages;
       const unsigned int use = tile_seq / kAStages;
       if (use >= 1) mbar_wait_bounded<20000>(&sh.a_empty[ab], (use - 1) & 1, 4);
@@ -180,18 +205,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (int kb = 0; kb < KB; kb++) {
         uint32_t w[8];  // 16 bf16: small integers are exact in bf16 = upper half of their fp32 pattern
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
-          const int e0 = kb * 16 + 2 * p, e1 = e0 + 1;
-          const uint32_t lo = e0 < DIM ? (__float_as_uint(x[e0 < DIM ? e0 : 0]) >> 16) : (e0 == DIM ? 0x3F80u : 0u);
-          const uint32_t hi = e1 < DIM ? (__float_as_uint(x[e1 < DIM ? e1 : 0]) >> 16) : (e1 == DIM ? 0x3F80u : 0u);
-          w[p] = lo | (hi << 16);
-        }
+        for (int p = 0; p < 8; p++) w[p] = a_elem(cur, kb * 16 + 2 * p) | (a_elem(cur, kb * 16 + 2 * p + 1) << 16);
         uint4 *dst = reinterpret_cast<uint4 *>(a_tile + kb * 4096 + row_off);
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]);  // k 0..7 of this block
         dst[8] = make_uint4(w[4], w[5], w[6], w[7]);  // k 8..15: next core matrix (+128 B)
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&sh.a_full[ab]);
+#pragma unroll
+      for (int i = 0; i < WORDS; i++) cur[i] = nxt[i];
     }
   } else if (warp <= 4 * kProdGroups + 4) {
     // =========================== mergers: combine the two column halves, store the per-query record ===========================
@@ -247,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       };
       auto reduce = [&](int cid, const float *v) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) top2_update8(v + q * 8, cid + q, best, second, chunk);
+        for (int q = 0; q < 4; q++) chunkmin_update8(v + q * 8, cid + q, best, second, chunk);
       };
       auto acquire = [&](unsigned int itg) -> uint32_t {  // wait for N tile `itg`, return its first column address
         const int buf = itg & 1;
@@ -347,9 +369,9 @@ __global__ void __launch_bounds__(256)
         }
         part += __shfl_xor_sync(gmask, part, 1);
         const float rr = sqrtf(part) + c_max_norm;
-        flag = !((rec.y - rec.x) > margin_coef * rr * rr);
+        const float margin = margin_coef * rr * rr;
         const float *rows = rows32 + (size_t)chunk * 8 * ROW32 + j * 8;
-        float sb = FLT_MAX;
+        float sb = FLT_MAX, s2 = FLT_MAX;  // best and second-best FP32 score among this lane's four rows
         int rbest = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -361,14 +383,20 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
           for (int t = 1; t < 8; t++) p = fmaf(xe[t], c[t], p);
           p += __shfl_xor_sync(gmask, p, 1);
+          s2 = fminf(s2, fmaxf(sb, p));
           if (p < sb) {
             sb = p;
             rbest = 2 * i + (j >> 1);
           }
         }
         const float so = __shfl_xor_sync(gmask, sb, 2);
+        const float s2o = __shfl_xor_sync(gmask, s2, 2);
         const int ro = __shfl_xor_sync(gmask, rbest, 2);
         if (so < sb || (so == sb && ro < rbest)) rbest = ro;
+        // decided: the winning chunk beats every other chunk (tensor-core scores) AND its best member beats the
+        // other seven (FP32 scores), both by more than the tensor-core margin
+        const float in_second = fmin3(fmaxf(sb, so), s2, s2o), in_best = fminf(sb, so);
+        flag = !((rec.y - rec.x) > margin && (in_second - in_best) > margin);
         if (j == 0) assign[v] = (uint32_t)(chunk * 8 + rbest) | (flag ? kUndecided : 0u);
         flag = flag && j == 0;
       }
@@ -396,10 +424,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int e = 0; e < DIM; e++) xn = fmaf(x[e], x[e], xn);
         const float rr = sqrtf(xn) + c_max_norm;
-        flag = !((second - best) > margin_coef * rr * rr);
+        const float margin = margin_coef * rr * rr;
         int bidx = chunk * 8;
-        if (!flag) {
-          float sb = FLT_MAX;
+        float sb = FLT_MAX, s2 = FLT_MAX;  // best / second-best FP32 score inside the winning chunk
+        {
           const float4 *rows = reinterpret_cast<const float4 *>(rows32 + (size_t)chunk * 8 * ROW32);
 #pragma unroll
           for (int c = 0; c < 8; c++) {
@@ -412,12 +440,14 @@ __global__ void __launch_bounds__(256)
             float s = cr[DIM];
 #pragma unroll
             for (int e = 0; e < DIM; e++) s = fmaf(x[e], cr[e], s);
+            s2 = fminf(s2, fmaxf(sb, s));
             if (s < sb) {
               sb = s;
               bidx = chunk * 8 + c;
             }
           }
         }
+        flag = !((second - best) > margin && (s2 - sb) > margin);
         assign[v] = (uint32_t)bidx | (flag ? kUndecided : 0u);
       }
       const unsigned int m = __ballot_sync(0xffffffffu, flag);
@@ -466,28 +496,28 @@ __global__ void __launch_bounds__(1024, 1)
 #pragma unroll
       for (int e = 0; e < DIM; e++) xn = fmaf(x[e], x[e], xn);
       const float rr = sqrtf(xn) + c_max_norm;
-      flag = !((second - best) > margin_coef * rr * rr);
+      const float margin = margin_coef * rr * rr;
       int bidx = chunk * 8;
-      if (!flag) {
-        float sb = FLT_MAX;
+      float sb = FLT_MAX, s2 = FLT_MAX;  // best / second-best FP32 score inside the winning chunk
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          const int r = chunk * 8 + c;
-          float cr[ROW32];
+      for (int c = 0; c < 8; c++) {
+        const int r = chunk * 8 + c;
+        float cr[ROW32];
 #pragma unroll
-          for (int q = 0; q < NF4; q++) {
-            const float4 t = s_rows[r * NF4 + slot(r, q)];
-            cr[4 * q] = t.x; cr[4 * q + 1] = t.y; cr[4 * q + 2] = t.z; cr[4 * q + 3] = t.w;
-          }
-          float sc = cr[DIM];
+        for (int q = 0; q < NF4; q++) {
+          const float4 t = s_rows[r * NF4 + slot(r, q)];
+          cr[4 * q] = t.x; cr[4 * q + 1] = t.y; cr[4 * q + 2] = t.z; cr[4 * q + 3] = t.w;
+        }
+        float sc = cr[DIM];
 #pragma unroll
-          for (int e = 0; e < DIM; e++) sc = fmaf(x[e], cr[e], sc);
-          if (sc < sb) {
-            sb = sc;
-            bidx = r;
-          }
+        for (int e = 0; e < DIM; e++) sc = fmaf(x[e], cr[e], sc);
+        s2 = fminf(s2, fmaxf(sb, sc));
+        if (sc < sb) {
+          sb = sc;
+          bidx = r;
         }
       }
+      flag = !((second - best) > margin && (s2 - sb) > margin);
       assign[v] = (uint32_t)bidx | (flag ? kUndecided : 0u);
     }
     const unsigned int m = __ballot_sync(0xffffffffu, flag);
