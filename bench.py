@@ -261,7 +261,7 @@ def cpp_compress_leg(band, xs, ys, w, h, nbits, steps, n_total, cb_expect):
 def run_gpu_arm(args):
     import torch
     import quant_b200 as qb
-    from quant_b200.distributed import make_allreduce
+    from quant_b200.distributed import join_peer_group, make_allreduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -291,7 +291,13 @@ def run_gpu_arm(args):
     stream = torch.cuda.Stream()
     ctx = qb.Context(local)
     ctx.set_stream(stream.cuda_stream)
-    allreduce = make_allreduce() if world > 1 else None
+    # the per-level sum all-reduce: the library's own peer-memory exchange (qb200_comm.cu; torch.distributed only
+    # carries the CUDA IPC handles once), or - with --nccl - NCCL through a torch.distributed callback per level
+    allreduce = None
+    if world > 1 and args.nccl:
+        allreduce = make_allreduce()
+    elif world > 1:
+        join_peer_group(ctx)
     exact = args.exact or os.environ.get("QB200_EXACT_CENTROIDS") == "1"
     ctx.set_exact_centroids(exact)
     if world > 1:
@@ -459,6 +465,8 @@ def run_gpu_arm(args):
                        "schedule": "reference HEAD: one assignment pass per split level, no empty-cell repair",
                        "centroids": ("exact: the reference's compensated FP64 member sums, executed in its order"
                                      if exact else "from integer per-cell sums (<= 4e-16 relative of the reference's)"),
+                       "allreduce": (None if world == 1 else "NCCL via torch.distributed callback" if args.nccl else
+                                     "libqb200 peer-memory all-reduce (qb200_comm.cu), CUDA IPC between the rank processes"),
                        "l2": "512 MiB flush (memset) before every timed step, outside the timed events"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(host_band.numel()) * world,
@@ -609,6 +617,9 @@ def main():
     ap.add_argument("--images", type=int, default=1024, help="images per rank of the encode-only workload c5")
     ap.add_argument("--cpu-budget", type=float, default=None, help="seconds of CPU work for the CPU arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl", action="store_true",
+                    help="multi-GPU: reduce through NCCL (torch.distributed callback per level) instead of the library's "
+                         "peer-memory all-reduce")
     ap.add_argument("--no-cpp", action="store_true", help="skip the C++ CompressedImage::compress end-to-end leg")
     ap.add_argument("--no-natural", action="store_true", help="skip the natural-image leg")
     ap.add_argument("--exact", action="store_true",

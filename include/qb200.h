@@ -14,9 +14,15 @@
  * host thread / per GPU.  There is NO CPU fallback: without a usable CUDA device qb200_create
  * fails with QB200_ERR_NODEV.
  *
- * Multi-GPU: each process (one per GPU) gives its context a SHARD of the image's block rows
- * (qb200_set_image_shard) and passes an all-reduce callback to qb200_train; the library calls it
- * once per split level on K*(dim+2) 64-bit integers that live in device memory.
+ * Multi-GPU: the vectors are sharded by contiguous bands of block rows; the only exchange is one
+ * sum all-reduce of K*(dim+2) 64-bit integers per split level, done by the library itself over NVLink peer memory
+ * (qb200_comm.cu: every rank reads every rank's words directly - no host round trip, no third-party library):
+ *   - ONE process driving several GPUs: qb200_create_multi gives a context that splits qb200_set_image over its
+ *     devices and runs qb200_train on all of them (one host thread and one stream per device);
+ *   - one process per GPU: every process creates its context, qb200_comm_export / qb200_comm_attach join them
+ *     through CUDA IPC handles (exchanged by whatever launcher the caller has), then each sets its own shard
+ *     (qb200_set_image_shard / _band) and calls qb200_train with allreduce == NULL;
+ *   - or the caller supplies the all-reduce as a callback (qb200_allreduce_fn), e.g. ncclAllReduce.
  */
 #ifndef QB200_H
 #define QB200_H
@@ -90,6 +96,14 @@ int qb200_version(void);
 /* Creates a context on CUDA device `device`.  Replaces nothing in the reference (it has no
  * device state); it is the analogue of constructing `Solution` (src/Quantizer.cpp:89-96). */
 int qb200_create(int device, qb200_ctx **out);
+/* One context over `ndev` devices of this process (dev_ids == NULL: devices 0..ndev-1; ndev <= 0: every visible
+ * device; at most 16; all pairs need peer access).  It accepts qb200_set_image (ONE host image: device r takes block rows
+ * [wB*r/ndev, wB*(r+1)/ndev)), qb200_set_vectors_u8/_f64 (contiguous ranges), qb200_train (allreduce must be NULL:
+ * the devices reduce among themselves), qb200_get_assign[_u64], qb200_decode, qb200_num_vectors/_dim, the qb200_set_*
+ * switches and qb200_destroy; every other call returns QB200_ERR_STATE.  Results are bit-identical to a single-device
+ * context's (integer sums; the exact-centroid chains continue from device to device in vector order).  This is what
+ * CompressedImage::compress uses when QB200_DEVICES is set (quant_b200/host). */
+int qb200_create_multi(int ndev, const int *dev_ids, qb200_ctx **out);
 void qb200_destroy(qb200_ctx *ctx);
 /* Last error text of this context (or of the failed qb200_create when ctx == NULL). */
 const char *qb200_last_error(const qb200_ctx *ctx);
@@ -121,6 +135,19 @@ int qb200_set_seed(qb200_ctx *ctx, uint64_t seed);
  * QB200_MODE_FULL_REPAIR (the ranks agree on the chosen members through the sum all-reduce) and by
  * qb200_set_exact_centroids. */
 int qb200_set_rank(qb200_ctx *ctx, int rank, int world);
+
+/* ---- one process per GPU: joining the contexts into an all-reduce group --------------------------
+ * qb200_comm_export allocates this context's exchange block (room for max_words 64-bit words per round, 0 = default
+ * 2^18; larger payloads take several rounds) and writes its CUDA IPC handle (QB200_COMM_HANDLE_BYTES bytes) to
+ * handle_out.  After the caller has gathered all ranks' handles (rank order), qb200_comm_attach maps the peers' blocks
+ * and makes this context rank `rank` of `world` (it implies qb200_set_rank).  From then on qb200_train with
+ * allreduce == NULL reduces over the group.  Every rank must make the same sequence of training calls. */
+#define QB200_COMM_HANDLE_BYTES 64
+int qb200_comm_export(qb200_ctx *ctx, size_t max_words, void *handle_out);
+int qb200_comm_attach(qb200_ctx *ctx, int world, int rank, const void *handles /* world * QB200_COMM_HANDLE_BYTES */);
+/* The group's sum all-reduce itself, in place on `count` 64-bit words in device memory, stream-ordered on the
+ * context's stream (diagnostics, tests, callers with their own reductions). */
+int qb200_allreduce_u64(qb200_ctx *ctx, void *dev_u64, size_t count);
 
 /* ---- training set ------------------------------------------------------------------------
  * Replaces getBlocksAsVectorsFromImage (src/Compressor.cpp:31-62).  The N x dim double vectors

@@ -31,6 +31,10 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void
 SIGNATURES = {
     "qb200_version": (C.c_int, []),
     "qb200_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "qb200_create_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "qb200_comm_export": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qb200_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "qb200_allreduce_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "qb200_destroy": (None, [C.c_void_p]),
     "qb200_last_error": (C.c_char_p, [C.c_void_p]),
     "qb200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

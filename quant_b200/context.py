@@ -16,12 +16,19 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 class Context:
-    """Owns one ``qb200_ctx``. ``device`` is the CUDA ordinal."""
+    """Owns one ``qb200_ctx``. ``device`` is the CUDA ordinal; ``devices`` (a list of ordinals, or "all") makes a
+    multi-device context instead (qb200_create_multi: one process driving several GPUs)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
         self.lib = _lib.load()
         h = C.c_void_p()
-        rc = self.lib.qb200_create(device, C.byref(h))
+        if devices is None:
+            rc = self.lib.qb200_create(device, C.byref(h))
+        elif isinstance(devices, str) and devices == "all":
+            rc = self.lib.qb200_create_multi(0, None, C.byref(h))
+        else:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.qb200_create_multi(len(devices), ids, C.byref(h))
         if rc != 0:
             raise Qb200Error(rc, (self.lib.qb200_last_error(None) or b"").decode())
         self.h = h
@@ -122,10 +129,26 @@ class Context:
         return int(self.lib.qb200_dim(self.h))
 
     # -- hot path ---------------------------------------------------------------------------
-    def set_exact_centroids(self, enable: bool):
+    def set_exact_centroids(self, enable):
         """Bit-exact centroids: run the reference's compensated member sums (src/Quantizer.cpp:59-70) instead of
-        deriving the centroid from integer sums; see include/qb200.h."""
-        self._check(self.lib.qb200_set_exact_centroids(self.h, 1 if enable else 0))
+        deriving the centroid from integer sums; see include/qb200.h.  False/0 off, True/1 on (parallel evaluation),
+        2 on with the literal sequential chain (same bits; for comparison)."""
+        self._check(self.lib.qb200_set_exact_centroids(self.h, int(enable)))
+
+    def comm_export(self, max_words: int = 0) -> bytes:
+        """This context's all-reduce exchange block as a CUDA IPC handle (64 bytes) - see qb200_comm_export."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.qb200_comm_export(self.h, max_words, buf))
+        return buf.raw
+
+    def comm_attach(self, world: int, rank: int, handles: bytes):
+        """Joins the group: ``handles`` = every rank's 64-byte handle, concatenated in rank order."""
+        if len(handles) != 64 * world:
+            raise ValueError("handles must hold 64 bytes per rank")
+        self._check(self.lib.qb200_comm_attach(self.h, world, rank, C.c_char_p(handles)))
+
+    def allreduce_u64(self, dev_ptr: int, count: int):
+        self._check(self.lib.qb200_allreduce_u64(self.h, C.c_void_p(dev_ptr), count))
 
     def set_seed(self, seed: int):
         self._check(self.lib.qb200_set_seed(self.h, seed))

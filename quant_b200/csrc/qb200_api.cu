@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kd_host.hpp"
@@ -75,10 +76,27 @@ struct qb200_ctx {
   DevBuf d_repair;
   // bit-exact centroid sums (qb200_set_exact_centroids; qb200_exact.cu)
   bool exact = false;
-  DevBuf d_exact, d_sort_keys, d_sort_iota, d_sort_order, d_sort_tmp;
+  bool exact_sequential = false;  // qb200_set_exact_centroids(ctx, 2): the literal sequential chain instead of its parallel evaluation
+  DevBuf d_exact, d_sort_keys, d_sort_iota, d_sort_order, d_sort_tmp, d_fx;
   size_t iota_n = 0;
   // general FP64 vectors (qb200_set_vectors_f64, CIE1931 images; qb200_generic.cu)
   DevBuf d_f64, d_partials, d_counts;
+  // peer-memory all-reduce (qb200_comm.cu): this rank's exchange block and the peers' blocks mapped here
+  struct Comm {
+    int world = 1, rank = 0;
+    char *block = nullptr;          // [flags 256 B | ticket 256 B | 2 x cap_words words]
+    size_t cap_words = 0;
+    std::vector<void *> ipc_opened;  // peers' blocks opened through CUDA IPC (closed on destroy)
+    CommPeers peers{};
+    unsigned long long epoch = 0;
+    bool attached = false;
+  } comm;
+  // multi-device parent (qb200_create_multi): owns one ordinary context per device, each a shard of the image
+  bool is_multi = false;
+  std::vector<qb200_ctx *> subs;
+  qb200_ctx *decode_ctx = nullptr;  // full-image context on the first device, made on demand by qb200_decode
+  const uint8_t *multi_rgb = nullptr;
+  int m_x = 0, m_y = 0, m_w = 0, m_h = 0, m_cs = 0;
 };
 
 namespace {
@@ -191,6 +209,16 @@ int tc_min_k() {
     return v >= 16 ? v : 128;
   }();
   return k;
+}
+
+// QB200_EXACT_SEQUENTIAL=1: the compensated member sums of lattice vectors run as the literal sequential chain
+// (kahan_sums_kernel) instead of its parallel evaluation (qb200_exact_fast.cuh) - same bits, for comparison.
+bool exact_fast_enabled() {
+  static const bool on = [] {
+    const char *e = std::getenv("QB200_EXACT_SEQUENTIAL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
 }
 
 LevelLayout level_layout(const qb200_ctx *ctx, uint32_t K, int dim) {
@@ -561,6 +589,90 @@ int set_common(qb200_ctx *ctx, size_t n_local, bool pack = true) {
   return QB200_OK;
 }
 
+
+// ---- peer-memory all-reduce plumbing (kernels: qb200_comm.cu) ----------------------------------------------------
+constexpr size_t kCommHeader = 512;  // flags at 0 (kCommMaxWorld x 8 B), ticket at 256
+
+void comm_free(qb200_ctx *ctx) {
+  auto &cm = ctx->comm;
+  for (void *p : cm.ipc_opened) cudaIpcCloseMemHandle(p);
+  cm.ipc_opened.clear();
+  if (cm.block) cudaFree(cm.block);
+  cm = qb200_ctx::Comm();
+}
+
+int comm_alloc(qb200_ctx *ctx, size_t cap_words) {
+  comm_free(ctx);
+  if (cap_words < 4096) cap_words = 4096;
+  const size_t bytes = kCommHeader + 2 * cap_words * 8;
+  cudaError_t e = cudaMalloc((void **)&ctx->comm.block, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ctx->comm.block = nullptr;
+    return fail(ctx, QB200_ERR_OOM, "cudaMalloc(%zu bytes) for the all-reduce exchange block: %s", bytes, cudaGetErrorString(e));
+  }
+  CU(cudaMemset(ctx->comm.block, 0, kCommHeader));
+  CU(cudaDeviceSynchronize());
+  ctx->comm.cap_words = cap_words;
+  return QB200_OK;
+}
+
+// bases[p]: rank p's exchange block as seen from this device
+int comm_bind(qb200_ctx *ctx, int world, int rank, void *const *bases) {
+  auto &cm = ctx->comm;
+  if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world)
+    return fail(ctx, QB200_ERR_ARG, "all-reduce group: rank %d of %d (at most %d ranks)", rank, world, kCommMaxWorld);
+  for (int p = 0; p < world; p++) {
+    cm.peers.flags[p] = (unsigned long long *)bases[p];
+    cm.peers.bufs[p] = (unsigned long long *)((char *)bases[p] + kCommHeader);
+  }
+  cm.world = world;
+  cm.rank = rank;
+  cm.epoch = 0;
+  cm.attached = true;
+  ctx->rank = rank;
+  ctx->world = world;
+  return QB200_OK;
+}
+
+// qb200_allreduce_fn over the peer exchange blocks: stream-ordered, in place, any count (split by the block's capacity)
+int comm_allreduce_cb(void *dev_u64, size_t count, void *cuda_stream, void *user) {
+  qb200_ctx *ctx = (qb200_ctx *)user;
+  auto &cm = ctx->comm;
+  unsigned long long *w = (unsigned long long *)dev_u64;
+  unsigned int *ticket = (unsigned int *)(cm.block + 256);
+  for (size_t off = 0; off < count; off += cm.cap_words) {
+    const size_t n = count - off < cm.cap_words ? count - off : cm.cap_words;
+    cm.epoch++;
+    if (launch_comm_allreduce(w + off, n, cm.peers, cm.cap_words, cm.rank, cm.world, cm.epoch, ticket, ctx->sm_count,
+                              (cudaStream_t)cuda_stream) != cudaSuccess)
+      return 1;
+  }
+  return 0;
+}
+
+// Runs fn(rank) for every sub-context of a multi-device parent on its own host thread; returns the first failure
+// (and copies that sub-context's error text into the parent).
+template <typename F>
+int multi_parallel(qb200_ctx *ctx, F fn) {
+  const int R = (int)ctx->subs.size();
+  std::vector<int> rc((size_t)R, QB200_OK);
+  std::vector<std::thread> th;
+  th.reserve((size_t)R);
+  for (int r = 1; r < R; r++) th.emplace_back([&, r] { rc[(size_t)r] = fn(r); });
+  rc[0] = fn(0);
+  for (auto &t : th) t.join();
+  for (int r = 0; r < R; r++)
+    if (rc[(size_t)r] != QB200_OK) {
+      ctx->err = "device " + std::to_string(ctx->subs[(size_t)r]->device) + ": " + ctx->subs[(size_t)r]->err;
+      return rc[(size_t)r];
+    }
+  return QB200_OK;
+}
+#define NOT_ON_MULTI(name)                                                                                    \
+  if (ctx && ctx->is_multi)                                                                                   \
+  return fail(ctx, QB200_ERR_STATE, name ": not available on a multi-device context (qb200_create_multi)")
+
 }  // namespace
 
 // ================================================================================================
@@ -609,19 +721,134 @@ int qb200_create(int device, qb200_ctx **out) {
   return QB200_OK;
 }
 
+int qb200_create_multi(int ndev, const int *dev_ids, qb200_ctx **out) {
+  if (!out) return fail(nullptr, QB200_ERR_ARG, "qb200_create_multi: out == NULL");
+  *out = nullptr;
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) {
+    cudaGetLastError();
+    return fail(nullptr, QB200_ERR_NODEV, "no CUDA device; libqb200 has no CPU fallback");
+  }
+  if (ndev <= 0) ndev = have;  // every visible device
+  if (ndev > kCommMaxWorld) return fail(nullptr, QB200_ERR_ARG, "qb200_create_multi: at most %d devices", kCommMaxWorld);
+  std::vector<int> ids((size_t)ndev);
+  for (int r = 0; r < ndev; r++) {
+    ids[(size_t)r] = dev_ids ? dev_ids[r] : r;
+    // QB200_ALLOW_SAME_DEVICE=1 (test hook): several ranks on one GPU, so that a single-GPU box exercises the sharded
+    // path and the peer all-reduce kernels
+    const char *same = std::getenv("QB200_ALLOW_SAME_DEVICE");
+    for (int q = 0; q < r && !(same && same[0] == '1'); q++)
+      if (ids[(size_t)q] == ids[(size_t)r]) return fail(nullptr, QB200_ERR_ARG, "qb200_create_multi: device %d listed twice", ids[(size_t)r]);
+  }
+  qb200_ctx *ctx = new (std::nothrow) qb200_ctx();
+  if (!ctx) return fail(nullptr, QB200_ERR_OOM, "out of host memory");
+  ctx->is_multi = true;
+  ctx->device = -1;
+  auto bail = [&](int code, const std::string &msg) {
+    qb200_destroy(ctx);
+    return fail(nullptr, code, "%s", msg.c_str());
+  };
+  for (int r = 0; r < ndev; r++) {
+    qb200_ctx *sub = nullptr;
+    const int rc = qb200_create(ids[(size_t)r], &sub);
+    if (rc) return bail(rc, g_create_error);
+    ctx->subs.push_back(sub);
+  }
+  ctx->sm_count = ctx->subs[0]->sm_count;
+  if (ndev > 1) {
+    // exchange blocks sized for the largest per-level payload that is common (K = 4096, dim 48); larger payloads are
+    // reduced in several rounds
+    const size_t cap_words = (size_t)1 << 18;
+    for (int r = 0; r < ndev; r++) {
+      cudaSetDevice(ids[(size_t)r]);
+      for (int q = 0; q < ndev; q++) {
+        if (q == r || ids[(size_t)q] == ids[(size_t)r]) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ids[(size_t)r], ids[(size_t)q]);
+        if (!can) return bail(QB200_ERR_NODEV, "devices " + std::to_string(ids[(size_t)r]) + " and " + std::to_string(ids[(size_t)q]) + " have no peer access");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ids[(size_t)q], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(QB200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      const int rc = comm_alloc(ctx->subs[(size_t)r], cap_words);
+      if (rc) return bail(rc, ctx->subs[(size_t)r]->err);
+    }
+    std::vector<void *> bases((size_t)ndev);
+    for (int r = 0; r < ndev; r++) bases[(size_t)r] = ctx->subs[(size_t)r]->comm.block;
+    for (int r = 0; r < ndev; r++) {
+      const int rc = comm_bind(ctx->subs[(size_t)r], ndev, r, bases.data());
+      if (rc) return bail(rc, ctx->subs[(size_t)r]->err);
+    }
+  }
+  *out = ctx;
+  return QB200_OK;
+}
+
+int qb200_comm_export(qb200_ctx *ctx, size_t max_words, void *handle_out) {
+  if (!ctx || !handle_out) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_comm_export");
+  CU(cudaSetDevice(ctx->device));
+  int rc = comm_alloc(ctx, max_words ? max_words : (size_t)1 << 18);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->comm.block));
+  static_assert(sizeof(cudaIpcMemHandle_t) == QB200_COMM_HANDLE_BYTES, "handle size");
+  std::memcpy(handle_out, &h, sizeof h);
+  return QB200_OK;
+}
+
+int qb200_comm_attach(qb200_ctx *ctx, int world, int rank, const void *handles) {
+  if (!ctx || !handles) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_comm_attach");
+  if (!ctx->comm.block) return fail(ctx, QB200_ERR_STATE, "qb200_comm_attach: call qb200_comm_export first");
+  if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world)
+    return fail(ctx, QB200_ERR_ARG, "qb200_comm_attach: rank %d of %d (at most %d ranks)", rank, world, kCommMaxWorld);
+  CU(cudaSetDevice(ctx->device));
+  std::vector<void *> bases((size_t)world);
+  for (int p = 0; p < world; p++) {
+    if (p == rank) {
+      bases[(size_t)p] = ctx->comm.block;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char *)handles + (size_t)p * sizeof h, sizeof h);
+    void *base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->comm.ipc_opened.push_back(base);
+    bases[(size_t)p] = base;
+  }
+  return comm_bind(ctx, world, rank, bases.data());
+}
+
+int qb200_allreduce_u64(qb200_ctx *ctx, void *dev_u64, size_t count) {
+  if (!ctx || (!dev_u64 && count)) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_allreduce_u64");
+  if (!ctx->comm.attached) return fail(ctx, QB200_ERR_STATE, "qb200_allreduce_u64: no all-reduce group attached");
+  CU(cudaSetDevice(ctx->device));
+  if (comm_allreduce_cb(dev_u64, count, (void *)ctx->stream, ctx) != 0) return fail(ctx, QB200_ERR_COMM, "peer all-reduce failed to launch");
+  return QB200_OK;
+}
+
 void qb200_destroy(qb200_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->is_multi) {
+    if (ctx->decode_ctx) qb200_destroy(ctx->decode_ctx);
+    for (qb200_ctx *s2 : ctx->subs) qb200_destroy(s2);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_ties, &ctx->d_dense, &ctx->d_rows, &ctx->d_rows_tc, &ctx->d_state, &ctx->d_cb64, &ctx->d_nodes,
                     &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc, &ctx->d_repair})
     free_buf(*b);
+  comm_free(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
   for (auto &e2 : ctx->pipe_ev)
     if (e2) cudaEventDestroy(e2);
   for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_exact, &ctx->d_sort_keys,
-                    &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp, &ctx->d_f64, &ctx->d_partials, &ctx->d_counts})
+                    &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp, &ctx->d_fx, &ctx->d_f64, &ctx->d_partials, &ctx->d_counts})
     free_buf(*b);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -638,24 +865,29 @@ const char *qb200_last_error(const qb200_ctx *ctx) { return ctx ? ctx->err.c_str
 
 int qb200_set_stream(qb200_ctx *ctx, void *cuda_stream) {
   if (!ctx) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_set_stream");
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return QB200_OK;
 }
 
 int qb200_set_tensor_cores(qb200_ctx *ctx, int enable) {
   if (!ctx) return QB200_ERR_ARG;
+  for (qb200_ctx *s2 : ctx->subs) qb200_set_tensor_cores(s2, enable);
   ctx->use_tc = enable != 0;
   return QB200_OK;
 }
 
 int qb200_set_exact_centroids(qb200_ctx *ctx, int enable) {
   if (!ctx) return QB200_ERR_ARG;
+  for (qb200_ctx *s2 : ctx->subs) qb200_set_exact_centroids(s2, enable);
   ctx->exact = enable != 0;
+  ctx->exact_sequential = enable == 2;
   return QB200_OK;
 }
 
 int qb200_set_seed(qb200_ctx *ctx, uint64_t seed) {
   if (!ctx) return QB200_ERR_ARG;
+  for (qb200_ctx *s2 : ctx->subs) qb200_set_seed(s2, seed);
   ctx->seed = seed;
   ctx->repair_round = 0;
   return QB200_OK;
@@ -663,6 +895,7 @@ int qb200_set_seed(qb200_ctx *ctx, uint64_t seed) {
 
 int qb200_set_rank(qb200_ctx *ctx, int rank, int world) {
   if (!ctx) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_set_rank");
   if (world < 1 || rank < 0 || rank >= world) return fail(ctx, QB200_ERR_ARG, "qb200_set_rank: rank %d of %d", rank, world);
   ctx->rank = rank;
   ctx->world = world;
@@ -671,6 +904,7 @@ int qb200_set_rank(qb200_ctx *ctx, int rank, int world) {
 
 int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
   if (!ctx) return QB200_ERR_ARG;
+  if (ctx->is_multi) ctx = ctx->subs[0];
   if (sm_count) *sm_count = ctx->sm_count;
   if (cc_major) *cc_major = ctx->cc_major;
   if (cc_minor) *cc_minor = ctx->cc_minor;
@@ -770,18 +1004,39 @@ static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySi
 
 int qb200_set_image(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth, int blockHeight,
                     int colorspace, int n_images, int rgb_is_device) {
+  if (ctx && ctx->is_multi) {
+    // every device takes a contiguous band of block rows: one H2D copy each, from its own host thread
+    if (n_images != 1 || rgb_is_device)
+      return fail(ctx, QB200_ERR_ARG, "qb200_set_image on a multi-device context takes ONE host image");
+    if (!rgb || xSize <= 0 || blockWidth <= 0) return fail(ctx, QB200_ERR_ARG, "qb200_set_image: bad arguments");
+    const size_t wB = ((size_t)xSize + blockWidth - 1) / blockWidth, R = ctx->subs.size();
+    ctx->have_set = false;
+    const int rc = multi_parallel(ctx, [&](int r) {
+      return qb200_set_image_shard(ctx->subs[(size_t)r], rgb, xSize, ySize, blockWidth, blockHeight, colorspace, wB * (size_t)r / R,
+                                   wB * (size_t)(r + 1) / R);
+    });
+    if (rc) return rc;
+    ctx->have_set = true;
+    ctx->is_image = true;
+    ctx->colorspace = colorspace;
+    ctx->multi_rgb = rgb;
+    ctx->m_x = xSize; ctx->m_y = ySize; ctx->m_w = blockWidth; ctx->m_h = blockHeight; ctx->m_cs = colorspace;
+    return QB200_OK;
+  }
   return set_image_impl(ctx, rgb, xSize, ySize, blockWidth, blockHeight, colorspace, n_images, rgb_is_device, false, 0,
                         0);
 }
 
 int qb200_set_image_shard(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int blockWidth, int blockHeight,
                           int colorspace, size_t row_begin, size_t row_end) {
+  NOT_ON_MULTI("qb200_set_image_shard");
   return set_image_impl(ctx, rgb, xSize, ySize, blockWidth, blockHeight, colorspace, 1, 0, true, row_begin, row_end);
 }
 
 int qb200_set_image_band(qb200_ctx *ctx, const uint8_t *band, size_t band_len, int band_is_device, int xSize,
                          int ySize, int blockWidth, int blockHeight, int colorspace, size_t row_begin,
                          size_t row_end) {
+  NOT_ON_MULTI("qb200_set_image_band");
   return set_image_impl(ctx, band, xSize, ySize, blockWidth, blockHeight, colorspace, 1, band_is_device, true,
                         row_begin, row_end, true, band_len);
 }
@@ -789,6 +1044,20 @@ int qb200_set_image_band(qb200_ctx *ctx, const uint8_t *band, size_t band_len, i
 int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors, int dim, int colorspace,
                          int bytes_is_device) {
   if (!ctx) return QB200_ERR_ARG;
+  if (ctx->is_multi) {  // contiguous ranges of the vectors, rank order = vector order
+    if (bytes_is_device || !bytes || dim <= 0) return fail(ctx, QB200_ERR_ARG, "qb200_set_vectors_u8 on a multi-device context takes a host matrix");
+    const size_t R = ctx->subs.size();
+    ctx->have_set = false;
+    const int rc = multi_parallel(ctx, [&](int r) {
+      const size_t a = n_vectors * (size_t)r / R, b = n_vectors * (size_t)(r + 1) / R;
+      return qb200_set_vectors_u8(ctx->subs[(size_t)r], bytes + a * (size_t)dim, b - a, dim, colorspace, 0);
+    });
+    if (rc) return rc;
+    ctx->have_set = true;
+    ctx->is_image = false;
+    ctx->colorspace = colorspace;
+    return QB200_OK;
+  }
   if (!bytes && n_vectors) return fail(ctx, QB200_ERR_ARG, "set_vectors_u8: bytes == NULL");
   if (dim <= 0 || dim > kMaxDim) return fail(ctx, QB200_ERR_ARG, "set_vectors_u8: dim %d outside [1,%d]", dim, kMaxDim);
   if (colorspace != QB200_CS_NORMAL && colorspace != QB200_CS_SCALED)
@@ -827,6 +1096,19 @@ int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors,
 
 int qb200_set_vectors_f64(qb200_ctx *ctx, const double *x, size_t n_vectors, int dim, int x_is_device) {
   if (!ctx) return QB200_ERR_ARG;
+  if (ctx->is_multi) {
+    if (x_is_device || !x || dim <= 0) return fail(ctx, QB200_ERR_ARG, "qb200_set_vectors_f64 on a multi-device context takes a host matrix");
+    const size_t R = ctx->subs.size();
+    ctx->have_set = false;
+    const int rc = multi_parallel(ctx, [&](int r) {
+      const size_t a = n_vectors * (size_t)r / R, b = n_vectors * (size_t)(r + 1) / R;
+      return qb200_set_vectors_f64(ctx->subs[(size_t)r], x + a * (size_t)dim, b - a, dim, 0);
+    });
+    if (rc) return rc;
+    ctx->have_set = true;
+    ctx->is_image = false;
+    return QB200_OK;
+  }
   if (!x && n_vectors) return fail(ctx, QB200_ERR_ARG, "set_vectors_f64: x == NULL");
   if (dim <= 0 || dim > kMaxDim) return fail(ctx, QB200_ERR_ARG, "set_vectors_f64: dim %d outside [1,%d]", dim, kMaxDim);
   if (n_vectors > 0xffffffffull) return fail(ctx, QB200_ERR_ARG, "set_vectors_f64: more than 2^32 vectors");
@@ -852,8 +1134,17 @@ int qb200_set_vectors_f64(qb200_ctx *ctx, const double *x, size_t n_vectors, int
   return set_common(ctx, n_vectors, false);
 }
 
-size_t qb200_num_vectors(const qb200_ctx *ctx) { return ctx && ctx->have_set ? (size_t)ctx->src.n_local : 0; }
-int qb200_dim(const qb200_ctx *ctx) { return ctx && ctx->have_set ? ctx->src.dim : 0; }
+size_t qb200_num_vectors(const qb200_ctx *ctx) {
+  if (!ctx || !ctx->have_set) return 0;
+  if (!ctx->is_multi) return (size_t)ctx->src.n_local;
+  size_t n = 0;
+  for (const qb200_ctx *s2 : ctx->subs) n += (size_t)s2->src.n_local;
+  return n;
+}
+int qb200_dim(const qb200_ctx *ctx) {
+  if (!ctx || !ctx->have_set) return 0;
+  return ctx->is_multi ? ctx->subs[0]->src.dim : ctx->src.dim;
+}
 
 int qb200_finalize_level(int colorspace, uint32_t K, int dim, uint64_t n_total, const uint64_t *count,
                          const int64_t *sum, const uint64_t *sqsum, const double *codebook_pre, double *codebook_post,
@@ -950,15 +1241,13 @@ int exact_prepare(qb200_ctx *ctx, uint32_t maxK) {
   const size_t n = (size_t)ctx->src.n_local;
   int rc;
   if ((rc = ensure(ctx, ctx->d_exact, (size_t)maxK * ctx->src.dim * 16 + 256))) return rc;
+  if (!ctx->src.f64 && ctx->colorspace == QB200_CS_SCALED && exact_fast_enabled() && !ctx->exact_sequential &&
+      (rc = ensure(ctx, ctx->d_fx, exact_fast_workspace_bytes(n, (int)maxK, ctx->src.dim))))
+    return rc;
   if (maxK > 1 && n) {
     if ((rc = ensure(ctx, ctx->d_sort_keys, n * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_sort_order, n * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->d_sort_tmp, exact_sort_temp_bytes(n) + 256))) return rc;
-    if (ctx->d_sort_iota.cap < n * 4 || ctx->iota_n != n) {
-      if ((rc = ensure(ctx, ctx->d_sort_iota, n * 4))) return rc;
-      CU(launch_exact_iota((uint32_t *)ctx->d_sort_iota.p, n, ctx->sm_count, ctx->stream));
-      ctx->iota_n = n;
-    }
+    if ((rc = ensure(ctx, ctx->d_sort_tmp, stable_sort_temp_bytes(n) + 256))) return rc;
   }
   return QB200_OK;
 }
@@ -978,15 +1267,19 @@ int exact_centroid_sums(qb200_ctx *ctx, uint32_t K, qb200_allreduce_fn ar, void 
   int key_bits = 0;
   while ((1u << key_bits) < K) key_bits++;
   if (K > 1 && n)
-    CU(launch_exact_sort((const uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_sort_keys.p, (const uint32_t *)ctx->d_sort_iota.p,
-                         (uint32_t *)ctx->d_sort_order.p, n, key_bits, ctx->d_sort_tmp.p, ctx->d_sort_tmp.cap, st));
+    CU(launch_stable_sort_by_cell((const uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_sort_keys.p, (uint32_t *)ctx->d_sort_order.p, n,
+                                  key_bits, ctx->d_sort_tmp.p, ctx->d_sort_tmp.cap, st));
   const int world = ar ? ctx->world : 1;
   for (int q = 0; q < world; q++) {
     if (!ar || q == ctx->rank) {
-      if (n)
-        CU(launch_kahan_sums(ctx->src, K > 1 ? (const uint32_t *)ctx->d_sort_keys.p : nullptr,
-                             K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr, (int)K,
-                             ctx->colorspace == QB200_CS_SCALED, (double *)ctx->d_exact.p, K > 1 ? counts : nullptr, st));
+      const uint32_t *keys = K > 1 ? (const uint32_t *)ctx->d_sort_keys.p : nullptr;
+      const uint32_t *order = K > 1 ? (const uint32_t *)ctx->d_sort_order.p : nullptr;
+      if (n && !ctx->src.f64 && ctx->colorspace == QB200_CS_SCALED && exact_fast_enabled() && !ctx->exact_sequential)
+        CU(launch_kahan_sums_fast(ctx->src, keys, order, (int)K, (double *)ctx->d_exact.p, K > 1 ? counts : nullptr, ctx->d_fx.p,
+                                  ctx->d_fx.cap, ctx->sm_count, st));
+      else if (n)
+        CU(launch_kahan_sums(ctx->src, keys, order, (int)K, ctx->colorspace == QB200_CS_SCALED, (double *)ctx->d_exact.p,
+                             K > 1 ? counts : nullptr, st));
     } else {
       CU(cudaMemsetAsync(ctx->d_exact.p, 0, words * 8, st));
     }
@@ -1298,6 +1591,37 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
                 void *allreduce_user, double *codebook_out, double *distortion_out, qb200_level_report *reports) {
   if (!ctx) return QB200_ERR_ARG;
   if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_train: no training set (call qb200_set_image first)");
+  if (ctx->is_multi) {
+    // one host thread per device; the only exchange is the per-level sum all-reduce over peer memory (qb200_comm.cu).
+    // Every rank finalises the same integers, so all of them end with the same codebook: rank 0's is returned.
+    if (allreduce) return fail(ctx, QB200_ERR_ARG, "qb200_train: a multi-device context brings its own all-reduce (pass NULL)");
+    if (nbits < 0 || nbits > 16 || !codebook_out) return fail(ctx, QB200_ERR_ARG, "qb200_train: bad arguments");
+    const uint64_t N = n_total ? n_total : (uint64_t)qb200_num_vectors(ctx);
+    const size_t cb_doubles = ((size_t)1 << nbits) * (size_t)qb200_dim(ctx);
+    std::vector<std::vector<double>> cbs(ctx->subs.size());
+    std::vector<double> dists(ctx->subs.size(), 0.0);
+    const int rc = multi_parallel(ctx, [&](int r) {
+      double *cb = codebook_out;
+      if (r) {
+        cbs[(size_t)r].resize(cb_doubles);
+        cb = cbs[(size_t)r].data();
+      }
+      return qb200_train(ctx->subs[(size_t)r], nbits, eps, mode, N, nullptr, nullptr, cb, &dists[(size_t)r], r ? nullptr : reports);
+    });
+    if (rc) return rc;
+    for (size_t r = 1; r < cbs.size(); r++)
+      if (std::memcmp(cbs[r].data(), codebook_out, cb_doubles * 8) != 0)
+        return fail(ctx, QB200_ERR_STATE, "qb200_train: device %d ended with a different codebook than device %d", ctx->subs[r]->device,
+                    ctx->subs[0]->device);
+    if (distortion_out) *distortion_out = dists[0];
+    ctx->assign_valid = true;
+    ctx->assign_K = 1u << nbits;
+    return QB200_OK;
+  }
+  if (!allreduce && ctx->comm.attached && ctx->comm.world > 1) {  // peer-memory all-reduce attached to this context
+    allreduce = comm_allreduce_cb;
+    allreduce_user = ctx;
+  }
   if (mode != QB200_MODE_PARITY && mode != QB200_MODE_FULL && mode != QB200_MODE_FULL_REPAIR)
     return fail(ctx, QB200_ERR_ARG, "qb200_train: unknown mode %d", mode);
   if (nbits < 0 || nbits > 16) return fail(ctx, QB200_ERR_ARG, "qb200_train: nbits %d outside [0,16]", nbits);
@@ -1405,6 +1729,12 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
 
 int qb200_get_assign(qb200_ctx *ctx, uint32_t *assign_out) {
   if (!ctx || !assign_out) return QB200_ERR_ARG;
+  if (ctx->is_multi) {  // bands in rank order = vector order
+    if (!ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_get_assign: no assignment computed yet");
+    std::vector<size_t> first(ctx->subs.size() + 1, 0);
+    for (size_t r = 0; r < ctx->subs.size(); r++) first[r + 1] = first[r] + (size_t)ctx->subs[r]->src.n_local;
+    return multi_parallel(ctx, [&](int r) { return qb200_get_assign(ctx->subs[(size_t)r], assign_out + first[(size_t)r]); });
+  }
   if (!ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_get_assign: no assignment computed yet");
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(assign_out, ctx->d_assign.p, (size_t)ctx->src.n_local * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1414,7 +1744,7 @@ int qb200_get_assign(qb200_ctx *ctx, uint32_t *assign_out) {
 
 int qb200_get_assign_u64(qb200_ctx *ctx, uint64_t *assign_out) {
   if (!ctx || !assign_out) return QB200_ERR_ARG;
-  const size_t n = (size_t)ctx->src.n_local;
+  const size_t n = qb200_num_vectors(ctx);
   // copy into the upper half of the caller's buffer, then widen in place front to back
   uint32_t *tmp = reinterpret_cast<uint32_t *>(assign_out) + n;
   int rc = qb200_get_assign(ctx, tmp);
@@ -1425,6 +1755,7 @@ int qb200_get_assign_u64(qb200_ctx *ctx, uint64_t *assign_out) {
 
 int qb200_get_assign_packed(qb200_ctx *ctx, int bits, uint8_t *out, size_t out_bytes) {
   if (!ctx || !out) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_get_assign_packed");
   if (!ctx->have_set || !ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_get_assign_packed: no assignment yet");
   if (bits < 1 || bits > 32) return fail(ctx, QB200_ERR_ARG, "qb200_get_assign_packed: bits %d outside [1,32]", bits);
   const unsigned long long n = ctx->src.n_local, need = (n * (unsigned long long)bits + 7) / 8, words = (need + 3) / 4;
@@ -1441,6 +1772,7 @@ int qb200_get_assign_packed(qb200_ctx *ctx, int bits, uint8_t *out, size_t out_b
 
 int qb200_assign_device_ptr(qb200_ctx *ctx, void **dev_ptr) {
   if (!ctx || !dev_ptr) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_assign_device_ptr");
   if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "no training set");
   *dev_ptr = ctx->d_assign.p;
   return QB200_OK;
@@ -1449,6 +1781,7 @@ int qb200_assign_device_ptr(qb200_ctx *ctx, void **dev_ptr) {
 int qb200_assign_accumulate(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32_t *assign_out,
                             uint64_t *count_out, int64_t *sum_out, uint64_t *sqsum_out, uint32_t *flagged_out) {
   if (!ctx) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_assign_accumulate");
   if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_assign_accumulate: no training set");
   if (!codebook || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_assign_accumulate: empty codebook");
   if (K > (1u << 24)) return fail(ctx, QB200_ERR_ARG, "qb200_assign_accumulate: K too large");
@@ -1502,6 +1835,7 @@ int qb200_assign_accumulate(qb200_ctx *ctx, const double *codebook, uint32_t K, 
 int qb200_assign_only(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32_t *flagged_out, float *ms_assign_out,
                       float *ms_resolve_out) {
   if (!ctx) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_assign_only");
   if (!ctx->have_set) return fail(ctx, QB200_ERR_STATE, "qb200_assign_only: no training set");
   if (!codebook || K == 0) return fail(ctx, QB200_ERR_ARG, "qb200_assign_only: empty codebook");
   if (K > (1u << 24)) return fail(ctx, QB200_ERR_ARG, "qb200_assign_only: K too large");
@@ -1519,6 +1853,27 @@ int qb200_assign_only(qb200_ctx *ctx, const double *codebook, uint32_t K, uint32
 
 int qb200_decode(qb200_ctx *ctx, const uint8_t *codebook_bytes, uint32_t K, uint8_t *rgb_out, double *mse_out) {
   if (!ctx) return QB200_ERR_ARG;
+  if (ctx->is_multi) {
+    // not on the hot path (the report's pixel MSE / decompress): the whole image and the gathered indices go to a
+    // single-device context on the first device
+    if (!ctx->have_set || !ctx->is_image || !ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_decode: no image / no assignment");
+    int rc;
+    if (!ctx->decode_ctx && (rc = qb200_create(ctx->subs[0]->device, &ctx->decode_ctx)))
+      return fail(ctx, rc, "qb200_decode: %s", qb200_last_error(nullptr));
+    qb200_ctx *d = ctx->decode_ctx;
+    if ((rc = qb200_set_image(d, ctx->multi_rgb, ctx->m_x, ctx->m_y, ctx->m_w, ctx->m_h, ctx->m_cs, 1, 0))) return fail(ctx, rc, "%s", d->err.c_str());
+    std::vector<uint32_t> a(qb200_num_vectors(ctx));
+    if ((rc = qb200_get_assign(ctx, a.data()))) return rc;
+    if (cudaSetDevice(d->device) != cudaSuccess ||
+        cudaMemcpyAsync(d->d_assign.p, a.data(), a.size() * 4, cudaMemcpyHostToDevice, d->stream) != cudaSuccess ||
+        cudaStreamSynchronize(d->stream) != cudaSuccess)
+      return fail(ctx, QB200_ERR_CUDA, "qb200_decode: upload of the indices failed");
+    d->assign_valid = true;
+    d->assign_K = ctx->assign_K;
+    rc = qb200_decode(d, codebook_bytes, K, rgb_out, mse_out);
+    if (rc) ctx->err = d->err;
+    return rc;
+  }
   if (!ctx->have_set || !ctx->is_image) return fail(ctx, QB200_ERR_STATE, "qb200_decode: the training set is not an image");
   if (ctx->is_shard) return fail(ctx, QB200_ERR_STATE, "qb200_decode: not available on a sharded context");
   if (!ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_decode: no assignment computed yet");
@@ -1550,6 +1905,7 @@ int qb200_decode(qb200_ctx *ctx, const uint8_t *codebook_bytes, uint32_t K, uint
 
 int qb200_measure_fp32_peak(qb200_ctx *ctx, double *tflops_out) {
   if (!ctx || !tflops_out) return QB200_ERR_ARG;
+  if (ctx->is_multi) return qb200_measure_fp32_peak(ctx->subs[0], tflops_out);
   CU(cudaSetDevice(ctx->device));
   const int blocks = ctx->sm_count * 4, iters = 4096;
   int rc = ensure(ctx, ctx->d_misc, (size_t)blocks * 512 * 4);
@@ -1584,6 +1940,7 @@ int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *orde
 
 int qb200_debug_filter_records(qb200_ctx *ctx, float *records_out) {
   if (!ctx || !records_out) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_debug_filter_records");
   if (!ctx->have_set || !ctx->d_state.p) return fail(ctx, QB200_ERR_STATE, "no tensor-core filter pass has run");
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(records_out, ctx->d_state.p, (size_t)ctx->src.n_local * 16, cudaMemcpyDeviceToHost, ctx->stream));

@@ -9,24 +9,20 @@
 // compensated sum has no closed form in the integer statistics (its second-order error depends on the order
 // of the addends), so this mode executes the reference's own operation sequence:
 //   1. stable radix sort of (cell, local vector index)  -> members of every cell in ascending index order
+//      (in-tree: qb200_sort.cu)
 //   2. kahan_sums_kernel: one warp per cell, one lane per dimension, the four dependent FP64 operations of the
 //      reference's loop per member (the chain is latency bound: ~N steps at K = 1, ~N/K at level K)
 //   3. finalize_split_kernel divides the sums by n.
 // The NORMAL colour space never needs it: its addends are integers, every partial sum is exact.
 // Ranks of a sharded run continue each other's chains in rank order (see exact_centroid_sums in qb200_api.cu).
 #include "qb200_launch.hpp"
+#include "qb200_exact_fast.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
+#include <cmath>
 
 namespace qb {
 
 namespace {
-
-__global__ void iota_kernel(uint32_t *__restrict__ out, const unsigned long long n) {
-  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)gridDim.x * blockDim.x)
-    out[i] = (uint32_t)i;
-}
 
 __device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -183,30 +179,6 @@ __global__ void __launch_bounds__(128)
 
 }  // namespace
 
-size_t exact_sort_temp_bytes(size_t n) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, (long long)n, 0, 32, (cudaStream_t)0);
-  return bytes;
-}
-
-cudaError_t launch_exact_iota(uint32_t *iota, size_t n, int sm_count, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  unsigned long long blocks = (n + 1023) / 1024;
-  if (blocks > (unsigned long long)sm_count * 8) blocks = (unsigned long long)sm_count * 8;
-  iota_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(iota, n);
-  count_launch();
-  return cudaGetLastError();
-}
-
-// Stable sort of (assign[v], v) by cell: keys_out ascending, order = the members of cell 0, cell 1, ... each in
-// ascending v.  CUB's radix sort is the one library call of this mode (stable by construction).
-cudaError_t launch_exact_sort(const uint32_t *assign, uint32_t *keys_out, const uint32_t *iota, uint32_t *order, size_t n,
-                              int key_bits, void *tmp, size_t tmp_bytes, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, assign, keys_out, iota, order, (long long)n, 0, key_bits, stream);
-}
-
 // state: K*dim pairs {sum, c}, read as the chain's initial state and overwritten with its final one.
 // counts (may be null): members of every cell on this context.  Reads the dense byte copy of the training set
 // (always made by set_image / set_vectors_u8) or, for general FP64 vectors, the doubles themselves.
@@ -236,6 +208,310 @@ cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted,
   else
     QB_KAHAN(6);
 #undef QB_KAHAN
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parallel evaluation of the same sums (SCALED lattice vectors): see qb200_exact_fast.cuh for the method.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+using fx::i128;
+using fx::u128;
+
+// Workspace carved out of one device block by launch_kahan_sums_fast (all offsets 256-byte aligned).
+struct FxWork {
+  uint32_t *cell_beg;   // K + 1 positions into the sorted member list
+  uint32_t *win_off;    // K + 1: first nominal window of every cell (windows are counted per cell, shared by its dimensions)
+  u128 *sumX;           // per (window, dimension), chain-major: window sums, then (in place) their exclusive prefix
+  signed char *need;    // per (window, dimension): highest state bit the window's members look at
+  u128 *total;          // per chain: sum of X over the whole chain
+  i128 *B;              // per chain (head)
+  long long *W0;        // per chain (head)
+  uint32_t *q_start;    // per chain (head): first window the chaining pass applies; 0xffffffff: finished by the head
+  fx::SegRecord *rec;   // per (window, dimension), chain-major
+  fx::Tables *tab;      // X_t table (device copy)
+};
+
+struct FxGeom {
+  const uint8_t *dense;
+  unsigned int stride;
+  const uint32_t *order;  // null: identity (K == 1)
+  int K, dim;
+  unsigned int C;         // nominal window length
+  unsigned int n;         // local vectors
+};
+
+struct FxAcc {
+  const uint8_t *dense;
+  const uint32_t *order;
+  unsigned int stride;
+  int e;
+  __device__ __forceinline__ int operator()(unsigned int p) const {
+    const unsigned int v = order ? __ldg(order + p) : p;
+    return (int)(__ldg(dense + (size_t)v * stride + e) ^ 0x80u);  // t = byte ^ 0x80
+  }
+};
+
+// record / window-array index of (cell k, dimension e, window q): contiguous along a chain
+__device__ __forceinline__ size_t fx_index(const FxWork &w, int dim, int k, int e, unsigned int q) {
+  const unsigned int w0 = w.win_off[k], cnt = w.win_off[k + 1] - w0;
+  return (size_t)w0 * dim + (size_t)e * cnt + q;
+}
+
+__global__ void fx_cells_kernel(const uint32_t *__restrict__ keys_sorted, const unsigned int n, const int K, const unsigned int C,
+                                FxWork w, unsigned long long *__restrict__ counts) {
+  // one block: cell boundaries by binary search, then the exclusive scan of the cells' window counts
+  __shared__ unsigned int s_carry;
+  __shared__ unsigned int s_part[1024];
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+    unsigned int lo = 0, hi = n;
+    if (keys_sorted) {
+      while (lo < hi) {
+        const unsigned int mid = lo + ((hi - lo) >> 1);
+        if (__ldg(keys_sorted + mid) < (unsigned int)k) lo = mid + 1; else hi = mid;
+      }
+    } else {
+      lo = k == 0 ? 0 : n;
+    }
+    w.cell_beg[k] = lo;
+  }
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < K; base += blockDim.x) {
+    const int k = base + threadIdx.x;
+    unsigned int cnt = 0;
+    if (k < K) {
+      const unsigned int members = w.cell_beg[k + 1] - w.cell_beg[k];
+      cnt = (members + C - 1) / C;
+      if (counts) counts[k] = members;
+    }
+    s_part[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {  // Hillis-Steele inclusive scan
+      const unsigned int add = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (k < K) w.win_off[k] = s_carry + s_part[threadIdx.x] - cnt;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry += s_part[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) w.win_off[K] = s_carry;
+}
+
+// (global window, dimension) -> cell, window inside the cell
+__device__ __forceinline__ void fx_locate(const FxWork &w, int K, unsigned int gw, int &k, unsigned int &q) {
+  int lo = 0, hi = K;  // last cell with win_off <= gw
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (w.win_off[mid] <= gw) lo = mid; else hi = mid;
+  }
+  k = lo;
+  q = gw - w.win_off[lo];
+}
+
+__global__ void __launch_bounds__(256) fx_pre_kernel(const FxGeom g, FxWork w) {
+  __shared__ fx::Tables tab;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
+  __syncthreads();
+  const unsigned long long total = (unsigned long long)w.win_off[g.K] * g.dim;
+  for (unsigned long long id = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; id < total;
+       id += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned int gw = (unsigned int)(id / (unsigned int)g.dim);
+    const int e = (int)(id - (unsigned long long)gw * g.dim);
+    int k;
+    unsigned int q;
+    fx_locate(w, g.K, gw, k, q);
+    const unsigned int beg = w.cell_beg[k], end = w.cell_beg[k + 1];
+    const unsigned int P = beg + q * g.C, P_end = end - P > g.C ? P + g.C : end;
+    const FxAcc acc{g.dense, g.order, g.stride, e};
+    u128 sx;
+    int nd;
+    fx::fx_window(acc, tab, P, P_end, sx, nd);
+    const size_t idx = fx_index(w, g.dim, k, e, q);
+    w.sumX[idx] = sx;
+    w.need[idx] = (signed char)nd;
+  }
+}
+
+// per chain: exclusive prefix of the window sums (in place) and the chain total
+__global__ void __launch_bounds__(128) fx_scan_kernel(const FxGeom g, FxWork w) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= g.K * g.dim) return;
+  const int k = chain / g.dim, e = chain - k * g.dim;
+  const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
+  u128 *p = w.sumX + fx_index(w, g.dim, k, e, 0);
+  u128 run = 0;
+  unsigned int q = 0;
+  for (; q + 4 <= cnt; q += 4) {  // loads first: they do not depend on the running sum
+    const u128 a = p[q], b = p[q + 1], c = p[q + 2], d = p[q + 3];
+    p[q] = run;
+    p[q + 1] = run + a;
+    p[q + 2] = run + a + b;
+    p[q + 3] = run + a + b + c;
+    run += a + b + c + d;
+  }
+  for (; q < cnt; q++) {
+    const u128 a = p[q];
+    p[q] = run;
+    run += a;
+  }
+  w.total[chain] = run;
+}
+
+__global__ void __launch_bounds__(128) fx_head_kernel(const FxGeom g, FxWork w, double *__restrict__ state) {
+  __shared__ fx::Tables tab;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
+  __syncthreads();
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= g.K * g.dim) return;
+  const int k = chain / g.dim, e = chain - k * g.dim;
+  const unsigned int beg = w.cell_beg[k], end = w.cell_beg[k + 1];
+  const FxAcc acc{g.dense, g.order, g.stride, e};
+  const fx::HeadOut h = fx::fx_head(acc, tab, beg, end, g.C, state[2 * (size_t)chain], state[2 * (size_t)chain + 1]);
+  w.B[chain] = h.B;
+  w.W0[chain] = h.W0;
+  w.q_start[chain] = h.done ? 0xffffffffu : h.q_start;
+  if (h.done) {
+    state[2 * (size_t)chain] = h.sum;
+    state[2 * (size_t)chain + 1] = h.c;
+  }
+}
+
+__global__ void __launch_bounds__(256) fx_runs_kernel(const FxGeom g, FxWork w) {
+  __shared__ fx::Tables tab;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
+  __syncthreads();
+  const unsigned long long total = (unsigned long long)w.win_off[g.K] * g.dim;
+  for (unsigned long long id = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; id < total;
+       id += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned int gw = (unsigned int)(id / (unsigned int)g.dim);
+    const int e = (int)(id - (unsigned long long)gw * g.dim);
+    int k;
+    unsigned int q;
+    fx_locate(w, g.K, gw, k, q);
+    const int chain = k * g.dim + e;
+    const unsigned int qs = w.q_start[chain];
+    if (q < qs) continue;  // covered by the head (0xffffffff: the whole chain)
+    const unsigned int beg = w.cell_beg[k], end = w.cell_beg[k + 1], cnt = w.win_off[k + 1] - w.win_off[k];
+    const FxAcc acc{g.dense, g.order, g.stride, e};
+    const size_t idx = fx_index(w, g.dim, k, e, q);
+    fx::SegRecord r;
+    const fx::Anchor a = fx::fx_anchor(acc, beg + q * g.C, end, tab);
+    r.begin = a.b;
+    r.end = q + 1 < cnt ? fx::fx_anchor(acc, beg + (q + 1) * g.C, end, tab).b : end;
+    r.je = (signed char)(a.je < 0 ? 0 : a.je);
+    const int n0 = w.need[idx], n1 = q + 1 < cnt ? (int)w.need[idx + 1] : -1;
+    r.top = (signed char)(n0 > n1 ? n0 : n1);
+    r.Eb = (u128)(w.B[chain] + (i128)w.sumX[idx] + (i128)(((u128)a.xsum_hi << 64) | a.xsum_lo));
+    r.ncls = 0;
+    r.pad = 0;
+    if (r.begin < r.end) fx::fx_run_segment(acc, tab, r);
+    w.rec[idx] = r;
+  }
+}
+
+__global__ void __launch_bounds__(128) fx_chain_kernel(const FxGeom g, FxWork w, double *__restrict__ state) {
+  __shared__ fx::Tables tab;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
+  __syncthreads();
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= g.K * g.dim) return;
+  const unsigned int qs = w.q_start[chain];
+  if (qs == 0xffffffffu) return;  // finished by the head
+  const int k = chain / g.dim, e = chain - k * g.dim;
+  const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
+  const fx::SegRecord *rec = w.rec + fx_index(w, g.dim, k, e, 0);
+  const FxAcc acc{g.dense, g.order, g.stride, e};
+  long long W = w.W0[chain];
+  for (unsigned int q = qs; q < cnt; q++) {
+    const fx::SegRecord r = rec[q];
+    if (!fx::fx_apply(r, W)) fx::fx_rerun(acc, tab, r, W);
+  }
+  const u128 A = (u128)(w.B[chain] + (i128)w.total[chain] + (i128)W);
+  double sum, c;
+  fx::fx_state_to_pair(A, sum, c);
+  state[2 * (size_t)chain] = sum;
+  state[2 * (size_t)chain + 1] = c;
+}
+
+size_t fx_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+unsigned int exact_fast_window(size_t n, int K) {
+  // balance of the speculative runs (work per thread ~ C) and the chaining pass (steps per chain ~ n / (K C))
+  double c = std::sqrt((double)n / (4.0 * (double)(K > 0 ? K : 1)));
+  unsigned int C = 128;
+  while (C < 1024 && (double)C < c) C <<= 1;
+  return C;
+}
+
+size_t exact_fast_workspace_bytes(size_t n, int K, int dim) {
+  const unsigned int C = 128;  // the smallest window gives the most windows
+  (void)exact_fast_window;
+  const size_t windows = n / C + (size_t)K + 1, per = windows * (size_t)dim, chains = (size_t)K * dim;
+  size_t b = 0;
+  b += fx_up(((size_t)K + 1) * 4) * 2;
+  b += fx_up(per * 16) + fx_up(per) + fx_up(chains * 16) * 2 + fx_up(chains * 8) + fx_up(chains * 4);
+  b += fx_up(per * sizeof(fx::SegRecord)) + fx_up(sizeof(fx::Tables));
+  return b + 256;
+}
+
+// Same contract as launch_kahan_sums for SCALED lattice sources: state holds K*dim pairs {sum, c}, read as the
+// chains' incoming state and overwritten with their final one; counts (may be null) receives the members per cell.
+cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, double *state,
+                                   unsigned long long *counts, void *workspace, size_t workspace_bytes, int sm_count,
+                                   cudaStream_t stream) {
+  if (!src.dense || src.f64) return cudaErrorInvalidValue;
+  const size_t n = (size_t)src.n_local;
+  const int dim = src.dim;
+  if (workspace_bytes < exact_fast_workspace_bytes(n, K, dim)) return cudaErrorInvalidValue;
+  const unsigned int C = exact_fast_window(n, K);
+  const size_t windows = n / 128 + (size_t)K + 1, per = windows * (size_t)dim, chains = (size_t)K * dim;
+  char *p = (char *)workspace;
+  FxWork w;
+  auto take = [&](size_t bytes) { char *r = p; p += fx_up(bytes); return r; };
+  w.cell_beg = (uint32_t *)take(((size_t)K + 1) * 4);
+  w.win_off = (uint32_t *)take(((size_t)K + 1) * 4);
+  w.sumX = (u128 *)take(per * 16);
+  w.need = (signed char *)take(per);
+  w.total = (u128 *)take(chains * 16);
+  w.B = (i128 *)take(chains * 16);
+  w.W0 = (long long *)take(chains * 8);
+  w.q_start = (uint32_t *)take(chains * 4);
+  w.rec = (fx::SegRecord *)take(per * sizeof(fx::SegRecord));
+  w.tab = (fx::Tables *)take(sizeof(fx::Tables));
+  static fx::Tables h_tab;
+  static bool h_tab_ready = false;
+  if (!h_tab_ready) {
+    fx::fx_fill_tables(h_tab);
+    h_tab_ready = true;
+  }
+  cudaError_t e = cudaMemcpyAsync(w.tab, &h_tab, sizeof h_tab, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  FxGeom g{src.dense, src.dense_stride, K > 1 ? order : nullptr, K, dim, C, (unsigned int)n};
+  fx_cells_kernel<<<1, 1024, 0, stream>>>(K > 1 ? keys_sorted : nullptr, (unsigned int)n, K, C, w, counts);
+  count_launch();
+  const unsigned long long ids = (unsigned long long)(n / C + (size_t)K + 1) * dim;  // upper bound of (window, dimension) pairs
+  unsigned long long blocks = (ids + 255) / 256;
+  const unsigned long long cap = (unsigned long long)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  const unsigned int chain_blocks = (unsigned int)((chains + 127) / 128);
+  fx_pre_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(g, w);
+  count_launch();
+  fx_scan_kernel<<<chain_blocks, 128, 0, stream>>>(g, w);
+  count_launch();
+  fx_head_kernel<<<chain_blocks, 128, 0, stream>>>(g, w, state);
+  count_launch();
+  fx_runs_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(g, w);
+  count_launch();
+  fx_chain_kernel<<<chain_blocks, 128, 0, stream>>>(g, w, state);
   count_launch();
   return cudaGetLastError();
 }

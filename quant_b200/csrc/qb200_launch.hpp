@@ -91,12 +91,18 @@ cudaError_t launch_finalize_split(const unsigned long long *stats, const double 
                                   double *cb_next, void *summary, cudaStream_t stream);
 // Bit-exact centroid sums (qb200_exact.cu): stable sort of the members by cell, then the reference's compensated
 // summation in ascending vector order, one warp per cell.
-size_t exact_sort_temp_bytes(size_t n);
-cudaError_t launch_exact_iota(uint32_t *iota, size_t n, int sm_count, cudaStream_t stream);
-cudaError_t launch_exact_sort(const uint32_t *assign, uint32_t *keys_out, const uint32_t *iota, uint32_t *order, size_t n,
-                              int key_bits, void *tmp, size_t tmp_bytes, cudaStream_t stream);
+// Stable LSD radix sort of (cell, vector index) by cell (qb200_sort.cu): keys_out ascending, order_out = original positions.
+size_t stable_sort_temp_bytes(size_t n);
+cudaError_t launch_stable_sort_by_cell(const uint32_t *keys, uint32_t *keys_out, uint32_t *order_out, size_t n, int key_bits, void *tmp,
+                                       size_t tmp_bytes, cudaStream_t stream);
 cudaError_t launch_kahan_sums(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, int scaled,
                               double *state, unsigned long long *counts, cudaStream_t stream);
+// The same sums evaluated in parallel (SCALED lattice sources only; method in qb200_exact_fast.cuh): bit-identical
+// to launch_kahan_sums at a small fraction of its latency-bound cost.  workspace: exact_fast_workspace_bytes(n, K, dim).
+size_t exact_fast_workspace_bytes(size_t n, int K, int dim);
+cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, double *state,
+                                   unsigned long long *counts, void *workspace, size_t workspace_bytes, int sm_count,
+                                   cudaStream_t stream);
 // General FP64 training vectors (qb200_generic.cu).
 // CIE1931 colour space (src/ColorSpace.cpp:31-39): the image's block vectors as doubles, n_local x dim.
 cudaError_t launch_cie_vectors(const VecSource &src, double *out, int sm_count, cudaStream_t stream);
@@ -118,6 +124,16 @@ cudaError_t launch_fetch_members(const VecSource &src, const long long *local_id
 cudaError_t launch_pack_indices(const uint32_t *assign, unsigned long long n, int bits, uint32_t *out,
                                 unsigned long long out_words, int sm_count, cudaStream_t stream);
 cudaError_t launch_ffma_probe(float *out, int blocks, int iters, float m, float c, cudaStream_t stream);
+
+// Peer-memory sum all-reduce (qb200_comm.cu).  Every rank owns an exchange block: an array of epoch flags (one slot
+// per rank) and a two-halved word buffer; `flags[p]` / `bufs[p]` are rank p's, mapped into this rank's address space.
+constexpr int kCommMaxWorld = 16;
+struct CommPeers {
+  unsigned long long *flags[kCommMaxWorld];
+  unsigned long long *bufs[kCommMaxWorld];
+};
+cudaError_t launch_comm_allreduce(unsigned long long *dev_words, size_t count, const CommPeers &peers, size_t cap_words, int rank,
+                                  int world, unsigned long long epoch, unsigned int *ticket, int sm_count, cudaStream_t stream);
 
 constexpr int kResolveDepthCap = 512;
 

@@ -36,6 +36,26 @@ def shard_byte_range(xSize: int, ySize: int, w: int, h: int, row_begin: int, row
     return lo, max(lo, min(hi, img_bytes))
 
 
+def join_peer_group(ctx, group=None, max_words: int = 0):
+    """One process per GPU: joins this rank's context to the library's own peer-memory all-reduce group
+    (qb200_comm_export / qb200_comm_attach; include/qb200.h).  torch.distributed only carries the 64-byte CUDA IPC
+    handles once; after this ``ctx.train(...)`` needs no callback - the per-level sum all-reduce runs inside
+    libqb200 over NVLink peer memory."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = ctx.comm_export(max_words)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    handles = b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+    ctx.comm_attach(world, rank, handles)
+    dist.barrier(group=group)          # nobody publishes before everybody has mapped everybody
+    return world, rank
+
+
 def make_allreduce(group=None):
     """Returns ``fn(dev_ptr, count, stream) -> int`` summing ``count`` uint64 words in place across
     the ranks of ``group`` with torch.distributed.  The words are viewed as int64 (two's complement

@@ -3,11 +3,18 @@
 //   host_test layout                CPU only: block -> vector -> char vector -> image round trips
 //   host_test quantize <in.ppm> w h n [cs]  needs a B200: getQuantizer(LBG)->quantize(vectors) must agree with
 //                                   CompressedImage::compress(image) (codebook bytes, indices)
+//   host_test multi xs ys w h n ndev [exact]  needs ndev B200s: one image trained on ONE device and on a
+//                                   qb200_create_multi context over ndev devices - codebook bits, indices and
+//                                   distortion must be identical (ndev = 0: every visible device)
 #include <cstdio>
 #include <cstring>
 #include <iostream>
 #include <string>
 
+#include <chrono>
+#include <vector>
+
+#include "../../include/qb200.h"
 #include "Compressor.hpp"
 #include "KDTree.hpp"
 
@@ -94,8 +101,62 @@ static int test_quantize(const std::string &ppm, int w, int h, int n, ColorSpace
   return failures;
 }
 
+static int test_multi(int xs, int ys, int w, int h, int n, int ndev, int exact) {
+  std::vector<uint8_t> rgb((size_t)xs * ys * 3);
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  for (auto &b : rgb) {  // xorshift noise with a flat patch of duplicates
+    st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+    b = (uint8_t)(st >> 24);
+  }
+  for (size_t i = 0; i < rgb.size() / 50; i++) rgb[i] = 200;
+  const size_t dim = (size_t)3 * w * h, K = (size_t)1 << n;
+  auto run = [&](qb200_ctx *ctx, std::vector<double> &cb, std::vector<uint64_t> &a, double &dist, double &ms) -> int {
+    if (qb200_set_exact_centroids(ctx, exact)) return 1;
+    cb.resize(K * dim);
+    for (int rep = 0; rep < 2; rep++) {  // second run timed: allocations and module loading are behind it
+      const auto t0 = std::chrono::steady_clock::now();
+      int rc = qb200_set_image(ctx, rgb.data(), xs, ys, w, h, QB200_CS_SCALED, 1, 0);
+      if (!rc) rc = qb200_train(ctx, n, 1e-6, QB200_MODE_PARITY, 0, nullptr, nullptr, cb.data(), &dist, nullptr);
+      a.resize(qb200_num_vectors(ctx));
+      if (!rc) rc = qb200_get_assign_u64(ctx, a.data());
+      if (rc) {
+        std::printf("libqb200 error %d: %s\n", rc, qb200_last_error(ctx));
+        return 1;
+      }
+      ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return 0;
+  };
+  qb200_ctx *one = nullptr, *many = nullptr;
+  if (qb200_create(0, &one) || qb200_create_multi(ndev, nullptr, &many)) {
+    std::printf("context creation failed: %s\n", qb200_last_error(nullptr));
+    return 1;
+  }
+  std::vector<double> cb1, cbm;
+  std::vector<uint64_t> a1, am;
+  double d1 = 0, dm = 0, ms1 = 0, msm = 0;
+  if (run(one, cb1, a1, d1, ms1) || run(many, cbm, am, dm, msm)) return 1;
+  EXPECT(cb1.size() == cbm.size() && std::memcmp(cb1.data(), cbm.data(), cb1.size() * 8) == 0);
+  EXPECT(a1 == am);
+  EXPECT(std::memcmp(&d1, &dm, 8) == 0);
+  std::vector<uint8_t> cbb(K * dim);
+  double mse1 = -1, msem = -2;
+  qb200_codebook_to_bytes(cb1.data(), K, (int)dim, QB200_CS_SCALED, cbb.data());
+  EXPECT(qb200_decode(one, cbb.data(), (uint32_t)K, nullptr, &mse1) == 0);
+  EXPECT(qb200_decode(many, cbb.data(), (uint32_t)K, nullptr, &msem) == 0);
+  EXPECT(mse1 == msem);
+  std::printf("multi: %dx%d %dx%d K=%zu%s: 1 device %.2f ms, %d devices %.2f ms per host-bytes-in -> indices-out train; distortion %.9g\n",
+              xs, ys, w, h, K, exact ? " (exact centroids)" : "", ms1, ndev, msm, d1);
+  qb200_destroy(one);
+  qb200_destroy(many);
+  return failures;
+}
+
 int main(int argc, char **argv) {
   try {
+    if (argc >= 8 && std::strcmp(argv[1], "multi") == 0)
+      return test_multi(std::atoi(argv[2]), std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6]),
+                        std::atoi(argv[7]), argc >= 9 ? std::atoi(argv[8]) : 0) ? 1 : (std::puts("multi ok"), 0);
     if (argc >= 2 && std::strcmp(argv[1], "layout") == 0) return test_layout() ? 1 : (std::puts("layout ok"), 0);
     if (argc >= 6 && std::strcmp(argv[1], "quantize") == 0)
       return test_quantize(argv[2], std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]),
