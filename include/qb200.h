@@ -68,7 +68,7 @@ typedef struct qb200_ctx qb200_ctx;
 /* Per-level report filled by qb200_train (all optional diagnostics). */
 typedef struct qb200_level_report {
   uint32_t K;             /* codebook size of this level */
-  uint32_t flagged;       /* queries whose FP32 top-2 gap was inside the error margin (this rank) */
+  uint32_t flagged;       /* queries whose FP32 top-2 gap was inside the error margin (this rank): re-solved in FP64 */
   uint32_t changed;       /* of those, how many the exact FP64 resolver moved to another index */
   uint32_t ties;          /* of those, how many had (near-)exact FP64 ties and took the KD-tree walk */
   uint32_t dead_cells;    /* cells with no member after the (global) reduction */
@@ -78,6 +78,8 @@ typedef struct qb200_level_report {
   float ms_assign;        /* device time of the filter (codebook staging + tensor-core or CUDA-core kernel [+ finalise]) */
   float ms_resolve;       /* device time of the exact resolver kernels (brute force + tree walk) */
   float ms_accumulate;    /* device time of the separate per-cell statistics kernel (~0 when the filter accumulates) */
+  uint32_t refiltered;    /* tensor-core levels: queries inside the tensor-core margin, re-ranked in FP32 (of which
+                             `flagged` were still undecided and went to the FP64 resolver); 0 on the other levels */
   double distortion_pre;  /* updateDistortion() before fixCodeVectors (src/Quantizer.cpp:100) */
   double distortion_post; /* updateDistortion() after fixCodeVectors  (src/Quantizer.cpp:104) */
 } qb200_level_report;

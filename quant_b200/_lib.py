@@ -21,7 +21,7 @@ class LevelReport(C.Structure):
     _fields_ = [("K", C.c_uint32), ("flagged", C.c_uint32), ("changed", C.c_uint32),
                 ("ties", C.c_uint32), ("dead_cells", C.c_uint32), ("kd_depth", C.c_uint32), ("iterations", C.c_uint32), ("repaired", C.c_uint32),
                 ("ms_assign", C.c_float),
-                ("ms_resolve", C.c_float), ("ms_accumulate", C.c_float),
+                ("ms_resolve", C.c_float), ("ms_accumulate", C.c_float), ("refiltered", C.c_uint32),
                 ("distortion_pre", C.c_double), ("distortion_post", C.c_double)]
 
 

@@ -61,7 +61,7 @@ struct qb200_ctx {
   const uint8_t *borrowed = nullptr;
 
   // per-vector
-  DevBuf d_assign, d_flags, d_ties, d_dense;
+  DevBuf d_assign, d_flags, d_flags2, d_ties, d_dense;
   // per-level
   DevBuf d_rows, d_rows_tc, d_state, d_cb64, d_nodes, d_vind, d_bbox, d_stats, d_counters, d_misc;
   // pinned staging
@@ -163,7 +163,7 @@ void free_buf(DevBuf &b) {
 // ---- level machinery --------------------------------------------------------------------------
 
 struct LevelOut {
-  unsigned int flagged = 0, changed = 0, ties = 0;
+  unsigned int flagged = 0, changed = 0, ties = 0, refiltered = 0;
   int kd_depth = 0;
   float ms_assign = 0, ms_resolve = 0, ms_accumulate = 0;
 };
@@ -268,10 +268,12 @@ int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uin
     CU(cudaMemcpyAsync(ctx->d_cb64.p, h_cb, cb_bytes, cudaMemcpyHostToDevice, st));
   }
   CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
-  unsigned int *cnt = (unsigned int *)ctx->d_counters.p;  // [0] flagged, [1] changed, [2] ties, [4] max|C| (float)
+  // [0] flagged (-> FP64 resolver), [1] changed, [2] ties, [3] undecided by the tensor-core filter (-> FP32 re-rank), [4] max|C| (float)
+  unsigned int *cnt = (unsigned int *)ctx->d_counters.p;
   const float *c_max_ptr = reinterpret_cast<const float *>(cnt + 4);
   if (L.use_tc && (rc = ensure(ctx, ctx->d_rows_tc, L.tc_bytes))) return rc;
   if (L.use_tc && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 16))) return rc;
+  if (L.use_tc && (rc = ensure(ctx, ctx->d_flags2, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 4))) return rc;
   if (want_stats) CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(K, dim) * 8, st));
   bool fused = false;  // did the filter kernel accumulate the per-cell statistics of the queries it decided?
   if (ev0) CU(cudaEventRecord(ev0, st));
@@ -294,11 +296,16 @@ int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uin
     a.c_max_ptr = c_max_ptr;
     a.state = (float *)ctx->d_state.p;
     a.assign = (uint32_t *)ctx->d_assign.p;
-    a.flag_list = (uint32_t *)ctx->d_flags.p;
-    a.flag_count = cnt;
+    a.flag_list = (uint32_t *)ctx->d_flags2.p;  // what the tensor-core margin leaves undecided ...
+    a.flag_count = cnt + 3;
     a.sm_count = ctx->sm_count;
     a.stream = st;
     CU(launch_assign_tc(a));
+    // ... is re-ranked in FP32 (exact top-2 over all rows, margin 2.5 x (dim + 3) x 2^-24: ~9x tighter at dim 12); only
+    // what that cannot decide either goes on the resolver's list
+    CU(launch_refilter(ctx->src, (const float *)ctx->d_rows.p, (int)L.K_rows, 2.5f * (float)(dim + 3) * 5.9604645e-8f, c_max_ptr,
+                       (uint32_t *)ctx->d_assign.p, (const uint32_t *)ctx->d_flags2.p, cnt + 3, (uint32_t *)ctx->d_flags.p, cnt,
+                       ctx->sm_count, st));
     // The statistics of the queries the filter decided do not depend on the resolver: run them on the side stream
     // while the main stream uploads the KD tree and re-solves the flagged queries (whose entries carry the
     // "undecided" mark and are skipped; the resolver adds them itself).  level_finish joins the two.
@@ -396,7 +403,7 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
                          ctx->sm_count, st));
   }
   if (ev3) CU(cudaEventRecord(ev3, st));
-  CU(cudaMemcpyAsync(counters_dst, ctx->d_counters.p, 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(counters_dst, ctx->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
   ctx->assign_valid = true;
   ctx->assign_K = K;
   if (kd_depth_out) *kd_depth_out = tree.depth;
@@ -424,6 +431,7 @@ int collect_level(qb200_ctx *ctx, uint32_t K, bool timed, LevelOut *out) {
   out->flagged = c[0];
   out->changed = c[1];
   out->ties = c[2];
+  out->refiltered = c[3];
   if (timed) {
     CU(cudaEventElapsedTime(&out->ms_assign, ctx->ev[0], ctx->ev[1]));
     CU(cudaEventElapsedTime(&out->ms_resolve, ctx->ev[1], ctx->ev[2]));
@@ -839,7 +847,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_ties, &ctx->d_dense, &ctx->d_rows, &ctx->d_rows_tc, &ctx->d_state, &ctx->d_cb64, &ctx->d_nodes,
+  for (DevBuf *b : {&ctx->d_img, &ctx->d_assign, &ctx->d_flags, &ctx->d_flags2, &ctx->d_ties, &ctx->d_dense, &ctx->d_rows, &ctx->d_rows_tc, &ctx->d_state, &ctx->d_cb64, &ctx->d_nodes,
                     &ctx->d_vind, &ctx->d_bbox, &ctx->d_stats, &ctx->d_counters, &ctx->d_misc, &ctx->d_repair})
     free_buf(*b);
   comm_free(ctx);
@@ -1394,6 +1402,7 @@ int train_generic(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t N, q
       r.flagged = lo.flagged;
       r.changed = lo.changed;
       r.ties = lo.ties;
+      r.refiltered = lo.refiltered;
       r.kd_depth = (uint32_t)lo.kd_depth;
       r.iterations = iterations;
       r.repaired = 0;
@@ -1453,6 +1462,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   if ((rc = ensure(ctx, ctx->d_stats, stats_words(maxK, dim) * 8))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_rows_tc, tc_max))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 16))) return rc;
+  if (tc_max && (rc = ensure(ctx, ctx->d_flags2, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->d_nodes, Lmax.off_cnt - Lmax.off_nodes))) return rc;
   if ((rc = ensure_pinned(ctx, Lmax.total))) return rc;
   for (int i = 0; i < 2; i++)
@@ -1552,6 +1562,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
       r.flagged = s.counters[0];
       r.changed = s.counters[1];
       r.ties = s.counters[2];
+      r.refiltered = s.counters[3];
       r.dead_cells = s.dead_cells;
       r.kd_depth = (uint32_t)depth[level];
       r.iterations = 1;
@@ -1700,6 +1711,7 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
       r.flagged = lo.flagged;
       r.changed = lo.changed;
       r.ties = lo.ties;
+      r.refiltered = lo.refiltered;
       r.kd_depth = (uint32_t)lo.kd_depth;
       r.iterations = iterations;
       r.repaired = repaired_total;

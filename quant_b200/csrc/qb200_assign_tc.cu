@@ -36,6 +36,7 @@
 // is itself more than twice the FP32 bound, so in both comparisons the winner beats everything else by more
 // than the rounding error of either side: the FP32 argmin over the chunk is the exact nearest codevector.
 #include <cfloat>
+#include <cstdlib>
 
 #include "qb200_launch.hpp"
 #include "qb200_ptx.cuh"
@@ -45,7 +46,9 @@ namespace qb {
 namespace {
 
 constexpr int kProdGroups = 1;          // producer groups of 4 warps taking alternate tiles (2 measured slower: register cap)
-constexpr int kTcThreads = 32 * (1 + 4 * kProdGroups + 4 + 8);  // MMA + producer + merger + epilogue warps
+// MMA + producer + merger + epilogue warps; the epilogue has S warps per TMEM lane quarter, each scanning 1/S of the columns
+constexpr int tc_threads(int S) { return 32 * (1 + 4 * kProdGroups + 4 + 4 * S); }
+constexpr int kMaxSplit = 4;
 constexpr int kAStages = 4;            // A tiles in flight (shared memory ring)
 constexpr int kResStages = 4;          // per-tile result records in flight
 // Bit 31 of a provisional index: the query is on the flag list.  The exact resolver always rewrites such entries;
@@ -67,8 +70,8 @@ struct TcShared {
       res_empty[kResStages];
   uint32_t tmem_base;
   uint32_t pad;
-  float res_best[kResStages][2][kTileQ], res_second[kResStages][2][kTileQ];
-  int res_chunk[kResStages][2][kTileQ];
+  float res_best[kResStages][kMaxSplit][kTileQ], res_second[kResStages][kMaxSplit][kTileQ];
+  int res_chunk[kResStages][kMaxSplit][kTileQ];
 };
 
 // minimum of eight scores merged into the running (best, runner-up) over CHUNK MINIMA; `chunk` remembers which group
@@ -80,8 +83,8 @@ __device__ __forceinline__ void chunkmin_update8(const float *a, int cid, float 
   best = fminf(best, m);
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int DIM, int S>
+__global__ void __launch_bounds__(tc_threads(S), 1)
     assign_tc_kernel(const VecSource src, const unsigned char *__restrict__ b_staged, const int k_rows, const int k_base,
                      const int first_pass, float *__restrict__ state, const unsigned long long tiles) {
   using Cfg = TcCfg<DIM>;
@@ -105,10 +108,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       for (int i = 0; i < 2; i++) {
         mbar_init(&sh.tmem_full[i], 1);
-        mbar_init(&sh.tmem_empty[i], 256);
+        mbar_init(&sh.tmem_empty[i], 128 * S);
       }
       for (int i = 0; i < kResStages; i++) {
-        mbar_init(&sh.res_full[i], 256);
+        mbar_init(&sh.res_full[i], 128 * S);
         mbar_init(&sh.res_empty[i], kTileQ);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -225,14 +228,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const unsigned long long v = tile * kTileQ + r;
       const int rb = tile_seq % kResStages;
       mbar_wait_bounded<20000>(&sh.res_full[rb], (tile_seq / kResStages) & 1, 5);
-      const float b0 = sh.res_best[rb][0][r], b1 = sh.res_best[rb][1][r];
-      const float s0 = sh.res_second[rb][0][r], s1 = sh.res_second[rb][1][r];
-      const int c0 = sh.res_chunk[rb][0][r], c1 = sh.res_chunk[rb][1][r];
-      mbar_arrive(&sh.res_empty[rb]);
-      if (v < src.n_local) {
-        reinterpret_cast<float4 *>(state)[v] =
-            make_float4(fminf(b0, b1), fmin3(fmaxf(b0, b1), s0, s1), __int_as_float(b1 < b0 ? c1 : c0), 0.f);
+      float best = sh.res_best[rb][0][r], runner = sh.res_second[rb][0][r];
+      int chunk = sh.res_chunk[rb][0][r];
+#pragma unroll
+      for (int i = 1; i < S; i++) {  // the column parts hold disjoint chunks: same rule as the running update
+        const float b = sh.res_best[rb][i][r];
+        runner = fmin3(runner, sh.res_second[rb][i][r], fmaxf(best, b));
+        chunk = b < best ? sh.res_chunk[rb][i][r] : chunk;
+        best = fminf(best, b);
       }
+      mbar_arrive(&sh.res_empty[rb]);
+      if (v < src.n_local) reinterpret_cast<float4 *>(state)[v] = make_float4(best, runner, __int_as_float(chunk), 0.f);
     }
   } else {
     // =========================== epilogue: TMEM -> registers -> running top-2 ===========================
@@ -253,23 +259,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           chunk = __float_as_int(rec.z);
         }
       }
-      // Per N tile this warp scans 128 columns as four chunks of 32, software-pipelined over two register
-      // buffers: the tcgen05.ld of the next chunk (the next N tile's first chunk included) is in flight while
+      // Per N tile this warp scans its kTileN / S columns as four pieces of CW, software-pipelined over two register
+      // buffers: the tcgen05.ld of the next piece (the next N tile's first piece included) is in flight while
       // the current one is reduced.  Everything but the buffer address and the chunk base is a constant.
-      constexpr int half_cols = kTileN / 2;
-      const int col0 = half * half_cols;
-      auto load32 = [&](uint32_t taddr, float *v) {
+      constexpr int part_cols = kTileN / S, CW = part_cols / 4;
+      const int col0 = half * part_cols;
+      auto loadp = [&](uint32_t taddr, float *v) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) tmem_ld8(taddr + q * 8, v + q * 8);
+        for (int q = 0; q < CW / 8; q++) tmem_ld8(taddr + q * 8, v + q * 8);
       };
-      auto landed = [&](float *v) {  // after this the chunk is in registers
+      auto landed = [&](float *v) {  // after this the piece is in registers
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; q++) tmem_ld_pin8(v + q * 8);
+        for (int q = 0; q < CW / 8; q++) tmem_ld_pin8(v + q * 8);
       };
       auto reduce = [&](int cid, const float *v) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) chunkmin_update8(v + q * 8, cid + q, best, second, chunk);
+        for (int q = 0; q < CW / 8; q++) chunkmin_update8(v + q * 8, cid + q, best, second, chunk);
       };
       auto acquire = [&](unsigned int itg) -> uint32_t {  // wait for N tile `itg`, return its first column address
         const int buf = itg & 1;
@@ -277,28 +283,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tc_fence_after();
         return lane_addr + (uint32_t)(buf * 256 + col0);
       };
-      float va[32], vb[32];
+      float va[CW], vb[CW];
       uint32_t taddr = acquire(it);
-      load32(taddr, va);
+      loadp(taddr, va);
       int cid = (k_base + col0) >> 3;
       for (int jt = 0; jt < n_tiles_n; jt++, cid += kTileN / 8) {
         landed(va);
-        load32(taddr + 32, vb);
+        loadp(taddr + CW, vb);
         reduce(cid, va);
         landed(vb);
-        load32(taddr + 64, va);
-        reduce(cid + 4, vb);
+        loadp(taddr + 2 * CW, va);
+        reduce(cid + CW / 8, vb);
         landed(va);
-        load32(taddr + 96, vb);
-        reduce(cid + 8, va);
+        loadp(taddr + 3 * CW, vb);
+        reduce(cid + 2 * (CW / 8), va);
         landed(vb);  // the whole N tile is in registers: hand the buffer back to the MMA
         tc_fence_before();
         mbar_arrive(&sh.tmem_empty[(it + jt) & 1]);
         if (jt + 1 < n_tiles_n) {
           taddr = acquire(it + jt + 1);
-          load32(taddr, va);
+          loadp(taddr, va);
         }
-        reduce(cid + 12, vb);
+        reduce(cid + 3 * (CW / 8), vb);
       }
       it += n_tiles_n;
       const int rb = tile_seq % kResStages;
@@ -560,12 +566,21 @@ static cudaError_t launch_tc_t(const AssignTcLaunch &a) {
   const unsigned long long tiles = (a.src.n_local + kTileQ - 1) / kTileQ;
   if (tiles == 0) return cudaSuccess;
   const size_t smem_max = (((size_t)chunk * Cfg::ROW_BYTES + 1023) & ~(size_t)1023) + kAStages * Cfg::A_BYTES + sizeof(TcShared) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(assign_tc_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  // epilogue warps per TMEM lane quarter: 2 (each scans 128 columns in pieces of 32) or 4 (64 columns in pieces of 16:
+  // more warps to cover the tcgen05.ld latency, fewer registers each); QB200_TC_SPLIT overrides
+  static const int split = [] {
+    const char *e = std::getenv("QB200_TC_SPLIT");
+    const int v = e ? std::atoi(e) : 0;
+    return v == 2 || v == 4 ? v : 2;
+  }();
+  auto kernel = split == 4 ? assign_tc_kernel<DIM, 4> : assign_tc_kernel<DIM, 2>;
+  const int threads = split == 4 ? tc_threads(4) : tc_threads(2);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return e;
   const unsigned int grid = (unsigned int)(tiles < (unsigned long long)a.sm_count ? tiles : a.sm_count);
   for (int k0 = 0; k0 < kp; k0 += chunk) {
     const int rows = kp - k0 < chunk ? kp - k0 : chunk;
-    assign_tc_kernel<DIM><<<grid, kTcThreads, smem_max, a.stream>>>(a.src, a.b_staged + (size_t)k0 * Cfg::ROW_BYTES, rows,
+    kernel<<<grid, threads, smem_max, a.stream>>>(a.src, a.b_staged + (size_t)k0 * Cfg::ROW_BYTES, rows,
                                                                     k0, k0 == 0, a.state, tiles);
     count_launch();
     e = cudaGetLastError();

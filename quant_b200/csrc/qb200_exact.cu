@@ -228,7 +228,8 @@ struct FxWork {
   signed char *need;    // per (window, dimension): highest state bit the window's members look at
   u128 *total;          // per chain: sum of X over the whole chain
   i128 *B;              // per chain (head)
-  long long *W0;        // per chain (head)
+  uint32_t *head_end;   // per chain (head): first member the segments cover
+  signed char *head_je; // per chain (head): trailing zeros of the state there
   uint32_t *q_start;    // per chain (head): first window the chaining pass applies; 0xffffffff: finished by the head
   fx::SegRecord *rec;   // per (window, dimension), chain-major
   fx::Tables *tab;      // X_t table (device copy)
@@ -338,29 +339,38 @@ __global__ void __launch_bounds__(256) fx_pre_kernel(const FxGeom g, FxWork w) {
   }
 }
 
-// per chain: exclusive prefix of the window sums (in place) and the chain total
+// per chain (one WARP each): exclusive prefix of the window sums (in place) and the chain total.  Lanes take 32
+// consecutive windows; the 128-bit values are scanned as three 32-bit limbs in 64-bit lanes (no carries inside the
+// scan: a limb sum over at most 2^22 windows stays below 2^54) and recombined.
 __global__ void __launch_bounds__(128) fx_scan_kernel(const FxGeom g, FxWork w) {
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = (int)((blockIdx.x * (unsigned int)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (chain >= g.K * g.dim) return;
   const int k = chain / g.dim, e = chain - k * g.dim;
   const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
   u128 *p = w.sumX + fx_index(w, g.dim, k, e, 0);
-  u128 run = 0;
-  unsigned int q = 0;
-  for (; q + 4 <= cnt; q += 4) {  // loads first: they do not depend on the running sum
-    const u128 a = p[q], b = p[q + 1], c = p[q + 2], d = p[q + 3];
-    p[q] = run;
-    p[q + 1] = run + a;
-    p[q + 2] = run + a + b;
-    p[q + 3] = run + a + b + c;
-    run += a + b + c + d;
+  u128 carry = 0;
+  for (unsigned int q0 = 0; q0 < cnt; q0 += 32) {
+    const unsigned int q = q0 + lane;
+    const u128 v = q < cnt ? p[q] : (u128)0;
+    unsigned long long l0 = (unsigned long long)v & 0xffffffffull, l1 = (unsigned long long)(v >> 32) & 0xffffffffull,
+                       l2 = (unsigned long long)(v >> 64);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long a0 = __shfl_up_sync(0xffffffffu, l0, o), a1 = __shfl_up_sync(0xffffffffu, l1, o),
+                               a2 = __shfl_up_sync(0xffffffffu, l2, o);
+      if (lane >= o) {
+        l0 += a0;
+        l1 += a1;
+        l2 += a2;
+      }
+    }
+    const u128 incl = (u128)l0 + ((u128)l1 << 32) + ((u128)l2 << 64);
+    if (q < cnt) p[q] = carry + incl - v;  // exclusive
+    const unsigned long long t0 = __shfl_sync(0xffffffffu, l0, 31), t1 = __shfl_sync(0xffffffffu, l1, 31),
+                             t2 = __shfl_sync(0xffffffffu, l2, 31);
+    carry += (u128)t0 + ((u128)t1 << 32) + ((u128)t2 << 64);
   }
-  for (; q < cnt; q++) {
-    const u128 a = p[q];
-    p[q] = run;
-    run += a;
-  }
-  w.total[chain] = run;
+  if (lane == 0) w.total[chain] = carry;
 }
 
 __global__ void __launch_bounds__(128) fx_head_kernel(const FxGeom g, FxWork w, double *__restrict__ state) {
@@ -374,7 +384,8 @@ __global__ void __launch_bounds__(128) fx_head_kernel(const FxGeom g, FxWork w, 
   const FxAcc acc{g.dense, g.order, g.stride, e};
   const fx::HeadOut h = fx::fx_head(acc, tab, beg, end, g.C, state[2 * (size_t)chain], state[2 * (size_t)chain + 1]);
   w.B[chain] = h.B;
-  w.W0[chain] = h.W0;
+  w.head_end[chain] = h.pos_end;
+  w.head_je[chain] = (signed char)h.je;
   w.q_start[chain] = h.done ? 0xffffffffu : h.q_start;
   if (h.done) {
     state[2 * (size_t)chain] = h.sum;
@@ -382,13 +393,26 @@ __global__ void __launch_bounds__(128) fx_head_kernel(const FxGeom g, FxWork w, 
   }
 }
 
-__global__ void __launch_bounds__(256) fx_runs_kernel(const FxGeom g, FxWork w) {
-  __shared__ fx::Tables tab;
+// Members of one (window, dimension) staged in shared memory, one byte column per thread: every later read of the
+// speculative runs (anchor scans, one pass per class) is a shared-memory load instead of two dependent global ones.
+constexpr int kFxRunThreads = 128;
+struct FxStaged {
+  const unsigned char *col;  // this thread's column: member p of the window at col[(p - base) * kFxRunThreads]
+  unsigned int base;
+  __device__ __forceinline__ int operator()(unsigned int p) const { return (int)col[(p - base) * kFxRunThreads]; }
+};
+
+__global__ void __launch_bounds__(kFxRunThreads) fx_runs_kernel(const FxGeom g, FxWork w) {
+  extern __shared__ __align__(16) unsigned char fx_smem[];
+  fx::Tables &tab = *reinterpret_cast<fx::Tables *>(fx_smem);
+  unsigned char *stage = fx_smem + sizeof(fx::Tables);  // [C + kFxAnchorWin][kFxRunThreads] bytes
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
   __syncthreads();
   const unsigned long long total = (unsigned long long)w.win_off[g.K] * g.dim;
-  for (unsigned long long id = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; id < total;
-       id += (unsigned long long)gridDim.x * blockDim.x) {
+  const unsigned long long rounds = (total + kFxRunThreads - 1) / kFxRunThreads;
+  for (unsigned long long rnd = blockIdx.x; rnd < rounds; rnd += gridDim.x) {
+    const unsigned long long id = rnd * kFxRunThreads + threadIdx.x;
+    if (id >= total) continue;
     const unsigned int gw = (unsigned int)(id / (unsigned int)g.dim);
     const int e = (int)(id - (unsigned long long)gw * g.dim);
     int k;
@@ -398,16 +422,24 @@ __global__ void __launch_bounds__(256) fx_runs_kernel(const FxGeom g, FxWork w) 
     const unsigned int qs = w.q_start[chain];
     if (q < qs) continue;  // covered by the head (0xffffffff: the whole chain)
     const unsigned int beg = w.cell_beg[k], end = w.cell_beg[k + 1], cnt = w.win_off[k + 1] - w.win_off[k];
-    const FxAcc acc{g.dense, g.order, g.stride, e};
+    const unsigned int P = beg + q * g.C;
+    const unsigned int len = end - P > g.C + fx::kFxAnchorWin ? g.C + fx::kFxAnchorWin : end - P;
+    {
+      const FxAcc src{g.dense, g.order, g.stride, e};
+      unsigned char *col = stage + threadIdx.x;
+#pragma unroll 8
+      for (unsigned int i = 0; i < len; i++) col[i * kFxRunThreads] = (unsigned char)src(P + i);
+    }
+    const FxStaged acc{stage + threadIdx.x, P};
     const size_t idx = fx_index(w, g.dim, k, e, q);
     fx::SegRecord r;
-    const fx::Anchor a = fx::fx_anchor(acc, beg + q * g.C, end, tab);
-    r.begin = a.b;
-    r.end = q + 1 < cnt ? fx::fx_anchor(acc, beg + (q + 1) * g.C, end, tab).b : end;
-    r.je = (signed char)(a.je < 0 ? 0 : a.je);
+    int je;
+    u128 before;
+    fx::fx_segment_bounds(acc, tab, beg, end, g.C, q, cnt, qs, w.head_end[chain], (int)w.head_je[chain], r.begin, r.end, je, before);
+    r.je = (signed char)je;
     const int n0 = w.need[idx], n1 = q + 1 < cnt ? (int)w.need[idx + 1] : -1;
     r.top = (signed char)(n0 > n1 ? n0 : n1);
-    r.Eb = (u128)(w.B[chain] + (i128)w.sumX[idx] + (i128)(((u128)a.xsum_hi << 64) | a.xsum_lo));
+    r.Eb = (u128)(w.B[chain] + (i128)w.sumX[idx] + (i128)before);
     r.ncls = 0;
     r.pad = 0;
     if (r.begin < r.end) fx::fx_run_segment(acc, tab, r);
@@ -415,28 +447,84 @@ __global__ void __launch_bounds__(256) fx_runs_kernel(const FxGeom g, FxWork w) 
   }
 }
 
-__global__ void __launch_bounds__(128) fx_chain_kernel(const FxGeom g, FxWork w, double *__restrict__ state) {
+// Chaining: one WARP per chain.  The lanes copy 32 records at a time into shared memory (coalesced), lane 0 applies
+// them in order (W = A - E is the only carried value); a segment whose summary does not cover W is staged into
+// shared memory by the whole warp and re-run by lane 0 from the exact state.
+constexpr int kFxChainWarps = 4;
+__global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGeom g, FxWork w, double *__restrict__ state) {
   __shared__ fx::Tables tab;
+  __shared__ __align__(16) fx::SegRecord s_rec[kFxChainWarps][2][32];
+  __shared__ unsigned char s_seg[kFxChainWarps][1024 + fx::kFxAnchorWin];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
   __syncthreads();
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x * kFxChainWarps + warp;
   if (chain >= g.K * g.dim) return;
   const unsigned int qs = w.q_start[chain];
   if (qs == 0xffffffffu) return;  // finished by the head
   const int k = chain / g.dim, e = chain - k * g.dim;
   const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
   const fx::SegRecord *rec = w.rec + fx_index(w, g.dim, k, e, 0);
-  const FxAcc acc{g.dense, g.order, g.stride, e};
-  long long W = w.W0[chain];
-  for (unsigned int q = qs; q < cnt; q++) {
-    const fx::SegRecord r = rec[q];
-    if (!fx::fx_apply(r, W)) fx::fx_rerun(acc, tab, r, W);
+  const FxAcc src{g.dense, g.order, g.stride, e};
+  static_assert(sizeof(fx::SegRecord) % 16 == 0, "records are copied as 16-byte words");
+  constexpr int kWords = (int)(sizeof(fx::SegRecord) / 16);
+  auto fetch = [&](unsigned int q0, int slot) {  // records q0 .. q0 + 31 -> s_rec[warp][slot]
+    const unsigned int n = cnt - q0 < 32u ? cnt - q0 : 32u;
+    const uint4 *srcw = reinterpret_cast<const uint4 *>(rec + q0);
+    uint4 *dst = reinterpret_cast<uint4 *>(&s_rec[warp][slot][0]);
+    for (unsigned int i = lane; i < n * kWords; i += 32) dst[i] = srcw[i];
+  };
+  long long W = 0;  // the head's state is exact: the first segment is entered with W = 0
+  int slot = 0;
+  if (qs < cnt) fetch(qs, 0);
+  __syncwarp();
+  for (unsigned int q0 = qs; q0 < cnt; q0 += 32, slot ^= 1) {
+    if (q0 + 32 < cnt) fetch(q0 + 32, slot ^ 1);  // next batch while lane 0 walks this one
+    const unsigned int n = cnt - q0 < 32u ? cnt - q0 : 32u;
+    unsigned int j = 0;
+    while (j < n) {
+      // lane 0 applies summaries until one does not cover W
+      int stop = 0;
+      if (lane == 0) {
+        for (; j < n; j++)
+          if (!fx::fx_apply(s_rec[warp][slot][j], W)) {
+            stop = 1;
+            break;
+          }
+      }
+      stop = __shfl_sync(0xffffffffu, stop, 0);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (!stop) break;
+      // exact re-run of segment j: the warp stages its members, lane 0 steps through them
+      const fx::SegRecord &r = s_rec[warp][slot][j];
+      const unsigned int len = r.end - r.begin;
+      if (len <= sizeof(s_seg[0])) {
+        for (unsigned int i = lane; i < len; i += 32) s_seg[warp][i] = (unsigned char)src(r.begin + i);
+        __syncwarp();
+        if (lane == 0) {
+          u128 a = (u128)((i128)r.Eb + W), xs = 0;
+          for (unsigned int i = 0; i < len; i++) {
+            const int t = s_seg[warp][i];
+            xs += tab.X[t];
+            a = fx::fx_step(a, t, tab);
+          }
+          W = (long long)((i128)a - (i128)(r.Eb + xs));
+        }
+        __syncwarp();
+      } else if (lane == 0) {
+        fx::fx_rerun(src, tab, r, W);
+      }
+      j++;
+    }
+    __syncwarp();
   }
-  const u128 A = (u128)(w.B[chain] + (i128)w.total[chain] + (i128)W);
-  double sum, c;
-  fx::fx_state_to_pair(A, sum, c);
-  state[2 * (size_t)chain] = sum;
-  state[2 * (size_t)chain + 1] = c;
+  if (lane == 0) {
+    const u128 A = (u128)(w.B[chain] + (i128)w.total[chain] + (i128)W);
+    double sum, c;
+    fx::fx_state_to_pair(A, sum, c);
+    state[2 * (size_t)chain] = sum;
+    state[2 * (size_t)chain + 1] = c;
+  }
 }
 
 size_t fx_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -444,11 +532,10 @@ size_t fx_up(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
 unsigned int exact_fast_window(size_t n, int K) {
-  // balance of the speculative runs (work per thread ~ C) and the chaining pass (steps per chain ~ n / (K C))
-  double c = std::sqrt((double)n / (4.0 * (double)(K > 0 ? K : 1)));
-  unsigned int C = 128;
-  while (C < 1024 && (double)C < c) C <<= 1;
-  return C;
+  // Short windows: a re-run costs one window's members sequentially, the chaining pass one cheap step per window.
+  (void)n;
+  (void)K;
+  return 128;
 }
 
 size_t exact_fast_workspace_bytes(size_t n, int K, int dim) {
@@ -457,7 +544,7 @@ size_t exact_fast_workspace_bytes(size_t n, int K, int dim) {
   const size_t windows = n / C + (size_t)K + 1, per = windows * (size_t)dim, chains = (size_t)K * dim;
   size_t b = 0;
   b += fx_up(((size_t)K + 1) * 4) * 2;
-  b += fx_up(per * 16) + fx_up(per) + fx_up(chains * 16) * 2 + fx_up(chains * 8) + fx_up(chains * 4);
+  b += fx_up(per * 16) + fx_up(per) + fx_up(chains * 16) * 2 + fx_up(chains * 4) * 2 + fx_up(chains);
   b += fx_up(per * sizeof(fx::SegRecord)) + fx_up(sizeof(fx::Tables));
   return b + 256;
 }
@@ -482,7 +569,8 @@ cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_so
   w.need = (signed char *)take(per);
   w.total = (u128 *)take(chains * 16);
   w.B = (i128 *)take(chains * 16);
-  w.W0 = (long long *)take(chains * 8);
+  w.head_end = (uint32_t *)take(chains * 4);
+  w.head_je = (signed char *)take(chains);
   w.q_start = (uint32_t *)take(chains * 4);
   w.rec = (fx::SegRecord *)take(per * sizeof(fx::SegRecord));
   w.tab = (fx::Tables *)take(sizeof(fx::Tables));
@@ -505,13 +593,19 @@ cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_so
   const unsigned int chain_blocks = (unsigned int)((chains + 127) / 128);
   fx_pre_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(g, w);
   count_launch();
-  fx_scan_kernel<<<chain_blocks, 128, 0, stream>>>(g, w);
+  fx_scan_kernel<<<(unsigned int)((chains * 32 + 127) / 128), 128, 0, stream>>>(g, w);
   count_launch();
   fx_head_kernel<<<chain_blocks, 128, 0, stream>>>(g, w, state);
   count_launch();
-  fx_runs_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(g, w);
-  count_launch();
-  fx_chain_kernel<<<chain_blocks, 128, 0, stream>>>(g, w, state);
+  {
+    const size_t smem = sizeof(fx::Tables) + (size_t)(C + fx::kFxAnchorWin) * kFxRunThreads;
+    unsigned long long rblocks = (ids + kFxRunThreads - 1) / kFxRunThreads;
+    const unsigned long long rcap = (unsigned long long)sm_count * 8;
+    if (rblocks > rcap) rblocks = rcap;
+    fx_runs_kernel<<<(unsigned int)rblocks, kFxRunThreads, smem, stream>>>(g, w);
+    count_launch();
+  }
+  fx_chain_kernel<<<(unsigned int)((chains + kFxChainWarps - 1) / kFxChainWarps), 32 * kFxChainWarps, 0, stream>>>(g, w, state);
   count_launch();
   return cudaGetLastError();
 }

@@ -324,14 +324,15 @@ QB_HD void fx_window(const Acc &acc, const Tables &tab, unsigned int P, unsigned
 }
 
 struct HeadOut {
-  i128 B;               // E(p) = B + (sum of X over [beg, p)): the trajectory without rounding corrections
-  long long W0;         // A - E at the first segment the chaining pass applies
-  unsigned int q_start; // that segment (window index); >= number of windows: the head finished the chain
+  i128 B;               // E(p) = B + (sum of X over [beg, p)): the trajectory without rounding corrections, E(pos_end) = A
+  unsigned int pos_end; // first member the segments cover (right after the head's anchor); the state there is exact
+  unsigned int q_start; // window that contains pos_end: the first segment of the chaining pass, entered with W = 0
+  int je;               // trailing zeros of the state at pos_end (the head's anchor)
   double sum, c;        // final pair when the head finished the chain
   int done;
 };
 // Head of a chain [beg, end) with nominal windows of C members: the reference's loop itself from the incoming pair
-// (sum, c) until sum >= 4, then integer steps up to the boundary of the first window that starts at or after that.
+// (sum, c) until sum >= 4, then integer steps up to the first anchor found after that point (fx_anchor).
 template <typename Acc>
 QB_HD HeadOut fx_head(const Acc &acc, const Tables &tab, unsigned int beg, unsigned int end, unsigned int C, double sum,
                       double c) {
@@ -348,31 +349,54 @@ QB_HD HeadOut fx_head(const Acc &acc, const Tables &tab, unsigned int beg, unsig
   o.sum = sum;
   o.c = c;
   o.B = 0;
-  o.W0 = 0;
-  const unsigned int n_win = (end - beg + C - 1) / C;
-  o.q_start = n_win;
+  o.pos_end = end;
+  o.q_start = 0;
+  o.je = 0;
   if (sum < 4.0) {
     o.done = 1;
     return o;
   }
   u128 A = fx_pair_to_state(sum, c);
-  o.B = (i128)A - (i128)px;
-  const unsigned int q = (pos - beg + C - 1) / C;   // first window starting at or after pos
-  unsigned int stop = end;
-  if (q < n_win) stop = fx_anchor(acc, beg + q * C, end, tab).b;
-  for (; pos < stop; pos++) {
-    const int t = acc(pos);
-    px += tab.X[t];
-    A = fx_step(A, t, tab);
+  if (pos < end) {
+    const Anchor a = fx_anchor(acc, pos, end, tab);
+    for (; pos < a.b; pos++) {
+      const int t = acc(pos);
+      px += tab.X[t];
+      A = fx_step(A, t, tab);
+    }
+    o.je = a.je < 0 ? 0 : a.je;
   }
-  if (q >= n_win) {
+  if (pos >= end) {
     fx_state_to_pair(A, o.sum, o.c);
     o.done = 1;
     return o;
   }
-  o.q_start = q;
-  o.W0 = (long long)((i128)A - (o.B + (i128)px));
+  o.B = (i128)A - (i128)px;
+  o.pos_end = pos;
+  o.q_start = (pos - beg) / C;
   return o;
+}
+
+// Geometry of segment q of a chain (windows of C members from beg): members [begin, end), entry trailing zeros je and
+// sum of X over [P_q, begin).  The head's segment starts at the head's end; the others right after their window's anchor.
+template <typename Acc>
+QB_HD void fx_segment_bounds(const Acc &acc, const Tables &tab, unsigned int beg, unsigned int end, unsigned int C, unsigned int q,
+                             unsigned int n_win, unsigned int q_start, unsigned int head_end, int head_je, unsigned int &seg_begin,
+                             unsigned int &seg_end, int &je, u128 &xsum_before) {
+  const unsigned int P = beg + q * C;
+  if (q == q_start) {
+    u128 xs = 0;
+    for (unsigned int p = P; p < head_end; p++) xs += tab.X[acc(p)];
+    seg_begin = head_end;
+    je = head_je;
+    xsum_before = xs;
+  } else {
+    const Anchor a = fx_anchor(acc, P, end, tab);
+    seg_begin = a.b;
+    je = a.je < 0 ? 0 : a.je;
+    xsum_before = ((u128)a.xsum_hi << 64) | a.xsum_lo;
+  }
+  seg_end = q + 1 < n_win ? fx_anchor(acc, beg + (q + 1) * C, end, tab).b : end;
 }
 
 }  // namespace fx

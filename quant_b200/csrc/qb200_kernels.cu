@@ -289,6 +289,166 @@ __global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
   }
 }
 
+// refilter_kernel: the FP32 MIDDLE TIER of the tensor-core levels.  The tensor-core filter's margin is three times a
+// deliberately generous bound on the tensor core's internal accumulation error (55 units of 2^-23 at dim 12); the
+// FP32 FMA score's bound is (dim + 3) * 2^-24, an order of magnitude tighter.  Queries the tensor-core filter could
+// not decide are therefore re-ranked here - same inner loop as assign_kernel (FFMA2 pairs against the staged
+// rows, exact top-2 over ALL codevectors) - and only what is still inside the FP32 margin goes on to the FP64
+// resolver, whose cost per query is K distance evaluations at FP64 rate.  Input: `list_in` (count on the device),
+// output: final indices for the decided ones, `list_out` (appended, warp-aggregated) for the rest; entries keep the
+// "undecided" mark in bit 31 until the resolver rewrites them.
+// Work split: the list is cut into one contiguous slice per CTA; thread t takes items t*Q .. t*Q+Q-1 of the
+// slice's current tile, so a short list keeps whole warps idle instead of wasting lanes on dead queries.
+template <int DIM>
+__global__ void __launch_bounds__(AssignCfg<DIM>::THREADS, 1)
+    refilter_kernel(const VecSource src, const float *__restrict__ cb_rows, const int K, const int k_chunk,
+                    const float margin_coef, const float *__restrict__ c_max_ptr, uint32_t *__restrict__ assign,
+                    const uint32_t *__restrict__ list_in, const unsigned int *__restrict__ count_in,
+                    uint32_t *__restrict__ list_out, unsigned int *__restrict__ count_out) {
+  using Cfg = AssignCfg<DIM>;
+  constexpr int ROW = Cfg::ROW, Q = Cfg::Q, THREADS = Cfg::THREADS;
+  const unsigned int total = *count_in;
+  const unsigned int per_cta = (total + gridDim.x - 1) / gridDim.x;
+  const unsigned int s_begin = min(total, blockIdx.x * per_cta), s_end = min(total, s_begin + per_cta);
+  if (s_begin >= s_end) return;
+  const float c_max_norm = *c_max_ptr;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *s_cb = reinterpret_cast<float *>(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x;
+  const int n_chunks = (K + k_chunk - 1) / k_chunk;
+  uint32_t phase = 0;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto stage_chunk = [&](int chunk) {
+    const int k0 = chunk * k_chunk;
+    const int kn = min(k_chunk, K - k0);
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)kn * ROW * 4u;
+      mbar_expect_tx(&s_bar, bytes);
+      const char *g = reinterpret_cast<const char *>(cb_rows + (size_t)k0 * ROW);
+      char *s = reinterpret_cast<char *>(s_cb);
+      for (uint32_t off = 0; off < bytes; off += 32768u) tma_load_1d(s + off, g + off, min(32768u, bytes - off), &s_bar);
+    }
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+    return kn;
+  };
+  int staged = -1;
+  for (unsigned int t0 = s_begin; t0 < s_end; t0 += THREADS * Q) {
+    unsigned long long xp[Q / 2][DIM];
+    float xn[Q];
+    bool live[Q];
+    uint32_t vq[Q];
+#pragma unroll
+    for (int qp = 0; qp < Q / 2; qp++) {
+      float x[2][DIM];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int q = 2 * qp + h;
+        const unsigned int item = t0 + (unsigned int)tid * Q + q;
+        live[q] = item < s_end;
+        vq[q] = live[q] ? __ldg(list_in + item) : 0u;
+        xn[q] = 0.f;
+        if (live[q]) {
+          gather_lattice<DIM>(src, vq[q], x[h]);
+#pragma unroll
+          for (int e = 0; e < DIM; e++) xn[q] = fmaf(x[h][e], x[h][e], xn[q]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < DIM; e++) x[h][e] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < DIM; e++) xp[qp][e] = pack2(x[0][e], x[1][e]);
+    }
+    const bool warp_live = __any_sync(0xffffffffu, live[0]);  // items are handed out thread by thread: q = 0 first
+    float best[Q], second[Q];
+    int bpair[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      best[q] = FLT_MAX;
+      second[q] = FLT_MAX;
+      bpair[q] = 0;
+    }
+    for (int chunk = 0; chunk < n_chunks; chunk++) {
+      int kn;
+      if (staged != chunk) {
+        __syncthreads();  // everyone is done reading the previous chunk
+        kn = stage_chunk(chunk);
+        staged = chunk;
+      } else {
+        kn = min(k_chunk, K - chunk * k_chunk);
+      }
+      if (!warp_live) continue;  // (the barrier above is taken by every warp)
+      const int k0 = chunk * k_chunk;
+      const float4 *rows = reinterpret_cast<const float4 *>(s_cb);
+#pragma unroll 1
+      for (int k = 0; k < kn; k += 2) {
+        float c0[ROW], c1[ROW];
+#pragma unroll
+        for (int r = 0; r < ROW / 4; r++) {
+          const float4 t = rows[k * (ROW / 4) + r];
+          const float4 u = rows[(k + 1) * (ROW / 4) + r];
+          c0[4 * r + 0] = t.x; c0[4 * r + 1] = t.y; c0[4 * r + 2] = t.z; c0[4 * r + 3] = t.w;
+          c1[4 * r + 0] = u.x; c1[4 * r + 1] = u.y; c1[4 * r + 2] = u.z; c1[4 * r + 3] = u.w;
+        }
+        const int kg = k0 + k;
+#pragma unroll
+        for (int qp = 0; qp < Q / 2; qp++) {
+          unsigned long long a0 = pack2(c0[DIM], c0[DIM]);
+          unsigned long long a1 = pack2(c1[DIM], c1[DIM]);
+#pragma unroll
+          for (int e = 0; e < DIM; e++) {
+            a0 = ffma2(xp[qp][e], pack2(c0[e], c0[e]), a0);
+            a1 = ffma2(xp[qp][e], pack2(c1[e], c1[e]), a1);
+          }
+          float s0[2], s1[2];
+          unpack2(a0, s0[0], s0[1]);
+          unpack2(a1, s1[0], s1[1]);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int q = 2 * qp + h;
+            const float lo = fminf(s0[h], s1[h]), hi = fmaxf(s0[h], s1[h]);
+            second[q] = fmin3(second[q], hi, fmaxf(lo, best[q]));
+            bpair[q] = lo < best[q] ? kg : bpair[q];
+            best[q] = fminf(best[q], lo);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      // which member of the winning pair: the same FMA sequence on the same operands gives the same bits as the loop
+      const float *r0 = cb_rows + (size_t)bpair[q] * ROW;
+      float t0s = __ldg(r0 + DIM), t1s = __ldg(r0 + ROW + DIM);
+#pragma unroll
+      for (int e = 0; e < DIM; e++) {
+        float lo_, hi_;
+        unpack2(xp[q / 2][e], lo_, hi_);
+        const float xe = (q & 1) ? hi_ : lo_;
+        t0s = fmaf(xe, __ldg(r0 + e), t0s);
+        t1s = fmaf(xe, __ldg(r0 + ROW + e), t1s);
+      }
+      const int bidx = bpair[q] + (t1s < t0s ? 1 : 0);
+      const float r = sqrtf(xn[q]) + c_max_norm;
+      const bool flag = live[q] && !((second[q] - best[q]) > margin_coef * r * r);
+      if (live[q]) assign[vq[q]] = (uint32_t)bidx | (flag ? 0x80000000u : 0u);
+      const unsigned int m = __ballot_sync(0xffffffffu, flag);
+      if (m) {
+        const int lane = tid & 31, leader = __ffs(m) - 1;
+        unsigned int basepos = 0;
+        if (lane == leader) basepos = atomicAdd(count_out, (unsigned int)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (flag) list_out[basepos + __popc(m & ((1u << lane) - 1u))] = vq[q];
+      }
+    }
+  }
+}
+
 // Early split levels (K <= 16): filter + per-cell statistics in ONE high-occupancy pass.  With a handful of
 // codevectors the work per vector is tiny, so the persistent one-CTA-per-SM kernel above and a separate
 // accumulate pass are both dominated by their fixed costs; here every thread takes one vector per iteration,
@@ -1492,6 +1652,35 @@ cudaError_t launch_assign(const AssignLaunch &a) {
                                                                         a.flag_count);
   g_launch_count++;
   return cudaGetLastError();
+}
+
+template <int DIM>
+static cudaError_t launch_refilter_t(const VecSource &src, const float *cb_rows, int K, float margin_coef, const float *c_max_ptr,
+                                     uint32_t *assign, const uint32_t *list_in, const unsigned int *count_in, uint32_t *list_out,
+                                     unsigned int *count_out, int sm_count, cudaStream_t stream) {
+  using Cfg = AssignCfg<DIM>;
+  const size_t row_bytes = (size_t)Cfg::ROW * 4, smem_cap = 200 * 1024;
+  int k_chunk = K;
+  if ((size_t)k_chunk * row_bytes > smem_cap) k_chunk = (int)(smem_cap / row_bytes) & ~7;
+  cudaError_t e = cudaFuncSetAttribute(refilter_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+  if (e != cudaSuccess) return e;
+  refilter_kernel<DIM><<<(unsigned int)sm_count, Cfg::THREADS, (size_t)k_chunk * row_bytes, stream>>>(
+      src, cb_rows, K, k_chunk, margin_coef, c_max_ptr, assign, list_in, count_in, list_out, count_out);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+
+// FP32 re-rank of the queries in list_in (see refilter_kernel).  K: staged rows (even).  Returns cudaErrorNotSupported
+// for dimensions without a template instance (the caller then feeds list_in straight to the resolver).
+cudaError_t launch_refilter(const VecSource &src, const float *cb_rows, int K, float margin_coef, const float *c_max_ptr,
+                            uint32_t *assign, const uint32_t *list_in, const unsigned int *count_in, uint32_t *list_out,
+                            unsigned int *count_out, int sm_count, cudaStream_t stream) {
+  switch (src.dim) {
+#define QB_RF(D) case D: return launch_refilter_t<D>(src, cb_rows, K, margin_coef, c_max_ptr, assign, list_in, count_in, list_out, count_out, sm_count, stream)
+    QB_RF(3); QB_RF(6); QB_RF(9); QB_RF(12); QB_RF(24); QB_RF(27); QB_RF(48);
+#undef QB_RF
+    default: return cudaErrorNotSupported;
+  }
 }
 
 // assign[v] = result[v] for every flagged query (see resolve_bruteforce_kernel)

@@ -33,6 +33,11 @@ cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_r
                                   float *rows32, unsigned char *tc_out, float *c_max, double *cb_t,
                                   cudaStream_t stream);
 cudaError_t launch_assign(const AssignLaunch &a);
+// FP32 middle tier of the tensor-core levels: exact top-2 re-rank of the queries in list_in against all K staged rows;
+// decided ones get their final index, the rest are appended to list_out (count_out must be zeroed).
+cudaError_t launch_refilter(const VecSource &src, const float *cb_rows, int K, float margin_coef, const float *c_max_ptr,
+                            uint32_t *assign, const uint32_t *list_in, const unsigned int *count_in, uint32_t *list_out,
+                            unsigned int *count_out, int sm_count, cudaStream_t stream);
 // Exact re-solve of the flagged queries: brute-force FP64 phase, then the reference's KD walk for
 // the (near-)exact ties it leaves in tie_list (capacity: n_local).  Counters are device words.
 cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, const double *cbt, int K,

@@ -58,19 +58,19 @@ static void fast_chain(const uint8_t *ts, unsigned int n, unsigned int C, double
   }
   // speculative runs, every window independently
   std::vector<SegRecord> rec(n_win);
-  for (unsigned int q = 0; q < n_win; q++) {
+  for (unsigned int q = h.q_start; q < n_win; q++) {
     SegRecord &r = rec[q];
-    const Anchor a = fx_anchor(acc, q * C, n, g_tab);
-    r.begin = a.b;
-    r.end = (q + 1 < n_win) ? fx_anchor(acc, (q + 1) * C, n, g_tab).b : n;
-    r.je = (signed char)(a.je < 0 ? 0 : a.je);
+    int je;
+    u128 before;
+    fx_segment_bounds(acc, g_tab, 0, n, C, q, n_win, h.q_start, h.pos_end, h.je, r.begin, r.end, je, before);
+    r.je = (signed char)je;
     r.top = (signed char)std::max(need[q], need[q + 1]);
-    r.Eb = (u128)(h.B + (i128)pref[q] + (i128)(((u128)a.xsum_hi << 64) | a.xsum_lo));
+    r.Eb = (u128)(h.B + (i128)pref[q] + (i128)before);
     r.ncls = 0;
-    if (q >= h.q_start && r.begin < r.end) fx_run_segment(acc, g_tab, r);
+    if (r.begin < r.end) fx_run_segment(acc, g_tab, r);
   }
-  // chaining
-  long long W = h.W0;
+  // chaining: the head's state is exact, so the first segment is entered with W = 0
+  long long W = 0;
   for (unsigned int q = h.q_start; q < n_win; q++) {
     if (rec[q].begin >= rec[q].end) continue;
     st.segments++;
