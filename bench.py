@@ -299,7 +299,7 @@ def run_gpu_arm(args):
     elif world > 1:
         join_peer_group(ctx)
     exact = args.exact or os.environ.get("QB200_EXACT_CENTROIDS") == "1"
-    ctx.set_exact_centroids(exact)
+    ctx.set_exact_centroids(1 if exact else ("auto" if args.centroids == "auto" else 0))
     if world > 1:
         ctx.set_rank(rank, world)
 
@@ -361,6 +361,7 @@ def run_gpu_arm(args):
     fp32_peak = ctx.measure_fp32_peak() if rank == 0 else None
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res, reps, launches, (t0, t1), cb_res, d_res = timed("resident", args.steps, args.warmup)
+    took_exact_res = bool(ctx.last_train_exact)
     ms_e2e, _, _, (t2, t3), cb_e2e, d_e2e = timed("e2e", args.steps, args.warmup)
     # clocks over both timed regions (a train lasts milliseconds: the e2e warm-up in between is under load as well)
     clocks = sampler.stop(t0, t3) if sampler else None
@@ -374,6 +375,7 @@ def run_gpu_arm(args):
         host_band.numpy()[:] = natural_band(bx, ys, rank * bx).reshape(-1)
         n_steps = min(args.steps, 3)
         ms_nr, reps_n, _, _, _, d_nat = timed("resident", n_steps, 3)
+        nat_exact = bool(ctx.last_train_exact)
         ms_ne, _, _, _, _, _ = timed("e2e", n_steps, 3)
         if rank == 0:
             ev = evals_per_train(n_total, nbits)
@@ -382,6 +384,8 @@ def run_gpu_arm(args):
                        "e2e": {"value": ev * n_steps / (ms_ne * 1e-3) / 1e9, "ms_per_step": ms_ne / n_steps}, "unit": UNIT,
                        "steps": n_steps, "distortion": d_nat,
                        "flagged_per_level": {str(r["K"]): int(r["flagged"]) for r in reps_n[-1]},
+                       "tie_sensitive_decisions": int(sum(r["sensitive"] for r in reps_n[-1])),
+                       "repeated_with_compensated_sums": nat_exact,
                        "kd_walk_ties_per_level": {str(r["K"]): int(r["ties"]) for r in reps_n[-1]},
                        "dead_cells_last_level": int(reps_n[-1][-1]["dead_cells"]),
                        "ms_resolve_per_train": float(np.mean([sum(r["ms_resolve"] for r in rep) for rep in reps_n]))}
@@ -404,6 +408,8 @@ def run_gpu_arm(args):
         per_level = {str(r["K"]): {k: round(float(np.mean([x[i][k] for x in reps])), 4)
                                    for k in ("ms_assign", "ms_resolve", "ms_accumulate")}
                      for i, r in enumerate(reps[0])}
+        sensitive_total = int(sum(r["sensitive"] for r in reps[-1]))
+        took_exact = took_exact_res
         flagged_last = int(last[-1]["flagged"])
         ties_last = int(last[-1]["ties"])
         flops = float(n_local) * K * 3.0 * dim            # algorithmic: sub, mul, add per dimension and evaluation
@@ -463,8 +469,12 @@ def run_gpu_arm(args):
                                             f"; weak scaling: {world} such bands, one per rank") if world > 1 else ""),
                        "block": [w, h], "nbits": nbits, "colorspace": "SCALED", "vectors_per_rank": n_local,
                        "schedule": "reference HEAD: one assignment pass per split level, no empty-cell repair",
-                       "centroids": ("exact: the reference's compensated FP64 member sums, executed in its order"
-                                     if exact else "from integer per-cell sums (<= 4e-16 relative of the reference's)"),
+                       "centroids": ("exact: the reference's compensated FP64 member sums (parallel bit-exact evaluation)" if exact else
+                                     ("auto (library default): integer per-cell sums; the timed trains had "
+                                      f"{sensitive_total} tie-sensitive decisions and "
+                                      + ("were repeated with the reference's compensated sums" if took_exact else
+                                         "needed no repeat: index-identical to the reference's by construction"))
+                                     if args.centroids == "auto" else "from integer per-cell sums (<= 4e-16 relative of the reference's)"),
                        "allreduce": (None if world == 1 else "NCCL via torch.distributed callback" if args.nccl else
                                      "libqb200 peer-memory all-reduce (qb200_comm.cu), CUDA IPC between the rank processes"),
                        "l2": "512 MiB flush (memset) before every timed step, outside the timed events"},
@@ -622,6 +632,9 @@ def main():
                          "peer-memory all-reduce")
     ap.add_argument("--no-cpp", action="store_true", help="skip the C++ CompressedImage::compress end-to-end leg")
     ap.add_argument("--no-natural", action="store_true", help="skip the natural-image leg")
+    ap.add_argument("--centroids", default="auto", choices=["auto", "integer"],
+                    help="auto (the library's default): integer-sum centroids, repeated with the reference's compensated sums "
+                         "when the train had tie-sensitive decisions; integer: integer sums only")
     ap.add_argument("--exact", action="store_true",
                     help="bit-exact centroid mode (qb200_set_exact_centroids): slower, identical to the reference on any input")
     ap.add_argument("--weak", action="store_true",

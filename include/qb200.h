@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QB200_VERSION 100 /* major*100 + minor */
+#define QB200_VERSION 200 /* major*100 + minor */
 
 /* Status codes (0 = success, negative = failure; qb200_last_error gives the text). */
 #define QB200_OK 0
@@ -82,6 +82,9 @@ typedef struct qb200_level_report {
                              `flagged` were still undecided and went to the FP64 resolver); 0 on the other levels */
   double distortion_pre;  /* updateDistortion() before fixCodeVectors (src/Quantizer.cpp:100) */
   double distortion_post; /* updateDistortion() after fixCodeVectors  (src/Quantizer.cpp:104) */
+  uint32_t sensitive;     /* of `flagged`: decisions with several codevectors within 2^-36 of the minimum (exact ties,
+                             tree-order ties) - the only ones the last bits of the codebook can change */
+  uint32_t reserved;
 } qb200_level_report;
 
 /* In-place sum all-reduce over `count` unsigned 64-bit integers at device address `dev_u64`.
@@ -119,18 +122,27 @@ int qb200_set_tensor_cores(qb200_ctx *ctx, int enable);
 int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                       size_t *total_mem);
 
-/* Bit-exact centroids (default 0 = off; the environment variable QB200_EXACT_CENTROIDS=1 turns it on for every
- * new context).  Off: a centroid is derived from the cell's integer sum, ((double)S_t / 255) / n, within 4e-16
- * relative of the reference's compensated FP64 sum (Solution::sumInArea, src/Quantizer.cpp:59-70) but not always
- * equal in the last bit; on inputs dominated by duplicated vectors (palettes, flat areas) that bit decides exact
- * ties of the next split level, so the final codebook and indices can differ from the reference's although every
- * assignment pass, given the same input codebook, is bit-identical.  On: the library runs the reference's
- * summation itself (stable sort by cell, then the same four FP64 operations per member in ascending vector
- * order), which makes the whole train bit-identical on any input at the cost of a latency-bound chain of
- * about 2 N dependent steps per train.  SCALED only (NORMAL sums are integers and always exact).  With an
- * all-reduce callback the ranks continue each other's chains: qb200_set_rank is required and rank order must
- * be vector order (rank r owns lower vector indices than rank r+1). */
-int qb200_set_exact_centroids(qb200_ctx *ctx, int enable);
+/* Centroid arithmetic of SCALED lattice vectors (NORMAL sums are integers and always exact; FP64 vectors always use
+ * the compensated sums).  The reference divides a COMPENSATED FP64 sum of the members, taken in ascending vector
+ * order (Solution::sumInArea / trainingSetSum, src/Quantizer.cpp:46-70), by their count.  Modes:
+ *   0  integer sums: centroid = ((double)S_t / 255) / n, within 4e-16 relative of the reference's but not always
+ *      equal in the last bit.  Every assignment pass is still bit-identical given the same codebook, but on inputs
+ *      with duplicated vectors (palettes, flat areas) that last bit can decide exact ties of the next split level.
+ *   1  the reference's sums themselves, evaluated in parallel (qb200_exact_fast.cuh: exact integer model of the
+ *      compensated loop, anchored segments, speculative residue classes, chained summaries): codebooks bit-identical
+ *      to the reference's on any input.
+ *   2  the same sums as one literal sequential chain per (cell, dimension) - same bits, ~2 N dependent steps per
+ *      train; kept for comparison.
+ *   3  AUTO (default): train with mode 0 while counting the decisions that hinged on (near-)ties of several
+ *      codevectors (qb200_level_report.sensitive).  If there were none on any rank the result is index-identical to
+ *      the reference's and is returned; otherwise the train is repeated with mode 1.  End-to-end identical to the
+ *      reference on every input, at the fast path's cost whenever the input allows it.
+ * The environment variable QB200_EXACT_CENTROIDS=0|1|2|auto sets the mode of every new context.  Sharded runs
+ * continue the chains from rank to rank: qb200_set_rank (or an attached group) is required and rank order must be
+ * vector order (rank r owns lower vector indices than rank r+1). */
+int qb200_set_exact_centroids(qb200_ctx *ctx, int mode);
+/* 1 when the last qb200_train on this context used (or, in auto mode, had to repeat itself with) the compensated sums. */
+int qb200_last_train_exact(const qb200_ctx *ctx);
 /* Seed of the empty-cell repair's member choice (default 0x5eed).  QB200_MODE_FULL_REPAIR only. */
 int qb200_set_seed(qb200_ctx *ctx, uint64_t seed);
 /* This context's rank among `world` contexts that train one sharded set together.  Needed by

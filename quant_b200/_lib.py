@@ -22,7 +22,8 @@ class LevelReport(C.Structure):
                 ("ties", C.c_uint32), ("dead_cells", C.c_uint32), ("kd_depth", C.c_uint32), ("iterations", C.c_uint32), ("repaired", C.c_uint32),
                 ("ms_assign", C.c_float),
                 ("ms_resolve", C.c_float), ("ms_accumulate", C.c_float), ("refiltered", C.c_uint32),
-                ("distortion_pre", C.c_double), ("distortion_post", C.c_double)]
+                ("distortion_pre", C.c_double), ("distortion_post", C.c_double),
+                ("sensitive", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)
@@ -39,6 +40,7 @@ SIGNATURES = {
     "qb200_last_error": (C.c_char_p, [C.c_void_p]),
     "qb200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qb200_set_exact_centroids": (C.c_int, [C.c_void_p, C.c_int]),
+    "qb200_last_train_exact": (C.c_int, [C.c_void_p]),
     "qb200_get_assign_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "qb200_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "qb200_set_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -131,9 +131,14 @@ class Context:
     # -- hot path ---------------------------------------------------------------------------
     def set_exact_centroids(self, enable):
         """Bit-exact centroids: run the reference's compensated member sums (src/Quantizer.cpp:59-70) instead of
-        deriving the centroid from integer sums; see include/qb200.h.  False/0 off, True/1 on (parallel evaluation),
-        2 on with the literal sequential chain (same bits; for comparison)."""
-        self._check(self.lib.qb200_set_exact_centroids(self.h, int(enable)))
+        deriving the centroid from integer sums; see include/qb200.h.  False/0 integer sums, True/1 compensated sums
+        (parallel evaluation), 2 the same as a literal sequential chain (for comparison), 3 or "auto" (the default):
+        integer sums unless the train had tie-sensitive decisions, then repeated with the compensated sums."""
+        self._check(self.lib.qb200_set_exact_centroids(self.h, 3 if enable == "auto" else int(enable)))
+
+    @property
+    def last_train_exact(self) -> bool:
+        return bool(self.lib.qb200_last_train_exact(self.h))
 
     def comm_export(self, max_words: int = 0) -> bytes:
         """This context's all-reduce exchange block as a CUDA IPC handle (64 bytes) - see qb200_comm_export."""

@@ -76,6 +76,8 @@ struct qb200_ctx {
   DevBuf d_repair;
   // bit-exact centroid sums (qb200_set_exact_centroids; qb200_exact.cu)
   bool exact = false;
+  bool exact_auto = true;         // qb200_set_exact_centroids(ctx, 3), the default: exact sums only when a train needed them
+  int last_train_exact = 0;       // 1: the last qb200_train ran (or re-ran) with the compensated member sums
   bool exact_sequential = false;  // qb200_set_exact_centroids(ctx, 2): the literal sequential chain instead of its parallel evaluation
   DevBuf d_exact, d_sort_keys, d_sort_iota, d_sort_order, d_sort_tmp, d_fx;
   size_t iota_n = 0;
@@ -163,7 +165,7 @@ void free_buf(DevBuf &b) {
 // ---- level machinery --------------------------------------------------------------------------
 
 struct LevelOut {
-  unsigned int flagged = 0, changed = 0, ties = 0, refiltered = 0;
+  unsigned int flagged = 0, changed = 0, ties = 0, refiltered = 0, sensitive = 0;
   int kd_depth = 0;
   float ms_assign = 0, ms_resolve = 0, ms_accumulate = 0;
 };
@@ -268,7 +270,8 @@ int level_begin(qb200_ctx *ctx, const double *cb_host, const double *cb_dev, uin
     CU(cudaMemcpyAsync(ctx->d_cb64.p, h_cb, cb_bytes, cudaMemcpyHostToDevice, st));
   }
   CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
-  // [0] flagged (-> FP64 resolver), [1] changed, [2] ties, [3] undecided by the tensor-core filter (-> FP32 re-rank), [4] max|C| (float)
+  // [0] flagged (-> FP64 resolver), [1] changed, [2] ties, [3] undecided by the tensor-core filter (-> FP32 re-rank), [4] max|C| (float),
+  // [5] decisions that hinged on (near-)ties of several codevectors (last-bit sensitive)
   unsigned int *cnt = (unsigned int *)ctx->d_counters.p;
   const float *c_max_ptr = reinterpret_cast<const float *>(cnt + 4);
   if (L.use_tc && (rc = ensure(ctx, ctx->d_rows_tc, L.tc_bytes))) return rc;
@@ -391,7 +394,7 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
   CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p,
                     (const double *)ctx->d_cb64.p + (size_t)K * dim, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
-                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, result, ctx->sm_count, st));
+                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, result, cnt + 5, ctx->sm_count, st));
   if (ctx->side_pending) {
     CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU(launch_commit_resolved((const uint32_t *)ctx->d_flags.p, cnt, result, (uint32_t *)ctx->d_assign.p, ctx->sm_count, st));
@@ -403,7 +406,7 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
                          ctx->sm_count, st));
   }
   if (ev3) CU(cudaEventRecord(ev3, st));
-  CU(cudaMemcpyAsync(counters_dst, ctx->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(counters_dst, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost, st));
   ctx->assign_valid = true;
   ctx->assign_K = K;
   if (kd_depth_out) *kd_depth_out = tree.depth;
@@ -432,6 +435,7 @@ int collect_level(qb200_ctx *ctx, uint32_t K, bool timed, LevelOut *out) {
   out->changed = c[1];
   out->ties = c[2];
   out->refiltered = c[3];
+  out->sensitive = c[5];
   if (timed) {
     CU(cudaEventElapsedTime(&out->ms_assign, ctx->ev[0], ctx->ev[1]));
     CU(cudaEventElapsedTime(&out->ms_resolve, ctx->ev[1], ctx->ev[2]));
@@ -724,7 +728,11 @@ int qb200_create(int device, qb200_ctx **out) {
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
   for (auto &ev : ctx->ev_side) cudaEventCreate(&ev);
-  if (const char *ex = std::getenv("QB200_EXACT_CENTROIDS")) ctx->exact = ex[0] == '1';
+  if (const char *ex = std::getenv("QB200_EXACT_CENTROIDS")) {  // 0 never | 1 always | 2 always, sequential chain | 3 or auto (default)
+    ctx->exact = ex[0] == '1' || ex[0] == '2';
+    ctx->exact_sequential = ex[0] == '2';
+    ctx->exact_auto = ex[0] == '3' || ex[0] == 'a';
+  }
   *out = ctx;
   return QB200_OK;
 }
@@ -888,8 +896,10 @@ int qb200_set_tensor_cores(qb200_ctx *ctx, int enable) {
 int qb200_set_exact_centroids(qb200_ctx *ctx, int enable) {
   if (!ctx) return QB200_ERR_ARG;
   for (qb200_ctx *s2 : ctx->subs) qb200_set_exact_centroids(s2, enable);
-  ctx->exact = enable != 0;
+  if (enable < 0 || enable > 3) return fail(ctx, QB200_ERR_ARG, "qb200_set_exact_centroids: mode %d outside [0,3]", enable);
+  ctx->exact = enable == 1 || enable == 2;
   ctx->exact_sequential = enable == 2;
+  ctx->exact_auto = enable == 3;
   return QB200_OK;
 }
 
@@ -1403,6 +1413,8 @@ int train_generic(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t N, q
       r.changed = lo.changed;
       r.ties = lo.ties;
       r.refiltered = lo.refiltered;
+      r.sensitive = lo.sensitive;
+      r.reserved = 0;
       r.kd_depth = (uint32_t)lo.kd_depth;
       r.iterations = iterations;
       r.repaired = 0;
@@ -1428,7 +1440,7 @@ int train_generic(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t N, q
 }
 
 struct PipeSlot {  // pinned, one per split level
-  unsigned int counters[4];
+  unsigned int counters[8];
   double dist_pre, dist_post;
   unsigned int dead_cells, pad;
   unsigned long long n_seen;
@@ -1563,6 +1575,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
       r.changed = s.counters[1];
       r.ties = s.counters[2];
       r.refiltered = s.counters[3];
+      r.sensitive = s.counters[5];
+      r.reserved = 0;
       r.dead_cells = s.dead_cells;
       r.kd_depth = (uint32_t)depth[level];
       r.iterations = 1;
@@ -1647,8 +1661,39 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
     if (mode == QB200_MODE_FULL_REPAIR) return fail(ctx, QB200_ERR_ARG, "qb200_train: QB200_MODE_FULL_REPAIR is not available for FP64 vectors");
     return train_generic(ctx, nbits, eps, mode, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);
   }
-  if (mode == QB200_MODE_PARITY && pipeline_enabled())
-    return train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);
+  if (mode == QB200_MODE_PARITY && pipeline_enabled()) {
+    // Auto mode (default): centroids from the integer sums first.  They can only change an index where a decision
+    // hinged on (near-)ties of several codevectors - the resolver counts those.  None anywhere (all ranks): the train
+    // is index-identical to the reference's, done.  Otherwise the train is repeated with the reference's compensated
+    // member sums, which makes it bit-identical on any input.
+    const bool lattice_scaled = ctx->colorspace == QB200_CS_SCALED;
+    const bool try_fast = ctx->exact_auto && !ctx->exact && lattice_scaled && nbits > 0;
+    ctx->last_train_exact = ctx->exact && lattice_scaled ? 1 : 0;
+    std::vector<qb200_level_report> own;
+    qb200_level_report *rep = reports;
+    if (try_fast && !rep) {
+      own.resize((size_t)nbits);
+      rep = own.data();
+    }
+    int rc = train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, rep);
+    if (rc || !try_fast) return rc;
+    unsigned long long sensitive = 0;
+    for (int l = 0; l < nbits; l++) sensitive += rep[l].sensitive;
+    if (allreduce) {  // the ranks must take the same decision
+      if ((rc = ensure(ctx, ctx->d_misc, 256))) return rc;
+      CU(cudaMemcpyAsync(ctx->d_misc.p, &sensitive, 8, cudaMemcpyHostToDevice, ctx->stream));
+      if (allreduce(ctx->d_misc.p, 1, (void *)ctx->stream, allreduce_user) != 0)
+        return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (tie census)");
+      CU(cudaMemcpyAsync(&sensitive, ctx->d_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (sensitive == 0) return QB200_OK;
+    ctx->exact = true;
+    ctx->last_train_exact = 1;
+    rc = train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);
+    ctx->exact = false;
+    return rc;
+  }
   const int dim = ctx->src.dim;
   const uint32_t maxK = 1u << nbits;
   std::vector<double> cb((size_t)maxK * dim), post((size_t)maxK * dim);
@@ -1712,6 +1757,8 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
       r.changed = lo.changed;
       r.ties = lo.ties;
       r.refiltered = lo.refiltered;
+      r.sensitive = lo.sensitive;
+      r.reserved = 0;
       r.kd_depth = (uint32_t)lo.kd_depth;
       r.iterations = iterations;
       r.repaired = repaired_total;
@@ -1958,6 +2005,12 @@ int qb200_debug_filter_records(qb200_ctx *ctx, float *records_out) {
   CU(cudaMemcpyAsync(records_out, ctx->d_state.p, (size_t)ctx->src.n_local * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return QB200_OK;
+}
+
+int qb200_last_train_exact(const qb200_ctx *ctx) {
+  if (!ctx) return 0;
+  if (ctx->is_multi) return ctx->subs[0]->last_train_exact;
+  return ctx->last_train_exact;
 }
 
 int qb200_launch_count(int reset) {

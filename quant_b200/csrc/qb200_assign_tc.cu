@@ -48,7 +48,7 @@ namespace {
 constexpr int kProdGroups = 1;          // producer groups of 4 warps taking alternate tiles (2 measured slower: register cap)
 // MMA + producer + merger + epilogue warps; the epilogue has S warps per TMEM lane quarter, each scanning 1/S of the columns
 constexpr int tc_threads(int S) { return 32 * (1 + 4 * kProdGroups + 4 + 4 * S); }
-constexpr int kMaxSplit = 4;
+
 constexpr int kAStages = 4;            // A tiles in flight (shared memory ring)
 constexpr int kResStages = 4;          // per-tile result records in flight
 // Bit 31 of a provisional index: the query is on the flag list.  The exact resolver always rewrites such entries;
@@ -65,13 +65,14 @@ struct TcCfg {
   static constexpr int ROW32 = ((DIM + 1 + 3) / 4) * 4;
 };
 
+template <int S>
 struct TcShared {
   uint64_t b_full, a_full[kAStages], a_empty[kAStages], tmem_full[2], tmem_empty[2], res_full[kResStages],
       res_empty[kResStages];
   uint32_t tmem_base;
   uint32_t pad;
-  float res_best[kResStages][kMaxSplit][kTileQ], res_second[kResStages][kMaxSplit][kTileQ];
-  int res_chunk[kResStages][kMaxSplit][kTileQ];
+  float res_best[kResStages][S][kTileQ], res_second[kResStages][S][kTileQ];
+  int res_chunk[kResStages][S][kTileQ];
 };
 
 // minimum of eight scores merged into the running (best, runner-up) over CHUNK MINIMA; `chunk` remembers which group
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(tc_threads(S), 1)
   const uint32_t b_bytes = (uint32_t)k_rows * Cfg::ROW_BYTES;
   unsigned char *s_b = smem_raw;
   unsigned char *s_a = smem_raw + ((b_bytes + 1023u) & ~1023u);
-  TcShared &sh = *reinterpret_cast<TcShared *>(s_a + kAStages * Cfg::A_BYTES);
+  TcShared<S> &sh = *reinterpret_cast<TcShared<S> *>(s_a + kAStages * Cfg::A_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = k_rows / kTileN;  // N tiles per query tile (the host pads the codebook to a multiple)
@@ -553,7 +554,8 @@ int tc_n_tile(int K) { (void)K; return kTileN; }
 // Rows per launch: what fits in shared memory next to the two A tiles, a multiple of the N tile.
 int tc_chunk_rows(int dim, int K) {
   const int kp = tc_padded_rows(K), nt = tc_n_tile(K);
-  const size_t budget = 208 * 1024 - kAStages * (size_t)tc_kblocks(dim) * 4096;
+  // 227 KB per CTA: B chunk + A ring + barriers/result ring (sizeof(TcShared<2>), 12 KB) + alignment slack
+  const size_t budget = 227 * 1024 - sizeof(TcShared<2>) - 2048 - kAStages * (size_t)tc_kblocks(dim) * 4096;
   int rows = (int)(budget / tc_row_bytes(dim));
   rows = (rows / nt) * nt;
   return rows < kp ? rows : kp;
@@ -565,16 +567,13 @@ static cudaError_t launch_tc_t(const AssignTcLaunch &a) {
   const int kp = tc_padded_rows(a.K), chunk = tc_chunk_rows(DIM, a.K);
   const unsigned long long tiles = (a.src.n_local + kTileQ - 1) / kTileQ;
   if (tiles == 0) return cudaSuccess;
-  const size_t smem_max = (((size_t)chunk * Cfg::ROW_BYTES + 1023) & ~(size_t)1023) + kAStages * Cfg::A_BYTES + sizeof(TcShared) + 1024;
-  // epilogue warps per TMEM lane quarter: 2 (each scans 128 columns in pieces of 32) or 4 (64 columns in pieces of 16:
-  // more warps to cover the tcgen05.ld latency, fewer registers each); QB200_TC_SPLIT overrides
-  static const int split = [] {
-    const char *e = std::getenv("QB200_TC_SPLIT");
-    const int v = e ? std::atoi(e) : 0;
-    return v == 2 || v == 4 ? v : 2;
-  }();
-  auto kernel = split == 4 ? assign_tc_kernel<DIM, 4> : assign_tc_kernel<DIM, 2>;
-  const int threads = split == 4 ? tc_threads(4) : tc_threads(2);
+  // Two epilogue warps per TMEM lane quarter (each scans 128 columns in pieces of 32).  Four (64 columns in pieces of
+  // 16) were measured as well: 0.675 against 0.686 ms at K = 1024 on config 2 - the epilogue is bound by the alu pipe,
+  // not by tcgen05.ld latency - and their larger result ring costs a third pass at K = 4096, so two it is.
+  constexpr int kSplit = 2;
+  const size_t smem_max = (((size_t)chunk * Cfg::ROW_BYTES + 1023) & ~(size_t)1023) + kAStages * Cfg::A_BYTES + sizeof(TcShared<kSplit>) + 1024;
+  auto kernel = assign_tc_kernel<DIM, kSplit>;
+  const int threads = tc_threads(kSplit);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return e;
   const unsigned int grid = (unsigned int)(tiles < (unsigned long long)a.sm_count ? tiles : a.sm_count);

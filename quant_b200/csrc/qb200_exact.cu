@@ -442,19 +442,37 @@ __global__ void __launch_bounds__(kFxRunThreads) fx_runs_kernel(const FxGeom g, 
     r.Eb = (u128)(w.B[chain] + (i128)w.sumX[idx] + (i128)before);
     r.ncls = 0;
     r.pad = 0;
-    if (r.begin < r.end) fx::fx_run_segment(acc, tab, r);
+    r.xs_low = 0;
+    r.pad2 = 0;
+    if (r.begin < r.end) fx::fx_run_segment_multi(acc, tab, r);
     w.rec[idx] = r;
   }
 }
 
-// Chaining: one WARP per chain.  The lanes copy 32 records at a time into shared memory (coalesced), lane 0 applies
-// them in order (W = A - E is the only carried value); a segment whose summary does not cover W is staged into
-// shared memory by the whole warp and re-run by lane 0 from the exact state.
+// Chaining: one WARP per chain, 32 segments at a time, one record per lane.  Where the batch allows it every lane
+// turns its record into a 4-state map and the warp composes them with a parallel prefix (fx_compose, five shuffle
+// rounds) instead of 32 dependent steps; the first segment whose validity interval does not contain W (or that is
+// marked sequential) is re-run exactly - the warp stages its members in shared memory, one lane steps through them -
+// and the prefix is redone behind it.  Batches whose class bits do not fit two adjacent positions are applied one
+// record after the other (fx_apply).
 constexpr int kFxChainWarps = 4;
+
+__device__ __forceinline__ fx::Map4 fx_map_shfl_up(const fx::Map4 &m, int o) {
+  fx::Map4 r;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    r.s[i] = __shfl_up_sync(0xffffffffu, m.s[i], o);
+    r.dW[i] = __shfl_up_sync(0xffffffffu, m.dW[i], o);
+    r.lo[i] = __shfl_up_sync(0xffffffffu, m.lo[i], o);
+    r.hi[i] = __shfl_up_sync(0xffffffffu, m.hi[i], o);
+  }
+  return r;
+}
+__device__ __forceinline__ int fx_pick(const int (&v)[4], int s) { return s == 0 ? v[0] : s == 1 ? v[1] : s == 2 ? v[2] : v[3]; }
+
 __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGeom g, FxWork w, double *__restrict__ state) {
   __shared__ fx::Tables tab;
-  __shared__ __align__(16) fx::SegRecord s_rec[kFxChainWarps][2][32];
-  __shared__ unsigned char s_seg[kFxChainWarps][1024 + fx::kFxAnchorWin];
+  __shared__ unsigned char s_seg[kFxChainWarps][256 + fx::kFxAnchorWin];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -466,57 +484,105 @@ __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGe
   const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
   const fx::SegRecord *rec = w.rec + fx_index(w, g.dim, k, e, 0);
   const FxAcc src{g.dense, g.order, g.stride, e};
-  static_assert(sizeof(fx::SegRecord) % 16 == 0, "records are copied as 16-byte words");
-  constexpr int kWords = (int)(sizeof(fx::SegRecord) / 16);
-  auto fetch = [&](unsigned int q0, int slot) {  // records q0 .. q0 + 31 -> s_rec[warp][slot]
-    const unsigned int n = cnt - q0 < 32u ? cnt - q0 : 32u;
-    const uint4 *srcw = reinterpret_cast<const uint4 *>(rec + q0);
-    uint4 *dst = reinterpret_cast<uint4 *>(&s_rec[warp][slot][0]);
-    for (unsigned int i = lane; i < n * kWords; i += 32) dst[i] = srcw[i];
-  };
-  long long W = 0;  // the head's state is exact: the first segment is entered with W = 0
-  int slot = 0;
-  if (qs < cnt) fetch(qs, 0);
-  __syncwarp();
-  for (unsigned int q0 = qs; q0 < cnt; q0 += 32, slot ^= 1) {
-    if (q0 + 32 < cnt) fetch(q0 + 32, slot ^ 1);  // next batch while lane 0 walks this one
-    const unsigned int n = cnt - q0 < 32u ? cnt - q0 : 32u;
-    unsigned int j = 0;
-    while (j < n) {
-      // lane 0 applies summaries until one does not cover W
-      int stop = 0;
+  long long W = 0;  // the head's state is exact: the first segment is entered with W = 0 (all lanes carry W)
+
+  // exact re-run of lane f's segment from the true state Eb + W; every lane returns the new W
+  auto rerun = [&](const fx::SegRecord &mine, int f) {
+    const unsigned int b = __shfl_sync(0xffffffffu, mine.begin, f), en = __shfl_sync(0xffffffffu, mine.end, f);
+    const unsigned long long e_lo = __shfl_sync(0xffffffffu, (unsigned long long)mine.Eb, f);
+    const unsigned long long e_hi = __shfl_sync(0xffffffffu, (unsigned long long)(mine.Eb >> 64), f);
+    const u128 Eb = ((u128)e_hi << 64) | e_lo;
+    const unsigned int len = en - b;
+    long long Wn = W;
+    if (len <= sizeof(s_seg[0])) {
+      for (unsigned int i = lane; i < len; i += 32) s_seg[warp][i] = (unsigned char)src(b + i);
+      __syncwarp();
       if (lane == 0) {
-        for (; j < n; j++)
-          if (!fx::fx_apply(s_rec[warp][slot][j], W)) {
-            stop = 1;
-            break;
-          }
-      }
-      stop = __shfl_sync(0xffffffffu, stop, 0);
-      j = __shfl_sync(0xffffffffu, j, 0);
-      if (!stop) break;
-      // exact re-run of segment j: the warp stages its members, lane 0 steps through them
-      const fx::SegRecord &r = s_rec[warp][slot][j];
-      const unsigned int len = r.end - r.begin;
-      if (len <= sizeof(s_seg[0])) {
-        for (unsigned int i = lane; i < len; i += 32) s_seg[warp][i] = (unsigned char)src(r.begin + i);
-        __syncwarp();
-        if (lane == 0) {
-          u128 a = (u128)((i128)r.Eb + W), xs = 0;
-          for (unsigned int i = 0; i < len; i++) {
-            const int t = s_seg[warp][i];
-            xs += tab.X[t];
-            a = fx::fx_step(a, t, tab);
-          }
-          W = (long long)((i128)a - (i128)(r.Eb + xs));
+        u128 a = (u128)((i128)Eb + W), xs = 0;
+        for (unsigned int i = 0; i < len; i++) {
+          const int t = s_seg[warp][i];
+          xs += tab.X[t];
+          a = fx::fx_step(a, t, tab);
         }
-        __syncwarp();
-      } else if (lane == 0) {
-        fx::fx_rerun(src, tab, r, W);
+        Wn = (long long)((i128)a - (i128)(Eb + xs));
       }
-      j++;
+      __syncwarp();
+    } else if (lane == 0) {
+      u128 a = (u128)((i128)Eb + W), xs = 0;
+      for (unsigned int p = b; p < en; p++) {
+        const int t = src(p);
+        xs += tab.X[t];
+        a = fx::fx_step(a, t, tab);
+      }
+      Wn = (long long)((i128)a - (i128)(Eb + xs));
     }
-    __syncwarp();
+    W = __shfl_sync(0xffffffffu, Wn, 0);
+  };
+
+  fx::SegRecord r;
+  auto load = [&](unsigned int q0) {
+    const unsigned int q = q0 + lane;
+    if (q < cnt) {
+      r = rec[q];
+    } else {
+      r.begin = r.end = 0;
+      r.ncls = 1;
+      r.je = 0;
+      r.top = -1;
+      r.Eb = 0;
+    }
+  };
+  for (unsigned int q0 = qs; q0 < cnt; q0 += 32) {
+    load(q0);
+    const bool live = r.begin < r.end, usable = live && r.ncls != 0;
+    const unsigned int live_mask = __ballot_sync(0xffffffffu, live);
+    if (!live_mask) continue;
+    const int je_min = __reduce_min_sync(0xffffffffu, usable ? (int)r.je : 99);
+    const int top_max = __reduce_max_sync(0xffffffffu, usable ? (int)r.top : -1);
+    int jb = 0;
+    const bool composable = je_min != 99 && fx::fx_batch_composable(je_min, 0, top_max, jb) && W < fx::kFxWLimit / 2 && W > -fx::kFxWLimit / 2;
+    if (!composable) {  // one record after the other
+      unsigned int todo = live_mask;
+      while (todo) {
+        const int f = __ffs(todo) - 1;
+        todo &= todo - 1;
+        long long Wn = W;
+        int ok = 1;
+        if (lane == f) ok = fx::fx_apply(r, Wn) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, f);
+        if (ok)
+          W = __shfl_sync(0xffffffffu, Wn, f);
+        else
+          rerun(r, f);
+      }
+      continue;
+    }
+    const fx::Map4 mine = fx::fx_map_of(r, jb);  // identity for empty records
+    const unsigned int e16 = (unsigned int)((unsigned long long)r.Eb & 0xffffu);
+    int j0 = 0;
+    while (true) {
+      const unsigned int rest = live_mask & (j0 >= 32 ? 0u : (0xffffffffu << j0));
+      if (!rest) break;
+      const int jl = __ffs(rest) - 1;  // first live record at or behind j0: its E gives the entry state
+      const int s0 = (int)((((long long)__shfl_sync(0xffffffffu, e16, jl) + W) >> jb) & 3);
+      fx::Map4 pm = lane >= j0 ? mine : fx::fx_map_identity();
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const fx::Map4 left = fx_map_shfl_up(pm, o);
+        if (lane >= o) pm = fx::fx_compose(left, pm);
+      }
+      const int lo = fx_pick(pm.lo, s0), hi = fx_pick(pm.hi, s0), dW = fx_pick(pm.dW, s0);
+      const bool valid = lo <= hi && W >= lo && W <= hi;
+      const unsigned int bad = __ballot_sync(0xffffffffu, !valid) & (j0 >= 32 ? 0u : (0xffffffffu << j0));
+      if (!bad) {
+        W += __shfl_sync(0xffffffffu, dW, 31);
+        break;
+      }
+      const int f = __ffs(bad) - 1;  // records j0 .. f-1 are covered; f is re-run exactly
+      if (f > j0) W += __shfl_sync(0xffffffffu, dW, f - 1);
+      if ((live_mask >> f) & 1u) rerun(r, f);
+      j0 = f + 1;
+    }
   }
   if (lane == 0) {
     const u128 A = (u128)(w.B[chain] + (i128)w.total[chain] + (i128)W);

@@ -44,6 +44,11 @@
 #else
 #define QB_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define QB_UNROLL _Pragma("unroll")
+#else
+#define QB_UNROLL
+#endif
 
 namespace qb {
 namespace fx {
@@ -234,6 +239,8 @@ struct SegRecord {
   signed char je, top;            // entry trailing zeros (>= 0) and highest bit looked at (-1: nothing but zeros)
   signed char ncls;               // 1..kFxMaxCls, or 0: run sequentially
   signed char pad;
+  unsigned short xs_low;          // (sum of X over the segment) mod 2^16
+  unsigned short pad2;
 };
 
 // centred representative of v modulo m (a power of two): in (-m/2, m/2]
@@ -295,6 +302,161 @@ QB_HD bool fx_apply(const SegRecord &rec, long long &W) {
   W += rec.dcorr[cls];
   return true;
 }
+// The same speculative runs, all classes in ONE pass over the members.  Steps with t < 255 look at the low bits of
+// the state only, so per class it is enough to carry the state modulo 2^16 and the accumulated rounding
+// correction; the addend's table lookup, level and the (128-bit) sum of X are shared by the classes.  A t = 255
+// step (binade edge, rare) rebuilds the full state of every class and takes the general step.
+template <typename Acc>
+QB_HD void fx_run_segment_multi(const Acc &acc, const Tables &tab, SegRecord &rec) {
+  const int je = rec.je;
+  const long long mod = fx_class_mod(je, rec.top);
+  if ((mod >> je) > kFxMaxCls) {
+    rec.ncls = 0;
+    return;
+  }
+  const int ncls = (int)(mod >> je);
+  rec.ncls = (signed char)ncls;
+  const long long e_low = (long long)((unsigned long long)rec.Eb & (unsigned long long)(mod - 1));
+  unsigned int lo16[kFxMaxCls];       // state mod 2^16
+  long long cc[kFxMaxCls];            // start offset of the class relative to E
+  int corr[kFxMaxCls];                // accumulated rounding corrections
+  unsigned long long mg[kFxMaxCls];
+QB_UNROLL
+  for (int cls = 0; cls < kFxMaxCls; cls++) {
+    cc[cls] = cls < ncls ? fx_centered(((long long)cls << je) - e_low, mod) : 0;
+    lo16[cls] = (unsigned int)((unsigned long long)((i128)rec.Eb + cc[cls])) & 0xffffu;
+    corr[cls] = 0;
+    mg[cls] = 0xffffffffffffffffull;
+  }
+  u128 xs = 0;
+  for (unsigned int p = rec.begin; p < rec.end; p++) {
+    const int t = acc(p);
+    if (t == 0) continue;
+    const unsigned long long X = tab.X[t];
+    if (t < 255) {
+      const int lev = fx_lev(t);
+      const unsigned int u = 1u << lev, xl = (unsigned int)X & 0xffffu;
+QB_UNROLL
+      for (int cls = 0; cls < kFxMaxCls; cls++) {
+        if (cls < ncls) {
+          const unsigned int a = lo16[cls], r = a & (u - 1);
+          const bool up = 2 * r > u || (2 * r == u && ((((unsigned int)(X >> lev)) ^ (a >> lev)) & 1u));
+          const int d = (int)(up ? u : 0u) - (int)r;
+          corr[cls] += d;
+          lo16[cls] = (a + xl + (unsigned int)d) & 0xffffu;
+        }
+      }
+    } else {
+QB_UNROLL
+      for (int cls = 0; cls < kFxMaxCls; cls++) {
+        if (cls < ncls) {
+          const u128 a = (u128)((i128)rec.Eb + cc[cls] + (i128)xs + (i128)corr[cls]);
+          const unsigned long long dm = fx_decision_margin(a);
+          if (dm < mg[cls]) mg[cls] = dm;
+          const u128 a2 = fx_step(a, 255, tab);
+          corr[cls] += (int)(long long)((i128)(a2 - a) - (i128)X);
+          lo16[cls] = (unsigned int)(unsigned long long)a2 & 0xffffu;
+        }
+      }
+    }
+    xs += X;
+  }
+  rec.xs_low = (unsigned short)((unsigned long long)xs & 0xffffu);
+QB_UNROLL
+  for (int cls = 0; cls < kFxMaxCls; cls++) {
+    if (cls < ncls) {
+      rec.dcorr[cls] = corr[cls];
+      rec.margin[cls] = mg[cls] == 0xffffffffffffffffull ? 0xffffffffu : (mg[cls] > 0xfffffffeull ? 0xfffffffeu : (unsigned int)mg[cls]);
+    }
+  }
+}
+
+// ---- chaining 32 segments at a time -----------------------------------------------------------------------
+// When the class bits of a batch of consecutive segments all lie in two adjacent bit positions [jb, jb + 1] (noise
+// and natural images: jb = 7, the bits an addend t >= 128 or t = 255 looks at), every segment is a map on the FOUR
+// states s = (A >> jb) & 3 of the true state A at its first member:
+//     s -> (state after the segment, dW = its rounding corrections, [lo, hi] = the entry W it is valid for).
+// Maps compose associatively, so a warp combines 32 of them with a parallel prefix (fx_compose) instead of 32
+// dependent steps.  An empty interval means "cannot happen / must be run exactly".
+struct Map4 {
+  int s[4], dW[4], lo[4], hi[4];
+};
+constexpr int kFxWLimit = 1 << 29;  // |W| beyond this is handled by the sequential path (32-bit intervals)
+
+QB_HD Map4 fx_map_identity() {
+  Map4 m;
+  for (int i = 0; i < 4; i++) {
+    m.s[i] = i;
+    m.dW[i] = 0;
+    m.lo[i] = -kFxWLimit;
+    m.hi[i] = kFxWLimit;
+  }
+  return m;
+}
+// Map of one segment for batch bit position jb; requires rec.je >= jb and max(rec.top, rec.je - 1) <= jb + 1.
+QB_HD Map4 fx_map_of(const SegRecord &rec, int jb) {
+  if (rec.begin >= rec.end) return fx_map_identity();
+  Map4 m;
+  const long long mod = fx_class_mod(rec.je, rec.top);
+  const long long e_low = (long long)((unsigned long long)rec.Eb & (unsigned long long)(mod - 1));
+  for (int s = 0; s < 4; s++) {
+    const long long a_low = (long long)s << jb;          // the true state modulo 2^(jb + 2)
+    m.s[s] = s;
+    m.dW[s] = 0;
+    m.lo[s] = 1;                                         // empty until proven usable
+    m.hi[s] = 0;
+    if (rec.ncls == 0 || (a_low & ((1ll << rec.je) - 1)) != 0) continue;  // sequential segment / impossible entry state
+    const int cls = (int)((a_low & (mod - 1)) >> rec.je);
+    const long long cc = fx_centered(((long long)cls << rec.je) - e_low, mod);
+    const unsigned int mgn = rec.margin[cls];
+    long long lo, hi;
+    if (mgn == 0xffffffffu) {
+      lo = -kFxWLimit;
+      hi = kFxWLimit;
+    } else {
+      const long long rad = mgn > 0 ? (long long)mgn - 1 : 0;  // |W - cc| < margin, or W == cc
+      lo = cc - rad;
+      hi = cc + rad;
+      if (lo < -kFxWLimit) lo = -kFxWLimit;
+      if (hi > kFxWLimit) hi = kFxWLimit;
+    }
+    m.lo[s] = (int)lo;
+    m.hi[s] = (int)hi;
+    m.dW[s] = rec.dcorr[cls];
+    m.s[s] = (int)(((a_low + (long long)rec.xs_low + (long long)rec.dcorr[cls]) >> jb) & 3);
+  }
+  return m;
+}
+// f first, then g
+QB_HD Map4 fx_compose(const Map4 &f, const Map4 &g) {
+  Map4 h;
+  for (int s = 0; s < 4; s++) {
+    const int mid = f.s[s];
+    h.s[s] = g.s[mid];
+    const long long dW = (long long)f.dW[s] + g.dW[mid];
+    long long lo = (long long)g.lo[mid] - f.dW[s], hi = (long long)g.hi[mid] - f.dW[s];
+    if (f.lo[s] > lo) lo = f.lo[s];
+    if (f.hi[s] < hi) hi = f.hi[s];
+    if (f.lo[s] > f.hi[s] || g.lo[mid] > g.hi[mid] || dW > kFxWLimit || dW < -kFxWLimit) {  // keep emptiness
+      lo = 1;
+      hi = 0;
+    }
+    if (lo < -kFxWLimit) lo = -kFxWLimit;
+    if (hi > kFxWLimit) hi = kFxWLimit;
+    h.dW[s] = (int)(dW > kFxWLimit ? kFxWLimit : (dW < -kFxWLimit ? -kFxWLimit : dW));
+    h.lo[s] = (int)lo;
+    h.hi[s] = (int)hi;
+  }
+  return h;
+}
+// Can a batch with these extremes (over its non-empty, non-sequential segments) be chained through 4-state maps?
+QB_HD bool fx_batch_composable(int je_min, int je_max_unused, int top_max, int &jb) {
+  (void)je_max_unused;
+  jb = je_min;
+  const int hi_bit = top_max > je_min ? top_max : je_min;  // highest class bit of any segment
+  return hi_bit <= jb + 1;
+}
+
 template <typename Acc>
 QB_HD void fx_rerun(const Acc &acc, const Tables &tab, const SegRecord &rec, long long &W) {
   u128 a = (u128)((i128)rec.Eb + W), xs = 0;

@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(128)
                               const unsigned int *__restrict__ flag_count, uint32_t *__restrict__ assign,
                               uint32_t *__restrict__ tie_list, unsigned int *__restrict__ tie_count,
                               unsigned int *__restrict__ changed, unsigned long long *__restrict__ stats,
-                              uint32_t *__restrict__ result) {
+                              uint32_t *__restrict__ result, unsigned int *__restrict__ sensitive) {
   // The filter's guess for a flagged query may carry the "undecided" mark in bit 31 (tensor-core finalise kernels: the
   // statistics pass that runs next to this kernel skips marked entries).  Every flagged query gets its exact index
   // written here or in phase B - to `result` when given (committed to `assign` once that pass is done), else in place.
@@ -849,6 +849,10 @@ __global__ void __launch_bounds__(128)
     if (__popc(holders) == 1 && multi == 0) {
       win = __shfl_sync(0xffffffffu, k1, __ffs(holders) - 1);
     } else {
+      // More than one codevector within the band of the minimum: the decision depends on exact ties / the tree's
+      // visiting order, i.e. on the LAST BITS of the codebook.  Counted: a train without any such decision cannot
+      // tell integer-derived centroids from the reference's compensated sums (qb200_set_exact_centroids, auto mode).
+      if (lane == 0 && sensitive) atomicAdd(sensitive, 1u);
       // EXACT ties only (every candidate's distance is bitwise the minimum: duplicated codevectors - dead
       // cells - or children 1.2c / 0.8c of a single-member cell): the walk keeps the FIRST candidate it
       // visits (leaf test `dist < worst` and KNNResultSet::addPoint are strict, nanoflann.hpp:1219-1224,
@@ -1704,12 +1708,12 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
-                           unsigned long long *stats, uint32_t *result, int sm_count, cudaStream_t stream) {
+                           unsigned long long *stats, uint32_t *result, unsigned int *sensitive, int sm_count, cudaStream_t stream) {
   // phase A: brute force, one warp per flagged query (the count is only known on the device)
   const unsigned int blocks_a = (unsigned int)sm_count * 8;
 #define QB_RESOLVE_A(CAP, DT)                                                                                        \
   resolve_bruteforce_kernel<CAP, DT><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, \
-                                                                   assign, tie_list, tie_count, changed, stats, result)
+                                                                   assign, tie_list, tie_count, changed, stats, result, sensitive)
   switch (src.dim) {
     case 3: QB_RESOLVE_A(3, 3); break;
     case 6: QB_RESOLVE_A(6, 6); break;

@@ -46,6 +46,7 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
                            unsigned long long *stats /* null unless the flagged queries' statistics are added here */,
                            uint32_t *result /* null: exact indices go straight to assign; else to result[v], see below */,
+                           unsigned int *sensitive /* device counter (may be null): decisions that hinged on (near-)ties */,
                            int sm_count, cudaStream_t stream);
 // assign[v] = result[v] for the flagged queries: used when a statistics pass read `assign` while the resolver ran.
 cudaError_t launch_commit_resolved(const uint32_t *flag_list, const unsigned int *flag_count, const uint32_t *result,

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/qb200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), "python binding and header disagree"
-    assert lib.qb200_version() == 100
+    assert lib.qb200_version() == 200
 
 
 def test_missing_library_fails_loudly(monkeypatch):
