@@ -82,8 +82,9 @@ typedef struct qb200_level_report {
                              `flagged` were still undecided and went to the FP64 resolver); 0 on the other levels */
   double distortion_pre;  /* updateDistortion() before fixCodeVectors (src/Quantizer.cpp:100) */
   double distortion_post; /* updateDistortion() after fixCodeVectors  (src/Quantizer.cpp:104) */
-  uint32_t sensitive;     /* of `flagged`: decisions with several codevectors within 2^-36 of the minimum (exact ties,
-                             tree-order ties) - the only ones the last bits of the codebook can change */
+  uint32_t sensitive;     /* of `flagged`: decisions with a second codevector within 2^-44 (relative to the largest
+                             distance) of the minimum - exact ties, tree-order ties: the only ones the last bits of
+                             the codebook can change */
   uint32_t reserved;
 } qb200_level_report;
 
@@ -136,7 +137,8 @@ int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *c
  *   3  AUTO (default): train with mode 0 while counting the decisions that hinged on (near-)ties of several
  *      codevectors (qb200_level_report.sensitive).  If there were none on any rank the result is index-identical to
  *      the reference's and is returned; otherwise the train is repeated with mode 1.  End-to-end identical to the
- *      reference on every input, at the fast path's cost whenever the input allows it.
+ *      reference on every input, at the fast path's cost whenever the input allows it.  (With a caller-supplied
+ *      all-reduce callback and no qb200_set_rank the chains cannot be continued across ranks: mode 0 is used.)
  * The environment variable QB200_EXACT_CENTROIDS=0|1|2|auto sets the mode of every new context.  Sharded runs
  * continue the chains from rank to rank: qb200_set_rank (or an attached group) is required and rank order must be
  * vector order (rank r owns lower vector indices than rank r+1). */

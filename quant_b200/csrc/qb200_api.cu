@@ -1667,7 +1667,8 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
     // is index-identical to the reference's, done.  Otherwise the train is repeated with the reference's compensated
     // member sums, which makes it bit-identical on any input.
     const bool lattice_scaled = ctx->colorspace == QB200_CS_SCALED;
-    const bool try_fast = ctx->exact_auto && !ctx->exact && lattice_scaled && nbits > 0;
+    // (a caller-supplied all-reduce without qb200_set_rank cannot continue the chains from rank to rank: integer sums)
+    const bool try_fast = ctx->exact_auto && !ctx->exact && lattice_scaled && nbits > 0 && !(allreduce && ctx->world <= 1);
     ctx->last_train_exact = ctx->exact && lattice_scaled ? 1 : 0;
     std::vector<qb200_level_report> own;
     qb200_level_report *rep = reports;

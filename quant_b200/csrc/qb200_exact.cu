@@ -420,7 +420,19 @@ __global__ void __launch_bounds__(kFxRunThreads) fx_runs_kernel(const FxGeom g, 
     fx_locate(w, g.K, gw, k, q);
     const int chain = k * g.dim + e;
     const unsigned int qs = w.q_start[chain];
-    if (q < qs) continue;  // covered by the head (0xffffffff: the whole chain)
+    if (q < qs) {  // covered by the head (0xffffffff: the whole chain): an empty record, so that later passes skip it
+      fx::SegRecord z;
+      z.Eb = 0;
+      z.begin = z.end = 0;
+      z.w_base = 0;
+      z.xs_low = 0;
+      z.je = 0;
+      z.top = -1;
+      z.ncls = 1;
+      z.flags = 0;
+      w.rec[fx_index(w, g.dim, k, e, q)] = z;
+      continue;
+    }
     const unsigned int beg = w.cell_beg[k], end = w.cell_beg[k + 1], cnt = w.win_off[k + 1] - w.win_off[k];
     const unsigned int P = beg + q * g.C;
     const unsigned int len = end - P > g.C + fx::kFxAnchorWin ? g.C + fx::kFxAnchorWin : end - P;
@@ -441,11 +453,49 @@ __global__ void __launch_bounds__(kFxRunThreads) fx_runs_kernel(const FxGeom g, 
     r.top = (signed char)(n0 > n1 ? n0 : n1);
     r.Eb = (u128)(w.B[chain] + (i128)w.sumX[idx] + (i128)before);
     r.ncls = 0;
-    r.pad = 0;
+    r.flags = 0;
     r.xs_low = 0;
-    r.pad2 = 0;
+    r.w_base = 0;
     if (r.begin < r.end) fx::fx_run_segment_multi(acc, tab, r);
     w.rec[idx] = r;
+  }
+}
+
+// Refinement round: the segments the first chaining pass marked (W outside their margin) are re-run around that
+// pass's estimate of W, so that the second pass finds them covered.
+__global__ void __launch_bounds__(kFxRunThreads) fx_refine_kernel(const FxGeom g, FxWork w) {
+  extern __shared__ __align__(16) unsigned char fx_smem[];
+  fx::Tables &tab = *reinterpret_cast<fx::Tables *>(fx_smem);
+  unsigned char *stage = fx_smem + sizeof(fx::Tables);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
+  __syncthreads();
+  const unsigned long long total = (unsigned long long)w.win_off[g.K] * g.dim;
+  for (unsigned long long id = blockIdx.x * (unsigned long long)kFxRunThreads + threadIdx.x; id < total;
+       id += (unsigned long long)gridDim.x * kFxRunThreads) {
+    // records are chain-major: id enumerates them in storage order, the dimension follows from the cell's layout
+    if (!(w.rec[id].flags & fx::kFxRefine)) continue;
+    fx::SegRecord r = w.rec[id];
+    const unsigned int gw_first = (unsigned int)(id / (unsigned int)g.dim);  // some window of the same cell
+    int k;
+    unsigned int q_unused;
+    fx_locate(w, g.K, gw_first, k, q_unused);
+    const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
+    const int e = (int)((id - (unsigned long long)w.win_off[k] * g.dim) / cnt);
+    const unsigned int len = r.end - r.begin;
+    if (len > g.C + fx::kFxAnchorWin) {  // cannot be staged (never with the window lengths in use): leave it to the exact pass
+      r.flags = 0;
+      r.ncls = 0;
+      w.rec[id] = r;
+      continue;
+    }
+    const FxAcc src{g.dense, g.order, g.stride, e};
+    unsigned char *col = stage + threadIdx.x;
+#pragma unroll 8
+    for (unsigned int i = 0; i < len; i++) col[i * kFxRunThreads] = (unsigned char)src(r.begin + i);
+    const FxStaged acc{stage + threadIdx.x, r.begin};
+    fx::fx_run_segment_multi(acc, tab, r);
+    r.flags = 0;
+    w.rec[id] = r;
   }
 }
 
@@ -470,7 +520,7 @@ __device__ __forceinline__ fx::Map4 fx_map_shfl_up(const fx::Map4 &m, int o) {
 }
 __device__ __forceinline__ int fx_pick(const int (&v)[4], int s) { return s == 0 ? v[0] : s == 1 ? v[1] : s == 2 ? v[2] : v[3]; }
 
-__global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGeom g, FxWork w, double *__restrict__ state) {
+__global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGeom g, FxWork w, double *__restrict__ state, const int pass) {
   __shared__ fx::Tables tab;
   __shared__ unsigned char s_seg[kFxChainWarps][256 + fx::kFxAnchorWin];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
@@ -482,44 +532,50 @@ __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGe
   if (qs == 0xffffffffu) return;  // finished by the head
   const int k = chain / g.dim, e = chain - k * g.dim;
   const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
-  const fx::SegRecord *rec = w.rec + fx_index(w, g.dim, k, e, 0);
+  fx::SegRecord *rec = w.rec + fx_index(w, g.dim, k, e, 0);
   const FxAcc src{g.dense, g.order, g.stride, e};
   long long W = 0;  // the head's state is exact: the first segment is entered with W = 0 (all lanes carry W)
+  int marked = 0;   // pass 0: segments marked for the refinement round (none: this pass's result is exact)
 
   // exact re-run of lane f's segment from the true state Eb + W; every lane returns the new W
   auto rerun = [&](const fx::SegRecord &mine, int f) {
-    const unsigned int b = __shfl_sync(0xffffffffu, mine.begin, f), en = __shfl_sync(0xffffffffu, mine.end, f);
+    fx::SegRecord seg;
+    seg.begin = __shfl_sync(0xffffffffu, mine.begin, f);
+    seg.end = __shfl_sync(0xffffffffu, mine.end, f);
     const unsigned long long e_lo = __shfl_sync(0xffffffffu, (unsigned long long)mine.Eb, f);
     const unsigned long long e_hi = __shfl_sync(0xffffffffu, (unsigned long long)(mine.Eb >> 64), f);
-    const u128 Eb = ((u128)e_hi << 64) | e_lo;
-    const unsigned int len = en - b;
+    seg.Eb = ((u128)e_hi << 64) | e_lo;
+    const unsigned int len = seg.end - seg.begin;
     long long Wn = W;
-    if (len <= sizeof(s_seg[0])) {
-      for (unsigned int i = lane; i < len; i += 32) s_seg[warp][i] = (unsigned char)src(b + i);
+    if (len <= sizeof(s_seg[0])) {  // the warp stages the members, one lane steps through them
+      for (unsigned int i = lane; i < len; i += 32) s_seg[warp][i] = (unsigned char)src(seg.begin + i);
       __syncwarp();
       if (lane == 0) {
-        u128 a = (u128)((i128)Eb + W), xs = 0;
-        for (unsigned int i = 0; i < len; i++) {
-          const int t = s_seg[warp][i];
-          xs += tab.X[t];
-          a = fx::fx_step(a, t, tab);
-        }
-        Wn = (long long)((i128)a - (i128)(Eb + xs));
+        struct Staged {
+          const unsigned char *p;
+          unsigned int base;
+          __device__ __forceinline__ int operator()(unsigned int q) const { return (int)p[q - base]; }
+        };
+        fx::fx_rerun(Staged{s_seg[warp], seg.begin}, tab, seg, Wn);
       }
       __syncwarp();
     } else if (lane == 0) {
-      u128 a = (u128)((i128)Eb + W), xs = 0;
-      for (unsigned int p = b; p < en; p++) {
-        const int t = src(p);
-        xs += tab.X[t];
-        a = fx::fx_step(a, t, tab);
-      }
-      Wn = (long long)((i128)a - (i128)(Eb + xs));
+      fx::fx_rerun(src, tab, seg, Wn);
     }
     W = __shfl_sync(0xffffffffu, Wn, 0);
   };
 
   fx::SegRecord r;
+  // pass 0: lane f's segment is not covered - note W in its record for the refinement round and move on with an estimate
+  auto mark = [&](int f, unsigned int q0) {
+    long long Wn = W;
+    if (lane == f) {
+      fx::fx_mark_and_estimate(r, Wn);
+      if (r.flags & fx::kFxRefine) rec[q0 + f] = r;
+    }
+    W = __shfl_sync(0xffffffffu, Wn, f);
+    marked = 1;  // (sequential segments count as well: only the exact pass can run them)
+  };
   auto load = [&](unsigned int q0) {
     const unsigned int q = q0 + lane;
     if (q < cnt) {
@@ -550,10 +606,13 @@ __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGe
         int ok = 1;
         if (lane == f) ok = fx::fx_apply(r, Wn) ? 1 : 0;
         ok = __shfl_sync(0xffffffffu, ok, f);
-        if (ok)
+        if (ok) {
           W = __shfl_sync(0xffffffffu, Wn, f);
-        else
+        } else if (pass == 0) {
+          mark(f, q0);
+        } else {
           rerun(r, f);
+        }
       }
       continue;
     }
@@ -564,7 +623,7 @@ __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGe
       const unsigned int rest = live_mask & (j0 >= 32 ? 0u : (0xffffffffu << j0));
       if (!rest) break;
       const int jl = __ffs(rest) - 1;  // first live record at or behind j0: its E gives the entry state
-      const int s0 = (int)((((long long)__shfl_sync(0xffffffffu, e16, jl) + W) >> jb) & 3);
+      const int s0 = (int)((((long long)__shfl_sync(0xffffffffu, e16, jl) + (W - (long long)__shfl_sync(0xffffffffu, r.w_base, jl))) >> jb) & 3);
       fx::Map4 pm = lane >= j0 ? mine : fx::fx_map_identity();
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -580,16 +639,23 @@ __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGe
       }
       const int f = __ffs(bad) - 1;  // records j0 .. f-1 are covered; f is re-run exactly
       if (f > j0) W += __shfl_sync(0xffffffffu, dW, f - 1);
-      if ((live_mask >> f) & 1u) rerun(r, f);
+      if ((live_mask >> f) & 1u) {
+        if (pass == 0)
+          mark(f, q0);
+        else
+          rerun(r, f);
+      }
       j0 = f + 1;
     }
   }
+  if (pass == 0 && marked) return;  // the exact pass redoes this chain after the refinement round
   if (lane == 0) {
     const u128 A = (u128)(w.B[chain] + (i128)w.total[chain] + (i128)W);
     double sum, c;
     fx::fx_state_to_pair(A, sum, c);
     state[2 * (size_t)chain] = sum;
     state[2 * (size_t)chain + 1] = c;
+    if (pass == 0) w.q_start[chain] = 0xffffffffu;  // nothing was marked: done, the exact pass skips this chain
   }
 }
 
@@ -663,6 +729,8 @@ cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_so
   count_launch();
   fx_head_kernel<<<chain_blocks, 128, 0, stream>>>(g, w, state);
   count_launch();
+  unsigned long long rblocks_saved = 1;
+  size_t smem_saved = 0;
   {
     const size_t smem = sizeof(fx::Tables) + (size_t)(C + fx::kFxAnchorWin) * kFxRunThreads;
     unsigned long long rblocks = (ids + kFxRunThreads - 1) / kFxRunThreads;
@@ -670,8 +738,15 @@ cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_so
     if (rblocks > rcap) rblocks = rcap;
     fx_runs_kernel<<<(unsigned int)rblocks, kFxRunThreads, smem, stream>>>(g, w);
     count_launch();
+    rblocks_saved = rblocks;
+    smem_saved = smem;
   }
-  fx_chain_kernel<<<(unsigned int)((chains + kFxChainWarps - 1) / kFxChainWarps), 32 * kFxChainWarps, 0, stream>>>(g, w, state);
+  const unsigned int cblocks = (unsigned int)((chains + kFxChainWarps - 1) / kFxChainWarps);
+  fx_chain_kernel<<<cblocks, 32 * kFxChainWarps, 0, stream>>>(g, w, state, 0);  // marks what its summaries do not cover
+  count_launch();
+  fx_refine_kernel<<<(unsigned int)rblocks_saved, kFxRunThreads, smem_saved, stream>>>(g, w);
+  count_launch();
+  fx_chain_kernel<<<cblocks, 32 * kFxChainWarps, 0, stream>>>(g, w, state, 1);  // exact
   count_launch();
   return cudaGetLastError();
 }

@@ -232,16 +232,20 @@ QB_HD Anchor fx_anchor(const Acc &acc, unsigned int P, unsigned int end, const T
 
 // Per (window, dimension) record written by the speculative runs and read by the chaining pass.
 struct SegRecord {
-  u128 Eb;                        // E at the segment's first member
-  int dcorr[kFxMaxCls];           // per class: (A_end - A_start) - sum of X over the segment
-  unsigned int margin[kFxMaxCls]; // per class: |W - cc| must stay below this (0xffffffff: no t = 255 in the segment)
+  u128 Eb;                        // E at the segment's first member, plus w_base
+  unsigned int margin[kFxMaxCls]; // per class: |W - w_base - cc| must stay below this (0xffffffff: no t = 255 in the segment)
+  short dcorr[kFxMaxCls];         // per class: (A_end - A_start) - sum of X over the segment (|.| <= 128 per member)
   unsigned int begin, end;        // members [begin, end)
+  int w_base;                     // the speculative runs were made around E + w_base (0 in the first round; the refinement
+                                  // round uses the first chaining pass's estimate of W, see kFxRefine)
+  unsigned short xs_low;          // (sum of X over the segment) mod 2^16
   signed char je, top;            // entry trailing zeros (>= 0) and highest bit looked at (-1: nothing but zeros)
   signed char ncls;               // 1..kFxMaxCls, or 0: run sequentially
-  signed char pad;
-  unsigned short xs_low;          // (sum of X over the segment) mod 2^16
-  unsigned short pad2;
+  unsigned char flags;            // kFxRefine: the first chaining pass found W outside this segment's margin
 };
+constexpr unsigned char kFxRefine = 1;
+constexpr long long kFxWLimitHost = 1ll << 29;
+static_assert(sizeof(SegRecord) == 96, "SegRecord is copied as six 16-byte words");
 
 // centred representative of v modulo m (a power of two): in (-m/2, m/2]
 QB_HD long long fx_centered(long long v, long long m) {
@@ -279,7 +283,7 @@ QB_HD void fx_run_segment(const Acc &acc, const Tables &tab, SegRecord &rec) {
       xs += tab.X[t];
       a = fx_step(a, t, tab);
     }
-    rec.dcorr[cls] = (int)(long long)((i128)(a - a0) - (i128)xs);
+    rec.dcorr[cls] = (short)(long long)((i128)(a - a0) - (i128)xs);
     rec.margin[cls] = mg == 0xffffffffffffffffull ? 0xffffffffu : (mg > 0xfffffffeull ? 0xfffffffeu : (unsigned int)mg);
   }
 }
@@ -291,11 +295,12 @@ QB_HD bool fx_apply(const SegRecord &rec, long long &W) {
   if (rec.ncls == 0) return false;
   const long long mod = fx_class_mod(rec.je, rec.top);
   const long long e_low = (long long)((unsigned long long)rec.Eb & (unsigned long long)(mod - 1));
-  const long long a_low = (e_low + W) & (mod - 1);   // true state modulo `mod` (W may be negative: two's complement)
+  const long long Wrel = W - rec.w_base;              // rec.Eb already contains w_base
+  const long long a_low = (e_low + Wrel) & (mod - 1); // true state modulo `mod` (two's complement for negative values)
   if ((a_low & ((1ll << rec.je) - 1)) != 0) return false;  // cannot happen; run exactly rather than trust it
   const int cls = (int)(a_low >> rec.je);
   const long long cc = fx_centered(((long long)cls << rec.je) - e_low, mod);
-  const long long shift = W - cc;                     // a multiple of `mod`: the run's decisions at t < 255 carry over
+  const long long shift = Wrel - cc;                  // a multiple of `mod`: the run's decisions at t < 255 carry over
   const unsigned long long mag = (unsigned long long)(shift < 0 ? -shift : shift);
   // shift == 0: the speculative run started at the true state itself (flat data, where no step ever rounds)
   if (rec.margin[cls] != 0xffffffffu && mag != 0 && mag >= (unsigned long long)rec.margin[cls]) return false;
@@ -305,25 +310,20 @@ QB_HD bool fx_apply(const SegRecord &rec, long long &W) {
 // The same speculative runs, all classes in ONE pass over the members.  Steps with t < 255 look at the low bits of
 // the state only, so per class it is enough to carry the state modulo 2^16 and the accumulated rounding
 // correction; the addend's table lookup, level and the (128-bit) sum of X are shared by the classes.  A t = 255
-// step (binade edge, rare) rebuilds the full state of every class and takes the general step.
-template <typename Acc>
-QB_HD void fx_run_segment_multi(const Acc &acc, const Tables &tab, SegRecord &rec) {
+// step (binade edge) needs where the state sits inside ulp(sum): the exponent comes from the shared E + sum of X
+// (the classes are within 2^16 of it; next to a power of two the general step is taken instead), the position
+// from the class's low 64 bits.  NC = unrolled class slots (4 covers the usual je = 7 segments).
+template <int NC, typename Acc>
+QB_HD void fx_run_classes(const Acc &acc, const Tables &tab, SegRecord &rec, const int ncls, const long long mod) {
   const int je = rec.je;
-  const long long mod = fx_class_mod(je, rec.top);
-  if ((mod >> je) > kFxMaxCls) {
-    rec.ncls = 0;
-    return;
-  }
-  const int ncls = (int)(mod >> je);
-  rec.ncls = (signed char)ncls;
   const long long e_low = (long long)((unsigned long long)rec.Eb & (unsigned long long)(mod - 1));
-  unsigned int lo16[kFxMaxCls];       // state mod 2^16
-  long long cc[kFxMaxCls];            // start offset of the class relative to E
-  int corr[kFxMaxCls];                // accumulated rounding corrections
-  unsigned long long mg[kFxMaxCls];
+  unsigned int lo16[NC];              // state mod 2^16
+  int cc[NC];                         // start offset of the class relative to E
+  int corr[NC];                       // accumulated rounding corrections
+  unsigned long long mg[NC];
 QB_UNROLL
-  for (int cls = 0; cls < kFxMaxCls; cls++) {
-    cc[cls] = cls < ncls ? fx_centered(((long long)cls << je) - e_low, mod) : 0;
+  for (int cls = 0; cls < NC; cls++) {
+    cc[cls] = cls < ncls ? (int)fx_centered(((long long)cls << je) - e_low, mod) : 0;
     lo16[cls] = (unsigned int)((unsigned long long)((i128)rec.Eb + cc[cls])) & 0xffffu;
     corr[cls] = 0;
     mg[cls] = 0xffffffffffffffffull;
@@ -335,27 +335,60 @@ QB_UNROLL
     const unsigned long long X = tab.X[t];
     if (t < 255) {
       const int lev = fx_lev(t);
-      const unsigned int u = 1u << lev, xl = (unsigned int)X & 0xffffu;
+      const unsigned int u = 1u << lev, xl = (unsigned int)X & 0xffffu, xpar = (unsigned int)(X >> lev);
 QB_UNROLL
-      for (int cls = 0; cls < kFxMaxCls; cls++) {
+      for (int cls = 0; cls < NC; cls++) {
         if (cls < ncls) {
           const unsigned int a = lo16[cls], r = a & (u - 1);
-          const bool up = 2 * r > u || (2 * r == u && ((((unsigned int)(X >> lev)) ^ (a >> lev)) & 1u));
+          const bool up = 2 * r > u || (2 * r == u && ((xpar ^ (a >> lev)) & 1u));
           const int d = (int)(up ? u : 0u) - (int)r;
           corr[cls] += d;
           lo16[cls] = (a + xl + (unsigned int)d) & 0xffffu;
         }
       }
     } else {
+      const u128 full = rec.Eb + xs;
+      const int n = fx_bitlen(full), sh = n - 53;
+      const u128 lo_edge = full - ((u128)1 << (n - 1)), hi_edge = ((u128)1 << n) - full;
+      const u128 edge128 = lo_edge < hi_edge ? lo_edge : hi_edge;
+      if (sh < 10 || sh > 48 || edge128 < ((u128)1 << 17)) {  // next to a power of two (or outside the regime): general step
 QB_UNROLL
-      for (int cls = 0; cls < kFxMaxCls; cls++) {
-        if (cls < ncls) {
-          const u128 a = (u128)((i128)rec.Eb + cc[cls] + (i128)xs + (i128)corr[cls]);
-          const unsigned long long dm = fx_decision_margin(a);
-          if (dm < mg[cls]) mg[cls] = dm;
-          const u128 a2 = fx_step(a, 255, tab);
-          corr[cls] += (int)(long long)((i128)(a2 - a) - (i128)X);
-          lo16[cls] = (unsigned int)(unsigned long long)a2 & 0xffffu;
+        for (int cls = 0; cls < NC; cls++) {
+          if (cls < ncls) {
+            const u128 a = (u128)((i128)full + cc[cls] + corr[cls]);
+            const unsigned long long dm = fx_decision_margin(a);
+            if (dm < mg[cls]) mg[cls] = dm;
+            const u128 a2 = fx_step(a, 255, tab);
+            corr[cls] += (int)(long long)((i128)(a2 - a) - (i128)X);
+            lo16[cls] = (unsigned int)(unsigned long long)a2 & 0xffffu;
+          }
+        }
+      } else {
+        const unsigned long long U = 1ull << sh, h = U >> 1, full_lo = (unsigned long long)full;
+        const long long lo_e = lo_edge > (u128)0x3fffffffffffffffull ? 0x3fffffffffffffffll : (long long)lo_edge;
+        const long long hi_e = hi_edge > (u128)0x3fffffffffffffffull ? 0x3fffffffffffffffll : (long long)hi_edge;
+QB_UNROLL
+        for (int cls = 0; cls < NC; cls++) {
+          if (cls < ncls) {
+            const long long delta = (long long)cc[cls] + corr[cls];
+            const unsigned long long a64 = full_lo + (unsigned long long)delta;
+            const unsigned long long r = a64 & (U - 1);
+            // fx_decision_margin: distance to 0, U/2, U inside the ulp, and to the binade edges
+            unsigned long long dist = r < U - r ? r : U - r;
+            const unsigned long long dh = r > h ? r - h : h - r;
+            dist = dh < dist ? dh : dist;
+            const long long le = lo_e == 0x3fffffffffffffffll ? lo_e : lo_e + delta, he = hi_e == 0x3fffffffffffffffll ? hi_e : hi_e - delta;
+            if ((unsigned long long)le < dist) dist = (unsigned long long)le;
+            if ((unsigned long long)he < dist) dist = (unsigned long long)he;
+            if (dist < mg[cls]) mg[cls] = dist;
+            // fx_step(t = 255): d = A - RN53(A); y = (X + d) rounded to 2^8 (d > 0) or 2^7 (d < 0), ties to even
+            const bool up = r > h || (r == h && ((a64 >> sh) & 1ull));
+            const long long d = up ? (long long)r - (long long)U : (long long)r;
+            long long step = 0;  // A' - A - X
+            if (d != 0) step = fx_round_even((long long)X + d, d > 0 ? 256 : 128) - d - (long long)X;
+            corr[cls] += (int)step;
+            lo16[cls] = (unsigned int)(a64 + (unsigned long long)X + (unsigned long long)step) & 0xffffu;
+          }
         }
       }
     }
@@ -363,12 +396,26 @@ QB_UNROLL
   }
   rec.xs_low = (unsigned short)((unsigned long long)xs & 0xffffu);
 QB_UNROLL
-  for (int cls = 0; cls < kFxMaxCls; cls++) {
+  for (int cls = 0; cls < NC; cls++) {
     if (cls < ncls) {
-      rec.dcorr[cls] = corr[cls];
+      rec.dcorr[cls] = (short)corr[cls];
       rec.margin[cls] = mg[cls] == 0xffffffffffffffffull ? 0xffffffffu : (mg[cls] > 0xfffffffeull ? 0xfffffffeu : (unsigned int)mg[cls]);
     }
   }
+}
+template <typename Acc>
+QB_HD void fx_run_segment_multi(const Acc &acc, const Tables &tab, SegRecord &rec) {
+  const long long mod = fx_class_mod(rec.je, rec.top);
+  const int ncls = (int)(mod >> rec.je);
+  if (ncls > kFxMaxCls) {
+    rec.ncls = 0;
+    return;
+  }
+  rec.ncls = (signed char)ncls;
+  if (ncls <= 4)
+    fx_run_classes<4>(acc, tab, rec, ncls, mod);
+  else
+    fx_run_classes<kFxMaxCls>(acc, tab, rec, ncls, mod);
 }
 
 // ---- chaining 32 segments at a time -----------------------------------------------------------------------
@@ -414,9 +461,9 @@ QB_HD Map4 fx_map_of(const SegRecord &rec, int jb) {
       lo = -kFxWLimit;
       hi = kFxWLimit;
     } else {
-      const long long rad = mgn > 0 ? (long long)mgn - 1 : 0;  // |W - cc| < margin, or W == cc
-      lo = cc - rad;
-      hi = cc + rad;
+      const long long rad = mgn > 0 ? (long long)mgn - 1 : 0;  // |W - w_base - cc| < margin, or equal
+      lo = cc - rad + rec.w_base;
+      hi = cc + rad + rec.w_base;
       if (lo < -kFxWLimit) lo = -kFxWLimit;
       if (hi > kFxWLimit) hi = kFxWLimit;
     }
@@ -457,17 +504,53 @@ QB_HD bool fx_batch_composable(int je_min, int je_max_unused, int top_max, int &
   return hi_bit <= jb + 1;
 }
 
-template <typename Acc>
-QB_HD void fx_rerun(const Acc &acc, const Tables &tab, const SegRecord &rec, long long &W) {
-  u128 a = (u128)((i128)rec.Eb + W), xs = 0;
-  for (unsigned int p = rec.begin; p < rec.end; p++) {
-    const int t = acc(p);
-    xs += tab.X[t];
-    a = fx_step(a, t, tab);
+// First chaining pass, segment not covered by its summary: note W as the point around which the refinement round
+// re-runs it, then move on with the summary anyway - W is then only an ESTIMATE (a flipped t = 255 decision is worth a
+// few hundred units), which is all the later marks of this pass need; the second pass is exact again.
+QB_HD void fx_mark_and_estimate(SegRecord &rec, long long &W) {
+  if (rec.begin >= rec.end || rec.ncls == 0) return;  // sequential segments are run exactly in the second pass
+  const long long mod = fx_class_mod(rec.je, rec.top);
+  const long long e_low = (long long)((unsigned long long)rec.Eb & (unsigned long long)(mod - 1));
+  const long long a_low = (e_low + (W - rec.w_base)) & (mod - 1);
+  const int cls = (int)(a_low >> rec.je) & (rec.ncls - 1);
+  const long long w_new = W;
+  W += rec.dcorr[cls];
+  if (w_new > -kFxWLimitHost && w_new < kFxWLimitHost) {
+    rec.Eb = (u128)((i128)rec.Eb + (w_new - rec.w_base));
+    rec.w_base = (int)w_new;
+    rec.flags |= kFxRefine;
   }
-  W = (long long)((i128)a - (i128)(rec.Eb + xs));
 }
 
+// Exact sequential run of a segment from the true state Eb + W (summary not usable): steps with t < 255 only need
+// the state modulo 2^16 and add their rounding correction to W; a t = 255 step rebuilds the full state.
+template <typename Acc>
+QB_HD void fx_rerun(const Acc &acc, const Tables &tab, const SegRecord &rec, long long &W) {
+  const u128 base = (u128)((i128)rec.Eb + (W - rec.w_base));
+  unsigned int lo16 = (unsigned int)(unsigned long long)base & 0xffffu;
+  long long corr = 0;
+  u128 xs = 0;
+  for (unsigned int p = rec.begin; p < rec.end; p++) {
+    const int t = acc(p);
+    if (t == 0) continue;
+    const unsigned long long X = tab.X[t];
+    if (t < 255) {
+      const int lev = fx_lev(t);
+      const unsigned int u = 1u << lev, r = lo16 & (u - 1);
+      const bool up = 2 * r > u || (2 * r == u && ((((unsigned int)(X >> lev)) ^ (lo16 >> lev)) & 1u));
+      const int d = (int)(up ? u : 0u) - (int)r;
+      corr += d;
+      lo16 = (lo16 + ((unsigned int)X & 0xffffu) + (unsigned int)d) & 0xffffu;
+    } else {
+      const u128 a = (u128)((i128)base + (i128)xs + corr);
+      const u128 a2 = fx_step(a, 255, tab);
+      corr += (long long)((i128)(a2 - a) - (i128)X);
+      lo16 = (unsigned int)(unsigned long long)a2 & 0xffffu;
+    }
+    xs += X;
+  }
+  W += corr;
+}
 
 // ---- per-thread bodies of the kernels (shared with the CPU check) ---------------------------------------------
 // Window summary: sum of X and the highest bit looked at over members [P, P_end).

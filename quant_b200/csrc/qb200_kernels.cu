@@ -845,14 +845,20 @@ __global__ void __launch_bounds__(128)
     const int mine = (d1 <= lim ? 1 : 0) + (d2 <= lim ? 1 : 0);
     const unsigned int holders = __ballot_sync(0xffffffffu, mine > 0);
     const unsigned int multi = __ballot_sync(0xffffffffu, mine > 1);
+    // Decisions the LAST BITS of the codebook could change: a second codevector within 2^-44 dmax of the minimum.
+    // (Centroids from the integer sums are within 4e-16 = 2^-51 relative of the reference's compensated sums; that
+    // moves a distance by less than 2^-48 dmax.)  Counted: a train without any such decision is index-identical with
+    // either centroid arithmetic (qb200_set_exact_centroids, auto mode).
+    if (sensitive) {
+      const double lim2 = wmin + wmax * 5.6843418860808015e-14;  // 2^-44
+      const int near2 = (d1 <= lim2 ? 1 : 0) + (d2 <= lim2 ? 1 : 0);
+      const unsigned int h2 = __ballot_sync(0xffffffffu, near2 > 0), m2 = __ballot_sync(0xffffffffu, near2 > 1);
+      if (lane == 0 && (__popc(h2) > 1 || m2 != 0)) atomicAdd(sensitive, 1u);
+    }
     int win = -1;
     if (__popc(holders) == 1 && multi == 0) {
       win = __shfl_sync(0xffffffffu, k1, __ffs(holders) - 1);
     } else {
-      // More than one codevector within the band of the minimum: the decision depends on exact ties / the tree's
-      // visiting order, i.e. on the LAST BITS of the codebook.  Counted: a train without any such decision cannot
-      // tell integer-derived centroids from the reference's compensated sums (qb200_set_exact_centroids, auto mode).
-      if (lane == 0 && sensitive) atomicAdd(sensitive, 1u);
       // EXACT ties only (every candidate's distance is bitwise the minimum: duplicated codevectors - dead
       // cells - or children 1.2c / 0.8c of a single-member cell): the walk keeps the FIRST candidate it
       // visits (leaf test `dist < worst` and KNNResultSet::addPoint are strict, nanoflann.hpp:1219-1224,

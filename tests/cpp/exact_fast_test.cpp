@@ -36,7 +36,7 @@ static void kahan_fp(const uint8_t *ts, size_t n, double &sum, double &c) {
 }
 
 struct Stats {
-  long segments = 0, reruns = 0, sequential = 0, classes = 0, batches = 0;
+  long segments = 0, reruns = 0, sequential = 0, classes = 0, batches = 0, refined = 0;
 };
 
 // The kernels' pipeline on one chain [0, n) with window length C, from the incoming pair (sum, c).
@@ -67,11 +67,13 @@ static void fast_chain(const uint8_t *ts, unsigned int n, unsigned int C, double
     r.top = (signed char)std::max(need[q], need[q + 1]);
     r.Eb = (u128)(h.B + (i128)pref[q] + (i128)before);
     r.ncls = 0;
+    r.w_base = 0;
+    r.flags = 0;
     if (r.begin < r.end) {
       fx_run_segment_multi(acc, g_tab, r);
       SegRecord chk = r;   // the one-pass evaluation must agree with the class-by-class one
       fx_run_segment(acc, g_tab, chk);
-      if (chk.ncls != r.ncls || std::memcmp(chk.dcorr, r.dcorr, sizeof(int) * (chk.ncls > 0 ? chk.ncls : 0)) ||
+      if (chk.ncls != r.ncls || std::memcmp(chk.dcorr, r.dcorr, sizeof(short) * (chk.ncls > 0 ? chk.ncls : 0)) ||
           std::memcmp(chk.margin, r.margin, sizeof(unsigned) * (chk.ncls > 0 ? chk.ncls : 0))) {
         std::printf("multi-class run differs from the class-by-class run (window %u)\n", q);
         std::exit(1);
@@ -79,55 +81,74 @@ static void fast_chain(const uint8_t *ts, unsigned int n, unsigned int C, double
     }
   }
   // chaining: the head's state is exact, so the first segment is entered with W = 0.  Batches of 32 segments, as
-  // the chain kernel walks them: 4-state maps and their prefix composition where the batch allows it.
+  // the chain kernel walks them: 4-state maps and their prefix composition where the batch allows it.  Two passes:
+  // the first only marks the segments whose summary does not cover W (and estimates W behind them), the marked ones
+  // are re-run around that estimate, the second pass is exact.
   long long W = 0;
-  auto sequential = [&](unsigned int q) {
-    if (rec[q].begin >= rec[q].end) return;
-    if (!fx_apply(rec[q], W)) {
-      fx_rerun(acc, g_tab, rec[q], W);
-      if (rec[q].ncls == 0) st.sequential++; else st.reruns++;
-    }
-  };
-  for (unsigned int q0 = h.q_start; q0 < n_win; q0 += 32) {
-    const unsigned int nb = std::min(32u, n_win - q0);
-    int je_min = 99, top_max = -1, live = 0;
-    for (unsigned int j = 0; j < nb; j++) {
-      const SegRecord &r = rec[q0 + j];
-      if (r.begin >= r.end) continue;
-      st.segments++;
-      st.classes += r.ncls;
-      live++;
-      if (r.ncls == 0) continue;
-      je_min = std::min(je_min, (int)r.je);
-      top_max = std::max(top_max, (int)r.top);
-    }
-    int jb = 0;
-    if (!live) continue;
-    if (je_min == 99 || !fx_batch_composable(je_min, 0, top_max, jb) || W > kFxWLimit / 2 || W < -kFxWLimit / 2) {
-      for (unsigned int j = 0; j < nb; j++) sequential(q0 + j);
-      continue;
-    }
-    st.batches++;
-    unsigned int j = 0;
-    while (j < nb) {
-      // prefix maps of records j .. nb-1 (the warp computes them with a parallel prefix)
-      const SegRecord &first = rec[q0 + j];
-      const int s0 = (int)(((((long long)((unsigned long long)first.Eb & 0xffffu)) + W) >> jb) & 3);
-      Map4 pre = fx_map_identity();
-      unsigned int applied = j;
-      long long W_after = W;
-      for (unsigned int i = j; i < nb; i++) {
-        pre = fx_compose(pre, fx_map_of(rec[q0 + i], jb));
-        if (!(pre.lo[s0] <= pre.hi[s0] && W >= pre.lo[s0] && W <= pre.hi[s0])) break;
-        applied = i + 1;
-        W_after = W + pre.dW[s0];
+  for (int pass = 0; pass < 2; pass++) {
+    W = 0;
+    auto sequential = [&](unsigned int q) {
+      if (rec[q].begin >= rec[q].end) return;
+      if (!fx_apply(rec[q], W)) {
+        if (pass == 0) {
+          fx_mark_and_estimate(rec[q], W);
+        } else {
+          fx_rerun(acc, g_tab, rec[q], W);
+          if (rec[q].ncls == 0) st.sequential++; else st.reruns++;
+        }
       }
-      W = W_after;
-      j = applied;
-      if (j < nb) {   // record j does not cover W (or is sequential): exact, then go on behind it
-        sequential(q0 + j);
-        j++;
+    };
+    for (unsigned int q0 = h.q_start; q0 < n_win; q0 += 32) {
+      const unsigned int nb = std::min(32u, n_win - q0);
+      int je_min = 99, top_max = -1, live = 0;
+      for (unsigned int j = 0; j < nb; j++) {
+        const SegRecord &r = rec[q0 + j];
+        if (r.begin >= r.end) continue;
+        if (pass == 1) {
+          st.segments++;
+          st.classes += r.ncls;
+        }
+        live++;
+        if (r.ncls == 0) continue;
+        je_min = std::min(je_min, (int)r.je);
+        top_max = std::max(top_max, (int)r.top);
       }
+      int jb = 0;
+      if (!live) continue;
+      if (je_min == 99 || !fx_batch_composable(je_min, 0, top_max, jb) || W > kFxWLimit / 2 || W < -kFxWLimit / 2) {
+        for (unsigned int j = 0; j < nb; j++) sequential(q0 + j);
+        continue;
+      }
+      if (pass == 1) st.batches++;
+      unsigned int j = 0;
+      while (j < nb) {
+        // prefix maps of records j .. nb-1 (the warp computes them with a parallel prefix)
+        const SegRecord &first = rec[q0 + j];
+        const int s0 = (int)(((((long long)((unsigned long long)first.Eb & 0xffffu)) + (W - first.w_base)) >> jb) & 3);
+        Map4 pre = fx_map_identity();
+        unsigned int applied = j;
+        long long W_after = W;
+        for (unsigned int i = j; i < nb; i++) {
+          pre = fx_compose(pre, fx_map_of(rec[q0 + i], jb));
+          if (!(pre.lo[s0] <= pre.hi[s0] && W >= pre.lo[s0] && W <= pre.hi[s0])) break;
+          applied = i + 1;
+          W_after = W + pre.dW[s0];
+        }
+        W = W_after;
+        j = applied;
+        if (j < nb) {   // record j does not cover W (or is sequential): mark / exact, then go on behind it
+          sequential(q0 + j);
+          j++;
+        }
+      }
+    }
+    if (pass == 0) {  // refinement round: the marked segments again, around the first pass's estimate of W
+      for (unsigned int q = h.q_start; q < n_win; q++)
+        if (rec[q].flags & kFxRefine) {
+          fx_run_segment_multi(acc, g_tab, rec[q]);
+          rec[q].flags = 0;
+          st.refined++;
+        }
     }
   }
   const u128 A = (u128)(h.B + (i128)pref[n_win] + W);
@@ -206,13 +227,13 @@ int main(int argc, char **argv) {
         std::printf("kind %d rep %d n %zu C %u cut %zu: MISMATCH (continued chain) sum %.17g vs %.17g, c %.17g vs %.17g\n", kind, rep, n,
                     C, cut, s2, s_ref, c2, c_ref);
       }
-      total.segments += st.segments; total.reruns += st.reruns; total.sequential += st.sequential; total.classes += st.classes; total.batches += st.batches;
+      total.segments += st.segments; total.reruns += st.reruns; total.sequential += st.sequential; total.classes += st.classes; total.batches += st.batches; total.refined += st.refined;
       if (rep == 0)
         std::printf("kind %2d n %7zu C %4u: %6ld segments, %5.2f classes each, %4ld margin re-runs, %4ld sequential   sum %.17g\n", kind, n, C,
                     st.segments, st.segments ? (double)st.classes / st.segments : 0.0, st.reruns, st.sequential, s_ref);
     }
   }
-  std::printf("%ld chains, %ld mismatches; %ld segments (%ld batches chained through composed maps), %ld re-run for their margin, %ld run sequentially\n",
-              chains, bad, total.segments, total.batches, total.reruns, total.sequential);
+  std::printf("%ld chains, %ld mismatches; %ld segments (%ld batches chained through composed maps), %ld refined around the first pass's estimate, %ld re-run exactly for their margin, %ld run sequentially\n",
+              chains, bad, total.segments, total.batches, total.refined, total.reruns, total.sequential);
   return bad != 0;
 }
