@@ -485,7 +485,8 @@ def run_gpu_arm(args):
             "e2e_cpp": e2e_cpp, "natural": natural,
             "gpu_launches": launches,
             "roofline": roof,
-            "per_level_ms": per_level, "flagged_last_level": flagged_last, "kd_walk_ties_last_level": ties_last,
+            "per_level_ms": per_level, "sensitive_per_level": {str(r["K"]): int(r["sensitive"]) for r in reps[-1]},
+            "flagged_last_level": flagged_last, "kd_walk_ties_last_level": ties_last,
             "distortion": d_res, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -659,6 +659,225 @@ __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGe
   }
 }
 
+// Long chains (few cells): one BLOCK per chain, kFxBlockWarps warps x 32 segments per round.  Every warp turns its 32
+// records into maps and scans them as above; the warps' totals are exchanged through shared memory, each warp
+// composes the totals in front of it to get its own entry (state, W) and checks its lanes; the first segment that is
+// not covered is handled by its warp (marked in pass 0, re-run in pass 1) and the round is re-evaluated behind it
+// (the per-record maps stay in registers, only one warp's scan and the small cross-warp composition are redone).
+constexpr int kFxBlockWarps = 8;
+
+__global__ void __launch_bounds__(32 * kFxBlockWarps) fx_chain_block_kernel(const FxGeom g, FxWork w, double *__restrict__ state,
+                                                                            const int pass) {
+  __shared__ fx::Tables tab;
+  __shared__ unsigned char s_seg[256 + fx::kFxAnchorWin];
+  __shared__ fx::Map4 s_tot[kFxBlockWarps];
+  __shared__ int s_fail[kFxBlockWarps], s_je[kFxBlockWarps], s_top[kFxBlockWarps], s_first[kFxBlockWarps];
+  __shared__ unsigned int s_live[kFxBlockWarps];
+  __shared__ long long s_erel[kFxBlockWarps], s_W;
+  __shared__ int s_marked;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
+  if (threadIdx.x == 0) s_marked = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chain = blockIdx.x;
+  const unsigned int qs = w.q_start[chain];
+  if (qs == 0xffffffffu) return;  // finished by the head or by pass 0 (uniform for the block)
+  const int k = chain / g.dim, e = chain - k * g.dim;
+  const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
+  fx::SegRecord *rec = w.rec + fx_index(w, g.dim, k, e, 0);
+  const FxAcc src{g.dense, g.order, g.stride, e};
+  long long W = 0;
+  fx::SegRecord r = {};
+  unsigned int my_q0 = 0;
+
+  auto rerun = [&](int f) {  // executed by ONE warp (all its lanes): exact re-run of lane f's segment from Eb + W
+    fx::SegRecord seg;
+    seg.begin = __shfl_sync(0xffffffffu, r.begin, f);
+    seg.end = __shfl_sync(0xffffffffu, r.end, f);
+    seg.w_base = __shfl_sync(0xffffffffu, r.w_base, f);
+    const unsigned long long e_lo = __shfl_sync(0xffffffffu, (unsigned long long)r.Eb, f);
+    const unsigned long long e_hi = __shfl_sync(0xffffffffu, (unsigned long long)(r.Eb >> 64), f);
+    seg.Eb = ((u128)e_hi << 64) | e_lo;
+    const unsigned int len = seg.end - seg.begin;
+    long long Wn = W;
+    if (len <= sizeof(s_seg)) {
+      for (unsigned int i = lane; i < len; i += 32) s_seg[i] = (unsigned char)src(seg.begin + i);
+      __syncwarp();
+      if (lane == 0) {
+        struct Staged {
+          const unsigned char *p;
+          unsigned int base;
+          __device__ __forceinline__ int operator()(unsigned int q) const { return (int)p[q - base]; }
+        };
+        fx::fx_rerun(Staged{s_seg, seg.begin}, tab, seg, Wn);
+      }
+      __syncwarp();
+    } else if (lane == 0) {
+      fx::fx_rerun(src, tab, seg, Wn);
+    }
+    W = __shfl_sync(0xffffffffu, Wn, 0);
+  };
+  auto mark = [&](int f) {  // pass 0, one warp: note W in lane f's record for the refinement round, move on with an estimate
+    long long Wn = W;
+    if (lane == f) {
+      fx::fx_mark_and_estimate(r, Wn);
+      if (r.flags & fx::kFxRefine) rec[my_q0 + f] = r;
+      s_marked = 1;
+    }
+    W = __shfl_sync(0xffffffffu, Wn, f);
+  };
+
+  for (unsigned int q0 = qs; q0 < cnt; q0 += 32 * kFxBlockWarps) {
+    my_q0 = q0 + 32 * warp;
+    const unsigned int q = my_q0 + lane;
+    if (q < cnt) {
+      r = rec[q];
+    } else {
+      r.begin = r.end = 0;
+      r.ncls = 1;
+      r.je = 0;
+      r.top = -1;
+      r.Eb = 0;
+      r.w_base = 0;
+      r.flags = 0;
+    }
+    const bool live = r.begin < r.end, usable = live && r.ncls != 0;
+    const unsigned int live_mask = __ballot_sync(0xffffffffu, live);
+    const int je_w = __reduce_min_sync(0xffffffffu, usable ? (int)r.je : 99);
+    const int top_w = __reduce_max_sync(0xffffffffu, usable ? (int)r.top : -1);
+    if (lane == 0) {
+      s_je[warp] = je_w;
+      s_top[warp] = top_w;
+      s_live[warp] = live_mask;
+      if (warp == 0) s_W = W;
+    }
+    __syncthreads();
+    int je_min = 99, top_max = -1;
+    unsigned int any_live = 0;
+#pragma unroll
+    for (int t = 0; t < kFxBlockWarps; t++) {
+      je_min = min(je_min, s_je[t]);
+      top_max = max(top_max, s_top[t]);
+      any_live |= s_live[t];
+    }
+    int jb = 0;
+    const bool composable = je_min != 99 && fx::fx_batch_composable(je_min, 0, top_max, jb) && W < fx::kFxWLimit / 2 && W > -fx::kFxWLimit / 2;
+    if (!any_live) {
+      __syncthreads();
+      continue;
+    }
+    if (!composable) {  // the warps take turns, one record after the other
+      for (int t = 0; t < kFxBlockWarps; t++) {
+        if (warp == t) {
+          unsigned int todo = live_mask;
+          while (todo) {
+            const int f = __ffs(todo) - 1;
+            todo &= todo - 1;
+            long long Wn = W;
+            int ok = 1;
+            if (lane == f) ok = fx::fx_apply(r, Wn) ? 1 : 0;
+            ok = __shfl_sync(0xffffffffu, ok, f);
+            if (ok)
+              W = __shfl_sync(0xffffffffu, Wn, f);
+            else if (pass == 0)
+              mark(f);
+            else
+              rerun(f);
+          }
+          if (lane == 0) s_W = W;
+        }
+        __syncthreads();
+        W = s_W;
+      }
+      __syncthreads();
+      continue;
+    }
+    const fx::Map4 mine = fx::fx_map_of(r, jb);
+    const long long erel = (long long)((unsigned long long)r.Eb & 0xffffu) - r.w_base;
+    int ws = 0, ls = 0;  // the round is evaluated from (warp ws, lane ls) on
+    while (ws < kFxBlockWarps) {
+      const bool active = warp > ws || (warp == ws && lane >= ls);
+      fx::Map4 pm = active ? mine : fx::fx_map_identity();
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const fx::Map4 left = fx_map_shfl_up(pm, o);
+        if (lane >= o) pm = fx::fx_compose(left, pm);
+      }
+      const unsigned int act_mask = warp > ws ? 0xffffffffu : (warp == ws ? (ls >= 32 ? 0u : (0xffffffffu << ls)) : 0u);
+      const unsigned int rest = live_mask & act_mask;
+      const int fl = rest ? __ffs(rest) - 1 : -1;
+      const long long erel_first = __shfl_sync(0xffffffffu, erel, fl < 0 ? 0 : fl);
+      if (lane == 31) s_tot[warp] = pm;
+      if (lane == 0) {
+        s_first[warp] = fl;
+        s_erel[warp] = erel_first;
+      }
+      __syncthreads();
+      int fwl = -1;
+#pragma unroll
+      for (int t = kFxBlockWarps - 1; t >= 0; t--)
+        if (t >= ws && s_first[t] >= 0) fwl = t;
+      if (fwl < 0) {  // nothing live behind the start: the round is done
+        __syncthreads();
+        break;
+      }
+      const int s0 = (int)(((s_erel[fwl] + W) >> jb) & 3);
+      fx::Map4 P = fx::fx_map_identity();
+      for (int t = ws; t < warp; t++) P = fx::fx_compose(P, s_tot[t]);
+      const int p_lo = fx_pick(P.lo, s0), p_hi = fx_pick(P.hi, s0);
+      const bool ok_prev = p_lo <= p_hi && W >= p_lo && W <= p_hi;
+      const int s_w = fx_pick(P.s, s0);
+      const long long W_w = W + fx_pick(P.dW, s0);
+      const int lo = fx_pick(pm.lo, s_w), hi = fx_pick(pm.hi, s_w), dW = fx_pick(pm.dW, s_w);
+      const bool valid = ok_prev && lo <= hi && W_w >= lo && W_w <= hi;
+      const unsigned int bad = __ballot_sync(0xffffffffu, !valid) & act_mask;
+      if (lane == 0) s_fail[warp] = bad ? __ffs(bad) - 1 : 32;
+      __syncthreads();
+      int fw = -1;
+#pragma unroll
+      for (int t = kFxBlockWarps - 1; t >= 0; t--)
+        if (t >= ws && s_fail[t] < 32) fw = t;
+      if (fw < 0) {  // everything behind the start is covered
+        fx::Map4 T = fx::fx_map_identity();
+        for (int t = ws; t < kFxBlockWarps; t++) T = fx::fx_compose(T, s_tot[t]);
+        W += fx_pick(T.dW, s0);
+        __syncthreads();
+        break;
+      }
+      const int f = s_fail[fw];
+      if (warp == fw) {
+        W = W_w + (f > 0 ? (long long)__shfl_sync(0xffffffffu, dW, f - 1) : 0ll);  // masked lanes are identities: dW = 0
+        if ((live_mask >> f) & 1u) {
+          if (pass == 0)
+            mark(f);
+          else
+            rerun(f);
+        }
+        if (lane == 0) s_W = W;
+      }
+      __syncthreads();
+      W = s_W;
+      ws = fw;
+      ls = f + 1;
+      if (ls == 32) {
+        ws++;
+        ls = 0;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (pass == 0 && s_marked) return;  // the exact pass redoes this chain after the refinement round
+  if (threadIdx.x == 0) {
+    const u128 A = (u128)(w.B[chain] + (i128)w.total[chain] + (i128)W);
+    double sum, c;
+    fx::fx_state_to_pair(A, sum, c);
+    state[2 * (size_t)chain] = sum;
+    state[2 * (size_t)chain + 1] = c;
+    if (pass == 0) w.q_start[chain] = 0xffffffffu;
+  }
+}
+
 size_t fx_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -741,13 +960,20 @@ cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_so
     rblocks_saved = rblocks;
     smem_saved = smem;
   }
+  // long chains (few cells): one block of kFxBlockWarps warps per chain; short ones: one warp per chain
+  const bool long_chains = n / (size_t)K >= (size_t)C * 32 * kFxBlockWarps && chains <= 65535;
   const unsigned int cblocks = (unsigned int)((chains + kFxChainWarps - 1) / kFxChainWarps);
-  fx_chain_kernel<<<cblocks, 32 * kFxChainWarps, 0, stream>>>(g, w, state, 0);  // marks what its summaries do not cover
-  count_launch();
+  auto chain_pass = [&](int pass) {
+    if (long_chains)
+      fx_chain_block_kernel<<<(unsigned int)chains, 32 * kFxBlockWarps, 0, stream>>>(g, w, state, pass);
+    else
+      fx_chain_kernel<<<cblocks, 32 * kFxChainWarps, 0, stream>>>(g, w, state, pass);
+    count_launch();
+  };
+  chain_pass(0);  // marks what its summaries do not cover
   fx_refine_kernel<<<(unsigned int)rblocks_saved, kFxRunThreads, smem_saved, stream>>>(g, w);
   count_launch();
-  fx_chain_kernel<<<cblocks, 32 * kFxChainWarps, 0, stream>>>(g, w, state, 1);  // exact
-  count_launch();
+  chain_pass(1);  // exact
   return cudaGetLastError();
 }
 
