@@ -48,7 +48,9 @@ struct qb200_ctx {
   std::vector<cudaEvent_t> pipe_ev;  // pipelined train: 6 timing events per level + 2 codebook-ready events
   void *h_pipe = nullptr;            // pinned slots of the pipelined train
   size_t h_pipe_cap = 0;
-  DevBuf d_cbnext[2], d_post, d_summary;
+  DevBuf d_cbnext[2], d_post, d_summary, d_levels;  // d_levels: every level's pre-fix codebook of the last pipelined train
+  std::vector<int> pipe_depth;
+  std::vector<char> pipe_side_used;
   std::string err;
 
   // training set
@@ -863,7 +865,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
   for (auto &e2 : ctx->pipe_ev)
     if (e2) cudaEventDestroy(e2);
-  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_exact, &ctx->d_sort_keys,
+  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_levels, &ctx->d_exact, &ctx->d_sort_keys,
                     &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp, &ctx->d_fx, &ctx->d_f64, &ctx->d_partials, &ctx->d_counts})
     free_buf(*b);
   for (auto &ev : ctx->ev)
@@ -1449,8 +1451,11 @@ struct PipeSlot {  // pinned, one per split level
 // HEAD schedule without host round trips between levels: centroids, distortions and the next split are
 // computed on the device (finalize_split_kernel); the host only builds each level's KD tree, from a codebook
 // copy that arrives while the GPU is already running that level's filter, and reads everything else at the end.
+// first_level > 0: RESTART of the train just run at that split level (its pre-fix codebook was kept in d_levels; the
+// pinned slots, events and reports of the earlier levels stay as they are) - used by the auto centroid mode, which
+// only needs the compensated sums from the level before the first tie-sensitive decision on.
 int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduce_fn ar, void *ar_user,
-                                double *codebook_out, double *distortion_out, qb200_level_report *reports) {
+                                double *codebook_out, double *distortion_out, qb200_level_report *reports, int first_level) {
   const int dim = ctx->src.dim;
   const uint32_t maxK = 1u << nbits;
   const size_t cb_max = (size_t)maxK * dim * 8;
@@ -1481,6 +1486,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     if ((rc = ensure(ctx, ctx->d_cbnext[i], cb_max + 256))) return rc;
   if ((rc = ensure(ctx, ctx->d_post, cb_max + 256))) return rc;
   if ((rc = ensure(ctx, ctx->d_summary, 64 * 32))) return rc;
+  if ((rc = ensure(ctx, ctx->d_levels, 2 * cb_max + 256))) return rc;
+  auto level_off = [&](int level) { return (((size_t)2 << level) - 2) * (size_t)dim * 8; };  // bytes before level's codebook
   // pinned: [slots | host codebook 0 | host codebook 1 | final codebook]
   const size_t off_cb0 = (sizeof(PipeSlot) * 20 + 255) & ~(size_t)255, need = off_cb0 + 3 * (cb_max + 256);
   if (need > ctx->h_pipe_cap) {
@@ -1506,6 +1513,19 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   cudaEvent_t *cb_ready = ctx->pipe_ev.data() + 6 * 17;
   char *summaries = (char *)ctx->d_summary.p;
 
+  if ((int)ctx->pipe_depth.size() < nbits + 1) ctx->pipe_depth.assign((size_t)nbits + 1, 0);
+  if ((int)ctx->pipe_side_used.size() < nbits + 1) ctx->pipe_side_used.assign((size_t)nbits + 1, 0);
+  std::vector<int> &depth = ctx->pipe_depth;
+  std::vector<char> &side_used = ctx->pipe_side_used;
+  uint32_t K = 1;
+  if (first_level > 0) {
+    const int cur = first_level & 1;
+    K = 1u << first_level;
+    const size_t bytes = (size_t)2 * K * dim * 8;
+    CU(cudaMemcpyAsync(ctx->d_cbnext[cur].p, (const char *)ctx->d_levels.p + level_off(first_level), bytes, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(h_cb[cur], ctx->d_cbnext[cur].p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(cb_ready[cur], st));
+  } else {
   // K = 1: mean of the training set (src/Quantizer.cpp:129-130), split into the first two codevectors
   CU(cudaMemsetAsync(ctx->d_stats.p, 0, stats_words(1, dim) * 8, st));
   CU(launch_accumulate(ctx->src, nullptr, 1, (unsigned long long *)ctx->d_stats.p, ctx->sm_count, st));
@@ -1519,13 +1539,12 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   if (nbits) {
     CU(cudaMemcpyAsync(h_cb[0], ctx->d_cbnext[0].p, (size_t)2 * dim * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(cb_ready[0], st));
+    CU(cudaMemcpyAsync((char *)ctx->d_levels.p + level_off(0), ctx->d_cbnext[0].p, (size_t)2 * dim * 8, cudaMemcpyDeviceToDevice, st));
   } else {
     CU(cudaMemcpyAsync(h_final, ctx->d_post.p, (size_t)dim * 8, cudaMemcpyDeviceToHost, st));
   }
-  std::vector<int> depth((size_t)nbits + 1, 0);
-  std::vector<char> side_used((size_t)nbits + 1, 0);
-  uint32_t K = 1;
-  for (int level = 0; level < nbits; level++) {
+  }
+  for (int level = first_level; level < nbits; level++) {
     K *= 2;
     const int cur = level & 1;
     const bool last = level == nbits - 1;
@@ -1550,6 +1569,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     if (!last) {
       CU(cudaMemcpyAsync(h_cb[cur ^ 1], ctx->d_cbnext[cur ^ 1].p, (size_t)2 * K * dim * 8, cudaMemcpyDeviceToHost, st));
       CU(cudaEventRecord(cb_ready[cur ^ 1], st));
+      CU(cudaMemcpyAsync((char *)ctx->d_levels.p + level_off(level + 1), ctx->d_cbnext[cur ^ 1].p, (size_t)2 * K * dim * 8,
+                         cudaMemcpyDeviceToDevice, st));
     } else {
       CU(cudaMemcpyAsync(h_final, ctx->d_post.p, (size_t)K * dim * 8, cudaMemcpyDeviceToHost, st));
     }
@@ -1597,9 +1618,9 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
 // Error exits of the body leave kernels and asynchronous copies into the pinned slots in flight: drain both streams
 // before the caller can retry (and reallocate those buffers), and never serve a partial assignment.
 int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduce_fn ar, void *ar_user,
-                           double *codebook_out, double *distortion_out, qb200_level_report *reports) {
+                           double *codebook_out, double *distortion_out, qb200_level_report *reports, int first_level = 0) {
   ctx->assign_valid = false;
-  const int rc = train_parity_pipelined_body(ctx, nbits, N, ar, ar_user, codebook_out, distortion_out, reports);
+  const int rc = train_parity_pipelined_body(ctx, nbits, N, ar, ar_user, codebook_out, distortion_out, reports, first_level);
   if (rc != QB200_OK) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
@@ -1678,20 +1699,28 @@ int qb200_train(qb200_ctx *ctx, int nbits, double eps, int mode, uint64_t n_tota
     }
     int rc = train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, rep);
     if (rc || !try_fast) return rc;
-    unsigned long long sensitive = 0;
-    for (int l = 0; l < nbits; l++) sensitive += rep[l].sensitive;
-    if (allreduce) {  // the ranks must take the same decision
-      if ((rc = ensure(ctx, ctx->d_misc, 256))) return rc;
-      CU(cudaMemcpyAsync(ctx->d_misc.p, &sensitive, 8, cudaMemcpyHostToDevice, ctx->stream));
-      if (allreduce(ctx->d_misc.p, 1, (void *)ctx->stream, allreduce_user) != 0)
+    // first split level with a tie-sensitive decision on ANY rank (the ranks must take the same decision)
+    std::vector<unsigned long long> census((size_t)nbits);
+    for (int l = 0; l < nbits; l++) census[(size_t)l] = rep[l].sensitive;
+    if (allreduce) {
+      if ((rc = ensure(ctx, ctx->d_misc, (size_t)nbits * 8 + 256))) return rc;
+      CU(cudaMemcpyAsync(ctx->d_misc.p, census.data(), (size_t)nbits * 8, cudaMemcpyHostToDevice, ctx->stream));
+      if (allreduce(ctx->d_misc.p, (size_t)nbits, (void *)ctx->stream, allreduce_user) != 0)
         return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (tie census)");
-      CU(cudaMemcpyAsync(&sensitive, ctx->d_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(census.data(), ctx->d_misc.p, (size_t)nbits * 8, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
     }
-    if (sensitive == 0) return QB200_OK;
+    int first_sensitive = -1;
+    for (int l = 0; l < nbits && first_sensitive < 0; l++)
+      if (census[(size_t)l]) first_sensitive = l;
+    if (first_sensitive < 0) return QB200_OK;
+    // Levels before it took no tie-sensitive decision: their indices are what the reference's are, with either
+    // centroid arithmetic.  So the compensated sums are only needed from the level BEFORE the first sensitive one on
+    // (its exact centroids feed the sensitive level): restart there from the codebook kept in d_levels.
     ctx->exact = true;
     ctx->last_train_exact = 1;
-    rc = train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, reports);
+    const int restart = first_sensitive > 0 ? first_sensitive - 1 : 0;
+    rc = train_parity_pipelined(ctx, nbits, N, allreduce, allreduce_user, codebook_out, distortion_out, reports, restart);
     ctx->exact = false;
     return rc;
   }

@@ -232,6 +232,8 @@ struct FxWork {
   signed char *head_je; // per chain (head): trailing zeros of the state there
   uint32_t *q_start;    // per chain (head): first window the chaining pass applies; 0xffffffff: finished by the head
   fx::SegRecord *rec;   // per (window, dimension), chain-major
+  unsigned int *refine_list;   // storage indices of the records the first chaining pass marked
+  unsigned int *refine_count;
   fx::Tables *tab;      // X_t table (device copy)
 };
 
@@ -301,7 +303,10 @@ __global__ void fx_cells_kernel(const uint32_t *__restrict__ keys_sorted, const 
     if (threadIdx.x == blockDim.x - 1) s_carry += s_part[threadIdx.x];
     __syncthreads();
   }
-  if (threadIdx.x == 0) w.win_off[K] = s_carry;
+  if (threadIdx.x == 0) {
+    w.win_off[K] = s_carry;
+    *w.refine_count = 0;
+  }
 }
 
 // (global window, dimension) -> cell, window inside the cell
@@ -349,11 +354,16 @@ __global__ void __launch_bounds__(128) fx_scan_kernel(const FxGeom g, FxWork w) 
   const unsigned int cnt = w.win_off[k + 1] - w.win_off[k];
   u128 *p = w.sumX + fx_index(w, g.dim, k, e, 0);
   u128 carry = 0;
-  for (unsigned int q0 = 0; q0 < cnt; q0 += 32) {
-    const unsigned int q = q0 + lane;
-    const u128 v = q < cnt ? p[q] : (u128)0;
-    unsigned long long l0 = (unsigned long long)v & 0xffffffffull, l1 = (unsigned long long)(v >> 32) & 0xffffffffull,
-                       l2 = (unsigned long long)(v >> 64);
+  for (unsigned int q0 = 0; q0 < cnt; q0 += 128) {  // four consecutive windows per lane
+    const unsigned int q = q0 + 4 * lane;
+    u128 v[4], loc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      v[i] = q + i < cnt ? p[q + i] : (u128)0;
+      loc += v[i];
+    }
+    unsigned long long l0 = (unsigned long long)loc & 0xffffffffull, l1 = (unsigned long long)(loc >> 32) & 0xffffffffull,
+                       l2 = (unsigned long long)(loc >> 64);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned long long a0 = __shfl_up_sync(0xffffffffu, l0, o), a1 = __shfl_up_sync(0xffffffffu, l1, o),
@@ -365,7 +375,12 @@ __global__ void __launch_bounds__(128) fx_scan_kernel(const FxGeom g, FxWork w) 
       }
     }
     const u128 incl = (u128)l0 + ((u128)l1 << 32) + ((u128)l2 << 64);
-    if (q < cnt) p[q] = carry + incl - v;  // exclusive
+    u128 run = carry + incl - loc;  // exclusive prefix of this lane's first window
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (q + i < cnt) p[q + i] = run;
+      run += v[i];
+    }
     const unsigned long long t0 = __shfl_sync(0xffffffffu, l0, 31), t1 = __shfl_sync(0xffffffffu, l1, 31),
                              t2 = __shfl_sync(0xffffffffu, l2, 31);
     carry += (u128)t0 + ((u128)t1 << 32) + ((u128)t2 << 64);
@@ -469,11 +484,10 @@ __global__ void __launch_bounds__(kFxRunThreads) fx_refine_kernel(const FxGeom g
   unsigned char *stage = fx_smem + sizeof(fx::Tables);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) tab.X[i] = w.tab->X[i];
   __syncthreads();
-  const unsigned long long total = (unsigned long long)w.win_off[g.K] * g.dim;
-  for (unsigned long long id = blockIdx.x * (unsigned long long)kFxRunThreads + threadIdx.x; id < total;
-       id += (unsigned long long)gridDim.x * kFxRunThreads) {
-    // records are chain-major: id enumerates them in storage order, the dimension follows from the cell's layout
-    if (!(w.rec[id].flags & fx::kFxRefine)) continue;
+  const unsigned int total = *w.refine_count;
+  for (unsigned int li = blockIdx.x * kFxRunThreads + threadIdx.x; li < total; li += gridDim.x * kFxRunThreads) {
+    // records are chain-major: id is a storage index, the dimension follows from the cell's layout
+    const unsigned long long id = w.refine_list[li];
     fx::SegRecord r = w.rec[id];
     const unsigned int gw_first = (unsigned int)(id / (unsigned int)g.dim);  // some window of the same cell
     int k;
@@ -571,7 +585,10 @@ __global__ void __launch_bounds__(32 * kFxChainWarps) fx_chain_kernel(const FxGe
     long long Wn = W;
     if (lane == f) {
       fx::fx_mark_and_estimate(r, Wn);
-      if (r.flags & fx::kFxRefine) rec[q0 + f] = r;
+      if (r.flags & fx::kFxRefine) {
+        rec[q0 + f] = r;
+        w.refine_list[atomicAdd(w.refine_count, 1u)] = (unsigned int)((rec + q0 + f) - w.rec);
+      }
     }
     W = __shfl_sync(0xffffffffu, Wn, f);
     marked = 1;  // (sequential segments count as well: only the exact pass can run them)
@@ -721,7 +738,10 @@ __global__ void __launch_bounds__(32 * kFxBlockWarps) fx_chain_block_kernel(cons
     long long Wn = W;
     if (lane == f) {
       fx::fx_mark_and_estimate(r, Wn);
-      if (r.flags & fx::kFxRefine) rec[my_q0 + f] = r;
+      if (r.flags & fx::kFxRefine) {
+        rec[my_q0 + f] = r;
+        w.refine_list[atomicAdd(w.refine_count, 1u)] = (unsigned int)((rec + my_q0 + f) - w.rec);
+      }
       s_marked = 1;
     }
     W = __shfl_sync(0xffffffffu, Wn, f);
@@ -896,7 +916,7 @@ size_t exact_fast_workspace_bytes(size_t n, int K, int dim) {
   size_t b = 0;
   b += fx_up(((size_t)K + 1) * 4) * 2;
   b += fx_up(per * 16) + fx_up(per) + fx_up(chains * 16) * 2 + fx_up(chains * 4) * 2 + fx_up(chains);
-  b += fx_up(per * sizeof(fx::SegRecord)) + fx_up(sizeof(fx::Tables));
+  b += fx_up(per * sizeof(fx::SegRecord)) + fx_up(sizeof(fx::Tables)) + fx_up(per * 4) + 256;
   return b + 256;
 }
 
@@ -924,6 +944,8 @@ cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_so
   w.head_je = (signed char *)take(chains);
   w.q_start = (uint32_t *)take(chains * 4);
   w.rec = (fx::SegRecord *)take(per * sizeof(fx::SegRecord));
+  w.refine_list = (unsigned int *)take(per * 4);
+  w.refine_count = (unsigned int *)take(256);
   w.tab = (fx::Tables *)take(sizeof(fx::Tables));
   static fx::Tables h_tab;
   static bool h_tab_ready = false;
