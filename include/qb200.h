@@ -284,7 +284,8 @@ int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *orde
 /* Diagnostic: the per-query records {best score, second best score, chunk index (bits), 0} the tensor-core
  * filter left behind in its last pass (num_vectors x 4 floats, lattice units: score = |C|^2 - 2<X,C>), so that
  * its rounding error can be audited against the bound its margin is derived from.  Valid right after
- * qb200_assign_only / qb200_assign_accumulate on a codebook of 128 or more entries. */
+ * qb200_assign_only / qb200_assign_accumulate on a codebook of 128 or more entries; set the environment variable
+ * QB200_DEBUG_RECORDS=1 first (the fused tensor-core kernel keeps no records otherwise). */
 int qb200_debug_filter_records(qb200_ctx *ctx, float *records_out);
 
 /* Number of kernels this library has launched in this process since the last reset

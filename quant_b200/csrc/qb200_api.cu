@@ -1464,7 +1464,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   cudaStream_t st = ctx->stream;
   int rc;
   const bool exact = ctx->exact && scaled;
-  if (exact && (rc = exact_prepare(ctx, maxK))) return rc;
+  // (auto mode: the buffers of a possible exact repeat are allocated now, while no rank is inside a collective)
+  if ((exact || (ctx->exact_auto && scaled)) && (rc = exact_prepare(ctx, maxK))) return rc;
   // everything the levels will need, at its final size: no buffer is reallocated while work is in flight
   const LevelLayout Lmax = level_layout(ctx, maxK, dim);
   size_t rows_max = 0, tc_max = 0;

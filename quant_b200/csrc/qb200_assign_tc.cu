@@ -84,17 +84,30 @@ __device__ __forceinline__ void chunkmin_update8(const float *a, int cid, float 
   best = fminf(best, m);
 }
 
-template <int DIM, int S>
+// What the FUSED variant needs on top: the FP32 rows (staged in shared memory next to the bf16 limbs) and the outputs
+// of the finalise step, which its merger warps then do themselves - no per-query record leaves the SM.
+struct TcFuse {
+  const float *rows32;
+  float margin_coef;
+  const float *c_max_ptr;
+  uint32_t *assign, *flag_list;
+  unsigned int *flag_count;
+  int keep_records;  // diagnostics (qb200_debug_filter_records): store the per-query records as the unfused path does
+};
+
+template <int DIM, int S, bool FUSE>
 __global__ void __launch_bounds__(tc_threads(S), 1)
     assign_tc_kernel(const VecSource src, const unsigned char *__restrict__ b_staged, const int k_rows, const int k_base,
-                     const int first_pass, float *__restrict__ state, const unsigned long long tiles) {
+                     const int first_pass, float *__restrict__ state, const unsigned long long tiles, const TcFuse fuse) {
   using Cfg = TcCfg<DIM>;
   constexpr int KB = Cfg::KB;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // [ B chunk | A tile ring | TcShared ]
+  // [ B chunk | (FUSE: FP32 rows) | A tile ring | TcShared ]
   const uint32_t b_bytes = (uint32_t)k_rows * Cfg::ROW_BYTES;
+  const uint32_t r_bytes = FUSE ? (uint32_t)k_rows * Cfg::ROW32 * 4u : 0u;
   unsigned char *s_b = smem_raw;
-  unsigned char *s_a = smem_raw + ((b_bytes + 1023u) & ~1023u);
+  float4 *s_rows4 = reinterpret_cast<float4 *>(smem_raw + ((b_bytes + 1023u) & ~1023u));
+  unsigned char *s_a = smem_raw + ((b_bytes + 1023u) & ~1023u) + ((r_bytes + 1023u) & ~1023u);
   TcShared<S> &sh = *reinterpret_cast<TcShared<S> *>(s_a + kAStages * Cfg::A_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,9 +238,35 @@ __global__ void __launch_bounds__(tc_threads(S), 1)
     // test and the index inside the winning chunk are done by tc_finalize_kernel after the last pass.
     const int r = (warp - 1 - 4 * kProdGroups) * 32 + lane;
     unsigned int tile_seq = 0;
+    constexpr int WORDS = (DIM + 3) / 4, ROW32 = Cfg::ROW32, NF4 = ROW32 / 4;
+    float c_max_norm = 0.f;
+    // slot of float4 number q of row `row`: 16-float rows sit 64 bytes apart, so lanes reading the same q of unrelated
+    // rows would hit two of the eight 16-byte bank groups; rotating by the row number spreads them over all eight
+    auto slot = [](int row, int q) { return NF4 == 4 ? ((q + (row >> 1)) & 3) : (NF4 == 2 ? ((q + (row >> 2)) & 1) : q); };
+    if (FUSE) {
+      // the four merger warps copy the FP32 rows into shared memory themselves (they have nothing else to do until
+      // the first tile is through the pipeline) and meet at their own named barrier
+      const float4 *g = reinterpret_cast<const float4 *>(fuse.rows32);
+      for (int i = r; i < k_rows * NF4; i += kTileQ) {
+        const int row = i / NF4, q = i - row * NF4;
+        s_rows4[row * NF4 + slot(row, q)] = __ldg(g + i);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      c_max_norm = *fuse.c_max_ptr;
+    }
     for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, tile_seq++) {
       const unsigned long long v = tile * kTileQ + r;
       const int rb = tile_seq % kResStages;
+      uint32_t xw[WORDS];
+      if (FUSE) {  // the query's bytes again (L2 hit: the producers read them a moment ago), before the wait
+#pragma unroll
+        for (int i = 0; i < WORDS; i++) xw[i] = 0u;
+        if (v < src.n_local) {
+          const uint32_t *p = reinterpret_cast<const uint32_t *>(src.dense + v * (unsigned long long)src.dense_stride);
+#pragma unroll
+          for (int i = 0; i < WORDS; i++) xw[i] = __ldg(p + i);
+        }
+      }
       mbar_wait_bounded<20000>(&sh.res_full[rb], (tile_seq / kResStages) & 1, 5);
       float best = sh.res_best[rb][0][r], runner = sh.res_second[rb][0][r];
       int chunk = sh.res_chunk[rb][0][r];
@@ -239,7 +278,53 @@ __global__ void __launch_bounds__(tc_threads(S), 1)
         best = fminf(best, b);
       }
       mbar_arrive(&sh.res_empty[rb]);
-      if (v < src.n_local) reinterpret_cast<float4 *>(state)[v] = make_float4(best, runner, __int_as_float(chunk), 0.f);
+      if (!FUSE || fuse.keep_records) {
+        if (v < src.n_local) reinterpret_cast<float4 *>(state)[v] = make_float4(best, runner, __int_as_float(chunk), 0.f);
+        if (!FUSE) continue;
+      }
+      // ---- fused finalise: FP32 rescoring of the winning chunk's eight rows from shared memory, margin test on both
+      // gaps (tensor-core scores across chunks, FP32 scores inside the chunk), index and flag - see tc_finalize_kernel
+      bool flag = false;
+      if (v < src.n_local) {
+        float x[DIM], xn = 0.f;
+#pragma unroll
+        for (int e = 0; e < DIM; e++) {
+          x[e] = (float)(int)(signed char)(xw[e >> 2] >> (8 * (e & 3)));
+          xn = fmaf(x[e], x[e], xn);
+        }
+        const float rr = sqrtf(xn) + c_max_norm;
+        const float margin = fuse.margin_coef * rr * rr;
+        float sb = FLT_MAX, s2 = FLT_MAX;
+        int bidx = chunk * 8;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int row = chunk * 8 + c;
+          float cr[ROW32];
+#pragma unroll
+          for (int q = 0; q < NF4; q++) {
+            const float4 t = s_rows4[row * NF4 + slot(row, q)];
+            cr[4 * q] = t.x; cr[4 * q + 1] = t.y; cr[4 * q + 2] = t.z; cr[4 * q + 3] = t.w;
+          }
+          float sc = cr[DIM];
+#pragma unroll
+          for (int e = 0; e < DIM; e++) sc = fmaf(x[e], cr[e], sc);
+          s2 = fminf(s2, fmaxf(sb, sc));
+          if (sc < sb) {
+            sb = sc;
+            bidx = row;
+          }
+        }
+        flag = !((runner - best) > margin && (s2 - sb) > margin);
+        fuse.assign[v] = (uint32_t)bidx | (flag ? kUndecided : 0u);
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, flag);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned int basepos = 0;
+        if (lane == leader) basepos = atomicAdd(fuse.flag_count, (unsigned int)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (flag) fuse.flag_list[basepos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+      }
     }
   } else {
     // =========================== epilogue: TMEM -> registers -> running top-2 ===========================
@@ -571,16 +656,38 @@ static cudaError_t launch_tc_t(const AssignTcLaunch &a) {
   // 16) were measured as well: 0.675 against 0.686 ms at K = 1024 on config 2 - the epilogue is bound by the alu pipe,
   // not by tcgen05.ld latency - and their larger result ring costs a third pass at K = 4096, so two it is.
   constexpr int kSplit = 2;
-  const size_t smem_max = (((size_t)chunk * Cfg::ROW_BYTES + 1023) & ~(size_t)1023) + kAStages * Cfg::A_BYTES + sizeof(TcShared<kSplit>) + 1024;
-  auto kernel = assign_tc_kernel<DIM, kSplit>;
+  const size_t b_smem = ((size_t)chunk * Cfg::ROW_BYTES + 1023) & ~(size_t)1023;
+  const size_t tail_smem = kAStages * Cfg::A_BYTES + sizeof(TcShared<kSplit>) + 1024;
+  const size_t rows_smem = ((size_t)kp * Cfg::ROW32 * 4 + 1023) & ~(size_t)1023;
+  const unsigned int grid = (unsigned int)(tiles < (unsigned long long)a.sm_count ? tiles : a.sm_count);
   const int threads = tc_threads(kSplit);
+  // FUSED: the whole codebook is one pass and its FP32 rows fit next to the bf16 limbs - the merger warps then do
+  // the finalise step (margin test, member of the winning chunk, index, flag) and no 16-byte per-query record is
+  // written and read back (QB200_TC_NO_FUSE=1 keeps the separate tc_finalize_kernel for comparison)
+  static const bool fuse_enabled = [] {
+    const char *e = std::getenv("QB200_TC_NO_FUSE");
+    return !(e && e[0] == '1');
+  }();
+  if (fuse_enabled && chunk == kp && b_smem + rows_smem + tail_smem <= 227 * 1024) {
+    const size_t smem = b_smem + rows_smem + tail_smem;
+    auto kernel = assign_tc_kernel<DIM, kSplit, true>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const char *dbg = std::getenv("QB200_DEBUG_RECORDS");
+    const TcFuse f{a.rows32, a.margin_coef, a.c_max_ptr, a.assign, a.flag_list, a.flag_count, dbg && dbg[0] == '1' ? 1 : 0};
+    kernel<<<grid, threads, smem, a.stream>>>(a.src, a.b_staged, kp, 0, 1, a.state, tiles, f);
+    count_launch();
+    return cudaGetLastError();
+  }
+  const size_t smem_max = b_smem + tail_smem;
+  auto kernel = assign_tc_kernel<DIM, kSplit, false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
   if (e != cudaSuccess) return e;
-  const unsigned int grid = (unsigned int)(tiles < (unsigned long long)a.sm_count ? tiles : a.sm_count);
+  const TcFuse no_fuse{};
   for (int k0 = 0; k0 < kp; k0 += chunk) {
     const int rows = kp - k0 < chunk ? kp - k0 : chunk;
     kernel<<<grid, threads, smem_max, a.stream>>>(a.src, a.b_staged + (size_t)k0 * Cfg::ROW_BYTES, rows,
-                                                                    k0, k0 == 0, a.state, tiles);
+                                                    k0, k0 == 0, a.state, tiles, no_fuse);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

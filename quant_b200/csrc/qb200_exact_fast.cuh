@@ -57,7 +57,9 @@ typedef unsigned __int128 u128;
 typedef __int128 i128;
 
 constexpr int kFxMaxCls = 8;   // speculative classes per segment; beyond that the segment is run sequentially
-constexpr int kFxAnchorWin = 16;  // members searched for an anchor at the start of a nominal window
+// members searched for an anchor at the start of a nominal window (16 was tried: a fifth less staging, but cells whose
+// high-level members are sparse then enter with a low je, their batches stop being composable and chaining slows 3-5x)
+constexpr int kFxAnchorWin = 64;
 
 struct Tables {
   unsigned long long X[256];  // X_t = fl(t/255) * 2^60 (host-filled: fx_fill_tables)
@@ -203,7 +205,7 @@ QB_HD void fx_fp_step(double &sum, double &c, int t) {
 struct Anchor {
   unsigned int b;
   int je;
-  unsigned long long xsum_lo;  // at most 16 * 2^60 < 2^65: low 64 bits and the carry bits
+  unsigned long long xsum_lo;  // at most 64 * 2^60 < 2^67: low 64 bits and the carry bits
   unsigned int xsum_hi;
 };
 template <typename Acc>
