@@ -48,7 +48,8 @@ struct qb200_ctx {
   std::vector<cudaEvent_t> pipe_ev;  // pipelined train: 6 timing events per level + 2 codebook-ready events
   void *h_pipe = nullptr;            // pinned slots of the pipelined train
   size_t h_pipe_cap = 0;
-  DevBuf d_cbnext[2], d_post, d_summary, d_levels;  // d_levels: every level's pre-fix codebook of the last pipelined train
+  DevBuf d_cbnext[2], d_post, d_summary, d_levels, d_cvexact;
+  const unsigned char *cv_exact_now = nullptr;  // flags of the codebook the level being run uses (pipelined train)  // d_levels: every level's pre-fix codebook of the last pipelined train
   std::vector<int> pipe_depth;
   std::vector<char> pipe_side_used;
   std::string err;
@@ -396,7 +397,7 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
   CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p,
                     (const double *)ctx->d_cb64.p + (size_t)K * dim, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
-                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, result, cnt + 5, ctx->sm_count, st));
+                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, result, cnt + 5, ctx->cv_exact_now, ctx->sm_count, st));
   if (ctx->side_pending) {
     CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU(launch_commit_resolved((const uint32_t *)ctx->d_flags.p, cnt, result, (uint32_t *)ctx->d_assign.p, ctx->sm_count, st));
@@ -865,7 +866,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
   for (auto &e2 : ctx->pipe_ev)
     if (e2) cudaEventDestroy(e2);
-  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_levels, &ctx->d_exact, &ctx->d_sort_keys,
+  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_levels, &ctx->d_cvexact, &ctx->d_exact, &ctx->d_sort_keys,
                     &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp, &ctx->d_fx, &ctx->d_f64, &ctx->d_partials, &ctx->d_counts})
     free_buf(*b);
   for (auto &ev : ctx->ev)
@@ -1466,6 +1467,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   const bool exact = ctx->exact && scaled;
   // (auto mode: the buffers of a possible exact repeat are allocated now, while no rank is inside a collective)
   if ((exact || (ctx->exact_auto && scaled)) && (rc = exact_prepare(ctx, maxK))) return rc;
+  if ((rc = ensure(ctx, ctx->d_misc, 4096))) return rc;  // the auto mode's tie census travels through it
   // everything the levels will need, at its final size: no buffer is reallocated while work is in flight
   const LevelLayout Lmax = level_layout(ctx, maxK, dim);
   size_t rows_max = 0, tc_max = 0;
@@ -1488,6 +1490,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   if ((rc = ensure(ctx, ctx->d_post, cb_max + 256))) return rc;
   if ((rc = ensure(ctx, ctx->d_summary, 64 * 32))) return rc;
   if ((rc = ensure(ctx, ctx->d_levels, 2 * cb_max + 256))) return rc;
+  if ((rc = ensure(ctx, ctx->d_cvexact, 2 * (size_t)maxK * 2 + 256))) return rc;  // two halves, alternating by level
+  auto cvx = [&](int level) { return (unsigned char *)ctx->d_cvexact.p + (size_t)(level & 1) * 2 * maxK; };
   auto level_off = [&](int level) { return (((size_t)2 << level) - 2) * (size_t)dim * 8; };  // bytes before level's codebook
   // pinned: [slots | host codebook 0 | host codebook 1 | final codebook]
   const size_t off_cb0 = (sizeof(PipeSlot) * 20 + 255) & ~(size_t)255, need = off_cb0 + 3 * (cb_max + 256);
@@ -1535,7 +1539,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   if (exact && (rc = exact_centroid_sums(ctx, 1, ar, ar_user))) return rc;
   CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, nullptr, exact ? (const double *)ctx->d_exact.p : nullptr,
                            1, dim, scaled, (double)N, f_up, f_dn,
-                           (double *)ctx->d_post.p, nbits ? (double *)ctx->d_cbnext[0].p : nullptr, summaries, st));
+                           (double *)ctx->d_post.p, nbits ? (double *)ctx->d_cbnext[0].p : nullptr, summaries,
+                           nbits ? cvx(0) : nullptr, st));
   CU(cudaMemcpyAsync(&slots[0].dist_pre, summaries, 32, cudaMemcpyDeviceToHost, st));
   if (nbits) {
     CU(cudaMemcpyAsync(h_cb[0], ctx->d_cbnext[0].p, (size_t)2 * dim * 8, cudaMemcpyDeviceToHost, st));
@@ -1555,6 +1560,9 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
                           ev ? ev[1] : nullptr, &fused, ev ? ev[4] : nullptr, ev ? ev[5] : nullptr)))
       return rc;
     side_used[level] = ctx->side_used;
+    // which codevectors of this level the integer path reproduces bit for bit (written by the previous finalise); not
+    // known after a restart and not needed with the compensated sums
+    ctx->cv_exact_now = (exact || first_level > 0) ? nullptr : cvx(level);
     CU(cudaEventSynchronize(cb_ready[cur]));  // this level's codebook has reached the host (the filter is already running)
     if ((rc = level_finish(ctx, h_cb[cur], K, true, fused, ev ? ev[2] : nullptr, ev ? ev[3] : nullptr,
                            slots[level + 1].counters, &depth[level])))
@@ -1565,7 +1573,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, (const double *)ctx->d_cb64.p,
                              exact ? (const double *)ctx->d_exact.p : nullptr, (int)K, dim, scaled,
                              (double)N, f_up, f_dn, (double *)ctx->d_post.p,
-                             last ? nullptr : (double *)ctx->d_cbnext[cur ^ 1].p, summaries + 32 * (level + 1), st));
+                             last ? nullptr : (double *)ctx->d_cbnext[cur ^ 1].p, summaries + 32 * (level + 1),
+                             last ? nullptr : cvx(level + 1), st));
     CU(cudaMemcpyAsync(&slots[level + 1].dist_pre, summaries + 32 * (level + 1), 32, cudaMemcpyDeviceToHost, st));
     if (!last) {
       CU(cudaMemcpyAsync(h_cb[cur ^ 1], ctx->d_cbnext[cur ^ 1].p, (size_t)2 * K * dim * 8, cudaMemcpyDeviceToHost, st));
@@ -1576,6 +1585,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
       CU(cudaMemcpyAsync(h_final, ctx->d_post.p, (size_t)K * dim * 8, cudaMemcpyDeviceToHost, st));
     }
   }
+  ctx->cv_exact_now = nullptr;
   if (nbits == 0) CU(cudaMemsetAsync(ctx->d_assign.p, 0, (size_t)ctx->src.n_local * 4, st));
   CU(cudaStreamSynchronize(st));
   if (slots[0].n_seen != N)
@@ -1622,6 +1632,7 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
                            double *codebook_out, double *distortion_out, qb200_level_report *reports, int first_level = 0) {
   ctx->assign_valid = false;
   const int rc = train_parity_pipelined_body(ctx, nbits, N, ar, ar_user, codebook_out, distortion_out, reports, first_level);
+  ctx->cv_exact_now = nullptr;
   if (rc != QB200_OK) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);

@@ -661,12 +661,16 @@ static cudaError_t launch_tc_t(const AssignTcLaunch &a) {
   const size_t rows_smem = ((size_t)kp * Cfg::ROW32 * 4 + 1023) & ~(size_t)1023;
   const unsigned int grid = (unsigned int)(tiles < (unsigned long long)a.sm_count ? tiles : a.sm_count);
   const int threads = tc_threads(kSplit);
-  // FUSED: the whole codebook is one pass and its FP32 rows fit next to the bf16 limbs - the merger warps then do
-  // the finalise step (margin test, member of the winning chunk, index, flag) and no 16-byte per-query record is
-  // written and read back (QB200_TC_NO_FUSE=1 keeps the separate tc_finalize_kernel for comparison)
+  // FUSED variant (opt-in, QB200_TC_FUSE=1): when the whole codebook is one pass and its FP32 rows fit next to the bf16
+  // limbs, the merger warps do the finalise step themselves (margin test, member of the winning chunk, index, flag)
+  // and no 16-byte per-query record is written and read back.  MEASURED SLOWER than the separate finalise kernel
+  // (config 2: 0.52 / 0.59 / 0.71 / 0.86 ms at K = 128 / 256 / 512 / 1024 against 0.36 / 0.36 / 0.47 / 0.69 ms for
+  // kernel + tc_finalize_kernel): the four merger warps handle one tile at a time - 32 LDS.128 and ~150 dependent
+  // FP32 operations per query behind the epilogue's hand-off - and become the pipeline's slowest stage, while the
+  // separate kernel runs the same work at full occupancy in 0.15 ms.  Kept for the record, off by default.
   static const bool fuse_enabled = [] {
-    const char *e = std::getenv("QB200_TC_NO_FUSE");
-    return !(e && e[0] == '1');
+    const char *e = std::getenv("QB200_TC_FUSE");
+    return e && e[0] == '1';
   }();
   if (fuse_enabled && chunk == kp && b_smem + rows_smem + tail_smem <= 227 * 1024) {
     const size_t smem = b_smem + rows_smem + tail_smem;

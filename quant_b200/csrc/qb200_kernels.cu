@@ -798,7 +798,8 @@ __global__ void __launch_bounds__(128)
                               const unsigned int *__restrict__ flag_count, uint32_t *__restrict__ assign,
                               uint32_t *__restrict__ tie_list, unsigned int *__restrict__ tie_count,
                               unsigned int *__restrict__ changed, unsigned long long *__restrict__ stats,
-                              uint32_t *__restrict__ result, unsigned int *__restrict__ sensitive) {
+                              uint32_t *__restrict__ result, unsigned int *__restrict__ sensitive,
+                              const unsigned char *__restrict__ cv_exact) {
   // The filter's guess for a flagged query may carry the "undecided" mark in bit 31 (tensor-core finalise kernels: the
   // statistics pass that runs next to this kernel skips marked entries).  Every flagged query gets its exact index
   // written here or in phase B - to `result` when given (committed to `assign` once that pass is done), else in place.
@@ -845,16 +846,13 @@ __global__ void __launch_bounds__(128)
     const int mine = (d1 <= lim ? 1 : 0) + (d2 <= lim ? 1 : 0);
     const unsigned int holders = __ballot_sync(0xffffffffu, mine > 0);
     const unsigned int multi = __ballot_sync(0xffffffffu, mine > 1);
-    // Decisions the LAST BITS of the codebook could change: a second codevector within 2^-44 dmax of the minimum.
-    // (Centroids from the integer sums are within 4e-16 = 2^-51 relative of the reference's compensated sums; that
-    // moves a distance by less than 2^-48 dmax.)  Counted: a train without any such decision is index-identical with
-    // either centroid arithmetic (qb200_set_exact_centroids, auto mode).
-    if (sensitive) {
-      const double lim2 = wmin + wmax * 5.6843418860808015e-14;  // 2^-44
-      const int near2 = (d1 <= lim2 ? 1 : 0) + (d2 <= lim2 ? 1 : 0);
-      const unsigned int h2 = __ballot_sync(0xffffffffu, near2 > 0), m2 = __ballot_sync(0xffffffffu, near2 > 1);
-      if (lane == 0 && (__popc(h2) > 1 || m2 != 0)) atomicAdd(sensitive, 1u);
-    }
+    // Decisions the LAST BITS of the codebook could change (counted for the auto centroid mode): a second codevector
+    // within lim2 = 2^-44 dmax of the minimum.  (Centroids from the integer sums are within 4e-16 = 2^-51 relative of the
+    // reference's compensated sums; that moves a distance by less than 2^-48 dmax.)  Refined below: when every
+    // codevector inside that band is one the integer path reproduces BIT FOR BIT (children of a cell whose members
+    // are all one vector, dead cells: cv_exact) and the minimum is attained once, the exact search returns that
+    // minimum whatever the other codevectors' last bits are - not sensitive.
+    const double lim2 = wmin + wmax * 5.6843418860808015e-14;  // 2^-44
     int win = -1;
     if (__popc(holders) == 1 && multi == 0) {
       win = __shfl_sync(0xffffffffu, k1, __ffs(holders) - 1);
@@ -868,6 +866,7 @@ __global__ void __launch_bounds__(128)
       unsigned int my_pos = 0xffffffffu;  // up to 32 candidates, one per lane
       int n_cand = 0;
       bool exact = true;
+      int near2 = 0, at_min = 0, inexact2 = 0;  // census of the 2^-44 band (this lane's share)
       for (int k0 = 0; k0 < K; k0 += 32) {
         const int k = k0 + lane;
         bool cand = false;
@@ -875,6 +874,11 @@ __global__ void __launch_bounds__(128)
           const double d = DIMT ? nanoflann_l2_t_fixed<DIMT ? DIMT : 1>(x, cbt + k, (size_t)K) : nanoflann_l2_t(x, cbt + k, (size_t)K, dim);
           cand = d <= lim;
           exact = exact && (!cand || d == wmin);
+          if (d <= lim2) {
+            near2++;
+            at_min += d == wmin;
+            inexact2 += !(cv_exact && cv_exact[k]);
+          }
         }
         const unsigned int m = __ballot_sync(0xffffffffu, cand);
         const int slot = n_cand + __popc(m & ((1u << lane) - 1u));
@@ -888,6 +892,12 @@ __global__ void __launch_bounds__(128)
           if (lane == s_slot) my_pos = s_pos;
         }
         n_cand += __popc(m);
+      }
+      if (sensitive) {
+        near2 = __reduce_add_sync(0xffffffffu, near2);
+        at_min = __reduce_add_sync(0xffffffffu, at_min);
+        inexact2 = __reduce_add_sync(0xffffffffu, inexact2);
+        if (lane == 0 && near2 > 1 && (inexact2 > 0 || at_min > 1)) atomicAdd(sensitive, 1u);
       }
       const bool all_exact = __all_sync(0xffffffffu, exact);
       if (all_exact && n_cand <= 32) {
@@ -1424,7 +1434,7 @@ __global__ void __launch_bounds__(1024)
     finalize_split_kernel(const unsigned long long *__restrict__ stats, const double *__restrict__ cb_pre,
                           const double *__restrict__ exact_state, const int K, const int dim, const int scaled, const double n_total, const double f_up, const double f_dn,
                           double *__restrict__ cb_post, double *__restrict__ cb_next,
-                          LevelSummary *__restrict__ summary) {
+                          LevelSummary *__restrict__ summary, unsigned char *__restrict__ exact_next) {
   __shared__ double s_pre[1024], s_post[1024];
   __shared__ unsigned int s_dead[1024];
   __shared__ unsigned long long s_n[1024];
@@ -1453,6 +1463,13 @@ __global__ void __launch_bounds__(1024)
         q += (unsigned long long)(m * m);
       }
       same = same && row[dim + 1] == n * q;
+    }
+    // children of this cell whose centroid the integer path reproduces bit for bit (one repeated vector, or empty);
+    // NORMAL sums are integers: always exact
+    if (exact_next) {
+      const unsigned char ex = (!scaled || n == 0 || same || exact_state) ? 1 : 0;
+      exact_next[k] = ex;
+      exact_next[K + k] = ex;
     }
     double st2 = 0.0, cross = 0.0, c2 = 0.0;
     for (int e = 0; e < dim; e++) {
@@ -1714,12 +1731,13 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            const KdDevice &tree,
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
-                           unsigned long long *stats, uint32_t *result, unsigned int *sensitive, int sm_count, cudaStream_t stream) {
+                           unsigned long long *stats, uint32_t *result, unsigned int *sensitive, const unsigned char *cv_exact,
+                           int sm_count, cudaStream_t stream) {
   // phase A: brute force, one warp per flagged query (the count is only known on the device)
   const unsigned int blocks_a = (unsigned int)sm_count * 8;
 #define QB_RESOLVE_A(CAP, DT)                                                                                        \
   resolve_bruteforce_kernel<CAP, DT><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, \
-                                                                   assign, tie_list, tie_count, changed, stats, result, sensitive)
+                                                                   assign, tie_list, tie_count, changed, stats, result, sensitive, cv_exact)
   switch (src.dim) {
     case 3: QB_RESOLVE_A(3, 3); break;
     case 6: QB_RESOLVE_A(6, 6); break;
@@ -1873,9 +1891,9 @@ cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_r
 
 cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, const double *exact_state, int K,
                                   int dim, int scaled, double n_total, double f_up, double f_dn, double *cb_post,
-                                  double *cb_next, void *summary, cudaStream_t stream) {
+                                  double *cb_next, void *summary, unsigned char *exact_next, cudaStream_t stream) {
   finalize_split_kernel<<<1, 1024, 0, stream>>>(stats, cb_pre, exact_state, K, dim, scaled, n_total, f_up, f_dn, cb_post,
-                                                cb_next, reinterpret_cast<LevelSummary *>(summary));
+                                                cb_next, reinterpret_cast<LevelSummary *>(summary), exact_next);
   g_launch_count++;
   return cudaGetLastError();
 }

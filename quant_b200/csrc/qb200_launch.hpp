@@ -47,6 +47,7 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            unsigned long long *stats /* null unless the flagged queries' statistics are added here */,
                            uint32_t *result /* null: exact indices go straight to assign; else to result[v], see below */,
                            unsigned int *sensitive /* device counter (may be null): decisions that hinged on (near-)ties */,
+                           const unsigned char *cv_exact /* per codevector (may be null): reproduced bit for bit by the integer path */,
                            int sm_count, cudaStream_t stream);
 // assign[v] = result[v] for the flagged queries: used when a statistics pass read `assign` while the resolver ran.
 cudaError_t launch_commit_resolved(const uint32_t *flag_list, const unsigned int *flag_count, const uint32_t *result,
@@ -94,7 +95,8 @@ cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32
 // centroid is then sum / n, the reference's own operation.
 cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, const double *exact_state, int K,
                                   int dim, int scaled, double n_total, double f_up, double f_dn, double *cb_post,
-                                  double *cb_next, void *summary, cudaStream_t stream);
+                                  double *cb_next, void *summary, unsigned char *exact_next /* 2K flags for cb_next, or null */,
+                                  cudaStream_t stream);
 // Bit-exact centroid sums (qb200_exact.cu): stable sort of the members by cell, then the reference's compensated
 // summation in ascending vector order, one warp per cell.
 // Stable LSD radix sort of (cell, vector index) by cell (qb200_sort.cu): keys_out ascending, order_out = original positions.
