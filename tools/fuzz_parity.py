@@ -1,6 +1,8 @@
 """Randomised parity fuzz on a GPU box: GPU assignment (both filter engines) and full trains vs the C oracle.
-   python tools/fuzz_parity.py [seconds] [seed] [exact]
-Without "exact", full trains on duplicate-heavy SCALED images can differ from the oracle (integer-sum centroids
+   python tools/fuzz_parity.py [seconds] [seed] [exact|auto]
+"auto" = the library's default centroid mode (integer sums, repeated with the compensated sums when the train had
+tie-sensitive decisions): like "exact", every train must end with the oracle's indices (0 tie-flips).
+Without "exact"/"auto" (integer sums only), full trains on duplicate-heavy SCALED images can differ from the oracle (integer-sum centroids
 differ from the reference's compensated sums in the last bit, which decides exact ties one level later): those
 are reported as "tie-flip" and only counted as failures when the per-level check with the ORACLE's codebooks as
 input also fails.  With "exact" (qb200_set_exact_centroids) every train must match bit for bit, codebook included."""
@@ -13,10 +15,11 @@ from oracle.pyoracle import PortLib
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 exact = len(sys.argv) > 3 and sys.argv[3] == "exact"
+auto = len(sys.argv) > 3 and sys.argv[3] == "auto"
 rng = np.random.default_rng(seed)
 P = PortLib()
 ctx = qb.Context(0)
-ctx.set_exact_centroids(exact)
+ctx.set_exact_centroids("auto" if auto else (1 if exact else 0))
 flips = 0
 t_end = time.time() + budget
 cases = bad = 0
@@ -106,7 +109,7 @@ while time.time() < t_end:
         cb, d, _ = ctx.train(nbits)
         a = ctx.get_assign().astype(np.uint64)
         ok = np.array_equal(a, a_o) and np.array_equal(qb.codebook_to_bytes(cb, cs), P.codebook_to_bytes(cb_o, cs))
-        if exact or cs != 1:
+        if exact or cs != 1 or (auto and ctx.last_train_exact):
             ok = ok and cb.tobytes() == np.ascontiguousarray(cb_o).tobytes()
         if not ok and not exact and cs == 1:
             # allowed only if every level, fed the oracle's own codebook, is bit-identical (indices, counts, sums)
@@ -126,5 +129,5 @@ while time.time() < t_end:
             bad += 1
             print(f"MISMATCH train kind={kind} xs={xs} ys={ys} w={w} h={h} cs={cs} nbits={nbits} N={N}: {int((a != a_o).sum())} indices", flush=True)
     cases += 1
-print(f"fuzz: {cases} cases, {bad} bad, {flips} end-to-end tie-flips with bit-identical levels (seed {seed}, exact={exact})")
-sys.exit(1 if bad else 0)
+print(f"fuzz: {cases} cases, {bad} bad, {flips} end-to-end tie-flips with bit-identical levels (seed {seed}, mode={'auto' if auto else 'exact' if exact else 'integer'})")
+sys.exit(1 if bad or (auto and flips) else 0)   # auto mode promises end-to-end identity: a tie-flip is a failure there
