@@ -77,8 +77,14 @@ def natural_band(xs, ys, first_line):
     return np.ascontiguousarray(_KODAK[lines][:, cols])
 
 
-def make_band(kind, xs, ys, seed, first_line=0):
-    return natural_band(xs, ys, first_line) if kind == "natural" else noise_band(xs, ys, seed)
+def make_band(kind, xs, ys, seed, first_line=0, total_lines=None):
+    """Lines [first_line, first_line + xs).  total_lines (strong scaling): the band is a slice of the ONE
+    total_lines-high workload image, so that every rank count trains the same image."""
+    if kind == "natural":
+        return natural_band(xs, ys, first_line)
+    if total_lines is not None and total_lines != xs:
+        return np.ascontiguousarray(noise_band(total_lines, ys, seed)[first_line:first_line + xs])
+    return noise_band(xs, ys, seed)
 
 
 def desc_of(desc, data):
@@ -303,7 +309,10 @@ def run_gpu_arm(args):
     if world > 1:
         ctx.set_rank(rank, world)
 
-    band_np = make_band(args.data, bx, ys, 1234 + rank, rank * bx).reshape(-1)
+    if args.strong:   # the same image whatever the rank count
+        band_np = make_band(args.data, bx, ys, 1234, rank * bx, total_lines=xs_total).reshape(-1)
+    else:
+        band_np = make_band(args.data, bx, ys, 1234 + rank, rank * bx).reshape(-1)
     host_band = torch.empty(band_np.size, dtype=torch.uint8, pin_memory=True)
     host_band.numpy()[:] = band_np
     host_assign = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
@@ -366,6 +375,18 @@ def run_gpu_arm(args):
     # clocks over both timed regions (a train lasts milliseconds: the e2e warm-up in between is under load as well)
     clocks = sampler.stop(t0, t3) if sampler else None
     assert np.array_equal(cb_res, cb_e2e) and d_res == d_e2e, "resident and e2e trains disagree"
+
+    # When the default (auto) mode had to repeat the train with the compensated sums, also time the integer-sum mode
+    # alone (mode 0): what the same workload costs without the end-to-end identity guarantee (round 1's default).
+    integer_only = None
+    if took_exact_res and not exact:
+        ctx.set_exact_centroids(0)
+        ms_int, _, _, _, _, _ = timed("resident", min(args.steps, 3), 2)
+        ctx.set_exact_centroids("auto" if args.centroids == "auto" else 0)
+        integer_only = {"ms_per_step": ms_int / min(args.steps, 3),
+                        "value": evals_per_train(n_total, nbits) / (ms_int / min(args.steps, 3) * 1e-3) / 1e9, "unit": UNIT,
+                        "what": "qb200_set_exact_centroids(ctx, 0): integer-sum centroids only; every assignment pass is still "
+                                "bit-identical given the same codebook, the final indices only on inputs without tie-sensitive decisions"}
 
     # The same shape on NATURAL data (kodim01 tiled): flat areas, duplicated blocks and dead cells push far more
     # queries through the exact FP64 resolver and its tree walk than noise does (and the reference's KD search is
@@ -482,7 +503,7 @@ def run_gpu_arm(args):
                     "h2d_bytes_per_step": int(host_band.numel()) * world,
                     "d2h_bytes_per_step": (n_local * 4) * world,
                     "seconds_per_train": ms_e2e / args.steps / 1e3},
-            "e2e_cpp": e2e_cpp, "natural": natural,
+            "e2e_cpp": e2e_cpp, "natural": natural, "integer_sum_mode": integer_only,
             "gpu_launches": launches,
             "roofline": roof,
             "per_level_ms": per_level, "sensitive_per_level": {str(r["K"]): int(r["sensitive"]) for r in reps[-1]},

@@ -3,6 +3,7 @@
 #include "kd_host.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <utility>
 
 namespace qb {
@@ -23,6 +24,7 @@ class Builder {
     out_.order.resize(n_);
     for (size_t i = 0; i < n_; i++) out_.order[i] = (unsigned int)i;
     out_.depth = 0;
+    out_.min_margin = 1.0;
     std::vector<Range> box(dim_);
     if (n_ == 0) {
       out_.box_low.assign(dim_, 0.0);
@@ -48,6 +50,13 @@ class Builder {
 
  private:
   double at(size_t point, int d) const { return pts_[point * (size_t)dim_ + d]; }
+  // Robustness census (KdHostTree::min_margin): the smallest relative distance of any comparison that shapes the tree
+  // from flipping.  Not part of nanoflann; it only observes.
+  void note(double a, double b) {
+    const double scale = std::max(std::fabs(a), std::fabs(b));
+    const double m = scale > 0 ? std::fabs(a - b) / scale : 0.0;
+    if (m < out_.min_margin) out_.min_margin = m;
+  }
   double via(size_t pos, int d) const { return at(out_.order[pos], d); }
 
   void span_of(size_t first, size_t count, int d, double &mn, double &mx) const {
@@ -96,24 +105,46 @@ class Builder {
       double span = box[d].hi - box[d].lo;
       if (span > max_span) max_span = span;
     }
-    double best_spread = -1;
+    double best_spread = -1, second_spread = -1;
     feat = 0;
     for (int d = 0; d < dim_; d++) {
       double span = box[d].hi - box[d].lo;
+      note(span, (1 - kEps) * max_span);  // eligibility of this dimension
       if (span > (1 - kEps) * max_span) {
         double mn, mx;
         span_of(first, count, d, mn, mx);
         double spread = mx - mn;
         if (spread > best_spread) {
           feat = d;
+          second_spread = best_spread;
           best_spread = spread;
+        } else if (spread > second_spread) {
+          second_spread = spread;
         }
       }
     }
+    if (second_spread >= 0) note(best_spread, second_spread);  // which eligible dimension wins
     double mid = (box[feat].lo + box[feat].hi) / 2;
     double mn, mx;
     span_of(first, count, feat, mn, mx);
     cut = mid < mn ? mn : (mid > mx ? mx : mid);
+    {
+      // every point against the cutting plane.  A point AT the plane is harmless only when the plane was clamped onto
+      // the data range (then the plane is that point's own coordinate and moves with it).
+      const bool clamped = cut == mn || cut == mx;
+      if (mn == mx) out_.min_margin = 0.0;  // all points equal along the cut: the split is decided by position alone
+      for (size_t i = 0; i < count; i++) {
+        const double v = via(first + i, feat);
+        if (v != cut)
+          note(v, cut);
+        else if (!clamped)
+          out_.min_margin = 0.0;
+      }
+      if (!clamped) {  // the clamp decisions themselves
+        note(mid, mn);
+        note(mid, mx);
+      }
+    }
     size_t lim1, lim2;
     partition(first, count, feat, cut, lim1, lim2);
     if (lim1 > count / 2) return lim1;

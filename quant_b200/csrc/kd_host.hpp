@@ -27,6 +27,11 @@ struct KdHostTree {
   std::vector<unsigned int> order;  // nanoflann's `vind` after the build
   std::vector<double> box_low, box_high;  // root bounding box as left behind by the build
   int depth = 0;
+  // Smallest relative distance from flipping of any comparison that shaped the tree (span eligibility, choice of the
+  // cut dimension, points against the cutting plane, the clamp of the plane).  Above ~1e-9 the tree keeps its SHAPE and
+  // point order for any codebook within a few ulps of this one - what the auto centroid mode needs to know about
+  // decisions that hinge on the visiting order (qb200_api.cu, resolve_bruteforce_kernel).  0: degenerate (duplicates).
+  double min_margin = 0.0;
 };
 
 // points: K x dim, row-major FP64 (colour-space domain, exactly the doubles the reference holds).

@@ -397,7 +397,7 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
   CU(launch_resolve(ctx->src, ctx->colorspace == QB200_CS_SCALED, (const double *)ctx->d_cb64.p,
                     (const double *)ctx->d_cb64.p + (size_t)K * dim, (int)K, kd,
                     (const uint32_t *)ctx->d_flags.p, cnt, (uint32_t *)ctx->d_assign.p, (uint32_t *)ctx->d_ties.p,
-                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, result, cnt + 5, ctx->cv_exact_now, ctx->sm_count, st));
+                    cnt + 2, cnt + 1, fused ? (unsigned long long *)ctx->d_stats.p : nullptr, result, cnt + 5, ctx->cv_exact_now, tree.min_margin > 1e-9 ? 1 : 0, ctx->sm_count, st));
   if (ctx->side_pending) {
     CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     CU(launch_commit_resolved((const uint32_t *)ctx->d_flags.p, cnt, result, (uint32_t *)ctx->d_assign.p, ctx->sm_count, st));

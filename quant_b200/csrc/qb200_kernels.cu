@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(128)
                               uint32_t *__restrict__ tie_list, unsigned int *__restrict__ tie_count,
                               unsigned int *__restrict__ changed, unsigned long long *__restrict__ stats,
                               uint32_t *__restrict__ result, unsigned int *__restrict__ sensitive,
-                              const unsigned char *__restrict__ cv_exact) {
+                              const unsigned char *__restrict__ cv_exact, const int tree_robust) {
   // The filter's guess for a flagged query may carry the "undecided" mark in bit 31 (tensor-core finalise kernels: the
   // statistics pass that runs next to this kernel skips marked entries).  Every flagged query gets its exact index
   // written here or in phase B - to `result` when given (committed to `assign` once that pass is done), else in place.
@@ -897,8 +897,8 @@ __global__ void __launch_bounds__(128)
         near2 = __reduce_add_sync(0xffffffffu, near2);
         at_min = __reduce_add_sync(0xffffffffu, at_min);
         inexact2 = __reduce_add_sync(0xffffffffu, inexact2);
-        if (lane == 0 && near2 > 1 && (inexact2 > 0 || at_min > 1)) atomicAdd(sensitive, 1u);
       }
+      bool fragile = false;  // a step of the descent below within rounding noise of going the other way
       const bool all_exact = __all_sync(0xffffffffu, exact);
       if (all_exact && n_cand <= 32) {
         int node = 0, lo = 0, hi = K;
@@ -914,7 +914,9 @@ __global__ void __launch_bounds__(128)
             double val = 0.0;  // x[nd.a] by selection: a dynamic index would push x[] out of registers
 #pragma unroll
             for (int e = 0; e < (DIMT ? DIMT : DIMCAP); e++) val = (e == nd.a) ? x[e] : val;
-            go1 = __dadd_rn(__dsub_rn(val, nd.divlow), __dsub_rn(val, nd.divhigh)) < 0;  // nearer child first
+            const double side = __dadd_rn(__dsub_rn(val, nd.divlow), __dsub_rn(val, nd.divhigh));
+            go1 = side < 0;  // nearer child first
+            fragile = fragile || fabs(side) <= 1e-9 * (fabs(val) + fabs(nd.divlow) + fabs(nd.divhigh));
           } else {
             go1 = any1;
           }
@@ -932,6 +934,14 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
         win = (int)tree.vind[first];
+      }
+      // Sensitive to the last bits of the codebook?  Yes when a codevector in the 2^-44 band is not reproduced bit for
+      // bit by the integer path.  When they all are and the minimum is attained once, no (the exact search returns
+      // it).  When it is attained several times the visiting order decides: that order is the same for any codebook
+      // within a few ulps when the tree's shape is robust (KdHostTree::min_margin) and every step of the descent is.
+      if (sensitive && lane == 0 && near2 > 1) {
+        const bool order_safe = tree_robust && all_exact && n_cand <= 32 && !fragile;
+        if (inexact2 > 0 || (at_min > 1 && !order_safe)) atomicAdd(sensitive, 1u);
       }
     }
     if (win >= 0) {
@@ -1732,12 +1742,12 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            const uint32_t *flag_list, const unsigned int *flag_count, uint32_t *assign,
                            uint32_t *tie_list, unsigned int *tie_count, unsigned int *changed,
                            unsigned long long *stats, uint32_t *result, unsigned int *sensitive, const unsigned char *cv_exact,
-                           int sm_count, cudaStream_t stream) {
+                           int tree_robust, int sm_count, cudaStream_t stream) {
   // phase A: brute force, one warp per flagged query (the count is only known on the device)
   const unsigned int blocks_a = (unsigned int)sm_count * 8;
 #define QB_RESOLVE_A(CAP, DT)                                                                                        \
   resolve_bruteforce_kernel<CAP, DT><<<blocks_a, 128, 0, stream>>>(src, scaled, cbt, K, tree, flag_list, flag_count, \
-                                                                   assign, tie_list, tie_count, changed, stats, result, sensitive, cv_exact)
+                                                                   assign, tie_list, tie_count, changed, stats, result, sensitive, cv_exact, tree_robust)
   switch (src.dim) {
     case 3: QB_RESOLVE_A(3, 3); break;
     case 6: QB_RESOLVE_A(6, 6); break;

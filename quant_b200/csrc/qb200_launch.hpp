@@ -48,6 +48,7 @@ cudaError_t launch_resolve(const VecSource &src, int scaled, const double *cb, c
                            uint32_t *result /* null: exact indices go straight to assign; else to result[v], see below */,
                            unsigned int *sensitive /* device counter (may be null): decisions that hinged on (near-)ties */,
                            const unsigned char *cv_exact /* per codevector (may be null): reproduced bit for bit by the integer path */,
+                           int tree_robust /* the tree keeps its shape under last-bit changes of the codebook (KdHostTree::min_margin) */,
                            int sm_count, cudaStream_t stream);
 // assign[v] = result[v] for the flagged queries: used when a statistics pass read `assign` while the resolver ran.
 cudaError_t launch_commit_resolved(const uint32_t *flag_list, const unsigned int *flag_count, const uint32_t *result,
