@@ -916,7 +916,16 @@ __global__ void __launch_bounds__(128)
             for (int e = 0; e < (DIMT ? DIMT : DIMCAP); e++) val = (e == nd.a) ? x[e] : val;
             const double side = __dadd_rn(__dsub_rn(val, nd.divlow), __dsub_rn(val, nd.divhigh));
             go1 = side < 0;  // nearer child first
-            fragile = fragile || fabs(side) <= 1e-9 * (fabs(val) + fabs(nd.divlow) + fabs(nd.divhigh));
+            // Robust against last-bit changes of the codebook?  Yes when the margin is comfortable - or when both
+            // plane coordinates ARE coordinates of tied candidates (the query midway between the children 1.2c / 0.8c
+            // of its own single-member cell makes `side` a pure rounding residue, but of bit-reproducible operands).
+            if (sensitive && fabs(side) <= 1e-9 * (fabs(val) + fabs(nd.divlow) + fabs(nd.divhigh))) {
+              double coord = 0.0;
+              if (in1 || in2) coord = cbt[(size_t)nd.a * K + tree.vind[my_pos]];
+              const bool lo_ok = __any_sync(0xffffffffu, in1 && coord == nd.divlow);
+              const bool hi_ok = __any_sync(0xffffffffu, in2 && coord == nd.divhigh);
+              fragile = fragile || !(lo_ok && hi_ok);
+            }
           } else {
             go1 = any1;
           }
