@@ -507,6 +507,7 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": roof,
             "per_level_ms": per_level, "sensitive_per_level": {str(r["K"]): int(r["sensitive"]) for r in reps[-1]},
+            "sensitive_diag": {str(r["K"]): int(r["reserved"]) for r in reps[-1] if r["reserved"]},
             "flagged_last_level": flagged_last, "kd_walk_ties_last_level": ties_last,
             "distortion": d_res, "clocks": clocks,
         }

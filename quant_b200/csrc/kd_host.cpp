@@ -11,12 +11,15 @@ namespace {
 
 struct Range {
   double lo, hi;
+  // robustness census only: the bound is a number the integer-sum and the compensated-sum codebooks share bit for bit
+  // (it comes from bit-reproducible points, or from a plane computed from such bounds)
+  bool lo_exact = false, hi_exact = false;
 };
 
 class Builder {
  public:
-  Builder(const double *pts, size_t n, int dim, int leaf_max, KdHostTree &out)
-      : pts_(pts), n_(n), dim_(dim), leaf_max_((size_t)leaf_max), out_(out) {}
+  Builder(const double *pts, size_t n, int dim, int leaf_max, KdHostTree &out, const unsigned char *exact)
+      : pts_(pts), n_(n), dim_(dim), leaf_max_((size_t)leaf_max), out_(out), exact_(exact) {}
 
   void run() {
     out_.nodes.clear();
@@ -39,6 +42,10 @@ class Builder {
         if (v < box[d].lo) box[d].lo = v;
         if (v > box[d].hi) box[d].hi = v;
       }
+    for (int d = 0; d < dim_; d++) {
+      double mn, mx;
+      span_of(0, n_, d, mn, mx, &box[d].lo_exact, &box[d].hi_exact);
+    }
     subdivide(0, n_, box, 1);
     out_.box_low.resize(dim_);
     out_.box_high.resize(dim_);
@@ -53,18 +60,33 @@ class Builder {
   // Robustness census (KdHostTree::min_margin): the smallest relative distance of any comparison that shapes the tree
   // from flipping.  Not part of nanoflann; it only observes.
   void note(double a, double b) {
+    // (0 against 0: a subtree of dead cells' zero vectors - the same zeros with either centroid arithmetic)
+    if (a == 0.0 && b == 0.0) return;
     const double scale = std::max(std::fabs(a), std::fabs(b));
     const double m = scale > 0 ? std::fabs(a - b) / scale : 0.0;
     if (m < out_.min_margin) out_.min_margin = m;
   }
   double via(size_t pos, int d) const { return at(out_.order[pos], d); }
 
-  void span_of(size_t first, size_t count, int d, double &mn, double &mx) const {
+  bool point_exact(size_t pos) const { return exact_ && exact_[out_.order[pos]]; }
+  // mn_exact / mx_exact (census only): every point attaining the extreme is bit-reproducible and no other kind of
+  // point is within rounding noise of it - the extreme is then the same number with either centroid arithmetic
+  void span_of(size_t first, size_t count, int d, double &mn, double &mx, bool *mn_exact = nullptr,
+               bool *mx_exact = nullptr) const {
     mn = mx = via(first, d);
     for (size_t i = 1; i < count; i++) {
       double v = via(first + i, d);
       if (v < mn) mn = v;
       if (v > mx) mx = v;
+    }
+    if (!mn_exact) return;
+    *mn_exact = *mx_exact = exact_ != nullptr;
+    const double tol = 1e-9 * std::max(std::fabs(mn), std::fabs(mx));
+    for (size_t i = 0; i < count && exact_; i++) {
+      if (point_exact(first + i)) continue;
+      const double v = via(first + i, d);
+      if (v <= mn + tol) *mn_exact = false;
+      if (v >= mx - tol) *mx_exact = false;
     }
   }
 
@@ -106,41 +128,52 @@ class Builder {
       if (span > max_span) max_span = span;
     }
     double best_spread = -1, second_spread = -1;
+    bool best_exact = false, second_exact = false;
     feat = 0;
     for (int d = 0; d < dim_; d++) {
       double span = box[d].hi - box[d].lo;
       note(span, (1 - kEps) * max_span);  // eligibility of this dimension
       if (span > (1 - kEps) * max_span) {
         double mn, mx;
-        span_of(first, count, d, mn, mx);
+        bool mn_e, mx_e;
+        span_of(first, count, d, mn, mx, &mn_e, &mx_e);
         double spread = mx - mn;
         if (spread > best_spread) {
           feat = d;
           second_spread = best_spread;
+          second_exact = best_exact;
           best_spread = spread;
+          best_exact = mn_e && mx_e;
         } else if (spread > second_spread) {
           second_spread = spread;
+          second_exact = mn_e && mx_e;
         }
       }
     }
-    if (second_spread >= 0) note(best_spread, second_spread);  // which eligible dimension wins
+    // which eligible dimension wins (a tie between two spreads that are the same numbers in both codebooks is harmless)
+    if (second_spread >= 0 && !(best_exact && second_exact)) note(best_spread, second_spread);
     double mid = (box[feat].lo + box[feat].hi) / 2;
+    const bool mid_exact = box[feat].lo_exact && box[feat].hi_exact;
     double mn, mx;
-    span_of(first, count, feat, mn, mx);
+    bool mn_exact, mx_exact;
+    span_of(first, count, feat, mn, mx, &mn_exact, &mx_exact);
     cut = mid < mn ? mn : (mid > mx ? mx : mid);
+    cut_exact_ = mid < mn ? mn_exact : (mid > mx ? mx_exact : mid_exact);
     {
-      // every point against the cutting plane.  A point AT the plane is harmless only when the plane was clamped onto
-      // the data range (then the plane is that point's own coordinate and moves with it).
+      // every point against the cutting plane.  A point AT the plane is harmless when the plane was clamped onto
+      // the data range (then the plane is that point's own coordinate and moves with it), or when point and plane
+      // are both bit-reproducible numbers.
       const bool clamped = cut == mn || cut == mx;
-      if (mn == mx) out_.min_margin = 0.0;  // all points equal along the cut: the split is decided by position alone
+      if (mn == mx && mn != 0.0 && !(mn_exact && mx_exact)) out_.min_margin = 0.0;  // all points equal along the cut
       for (size_t i = 0; i < count; i++) {
         const double v = via(first + i, feat);
+        if (cut_exact_ && point_exact(first + i)) continue;
         if (v != cut)
           note(v, cut);
         else if (!clamped)
           out_.min_margin = 0.0;
       }
-      if (!clamped) {  // the clamp decisions themselves
+      if (!clamped && !(mid_exact && mn_exact && mx_exact)) {  // the clamp decisions themselves
         note(mid, mn);
         note(mid, mx);
       }
@@ -175,11 +208,14 @@ class Builder {
     int feat;
     double cut;
     size_t nleft = choose_split(first, last - first, box, feat, cut);
+    const bool cut_exact = cut_exact_;
     std::vector<Range> lbox(box);
     lbox[feat].hi = cut;
+    lbox[feat].hi_exact = cut_exact;
     int c1 = subdivide(first, first + nleft, lbox, level + 1);
     std::vector<Range> rbox(box);
     rbox[feat].lo = cut;
+    rbox[feat].lo_exact = cut_exact;
     int c2 = subdivide(first + nleft, last, rbox, level + 1);
     KdNode &nd = out_.nodes[me];
     nd.child1 = c1;
@@ -200,12 +236,14 @@ class Builder {
   int dim_;
   size_t leaf_max_;
   KdHostTree &out_;
+  const unsigned char *exact_;  // per point (may be null): bit-reproducible with either centroid arithmetic
+  bool cut_exact_ = false;      // of the plane choose_split just returned
 };
 
 }  // namespace
 
-void build_kd_tree(const double *points, size_t K, int dim, int leaf_max, KdHostTree &out) {
-  Builder(points, K, dim, leaf_max, out).run();
+void build_kd_tree(const double *points, size_t K, int dim, int leaf_max, KdHostTree &out, const unsigned char *exact) {
+  Builder(points, K, dim, leaf_max, out, exact).run();
 }
 
 }  // namespace qb

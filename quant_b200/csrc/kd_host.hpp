@@ -35,6 +35,8 @@ struct KdHostTree {
 };
 
 // points: K x dim, row-major FP64 (colour-space domain, exactly the doubles the reference holds).
-void build_kd_tree(const double *points, size_t K, int dim, int leaf_max, KdHostTree &out);
+// exact (may be null): per point, 1 when its coordinates are the same numbers with either centroid arithmetic (dead
+// cells, children of one-vector cells) - only used for the robustness census (min_margin).
+void build_kd_tree(const double *points, size_t K, int dim, int leaf_max, KdHostTree &out, const unsigned char *exact = nullptr);
 
 }  // namespace qb

@@ -49,7 +49,8 @@ struct qb200_ctx {
   void *h_pipe = nullptr;            // pinned slots of the pipelined train
   size_t h_pipe_cap = 0;
   DevBuf d_cbnext[2], d_post, d_summary, d_levels, d_cvexact;
-  const unsigned char *cv_exact_now = nullptr;  // flags of the codebook the level being run uses (pipelined train)  // d_levels: every level's pre-fix codebook of the last pipelined train
+  const unsigned char *cv_exact_now = nullptr;  // flags of the codebook the level being run uses (pipelined train)
+  const unsigned char *cv_exact_host = nullptr;  // ... and their host copy, for the KD tree's robustness census  // d_levels: every level's pre-fix codebook of the last pipelined train
   std::vector<int> pipe_depth;
   std::vector<char> pipe_side_used;
   std::string err;
@@ -365,11 +366,13 @@ int level_finish(qb200_ctx *ctx, const double *cb, uint32_t K, bool want_stats, 
   int rc;
   // While the filter runs: build the reference's KD tree for this codebook on the host.
   KdHostTree tree;
-  build_kd_tree(cb, K, dim, 10 /* src/KDTree.cpp:4 */, tree);
+  build_kd_tree(cb, K, dim, 10 /* src/KDTree.cpp:4 */, tree, ctx->cv_exact_host);
   if (tree.depth > kResolveDepthCap)
     return fail(ctx, QB200_ERR_ARG, "KD tree depth %d exceeds the resolver's stack (%d)", tree.depth,
                 kResolveDepthCap);
   if (tree.nodes.size() > max_nodes) return fail(ctx, QB200_ERR_STATE, "KD tree larger than expected");
+  if (const char *dbg = std::getenv("QB200_DEBUG_TREE"))
+    if (dbg[0] == '1') std::fprintf(stderr, "libqb200: K=%u KD tree depth %d, %zu nodes, robustness margin %.3g\n", K, tree.depth, tree.nodes.size(), tree.min_margin);
   // nodes | vind | inverse | bounding box: contiguous in the pinned block, so one copy into one device block
   const size_t tree_bytes = L.off_cnt - off_nodes;
   if ((rc = ensure(ctx, ctx->d_nodes, tree_bytes))) return rc;
@@ -1494,7 +1497,8 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   auto cvx = [&](int level) { return (unsigned char *)ctx->d_cvexact.p + (size_t)(level & 1) * 2 * maxK; };
   auto level_off = [&](int level) { return (((size_t)2 << level) - 2) * (size_t)dim * 8; };  // bytes before level's codebook
   // pinned: [slots | host codebook 0 | host codebook 1 | final codebook]
-  const size_t off_cb0 = (sizeof(PipeSlot) * 20 + 255) & ~(size_t)255, need = off_cb0 + 3 * (cb_max + 256);
+  const size_t off_cb0 = (sizeof(PipeSlot) * 20 + 255) & ~(size_t)255, off_flags = off_cb0 + 3 * (cb_max + 256);
+  const size_t need = off_flags + 2 * ((size_t)maxK + 256);
   if (need > ctx->h_pipe_cap) {
     if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
     ctx->h_pipe = nullptr;
@@ -1508,6 +1512,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   PipeSlot *slots = (PipeSlot *)ctx->h_pipe;
   double *h_cb[2] = {(double *)((char *)ctx->h_pipe + off_cb0), (double *)((char *)ctx->h_pipe + off_cb0 + cb_max + 256)};
   double *h_final = (double *)((char *)ctx->h_pipe + off_cb0 + 2 * (cb_max + 256));
+  unsigned char *h_flags[2] = {(unsigned char *)ctx->h_pipe + off_flags, (unsigned char *)ctx->h_pipe + off_flags + maxK + 256};
   const size_t n_ev = 6 * 17 + 2;
   while (ctx->pipe_ev.size() < n_ev) {
     cudaEvent_t e;
@@ -1544,6 +1549,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   CU(cudaMemcpyAsync(&slots[0].dist_pre, summaries, 32, cudaMemcpyDeviceToHost, st));
   if (nbits) {
     CU(cudaMemcpyAsync(h_cb[0], ctx->d_cbnext[0].p, (size_t)2 * dim * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_flags[0], cvx(0), 2, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(cb_ready[0], st));
     CU(cudaMemcpyAsync((char *)ctx->d_levels.p + level_off(0), ctx->d_cbnext[0].p, (size_t)2 * dim * 8, cudaMemcpyDeviceToDevice, st));
   } else {
@@ -1563,6 +1569,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     // which codevectors of this level the integer path reproduces bit for bit (written by the previous finalise); not
     // known after a restart and not needed with the compensated sums
     ctx->cv_exact_now = (exact || first_level > 0) ? nullptr : cvx(level);
+    ctx->cv_exact_host = ctx->cv_exact_now ? h_flags[cur] : nullptr;
     CU(cudaEventSynchronize(cb_ready[cur]));  // this level's codebook has reached the host (the filter is already running)
     if ((rc = level_finish(ctx, h_cb[cur], K, true, fused, ev ? ev[2] : nullptr, ev ? ev[3] : nullptr,
                            slots[level + 1].counters, &depth[level])))
@@ -1578,6 +1585,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     CU(cudaMemcpyAsync(&slots[level + 1].dist_pre, summaries + 32 * (level + 1), 32, cudaMemcpyDeviceToHost, st));
     if (!last) {
       CU(cudaMemcpyAsync(h_cb[cur ^ 1], ctx->d_cbnext[cur ^ 1].p, (size_t)2 * K * dim * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(h_flags[cur ^ 1], cvx(level + 1), (size_t)2 * K, cudaMemcpyDeviceToHost, st));
       CU(cudaEventRecord(cb_ready[cur ^ 1], st));
       CU(cudaMemcpyAsync((char *)ctx->d_levels.p + level_off(level + 1), ctx->d_cbnext[cur ^ 1].p, (size_t)2 * K * dim * 8,
                          cudaMemcpyDeviceToDevice, st));
@@ -1586,6 +1594,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     }
   }
   ctx->cv_exact_now = nullptr;
+  ctx->cv_exact_host = nullptr;
   if (nbits == 0) CU(cudaMemsetAsync(ctx->d_assign.p, 0, (size_t)ctx->src.n_local * 4, st));
   CU(cudaStreamSynchronize(st));
   if (slots[0].n_seen != N)
@@ -1608,7 +1617,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
       r.ties = s.counters[2];
       r.refiltered = s.counters[3];
       r.sensitive = s.counters[5];
-      r.reserved = 0;
+      r.reserved = s.counters[6] | (s.counters[7] << 16);  // diagnostics: inexact-candidate count | order-unsafe reasons
       r.dead_cells = s.dead_cells;
       r.kd_depth = (uint32_t)depth[level];
       r.iterations = 1;
@@ -1633,6 +1642,7 @@ int train_parity_pipelined(qb200_ctx *ctx, int nbits, uint64_t N, qb200_allreduc
   ctx->assign_valid = false;
   const int rc = train_parity_pipelined_body(ctx, nbits, N, ar, ar_user, codebook_out, distortion_out, reports, first_level);
   ctx->cv_exact_now = nullptr;
+  ctx->cv_exact_host = nullptr;
   if (rc != QB200_OK) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);

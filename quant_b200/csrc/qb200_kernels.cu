@@ -951,6 +951,10 @@ __global__ void __launch_bounds__(128)
       if (sensitive && lane == 0 && near2 > 1) {
         const bool order_safe = tree_robust && all_exact && n_cand <= 32 && !fragile;
         if (inexact2 > 0 || (at_min > 1 && !order_safe)) atomicAdd(sensitive, 1u);
+        // diagnostics: sensitive[1] counts the first kind, sensitive[2] collects why a visiting order was not safe
+        if (inexact2 > 0) atomicAdd(sensitive + 1, 1u);
+        if (inexact2 == 0 && at_min > 1 && !order_safe)
+          atomicOr(sensitive + 2, (tree_robust ? 0u : 1u) | (all_exact ? 0u : 2u) | (n_cand <= 32 ? 0u : 4u) | (fragile ? 8u : 0u));
       }
     }
     if (win >= 0) {
