@@ -281,6 +281,12 @@ int qb200_measure_fp32_peak(qb200_ctx *ctx, double *tflops_out);
 int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *order_out,
                          int *n_nodes_out, int *depth_out);
 
+/* Host-only diagnostic: the robustness margin of that tree (kd_host.hpp, KdHostTree::min_margin) - the smallest
+ * relative distance from flipping of any comparison that shaped it; exact_flags (K bytes or NULL) marks the points
+ * whose coordinates are the same numbers with either centroid arithmetic.  The auto centroid mode trusts the tree's
+ * visiting order only above 1e-9. */
+int qb200_debug_kd_margin(const double *points, size_t K, int dim, const uint8_t *exact_flags, double *margin_out);
+
 /* Diagnostic: the per-query records {best score, second best score, chunk index (bits), 0} the tensor-core
  * filter left behind in its last pass (num_vectors x 4 floats, lattice units: score = |C|^2 - 2<X,C>), so that
  * its rounding error can be audited against the bound its margin is derived from.  Valid right after

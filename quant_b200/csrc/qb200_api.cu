@@ -2049,6 +2049,14 @@ int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *orde
   return QB200_OK;
 }
 
+int qb200_debug_kd_margin(const double *points, size_t K, int dim, const uint8_t *exact_flags, double *margin_out) {
+  if (!points || K == 0 || dim <= 0 || !margin_out) return QB200_ERR_ARG;
+  KdHostTree t;
+  build_kd_tree(points, K, dim, 10, t, exact_flags);
+  *margin_out = t.min_margin;
+  return QB200_OK;
+}
+
 int qb200_debug_filter_records(qb200_ctx *ctx, float *records_out) {
   if (!ctx || !records_out) return QB200_ERR_ARG;
   NOT_ON_MULTI("qb200_debug_filter_records");

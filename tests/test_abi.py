@@ -84,3 +84,33 @@ def test_kd_build_matches_oracle_tree(port):
                                           order.ctypes.data_as(C.c_void_p), C.byref(nn), C.byref(dp)) == 0
     depth, nodes, oorder = port.kd_order(cb)
     assert (dp.value, nn.value) == (depth, nodes) and np.array_equal(order, oorder)
+
+
+def test_kd_tree_robustness_margin():
+    """The census behind the auto centroid mode's trust in the tree's visiting order (qb200_debug_kd_margin): generic
+    points give a comfortable margin, duplicated non-zero points none, and the same duplicates count as harmless when
+    they are flagged bit-reproducible or are dead cells' zero vectors."""
+    import ctypes as C
+    import numpy as np
+    from quant_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+
+    def margin(pts, flags=None):
+        pts = np.ascontiguousarray(pts, np.float64)
+        m = C.c_double()
+        f = None if flags is None else np.ascontiguousarray(flags, np.uint8).ctypes.data_as(C.c_void_p)
+        assert lib.qb200_debug_kd_margin(pts.ctypes.data_as(C.c_void_p), pts.shape[0], pts.shape[1], f, C.byref(m)) == 0
+        return m.value
+
+    pts = rng.random((500, 12))
+    assert margin(pts) > 1e-9
+    dup = pts.copy()
+    dup[100:140] = dup[100]                       # 40 copies of one non-zero point
+    assert margin(dup) == 0.0
+    flags = np.zeros(500, np.uint8)
+    flags[100:140] = 1
+    assert margin(dup, flags) > 1e-9
+    dead = pts.copy()
+    dead[200:260] = 0.0                           # dead cells
+    assert margin(dead) > 1e-9
