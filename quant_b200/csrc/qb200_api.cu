@@ -48,7 +48,7 @@ struct qb200_ctx {
   std::vector<cudaEvent_t> pipe_ev;  // pipelined train: 6 timing events per level + 2 codebook-ready events
   void *h_pipe = nullptr;            // pinned slots of the pipelined train
   size_t h_pipe_cap = 0;
-  DevBuf d_cbnext[2], d_post, d_summary, d_levels, d_cvexact;
+  DevBuf d_cbnext[2], d_post, d_summary, d_levels, d_cvexact, d_small;
   const unsigned char *cv_exact_now = nullptr;  // flags of the codebook the level being run uses (pipelined train)
   const unsigned char *cv_exact_host = nullptr;  // ... and their host copy, for the KD tree's robustness census  // d_levels: every level's pre-fix codebook of the last pipelined train
   std::vector<int> pipe_depth;
@@ -869,7 +869,7 @@ void qb200_destroy(qb200_ctx *ctx) {
   if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
   for (auto &e2 : ctx->pipe_ev)
     if (e2) cudaEventDestroy(e2);
-  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_levels, &ctx->d_cvexact, &ctx->d_exact, &ctx->d_sort_keys,
+  for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_levels, &ctx->d_cvexact, &ctx->d_small, &ctx->d_exact, &ctx->d_sort_keys,
                     &ctx->d_sort_iota, &ctx->d_sort_order, &ctx->d_sort_tmp, &ctx->d_fx, &ctx->d_f64, &ctx->d_partials, &ctx->d_counts})
     free_buf(*b);
   for (auto &ev : ctx->ev)
@@ -1482,7 +1482,18 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   if ((rc = ensure(ctx, ctx->d_rows, std::max(rows_max, (size_t)256)))) return rc;
   if ((rc = ensure(ctx, ctx->d_cb64, 2 * cb_max + 256))) return rc;
   if ((rc = ensure(ctx, ctx->d_counters, 64))) return rc;
-  if ((rc = ensure(ctx, ctx->d_stats, stats_words(maxK, dim) * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->d_stats, (stats_words(maxK, dim) + maxK) * 8))) return rc;  // + the small cells' per-rank counts
+  // small cells (auto mode, integer sums): their compensated sums make their centroids provably the reference's
+  constexpr size_t kSmallTableCap = (size_t)32 << 20;
+  const bool small_ok = ctx->exact_auto && !exact && scaled && ctx->src.dense && !ctx->src.f64 && first_level == 0 &&
+                        (!ar || (ctx->world > 1 && ctx->world <= 16));
+  auto small_at = [&](uint32_t Kl) { return small_ok && small_cells_table_words((int)Kl, dim) * 8 <= kSmallTableCap; };
+  {
+    uint32_t Ks = 0;
+    for (uint32_t Kl = 2; Kl <= maxK && Kl; Kl *= 2)
+      if (small_at(Kl)) Ks = Kl;
+    if (Ks && (rc = ensure(ctx, ctx->d_small, small_cells_workspace_bytes((int)Ks, dim)))) return rc;
+  }
   if (tc_max && (rc = ensure(ctx, ctx->d_rows_tc, tc_max))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 16))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_flags2, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 4))) return rc;
@@ -1545,7 +1556,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
   CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, nullptr, exact ? (const double *)ctx->d_exact.p : nullptr,
                            1, dim, scaled, (double)N, f_up, f_dn,
                            (double *)ctx->d_post.p, nbits ? (double *)ctx->d_cbnext[0].p : nullptr, summaries,
-                           nbits ? cvx(0) : nullptr, st));
+                           nbits ? cvx(0) : nullptr, nullptr, nullptr, st));
   CU(cudaMemcpyAsync(&slots[0].dist_pre, summaries, 32, cudaMemcpyDeviceToHost, st));
   if (nbits) {
     CU(cudaMemcpyAsync(h_cb[0], ctx->d_cbnext[0].p, (size_t)2 * dim * 8, cudaMemcpyDeviceToHost, st));
@@ -1574,14 +1585,25 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     if ((rc = level_finish(ctx, h_cb[cur], K, true, fused, ev ? ev[2] : nullptr, ev ? ev[3] : nullptr,
                            slots[level + 1].counters, &depth[level])))
       return rc;
-    if (ar && ar(ctx->d_stats.p, stats_words(K, dim), (void *)st, ar_user) != 0)
+    const bool small = small_at(K);
+    unsigned long long *small_packed = (unsigned long long *)ctx->d_stats.p + stats_words(K, dim);  // reduced with the statistics
+    if (small && ar) CU(launch_small_cells_count((const unsigned long long *)ctx->d_stats.p, (int)K, dim, ctx->rank, small_packed, st));
+    if (ar && ar(ctx->d_stats.p, stats_words(K, dim) + (small ? K : 0), (void *)st, ar_user) != 0)
       return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed at K=%u", K);
     if (exact && (rc = exact_centroid_sums(ctx, K, ar, ar_user))) return rc;
+    if (small) {
+      CU(launch_small_cells_collect(ctx->src, (const uint32_t *)ctx->d_assign.p, (const unsigned long long *)ctx->d_stats.p,
+                                    ar ? small_packed : nullptr, (int)K, ar ? ctx->rank : 0, ctx->d_small.p, ctx->sm_count, st));
+      if (ar && ar(small_cells_table(ctx->d_small.p, (int)K, dim), small_cells_table_words((int)K, dim), (void *)st, ar_user) != 0)
+        return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (small cells, K=%u)", K);
+      CU(launch_small_cells_sums((const unsigned long long *)ctx->d_stats.p, (int)K, dim, ctx->d_small.p, st));
+    }
     CU(launch_finalize_split((const unsigned long long *)ctx->d_stats.p, (const double *)ctx->d_cb64.p,
                              exact ? (const double *)ctx->d_exact.p : nullptr, (int)K, dim, scaled,
                              (double)N, f_up, f_dn, (double *)ctx->d_post.p,
                              last ? nullptr : (double *)ctx->d_cbnext[cur ^ 1].p, summaries + 32 * (level + 1),
-                             last ? nullptr : cvx(level + 1), st));
+                             last ? nullptr : cvx(level + 1), small ? small_cells_flags(ctx->d_small.p, (int)K, dim) : nullptr,
+                             small ? small_cells_sums(ctx->d_small.p, (int)K, dim) : nullptr, st));
     CU(cudaMemcpyAsync(&slots[level + 1].dist_pre, summaries + 32 * (level + 1), 32, cudaMemcpyDeviceToHost, st));
     if (!last) {
       CU(cudaMemcpyAsync(h_cb[cur ^ 1], ctx->d_cbnext[cur ^ 1].p, (size_t)2 * K * dim * 8, cudaMemcpyDeviceToHost, st));

@@ -999,4 +999,189 @@ cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_so
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// small cells: the reference's sums of cells with at most kSmallCellMax members, next to the integer sums
+// ------------------------------------------------------------------------------------------------
+// The integer-sum centroids (S/255)/n differ from the reference's compensated sums in the last bits, which the
+// auto centroid mode has to assume for every codevector it cannot prove exact (qb200_train).  Cells with a handful
+// of members are where exact distance ties are STRUCTURAL rather than accidental (a 2-member cell of two equal-norm
+// vectors is split into 1.2c / 0.8c, both equally far from either member), and they are also the cheap ones: their
+// members are found by one pass over the assignment and their sums are the literal loop of
+// Solution::sumInArea (/root/reference/src/Quantizer.cpp:59-70) over <= 8 values.  Sharded runs: a rank's members of
+// a cell are contiguous in the cell's (ascending vector index) order, behind those of the lower ranks, so every rank
+// writes its members' bytes at their final positions of a zeroed table and the table is summed over the ranks -
+// the same all-reduce as the statistics.  How many members each rank holds travels as one nibble per rank in a
+// 64-bit word per cell (<= 16 ranks, <= 8 members).
+namespace {
+
+__global__ void __launch_bounds__(256)
+    small_count_kernel(const unsigned long long *__restrict__ stats_local, const int K, const int row_words, const int rank,
+                       unsigned long long *__restrict__ packed) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const unsigned long long n = stats_local[(size_t)k * row_words];
+  packed[k] = (n < 15ull ? n : 15ull) << (4 * rank);  // 9..15: "too many" (the reduced count decides anyway)
+}
+
+// flag[k] = the cell takes this path; off[k] = members of the cell on lower ranks
+__global__ void __launch_bounds__(256)
+    small_mark_kernel(const unsigned long long *__restrict__ stats, const unsigned long long *__restrict__ packed, const int K,
+                      const int row_words, const int rank, unsigned char *__restrict__ flag, unsigned char *__restrict__ off) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const unsigned long long n = stats[(size_t)k * row_words];
+  const bool small = n >= 1 && n <= (unsigned long long)kSmallCellMax;
+  flag[k] = small ? 1 : 0;
+  unsigned int before = 0;
+  if (small && packed) {
+    const unsigned long long w = packed[k];
+    for (int q = 0; q < rank; q++) before += (unsigned int)(w >> (4 * q)) & 15u;
+  }
+  off[k] = (unsigned char)before;
+}
+
+__global__ void __launch_bounds__(256)
+    small_collect_kernel(const uint32_t *__restrict__ assign, const unsigned int n, const unsigned char *__restrict__ flag,
+                         unsigned int *__restrict__ cnt, uint32_t *__restrict__ list) {
+  for (unsigned int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const uint32_t k = __ldg(assign + v) & 0x7fffffffu;
+    if (!flag[k]) continue;
+    const unsigned int pos = atomicAdd(cnt + k, 1u);
+    if (pos < (unsigned int)kSmallCellMax) list[(size_t)k * kSmallCellMax + pos] = v;  // (always: local count <= reduced count)
+  }
+}
+
+// one thread per cell: its local members in ascending order, their bytes t = L + 128 packed eight to a word
+__global__ void __launch_bounds__(128)
+    small_pack_kernel(const VecSource src, const int K, const int words, const unsigned char *__restrict__ flag,
+                      const unsigned char *__restrict__ off, const unsigned int *__restrict__ cnt, const uint32_t *__restrict__ list,
+                      unsigned long long *__restrict__ table) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K || !flag[k]) return;
+  unsigned int c = cnt[k];
+  if (c > (unsigned int)kSmallCellMax) c = kSmallCellMax;
+  uint32_t idx[kSmallCellMax];
+#pragma unroll
+  for (int i = 0; i < kSmallCellMax; i++) idx[i] = i < (int)c ? list[(size_t)k * kSmallCellMax + i] : 0xffffffffu;
+#pragma unroll
+  for (int i = 1; i < kSmallCellMax; i++)  // insertion sort with compile-time bounds: idx stays in registers
+#pragma unroll
+    for (int j = i; j > 0; j--) {
+      const uint32_t a = idx[j - 1], b = idx[j];
+      idx[j - 1] = a < b ? a : b;
+      idx[j] = a < b ? b : a;
+    }
+  const int dim = src.dim;
+#pragma unroll
+  for (int i = 0; i < kSmallCellMax; i++) {
+    if (i >= (int)c) break;
+    const unsigned int slot = (unsigned int)off[k] + i;
+    if (slot >= (unsigned int)kSmallCellMax) break;
+    const uint8_t *row = src.dense + (unsigned long long)idx[i] * src.dense_stride;
+    for (int w = 0; w < words; w++) {
+      unsigned long long word = 0;
+      for (int b = 0; b < 8 && 8 * w + b < dim; b++) word |= (unsigned long long)(uint8_t)(row[8 * w + b] ^ 0x80u) << (8 * b);
+      table[((size_t)k * kSmallCellMax + slot) * words + w] = word;
+    }
+  }
+}
+
+// one thread per (cell, dimension): src/Quantizer.cpp:64-67 over the cell's members in vector order
+__global__ void __launch_bounds__(256)
+    small_sums_kernel(const unsigned long long *__restrict__ stats, const int K, const int dim, const int row_words, const int words,
+                      const unsigned char *__restrict__ flag, const unsigned long long *__restrict__ table, double *__restrict__ sums) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)K * dim) return;
+  const int k = (int)(i / dim), e = (int)(i - (size_t)k * dim);
+  if (!flag[k]) return;
+  const int n = (int)stats[(size_t)k * row_words];
+  double sum = 0.0, c = 0.0;
+  for (int m = 0; m < n; m++) {
+    const unsigned int t = (unsigned int)(table[((size_t)k * kSmallCellMax + m) * words + (e >> 3)] >> (8 * (e & 7))) & 255u;
+    const double x = __ddiv_rn((double)t, 255.0);  // ScaledColor: (L + 128) / 255 (src/ColorSpace.cpp:16-21)
+    const double y = __dsub_rn(x, c);
+    const double s = __dadd_rn(sum, y);
+    c = __dsub_rn(__dsub_rn(s, sum), y);
+    sum = s;
+  }
+  sums[i] = sum;
+}
+
+struct SmallWork {
+  unsigned int *cnt;
+  uint32_t *list;
+  unsigned char *flag, *off;
+  unsigned long long *table;
+  double *sums;
+};
+inline size_t small_up(size_t x) { return (x + 255) & ~(size_t)255; }
+SmallWork small_carve(void *ws, int K, int dim) {
+  const size_t words = (size_t)(dim + 7) / 8;
+  char *p = (char *)ws;
+  SmallWork w;
+  w.cnt = (unsigned int *)p;
+  p += small_up((size_t)K * 4);
+  w.list = (uint32_t *)p;
+  p += small_up((size_t)K * kSmallCellMax * 4);
+  w.flag = (unsigned char *)p;
+  p += small_up((size_t)K);
+  w.off = (unsigned char *)p;
+  p += small_up((size_t)K);
+  w.table = (unsigned long long *)p;
+  p += small_up((size_t)K * kSmallCellMax * words * 8);
+  w.sums = (double *)p;
+  return w;
+}
+
+}  // namespace
+
+size_t small_cells_table_words(int K, int dim) { return (size_t)K * kSmallCellMax * (size_t)((dim + 7) / 8); }
+size_t small_cells_workspace_bytes(int K, int dim) {
+  return small_up((size_t)K * 4) + small_up((size_t)K * kSmallCellMax * 4) + 2 * small_up((size_t)K) +
+         small_up(small_cells_table_words(K, dim) * 8) + small_up((size_t)K * dim * 8) + 256;
+}
+unsigned long long *small_cells_table(void *ws, int K, int dim) { return small_carve(ws, K, dim).table; }
+const unsigned char *small_cells_flags(void *ws, int K, int dim) { return small_carve(ws, K, dim).flag; }
+const double *small_cells_sums(void *ws, int K, int dim) { return small_carve(ws, K, dim).sums; }
+
+// before the statistics are reduced: this rank's member counts, one nibble per rank (packed: K words, summed with the statistics)
+cudaError_t launch_small_cells_count(const unsigned long long *stats_local, int K, int dim, int rank, unsigned long long *packed,
+                                     cudaStream_t stream) {
+  small_count_kernel<<<(K + 255) / 256, 256, 0, stream>>>(stats_local, K, dim + 2, rank, packed);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// after the reduction: mark the small cells and write this rank's members into the (zeroed) table
+cudaError_t launch_small_cells_collect(const VecSource &src, const uint32_t *assign, const unsigned long long *stats,
+                                       const unsigned long long *packed, int K, int rank, void *ws, int sm_count, cudaStream_t stream) {
+  const int dim = src.dim, words = (dim + 7) / 8;
+  const SmallWork w = small_carve(ws, K, dim);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(w.cnt, 0, (size_t)K * 4, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(w.table, 0, small_cells_table_words(K, dim) * 8, stream)) != cudaSuccess) return e;
+  small_mark_kernel<<<(K + 255) / 256, 256, 0, stream>>>(stats, packed, K, dim + 2, rank, w.flag, w.off);
+  count_launch();
+  const unsigned int n = (unsigned int)src.n_local;
+  if (n) {
+    unsigned int blocks = (n + 255) / 256;
+    const unsigned int cap = (unsigned int)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    small_collect_kernel<<<blocks, 256, 0, stream>>>(assign, n, w.flag, w.cnt, w.list);
+    count_launch();
+    small_pack_kernel<<<(K + 127) / 128, 128, 0, stream>>>(src, K, words, w.flag, w.off, w.cnt, w.list, w.table);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+// after the table is reduced: the compensated sums of the small cells (small_cells_sums; cells not flagged are not written)
+cudaError_t launch_small_cells_sums(const unsigned long long *stats, int K, int dim, void *ws, cudaStream_t stream) {
+  const SmallWork w = small_carve(ws, K, dim);
+  const size_t total = (size_t)K * dim;
+  small_sums_kernel<<<(unsigned int)((total + 255) / 256), 256, 0, stream>>>(stats, K, dim, dim + 2, (dim + 7) / 8, w.flag, w.table, w.sums);
+  count_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace qb

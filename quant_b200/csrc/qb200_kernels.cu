@@ -1457,7 +1457,8 @@ __global__ void __launch_bounds__(1024)
     finalize_split_kernel(const unsigned long long *__restrict__ stats, const double *__restrict__ cb_pre,
                           const double *__restrict__ exact_state, const int K, const int dim, const int scaled, const double n_total, const double f_up, const double f_dn,
                           double *__restrict__ cb_post, double *__restrict__ cb_next,
-                          LevelSummary *__restrict__ summary, unsigned char *__restrict__ exact_next) {
+                          LevelSummary *__restrict__ summary, unsigned char *__restrict__ exact_next,
+                          const unsigned char *__restrict__ small_flag, const double *__restrict__ small_sums) {
   __shared__ double s_pre[1024], s_post[1024];
   __shared__ unsigned int s_dead[1024];
   __shared__ unsigned long long s_n[1024];
@@ -1489,8 +1490,10 @@ __global__ void __launch_bounds__(1024)
     }
     // children of this cell whose centroid the integer path reproduces bit for bit (one repeated vector, or empty);
     // NORMAL sums are integers: always exact
+    // small cell: its compensated sums were computed beside the integer ones (qb200_exact.cu, "small cells")
+    const bool small = small_flag && small_flag[k] && n > 0 && !exact_state;
     if (exact_next) {
-      const unsigned char ex = (!scaled || n == 0 || same || exact_state) ? 1 : 0;
+      const unsigned char ex = (!scaled || n == 0 || same || small || exact_state) ? 1 : 0;
       exact_next[k] = ex;
       exact_next[K + k] = ex;
     }
@@ -1500,6 +1503,7 @@ __global__ void __launch_bounds__(1024)
       // exact_state: the reference's compensated sum itself (qb200_exact.cu), divided as in src/Quantizer.cpp:84-85
       const double c = !n ? 0.0
                           : exact_state ? __ddiv_rn(exact_state[((size_t)k * dim + e) * 2], (double)n)
+                          : small ? __ddiv_rn(small_sums[(size_t)k * dim + e], (double)n)
                           : same ? __ddiv_rn(__dmul_rn((double)n, __ddiv_rn((double)(St / (long long)n), unit)), (double)n)
                                  : __ddiv_rn(__ddiv_rn((double)St, unit), (double)n);
       cb_post[(size_t)k * dim + e] = c;
@@ -1914,9 +1918,10 @@ cudaError_t launch_stage_codebook(const double *cb, int K, int k_rows32, int k_r
 
 cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, const double *exact_state, int K,
                                   int dim, int scaled, double n_total, double f_up, double f_dn, double *cb_post,
-                                  double *cb_next, void *summary, unsigned char *exact_next, cudaStream_t stream) {
+                                  double *cb_next, void *summary, unsigned char *exact_next, const unsigned char *small_flag,
+                                  const double *small_sums, cudaStream_t stream) {
   finalize_split_kernel<<<1, 1024, 0, stream>>>(stats, cb_pre, exact_state, K, dim, scaled, n_total, f_up, f_dn, cb_post,
-                                                cb_next, reinterpret_cast<LevelSummary *>(summary), exact_next);
+                                                cb_next, reinterpret_cast<LevelSummary *>(summary), exact_next, small_flag, small_sums);
   g_launch_count++;
   return cudaGetLastError();
 }

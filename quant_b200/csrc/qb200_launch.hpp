@@ -97,6 +97,7 @@ cudaError_t launch_decode(const DecodeGeom &g, const uint8_t *orig, const uint32
 cudaError_t launch_finalize_split(const unsigned long long *stats, const double *cb_pre, const double *exact_state, int K,
                                   int dim, int scaled, double n_total, double f_up, double f_dn, double *cb_post,
                                   double *cb_next, void *summary, unsigned char *exact_next /* 2K flags for cb_next, or null */,
+                                  const unsigned char *small_flag, const double *small_sums /* small cells, or null */,
                                   cudaStream_t stream);
 // Bit-exact centroid sums (qb200_exact.cu): stable sort of the members by cell, then the reference's compensated
 // summation in ascending vector order, one warp per cell.
@@ -112,6 +113,19 @@ size_t exact_fast_workspace_bytes(size_t n, int K, int dim);
 cudaError_t launch_kahan_sums_fast(const VecSource &src, const uint32_t *keys_sorted, const uint32_t *order, int K, double *state,
                                    unsigned long long *counts, void *workspace, size_t workspace_bytes, int sm_count,
                                    cudaStream_t stream);
+// Small cells (<= kSmallCellMax members): the reference's compensated sums next to the integer statistics, so that the
+// auto centroid mode can treat their centroids as reproduced bit for bit (qb200_exact.cu, "small cells").
+constexpr int kSmallCellMax = 8;
+size_t small_cells_workspace_bytes(int K, int dim);
+size_t small_cells_table_words(int K, int dim);
+unsigned long long *small_cells_table(void *ws, int K, int dim);
+const unsigned char *small_cells_flags(void *ws, int K, int dim);
+const double *small_cells_sums(void *ws, int K, int dim);
+cudaError_t launch_small_cells_count(const unsigned long long *stats_local, int K, int dim, int rank, unsigned long long *packed,
+                                     cudaStream_t stream);
+cudaError_t launch_small_cells_collect(const VecSource &src, const uint32_t *assign, const unsigned long long *stats,
+                                       const unsigned long long *packed, int K, int rank, void *ws, int sm_count, cudaStream_t stream);
+cudaError_t launch_small_cells_sums(const unsigned long long *stats, int K, int dim, void *ws, cudaStream_t stream);
 // General FP64 training vectors (qb200_generic.cu).
 // CIE1931 colour space (src/ColorSpace.cpp:31-39): the image's block vectors as doubles, n_local x dim.
 cudaError_t launch_cie_vectors(const VecSource &src, double *out, int sm_count, cudaStream_t stream);
