@@ -452,11 +452,12 @@ def run_gpu_arm(args):
         tc_flops = float(((n_local + 127) // 128) * 128) * k_pad * (3 * 16 * kb) * 2.0
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch, from the committed ncu capture
         # of this workload (profiles/traffic.json, written by tools/ncu_summary.py); null when there is none
-        traffic = None
+        traffic = traffic_note = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             key = f"{wl}/n{world}/{'tc' if uses_tc else 'cc'}"
             traffic = tj.get(key, {}).get("bytes")
+            traffic_note = tj.get(key, {}).get("note") or None
         except (OSError, ValueError):
             pass
         if uses_tc:
@@ -472,6 +473,8 @@ def run_gpu_arm(args):
             roof = {"bound": "fp32", "kernel": f"assign_kernel<{dim}> at K={K}, last split level", "achieved": alg_tflops,
                     "peak": fp32_peak, "unit": "TFLOP/s", "frac": alg_tflops / fp32_peak,
                     "peak_source": "FP32 FFMA probe in this run (FMA = 2 flop)", "ms_per_launch": ms_assign, "traffic": traffic}
+        if traffic_note:
+            roof["traffic_note"] = traffic_note   # which launch of the step the capture is (profiles/traffic.json)
         roof["gdist_evals_per_s"] = float(n_local) * K / (ms_assign * 1e-3) / 1e9
         roof["fp32_equivalent"] = {"achieved": alg_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": alg_tflops / fp32_peak,
                                    "algorithmic": "3*dim flop per distance evaluation x N*K evaluations (the reference's sub, mul, add)",

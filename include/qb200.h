@@ -286,6 +286,9 @@ int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *orde
  * whose coordinates are the same numbers with either centroid arithmetic.  The auto centroid mode trusts the tree's
  * visiting order only above 1e-9. */
 int qb200_debug_kd_margin(const double *points, size_t K, int dim, const uint8_t *exact_flags, double *margin_out);
+/* Diagnostics: the codebook split level `level` (0-based: 2^(level+1) codevectors, before their centroid update)
+ * of the last HEAD-schedule train started from, as kept on the device for the auto mode's restart. */
+int qb200_debug_level_codebook(qb200_ctx *ctx, int level, double *codebook_out);
 
 /* Diagnostic: the per-query records {best score, second best score, chunk index (bits), 0} the tensor-core
  * filter left behind in its last pass (num_vectors x 4 floats, lattice units: score = |C|^2 - 2<X,C>), so that

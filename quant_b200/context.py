@@ -140,6 +140,12 @@ class Context:
     def last_train_exact(self) -> bool:
         return bool(self.lib.qb200_last_train_exact(self.h))
 
+    def debug_level_codebook(self, level: int) -> np.ndarray:
+        """Diagnostics: the 2^(level+1) codevectors split level `level` of the last train started from."""
+        out = np.empty((2 << level, self.dim), np.float64)
+        self._check(self.lib.qb200_debug_level_codebook(self.h, level, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def comm_export(self, max_words: int = 0) -> bytes:
         """This context's all-reduce exchange block as a CUDA IPC handle (64 bytes) - see qb200_comm_export."""
         buf = C.create_string_buffer(64)

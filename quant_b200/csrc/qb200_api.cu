@@ -47,6 +47,8 @@ struct qb200_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;  // pipelined train: 6 timing events per level + 2 codebook-ready events
   void *h_pipe = nullptr;            // pinned slots of the pipelined train
+  void *h_xfer[2] = {nullptr, nullptr};  // pinned staging of the pageable-memory transfers (staged_upload, qb200_get_assign_u64)
+  cudaEvent_t ev_xfer[2] = {nullptr, nullptr};
   size_t h_pipe_cap = 0;
   DevBuf d_cbnext[2], d_post, d_summary, d_levels, d_cvexact, d_small;
   const unsigned char *cv_exact_now = nullptr;  // flags of the codebook the level being run uses (pipelined train)
@@ -867,6 +869,10 @@ void qb200_destroy(qb200_ctx *ctx) {
   comm_free(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->h_xfer[i]) cudaFreeHost(ctx->h_xfer[i]);
+    if (ctx->ev_xfer[i]) cudaEventDestroy(ctx->ev_xfer[i]);
+  }
   for (auto &e2 : ctx->pipe_ev)
     if (e2) cudaEventDestroy(e2);
   for (DevBuf *b : {&ctx->d_cbnext[0], &ctx->d_cbnext[1], &ctx->d_post, &ctx->d_summary, &ctx->d_levels, &ctx->d_cvexact, &ctx->d_small, &ctx->d_exact, &ctx->d_sort_keys,
@@ -938,6 +944,75 @@ int qb200_device_info(const qb200_ctx *ctx, int *sm_count, int *cc_major, int *c
 
 // band_only: `rgb` points at the first byte the shard needs (image byte row_begin*w*ySize*3) and
 // holds `band_len` bytes, instead of being the whole image.
+extern "C++" {
+// ------------------------------------------------------------------------------------------------
+// transfers to and from PAGEABLE host memory (what the reference-facing C++ layer hands over: std::vector storage)
+// ------------------------------------------------------------------------------------------------
+// cudaMemcpy from pageable memory is staged by the driver through one thread; here chunks go through two pinned
+// buffers, filled (or drained) by a few host threads while the previous chunk is on the bus.
+constexpr size_t kXferChunk = (size_t)32 << 20;
+constexpr size_t kXferMin = (size_t)8 << 20;  // below this the plain copy is as fast
+
+static int xfer_threads() {
+  const unsigned hc = std::thread::hardware_concurrency();
+  return (int)std::min(8u, std::max(1u, hc / 2));
+}
+template <class F>
+static void host_parallel(size_t n, size_t grain, F f) {  // f(begin, end) over [0, n) on a few threads
+  const int T = (int)std::min<size_t>((size_t)xfer_threads(), (n + grain - 1) / grain);
+  if (T <= 1) {
+    f((size_t)0, n);
+    return;
+  }
+  const size_t per = ((n + T - 1) / T + 63) & ~(size_t)63;
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) {
+    const size_t b = std::min(n, per * t), e = std::min(n, per * (t + 1));
+    if (b < e) th.emplace_back([=] { f(b, e); });
+  }
+  f((size_t)0, std::min(n, per));
+  for (auto &x : th) x.join();
+}
+static int ensure_xfer(qb200_ctx *ctx) {
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->h_xfer[i] && cudaMallocHost(&ctx->h_xfer[i], kXferChunk) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, QB200_ERR_OOM, "cudaMallocHost(%zu bytes, transfer staging)", kXferChunk);
+    }
+    if (!ctx->ev_xfer[i]) CU(cudaEventCreateWithFlags(&ctx->ev_xfer[i], cudaEventDisableTiming));
+  }
+  return QB200_OK;
+}
+static bool host_pointer_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  const bool pinned = cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return pinned;
+}
+// host -> device on ctx->stream; like cudaMemcpyAsync from pageable memory, the source may be reused on return
+static int staged_upload(qb200_ctx *ctx, void *dst_dev, const uint8_t *src, size_t bytes) {
+  if (bytes < kXferMin || host_pointer_is_pinned(src)) {
+    CU(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return QB200_OK;
+  }
+  int rc = ensure_xfer(ctx);
+  if (rc) return rc;
+  size_t c = 0;
+  for (size_t off = 0; off < bytes; off += kXferChunk, c++) {
+    const size_t n = std::min(kXferChunk, bytes - off);
+    const int slot = (int)(c & 1);
+    if (c >= 2) CU(cudaEventSynchronize(ctx->ev_xfer[slot]));  // the copy that last used this buffer has left it
+    uint8_t *stage = (uint8_t *)ctx->h_xfer[slot];
+    host_parallel(n, (size_t)1 << 20, [=](size_t b, size_t e) { std::memcpy(stage + b, src + off + b, e - b); });
+    CU(cudaMemcpyAsync((uint8_t *)dst_dev + off, stage, n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_xfer[slot], ctx->stream));
+  }
+  for (int i = 0; i < 2; i++) CU(cudaEventSynchronize(ctx->ev_xfer[i]));  // the staging buffers are free for the next caller
+  return QB200_OK;
+}
+
+}  // extern "C++"
+
 static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySize, int w, int h, int colorspace,
                           int n_images, int on_device, bool shard, size_t row_begin, size_t row_end,
                           bool band_only = false, size_t band_len = 0) {
@@ -1001,7 +1076,7 @@ static int set_image_impl(qb200_ctx *ctx, const uint8_t *rgb, int xSize, int ySi
   } else {
     int rc = ensure(ctx, ctx->d_img, (size_t)(hi - lo) + 16);
     if (rc) return rc;
-    if (hi > lo) CU(cudaMemcpyAsync(ctx->d_img.p, first, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+    if (hi > lo && (rc = staged_upload(ctx, ctx->d_img.p, first, (size_t)(hi - lo)))) return rc;
     s.buf = (const uint8_t *)ctx->d_img.p;
   }
   finish_source(s, (unsigned long long)n_images, xSize % w == 0 && ySize % h == 0);
@@ -1107,7 +1182,7 @@ int qb200_set_vectors_u8(qb200_ctx *ctx, const uint8_t *bytes, size_t n_vectors,
   } else {
     int rc = ensure(ctx, ctx->d_img, (size_t)s.img_bytes + 16);
     if (rc) return rc;
-    if (s.img_bytes) CU(cudaMemcpyAsync(ctx->d_img.p, bytes, (size_t)s.img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (s.img_bytes && (rc = staged_upload(ctx, ctx->d_img.p, bytes, (size_t)s.img_bytes))) return rc;
     s.buf = (const uint8_t *)ctx->d_img.p;
   }
   finish_source(s, 1, true);
@@ -1493,6 +1568,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     for (uint32_t Kl = 2; Kl <= maxK && Kl; Kl *= 2)
       if (small_at(Kl)) Ks = Kl;
     if (Ks && (rc = ensure(ctx, ctx->d_small, small_cells_workspace_bytes((int)Ks, dim)))) return rc;
+    if (Ks) CU(launch_small_cells_reset(ctx->d_small.p, st));
   }
   if (tc_max && (rc = ensure(ctx, ctx->d_rows_tc, tc_max))) return rc;
   if (tc_max && (rc = ensure(ctx, ctx->d_state, (size_t)(ctx->src.n_local ? ctx->src.n_local : 1) * 16))) return rc;
@@ -1593,7 +1669,7 @@ int train_parity_pipelined_body(qb200_ctx *ctx, int nbits, uint64_t N, qb200_all
     if (exact && (rc = exact_centroid_sums(ctx, K, ar, ar_user))) return rc;
     if (small) {
       CU(launch_small_cells_collect(ctx->src, (const uint32_t *)ctx->d_assign.p, (const unsigned long long *)ctx->d_stats.p,
-                                    ar ? small_packed : nullptr, (int)K, ar ? ctx->rank : 0, ctx->d_small.p, ctx->sm_count, st));
+                                    ar ? small_packed : nullptr, (int)K, ar ? ctx->rank : 0, level, ctx->d_small.p, ctx->sm_count, st));
       if (ar && ar(small_cells_table(ctx->d_small.p, (int)K, dim), small_cells_table_words((int)K, dim), (void *)st, ar_user) != 0)
         return fail(ctx, QB200_ERR_COMM, "all-reduce callback failed (small cells, K=%u)", K);
       CU(launch_small_cells_sums((const unsigned long long *)ctx->d_stats.p, (int)K, dim, ctx->d_small.p, st));
@@ -1878,6 +1954,35 @@ int qb200_get_assign(qb200_ctx *ctx, uint32_t *assign_out) {
 int qb200_get_assign_u64(qb200_ctx *ctx, uint64_t *assign_out) {
   if (!ctx || !assign_out) return QB200_ERR_ARG;
   const size_t n = qb200_num_vectors(ctx);
+  if (!ctx->is_multi && n * 4 >= kXferMin) {
+    // chunks of the 32-bit indices land in two pinned buffers; host threads widen one while the next is on the bus
+    if (!ctx->assign_valid) return fail(ctx, QB200_ERR_STATE, "qb200_get_assign_u64: no assignment computed yet");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_xfer(ctx);
+    if (rc) return rc;
+    const size_t per = kXferChunk / 4;
+    auto widen = [&](size_t c) {
+      const size_t off = c * per, cnt = std::min(per, n - off);
+      const uint32_t *stage = (const uint32_t *)ctx->h_xfer[c & 1];
+      uint64_t *dst = assign_out + off;
+      host_parallel(cnt, (size_t)1 << 18, [=](size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) dst[i] = stage[i];
+      });
+    };
+    const size_t chunks = (n + per - 1) / per;
+    for (size_t c = 0; c < chunks; c++) {
+      const size_t off = c * per, cnt = std::min(per, n - off);
+      CU(cudaMemcpyAsync(ctx->h_xfer[c & 1], (const uint32_t *)ctx->d_assign.p + off, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaEventRecord(ctx->ev_xfer[c & 1], ctx->stream));
+      if (c > 0) {
+        CU(cudaEventSynchronize(ctx->ev_xfer[(c - 1) & 1]));
+        widen(c - 1);
+      }
+    }
+    CU(cudaEventSynchronize(ctx->ev_xfer[(chunks - 1) & 1]));
+    widen(chunks - 1);
+    return QB200_OK;
+  }
   // copy into the upper half of the caller's buffer, then widen in place front to back
   uint32_t *tmp = reinterpret_cast<uint32_t *>(assign_out) + n;
   int rc = qb200_get_assign(ctx, tmp);
@@ -2076,6 +2181,18 @@ int qb200_debug_kd_margin(const double *points, size_t K, int dim, const uint8_t
   KdHostTree t;
   build_kd_tree(points, K, dim, 10, t, exact_flags);
   *margin_out = t.min_margin;
+  return QB200_OK;
+}
+
+int qb200_debug_level_codebook(qb200_ctx *ctx, int level, double *codebook_out) {
+  if (!ctx || !codebook_out || level < 0 || level > 23) return QB200_ERR_ARG;
+  NOT_ON_MULTI("qb200_debug_level_codebook");
+  const size_t dim = (size_t)ctx->src.dim, off = (((size_t)2 << level) - 2) * dim * 8, bytes = ((size_t)2 << level) * dim * 8;
+  if (!ctx->have_set || !ctx->d_levels.p || off + bytes > ctx->d_levels.cap)
+    return fail(ctx, QB200_ERR_STATE, "qb200_debug_level_codebook: no pipelined train has kept level %d", level);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(codebook_out, (const char *)ctx->d_levels.p + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return QB200_OK;
 }
 

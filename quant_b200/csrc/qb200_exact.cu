@@ -1023,26 +1023,36 @@ __global__ void __launch_bounds__(256)
   packed[k] = (n < 15ull ? n : 15ull) << (4 * rank);  // 9..15: "too many" (the reduced count decides anyway)
 }
 
-// flag[k] = the cell takes this path; off[k] = members of the cell on lower ranks
+// flag[k] = the cell takes this path; off[k] = members of the cell on lower ranks.  Also clears the cell's member
+// counter and its rows of the exchange table, and raises *any (this level's word) when at least one cell is small -
+// the member scan returns at once otherwise.  Rows of cells that are not small keep stale words: never read.
 __global__ void __launch_bounds__(256)
     small_mark_kernel(const unsigned long long *__restrict__ stats, const unsigned long long *__restrict__ packed, const int K,
-                      const int row_words, const int rank, unsigned char *__restrict__ flag, unsigned char *__restrict__ off) {
+                      const int row_words, const int rank, const int words, unsigned char *__restrict__ flag,
+                      unsigned char *__restrict__ off, unsigned int *__restrict__ cnt, unsigned long long *__restrict__ table,
+                      unsigned int *__restrict__ any) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const unsigned long long n = stats[(size_t)k * row_words];
   const bool small = n >= 1 && n <= (unsigned long long)kSmallCellMax;
   flag[k] = small ? 1 : 0;
+  cnt[k] = 0;
   unsigned int before = 0;
-  if (small && packed) {
-    const unsigned long long w = packed[k];
-    for (int q = 0; q < rank; q++) before += (unsigned int)(w >> (4 * q)) & 15u;
+  if (small) {
+    if (packed) {
+      const unsigned long long w = packed[k];
+      for (int q = 0; q < rank; q++) before += (unsigned int)(w >> (4 * q)) & 15u;
+    }
+    for (int i = 0; i < kSmallCellMax * words; i++) table[(size_t)k * kSmallCellMax * words + i] = 0;
+    *any = 1u;  // same value from every writer; cleared once per train (launch_small_cells_reset)
   }
   off[k] = (unsigned char)before;
 }
 
 __global__ void __launch_bounds__(256)
     small_collect_kernel(const uint32_t *__restrict__ assign, const unsigned int n, const unsigned char *__restrict__ flag,
-                         unsigned int *__restrict__ cnt, uint32_t *__restrict__ list) {
+                         unsigned int *__restrict__ cnt, uint32_t *__restrict__ list, const unsigned int *__restrict__ any) {
+  if (!*any) return;
   for (unsigned int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     const uint32_t k = __ldg(assign + v) & 0x7fffffffu;
     if (!flag[k]) continue;
@@ -1055,9 +1065,9 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(128)
     small_pack_kernel(const VecSource src, const int K, const int words, const unsigned char *__restrict__ flag,
                       const unsigned char *__restrict__ off, const unsigned int *__restrict__ cnt, const uint32_t *__restrict__ list,
-                      unsigned long long *__restrict__ table) {
+                      unsigned long long *__restrict__ table, const unsigned int *__restrict__ any) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K || !flag[k]) return;
+  if (!*any || k >= K || !flag[k]) return;
   unsigned int c = cnt[k];
   if (c > (unsigned int)kSmallCellMax) c = kSmallCellMax;
   uint32_t idx[kSmallCellMax];
@@ -1108,6 +1118,7 @@ __global__ void __launch_bounds__(256)
 }
 
 struct SmallWork {
+  unsigned int *any;  // one word per split level (cleared once per train): some cell of that level is small
   unsigned int *cnt;
   uint32_t *list;
   unsigned char *flag, *off;
@@ -1119,6 +1130,8 @@ SmallWork small_carve(void *ws, int K, int dim) {
   const size_t words = (size_t)(dim + 7) / 8;
   char *p = (char *)ws;
   SmallWork w;
+  w.any = (unsigned int *)p;
+  p += 256;
   w.cnt = (unsigned int *)p;
   p += small_up((size_t)K * 4);
   w.list = (uint32_t *)p;
@@ -1138,11 +1151,14 @@ SmallWork small_carve(void *ws, int K, int dim) {
 size_t small_cells_table_words(int K, int dim) { return (size_t)K * kSmallCellMax * (size_t)((dim + 7) / 8); }
 size_t small_cells_workspace_bytes(int K, int dim) {
   return small_up((size_t)K * 4) + small_up((size_t)K * kSmallCellMax * 4) + 2 * small_up((size_t)K) +
-         small_up(small_cells_table_words(K, dim) * 8) + small_up((size_t)K * dim * 8) + 256;
+         small_up(small_cells_table_words(K, dim) * 8) + small_up((size_t)K * dim * 8) + 512;
 }
 unsigned long long *small_cells_table(void *ws, int K, int dim) { return small_carve(ws, K, dim).table; }
 const unsigned char *small_cells_flags(void *ws, int K, int dim) { return small_carve(ws, K, dim).flag; }
 const double *small_cells_sums(void *ws, int K, int dim) { return small_carve(ws, K, dim).sums; }
+
+// once per train, before the first level
+cudaError_t launch_small_cells_reset(void *ws, cudaStream_t stream) { return cudaMemsetAsync(ws, 0, 256, stream); }
 
 // before the statistics are reduced: this rank's member counts, one nibble per rank (packed: K words, summed with the statistics)
 cudaError_t launch_small_cells_count(const unsigned long long *stats_local, int K, int dim, int rank, unsigned long long *packed,
@@ -1154,22 +1170,21 @@ cudaError_t launch_small_cells_count(const unsigned long long *stats_local, int 
 
 // after the reduction: mark the small cells and write this rank's members into the (zeroed) table
 cudaError_t launch_small_cells_collect(const VecSource &src, const uint32_t *assign, const unsigned long long *stats,
-                                       const unsigned long long *packed, int K, int rank, void *ws, int sm_count, cudaStream_t stream) {
+                                       const unsigned long long *packed, int K, int rank, int level, void *ws, int sm_count,
+                                       cudaStream_t stream) {
   const int dim = src.dim, words = (dim + 7) / 8;
   const SmallWork w = small_carve(ws, K, dim);
-  cudaError_t e;
-  if ((e = cudaMemsetAsync(w.cnt, 0, (size_t)K * 4, stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(w.table, 0, small_cells_table_words(K, dim) * 8, stream)) != cudaSuccess) return e;
-  small_mark_kernel<<<(K + 255) / 256, 256, 0, stream>>>(stats, packed, K, dim + 2, rank, w.flag, w.off);
+  unsigned int *any = w.any + (level & 63);
+  small_mark_kernel<<<(K + 255) / 256, 256, 0, stream>>>(stats, packed, K, dim + 2, rank, words, w.flag, w.off, w.cnt, w.table, any);
   count_launch();
   const unsigned int n = (unsigned int)src.n_local;
   if (n) {
     unsigned int blocks = (n + 255) / 256;
     const unsigned int cap = (unsigned int)sm_count * 8;
     if (blocks > cap) blocks = cap;
-    small_collect_kernel<<<blocks, 256, 0, stream>>>(assign, n, w.flag, w.cnt, w.list);
+    small_collect_kernel<<<blocks, 256, 0, stream>>>(assign, n, w.flag, w.cnt, w.list, any);
     count_launch();
-    small_pack_kernel<<<(K + 127) / 128, 128, 0, stream>>>(src, K, words, w.flag, w.off, w.cnt, w.list, w.table);
+    small_pack_kernel<<<(K + 127) / 128, 128, 0, stream>>>(src, K, words, w.flag, w.off, w.cnt, w.list, w.table, any);
     count_launch();
   }
   return cudaGetLastError();

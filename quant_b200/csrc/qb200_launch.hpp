@@ -121,10 +121,12 @@ size_t small_cells_table_words(int K, int dim);
 unsigned long long *small_cells_table(void *ws, int K, int dim);
 const unsigned char *small_cells_flags(void *ws, int K, int dim);
 const double *small_cells_sums(void *ws, int K, int dim);
+cudaError_t launch_small_cells_reset(void *ws, cudaStream_t stream);
 cudaError_t launch_small_cells_count(const unsigned long long *stats_local, int K, int dim, int rank, unsigned long long *packed,
                                      cudaStream_t stream);
 cudaError_t launch_small_cells_collect(const VecSource &src, const uint32_t *assign, const unsigned long long *stats,
-                                       const unsigned long long *packed, int K, int rank, void *ws, int sm_count, cudaStream_t stream);
+                                       const unsigned long long *packed, int K, int rank, int level, void *ws, int sm_count,
+                                       cudaStream_t stream);
 cudaError_t launch_small_cells_sums(const unsigned long long *stats, int K, int dim, void *ws, cudaStream_t stream);
 // General FP64 training vectors (qb200_generic.cu).
 // CIE1931 colour space (src/ColorSpace.cpp:31-39): the image's block vectors as doubles, n_local x dim.

@@ -10,10 +10,12 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <exception>
 #include <fstream>
 #include <iomanip>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 
 #include "../../../include/qb200.h"
 #include "B200Context.hpp"
@@ -131,9 +133,20 @@ std::pair<CompressedImage, CompressionRaport> CompressedImage::compress(const RG
   qbhost::check(qb200_set_image(ctx, reinterpret_cast<const uint8_t *>(image.img.data()), image.xSize, image.ySize,
                                 blockWidth, blockHeight, cs, 1, 0),
                 "qb200_set_image");
-  qbhost::check(qb200_train(ctx, N, eps, training_mode(), 0, nullptr, nullptr, cb.data(), &lbg_distortion, nullptr),
-                "qb200_train");
-  res.assignedCodeVector.resize(qb200_num_vectors(ctx));
+  // the index vector (8 bytes per block) is allocated and first touched by a host thread while the GPU trains
+  const size_t n_blocks = qb200_num_vectors(ctx);
+  std::exception_ptr alloc_error;
+  std::thread prefault([&] {
+    try {
+      res.assignedCodeVector.resize(n_blocks);
+    } catch (...) {
+      alloc_error = std::current_exception();
+    }
+  });
+  const int train_rc = qb200_train(ctx, N, eps, training_mode(), 0, nullptr, nullptr, cb.data(), &lbg_distortion, nullptr);
+  prefault.join();
+  if (alloc_error) std::rethrow_exception(alloc_error);
+  qbhost::check(train_rc, "qb200_train");
   qbhost::check(qb200_get_assign_u64(ctx, reinterpret_cast<uint64_t *>(res.assignedCodeVector.data())),
                 "qb200_get_assign_u64");
   const auto t1 = std::chrono::system_clock::now();

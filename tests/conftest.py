@@ -6,6 +6,10 @@ import sys
 import numpy as np
 import pytest
 
+# Several ranks of the multi-device tests share ONE GPU on a single-GPU box, and a rank waits inside a kernel for its
+# peers' kernels: their streams must not be folded onto the same hardware queue (default: 8 queues per context).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")

@@ -125,6 +125,15 @@ while time.time() < t_end:
             if level_ok:
                 flips += 1
                 ok = True
+                if auto:   # a promise broken: keep everything needed to replay the case off-line
+                    os.makedirs("gpurun_out", exist_ok=True)
+                    lev = {f"gpu_level_{l}": ctx.debug_level_codebook(l) for l in range(nbits)}
+                    np.savez_compressed(f"gpurun_out/fuzz_flip_{seed}_{cases}.npz", rgb=rgb, xs=xs, ys=ys, w=w, h=h, cs=cs, nbits=nbits,
+                                        kind=kind, gpu_assign=a, gpu_codebook=cb, took_exact=bool(ctx.last_train_exact),
+                                        sensitive=np.array([r["sensitive"] for r in _]), **lev)
+                    print(f"TIE-FLIP in auto mode: kind={kind} xs={xs} ys={ys} w={w} h={h} cs={cs} nbits={nbits} N={N} "
+                          f"{int((a != a_o).sum())} indices, took_exact={ctx.last_train_exact}, "
+                          f"sensitive={[r['sensitive'] for r in _]}", flush=True)
         if not ok:
             bad += 1
             print(f"MISMATCH train kind={kind} xs={xs} ys={ys} w={w} h={h} cs={cs} nbits={nbits} N={N}: {int((a != a_o).sum())} indices", flush=True)

@@ -1,22 +1,24 @@
 #!/bin/bash
-# small-cell sums (auto mode): tests, fuzz in the default mode, bench lines of every workload
+# small-cell sums (auto mode) + staged pageable transfers: tests, fuzz in the default mode, bench lines
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r2small}
-timeout 900 python -m pytest tests -m gpu -x -q -k "small_cells or multi_device or auto_mode or full_train or duplicate_heavy or two_rank or sharded" > gpurun_out/pytest_small_$TAG.log 2>&1
-echo "pytest exit $?"; tail -5 gpurun_out/pytest_small_$TAG.log
-timeout 200 python tools/fuzz_parity.py 100 77 auto 2>&1 | tail -4
-timeout 900 python bench.py --steps 5 > gpurun_out/bench_c3_$TAG.json 2> gpurun_out/bench_c3_$TAG.err
-echo "bench c3 exit $?"; python - <<PY
-import json
-d=json.load(open("gpurun_out/bench_c3_$TAG.json"))
-print("c3 ms", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], "centroids", d["config"].get("centroids"), "sens", d.get("sensitive_per_level"), "nat", d.get("natural"))
-PY
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1
+echo "pytest exit $?"; tail -8 gpurun_out/pytest_gpu_$TAG.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 300 python tools/fuzz_parity.py 150 77 auto 2>&1 | tail -6
+timeout 900 python bench.py > gpurun_out/bench_c3_$TAG.json 2> gpurun_out/bench_c3_$TAG.err
+echo "bench c3 exit $?"; tail -3 gpurun_out/bench_c3_$TAG.err
 for wl in c2 c4 c1; do
-timeout 600 python bench.py --workload $wl --no-cpu > gpurun_out/bench_${wl}_$TAG.json 2> gpurun_out/bench_${wl}_$TAG.err
-echo "bench $wl exit $?"; python - <<PY
-import json
-d=json.load(open("gpurun_out/bench_${wl}_$TAG.json"))
-print("$wl ms", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], "centroids", d["config"].get("centroids"), "sens", d.get("sensitive_per_level"), "nat", d.get("natural"))
-PY
+timeout 600 python bench.py --workload $wl > gpurun_out/bench_${wl}_$TAG.json 2> gpurun_out/bench_${wl}_$TAG.err
+echo "bench $wl exit $?"
 done
+python - <<PY
+import json
+for wl in ("c3","c2","c4","c1"):
+    try:
+        d=json.load(open(f"gpurun_out/bench_{wl}_$TAG.json"))
+        print(wl, "ms", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["ms_per_step"],3), "cpp", (d.get("e2e_cpp") or {}).get("seconds_per_train"),
+              "sens", sum((d.get("sensitive_per_level") or {}).values()), "nat", (d.get("natural") or {}).get("ms_per_step"), (d.get("natural") or {}).get("tie_sensitive_decisions"))
+    except Exception as e: print(wl, "no json", e)
+PY
