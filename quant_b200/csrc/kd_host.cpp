@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <utility>
 
 namespace qb {
@@ -180,6 +182,10 @@ class Builder {
     }
     size_t lim1, lim2;
     partition(first, count, feat, cut, lim1, lim2);
+    static const bool trace = std::getenv("QB200_KD_TRACE") != nullptr;  // diagnostics: one line per inner node
+    if (trace)
+      std::fprintf(stderr, "kd node first=%zu count=%zu feat=%d cut=%.17g (exact %d) lim1=%zu lim2=%zu margin=%.3g\n", first, count, feat,
+                   cut, (int)cut_exact_, lim1, lim2, out_.min_margin);
     if (lim1 > count / 2) return lim1;
     if (lim2 < count / 2) return lim2;
     return count / 2;
@@ -217,10 +223,22 @@ class Builder {
     rbox[feat].lo = cut;
     rbox[feat].lo_exact = cut_exact;
     int c2 = subdivide(first + nleft, last, rbox, level + 1);
+    // census only: are the two plane coordinates numbers both codebooks share bit for bit?  divlow is the largest
+    // coordinate of the left child, divhigh the smallest of the right one (span_of: attained only by bit-reproducible
+    // points, no other point within rounding noise of it).  Kept in bits 16 / 17 of the node's `a`.
+    int div_flags = 0;
+    if (exact_) {
+      double mn, mx;
+      bool mn_e, mx_e;
+      span_of(first, nleft, feat, mn, mx, &mn_e, &mx_e);
+      if (mx_e) div_flags |= kKdDivLowExact;
+      span_of(first + nleft, last - first - nleft, feat, mn, mx, &mn_e, &mx_e);
+      if (mn_e) div_flags |= kKdDivHighExact;
+    }
     KdNode &nd = out_.nodes[me];
     nd.child1 = c1;
     nd.child2 = c2;
-    nd.a = feat;
+    nd.a = feat | div_flags;
     nd.b = (int)(first + nleft);  // child1 covers order[first, b), child2 order[b, last)
     nd.divlow = lbox[feat].hi;
     nd.divhigh = rbox[feat].lo;

@@ -132,9 +132,12 @@ __device__ __forceinline__ void gather_lattice(const VecSource &s, unsigned long
 }
 
 // Flattened KD tree in nanoflann's shape (see kd_host.hpp); 32 bytes per node.
+constexpr int kKdFeatMask = 0xffff;      // inner node: a & kKdFeatMask = divfeat
+constexpr int kKdDivLowExact = 1 << 16;  // inner node, census of the auto centroid mode only: divlow / divhigh is a number
+constexpr int kKdDivHighExact = 1 << 17; // the integer-sum and the compensated-sum codebooks share bit for bit
 struct KdNode {
   int child1, child2;  // -1/-1: leaf
-  int a;               // inner: divfeat; leaf: left (first position in vind)
+  int a;               // inner: divfeat (+ the two census bits above); leaf: left (first position in vind)
   int b;               // leaf: right (one past the last position in vind); inner: first position of child2's range
   double divlow, divhigh;
 };

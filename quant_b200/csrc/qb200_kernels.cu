@@ -911,19 +911,22 @@ __global__ void __launch_bounds__(128)
           const bool any1 = __any_sync(0xffffffffu, in1), any2 = __any_sync(0xffffffffu, in2);
           bool go1;
           if (any1 && any2) {
-            double val = 0.0;  // x[nd.a] by selection: a dynamic index would push x[] out of registers
+            double val = 0.0;  // x[feat] by selection: a dynamic index would push x[] out of registers
+            const int feat = nd.a & kKdFeatMask;
 #pragma unroll
-            for (int e = 0; e < (DIMT ? DIMT : DIMCAP); e++) val = (e == nd.a) ? x[e] : val;
+            for (int e = 0; e < (DIMT ? DIMT : DIMCAP); e++) val = (e == feat) ? x[e] : val;
             const double side = __dadd_rn(__dsub_rn(val, nd.divlow), __dsub_rn(val, nd.divhigh));
             go1 = side < 0;  // nearer child first
             // Robust against last-bit changes of the codebook?  Yes when the margin is comfortable - or when both
             // plane coordinates ARE coordinates of tied candidates (the query midway between the children 1.2c / 0.8c
-            // of its own single-member cell makes `side` a pure rounding residue, but of bit-reproducible operands).
+            // of its own single-member cell makes `side` a pure rounding residue, but of bit-reproducible operands)
+            // AND no other codevector's coordinate is within rounding noise of them (an inexact point a last bit above
+            // 0.8c in the reference's codebook would be the plane there: the host's census bits of this node).
             if (sensitive && fabs(side) <= 1e-9 * (fabs(val) + fabs(nd.divlow) + fabs(nd.divhigh))) {
               double coord = 0.0;
-              if (in1 || in2) coord = cbt[(size_t)nd.a * K + tree.vind[my_pos]];
-              const bool lo_ok = __any_sync(0xffffffffu, in1 && coord == nd.divlow);
-              const bool hi_ok = __any_sync(0xffffffffu, in2 && coord == nd.divhigh);
+              if (in1 || in2) coord = cbt[(size_t)feat * K + tree.vind[my_pos]];
+              const bool lo_ok = (nd.a & kKdDivLowExact) && __any_sync(0xffffffffu, in1 && coord == nd.divlow);
+              const bool hi_ok = (nd.a & kKdDivHighExact) && __any_sync(0xffffffffu, in2 && coord == nd.divhigh);
               fragile = fragile || !(lo_ok && hi_ok);
             }
           } else {
@@ -1096,7 +1099,7 @@ __global__ void __launch_bounds__(128)
           sp--;
           continue;
         }
-        const int feat = nd.a;
+        const int feat = nd.a & kKdFeatMask;
         double val;
         if (DIMT) {  // by selection: a dynamic index would push x[] out of registers
           val = 0.0;

@@ -67,7 +67,7 @@ def golden_names():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
     # *_cie / generic_*: FP64-vector fixtures (no byte lattice), covered by their own tests
     return [n for n in names if n not in ("letters_layout", "encode_only_k1024") and not n.endswith("_cie")
-            and not n.startswith("generic_")]
+            and not n.startswith("generic_") and not n.startswith("regress_")]
 
 
 class Golden:
