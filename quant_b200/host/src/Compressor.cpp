@@ -130,11 +130,11 @@ std::pair<CompressedImage, CompressionRaport> CompressedImage::compress(const RG
 
   // ---- the reference's timed region (src/Compressor.cpp:118-123): block extraction + quantize ----
   const auto t0 = std::chrono::system_clock::now();
-  qbhost::check(qb200_set_image(ctx, reinterpret_cast<const uint8_t *>(image.img.data()), image.xSize, image.ySize,
-                                blockWidth, blockHeight, cs, 1, 0),
-                "qb200_set_image");
-  // the index vector (8 bytes per block) is allocated and first touched by a host thread while the GPU trains
-  const size_t n_blocks = qb200_num_vectors(ctx);
+  // the index vector (8 bytes per block) is allocated and first touched by a host thread while the image is uploaded
+  // and the GPU trains
+  const size_t n_blocks = (blockWidth > 0 && blockHeight > 0)   // (invalid shapes: qb200_set_image reports them below)
+                              ? ceil_div((size_t)image.xSize, (size_t)blockWidth) * ceil_div((size_t)image.ySize, (size_t)blockHeight)
+                              : 0;
   std::exception_ptr alloc_error;
   std::thread prefault([&] {
     try {
@@ -143,10 +143,17 @@ std::pair<CompressedImage, CompressionRaport> CompressedImage::compress(const RG
       alloc_error = std::current_exception();
     }
   });
-  const int train_rc = qb200_train(ctx, N, eps, training_mode(), 0, nullptr, nullptr, cb.data(), &lbg_distortion, nullptr);
+  int rc = qb200_set_image(ctx, reinterpret_cast<const uint8_t *>(image.img.data()), image.xSize, image.ySize, blockWidth,
+                           blockHeight, cs, 1, 0);
+  const char *what = "qb200_set_image";
+  if (rc == QB200_OK) {
+    rc = qb200_train(ctx, N, eps, training_mode(), 0, nullptr, nullptr, cb.data(), &lbg_distortion, nullptr);
+    what = "qb200_train";
+  }
   prefault.join();
   if (alloc_error) std::rethrow_exception(alloc_error);
-  qbhost::check(train_rc, "qb200_train");
+  qbhost::check(rc, what);
+  if (qb200_num_vectors(ctx) != n_blocks) res.assignedCodeVector.resize(qb200_num_vectors(ctx));
   qbhost::check(qb200_get_assign_u64(ctx, reinterpret_cast<uint64_t *>(res.assignedCodeVector.data())),
                 "qb200_get_assign_u64");
   const auto t1 = std::chrono::system_clock::now();
