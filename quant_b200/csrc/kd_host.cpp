@@ -129,9 +129,10 @@ class Builder {
       double span = box[d].hi - box[d].lo;
       if (span > max_span) max_span = span;
     }
-    double best_spread = -1, second_spread = -1;
-    bool best_exact = false, second_exact = false;
+    double best_spread = -1;
+    bool best_exact = false;
     feat = 0;
+    spreads_.clear();
     for (int d = 0; d < dim_; d++) {
       double span = box[d].hi - box[d].lo;
       note(span, (1 - kEps) * max_span);  // eligibility of this dimension
@@ -140,20 +141,18 @@ class Builder {
         bool mn_e, mx_e;
         span_of(first, count, d, mn, mx, &mn_e, &mx_e);
         double spread = mx - mn;
+        if (exact_) spreads_.push_back({spread, d, mn_e && mx_e});
         if (spread > best_spread) {
           feat = d;
-          second_spread = best_spread;
-          second_exact = best_exact;
           best_spread = spread;
           best_exact = mn_e && mx_e;
-        } else if (spread > second_spread) {
-          second_spread = spread;
-          second_exact = mn_e && mx_e;
         }
       }
     }
-    // which eligible dimension wins (a tie between two spreads that are the same numbers in both codebooks is harmless)
-    if (second_spread >= 0 && !(best_exact && second_exact)) note(best_spread, second_spread);
+    // which eligible dimension wins: the winner against EVERY other eligible one (several dimensions can share the
+    // runner-up spread).  A tie between two spreads that are the same numbers in both codebooks is harmless.
+    for (const Spread &sp : spreads_)
+      if (sp.dim != feat && !(best_exact && sp.exact)) note(best_spread, sp.value);
     double mid = (box[feat].lo + box[feat].hi) / 2;
     const bool mid_exact = box[feat].lo_exact && box[feat].hi_exact;
     double mn, mx;
@@ -255,6 +254,12 @@ class Builder {
   size_t leaf_max_;
   KdHostTree &out_;
   const unsigned char *exact_;  // per point (may be null): bit-reproducible with either centroid arithmetic
+  struct Spread {
+    double value;
+    int dim;
+    bool exact;
+  };
+  std::vector<Spread> spreads_;  // census scratch of choose_split: the eligible dimensions of the node
   bool cut_exact_ = false;      // of the plane choose_split just returned
 };
 

@@ -114,3 +114,35 @@ def test_kd_tree_robustness_margin():
     dead = pts.copy()
     dead[200:260] = 0.0                           # dead cells
     assert margin(dead) > 1e-9
+
+
+def test_kd_census_compares_the_winning_spread_with_every_eligible_dimension():
+    """Fuzz find of round 2: three dimensions share the root's largest spread exactly (attained by bit-reproducible
+    points); a point that is NOT bit-reproducible sits one ulp below the maximum of the last of them.  In the reference's
+    codebook that point may be one ulp above and make that dimension the root cut, so the census must report no margin -
+    also when an earlier runner-up with the same spread is entirely bit-reproducible."""
+    import ctypes as C
+    import numpy as np
+    from quant_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    pts = rng.random((64, 3)) * 0.8 + 0.1          # everything inside (0.1, 0.9)
+    pts[0] = [0.0, 0.0, 0.0]
+    pts[1] = [1.0, 1.0, 1.0]                      # spreads of all three dimensions: exactly 1.0
+    flags = np.ones(64, np.uint8)
+
+    def margin(p, f):
+        p = np.ascontiguousarray(p, np.float64)
+        m = C.c_double()
+        assert lib.qb200_debug_kd_margin(p.ctypes.data_as(C.c_void_p), p.shape[0], p.shape[1],
+                                         np.ascontiguousarray(f, np.uint8).ctypes.data_as(C.c_void_p), C.byref(m)) == 0
+        return m.value
+
+    assert margin(pts, flags) > 1e-9               # all three ties are between numbers both codebooks share
+    near = pts.copy()
+    near[5, 2] = np.nextafter(1.0, 0.0)            # one ulp below the maximum of the LAST dimension ...
+    f2 = flags.copy()
+    f2[5] = 0                                      # ... and not bit-reproducible
+    assert margin(near, f2) < 1e-12
+    f2[5] = 1
+    assert margin(near, f2) > 1e-9                 # the same point, bit-reproducible: harmless
