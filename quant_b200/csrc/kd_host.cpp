@@ -141,7 +141,7 @@ class Builder {
         bool mn_e, mx_e;
         span_of(first, count, d, mn, mx, &mn_e, &mx_e);
         double spread = mx - mn;
-        if (exact_) spreads_.push_back({spread, d, mn_e && mx_e});
+        spreads_.push_back({spread, d, mn_e && mx_e});
         if (spread > best_spread) {
           feat = d;
           best_spread = spread;
@@ -166,14 +166,22 @@ class Builder {
       // are both bit-reproducible numbers.
       const bool clamped = cut == mn || cut == mx;
       if (mn == mx && mn != 0.0 && !(mn_exact && mx_exact)) out_.min_margin = 0.0;  // all points equal along the cut
+      size_t at_cut = 0, at_cut_inexact = 0;
       for (size_t i = 0; i < count; i++) {
         const double v = via(first + i, feat);
+        if (v == cut) {
+          at_cut++;
+          at_cut_inexact += !point_exact(first + i);
+        }
         if (cut_exact_ && point_exact(first + i)) continue;
         if (v != cut)
           note(v, cut);
         else if (!clamped)
           out_.min_margin = 0.0;
       }
+      // clamped plane shared by several points, not all of them bit-reproducible: in the other codebook they may sit an
+      // ulp apart, and how many are <= the plane (planeSplit's second limit) changes
+      if (clamped && at_cut > 1 && at_cut_inexact > 0 && cut != 0.0) out_.min_margin = 0.0;
       if (!clamped && !(mid_exact && mn_exact && mx_exact)) {  // the clamp decisions themselves
         note(mid, mn);
         note(mid, mx);
