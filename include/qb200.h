@@ -286,6 +286,11 @@ int qb200_debug_kd_build(const double *points, size_t K, int dim, uint32_t *orde
  * whose coordinates are the same numbers with either centroid arithmetic.  The auto centroid mode trusts the tree's
  * visiting order only above 1e-9. */
 int qb200_debug_kd_margin(const double *points, size_t K, int dim, const uint8_t *exact_flags, double *margin_out);
+/* Diagnostics: the whole host KD tree of a codebook - nodes (32 bytes each: int child1, child2, a, b; double divlow,
+ * divhigh; inner nodes: a = cut dimension | census bits 16, 17; leaves: children -1, [a, b) = positions in order_out),
+ * nanoflann's point order and the robustness margin.  nodes_out may be NULL (count only). */
+int qb200_debug_kd_tree(const double *points, size_t K, int dim, const uint8_t *exact_flags, void *nodes_out, size_t nodes_cap,
+                        int *n_nodes_out, uint32_t *order_out, double *margin_out);
 /* Diagnostics: the codebook split level `level` (0-based: 2^(level+1) codevectors, before their centroid update)
  * of the last HEAD-schedule train started from, as kept on the device for the auto mode's restart. */
 int qb200_debug_level_codebook(qb200_ctx *ctx, int level, double *codebook_out);

@@ -77,6 +77,8 @@ SIGNATURES = {
     "qb200_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "qb200_debug_kd_build": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "qb200_debug_kd_tree": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
+                                      C.c_void_p, C.POINTER(C.c_double)]),
     "qb200_debug_level_codebook": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "qb200_debug_kd_margin": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_double)]),
     "qb200_debug_filter_records": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -2184,6 +2184,22 @@ int qb200_debug_kd_margin(const double *points, size_t K, int dim, const uint8_t
   return QB200_OK;
 }
 
+int qb200_debug_kd_tree(const double *points, size_t K, int dim, const uint8_t *exact_flags, void *nodes_out, size_t nodes_cap,
+                        int *n_nodes_out, uint32_t *order_out, double *margin_out) {
+  if (!points || K == 0 || dim <= 0 || !n_nodes_out) return QB200_ERR_ARG;
+  KdHostTree t;
+  build_kd_tree(points, K, dim, 10, t, exact_flags);
+  *n_nodes_out = (int)t.nodes.size();
+  if (nodes_out) {
+    if (nodes_cap < t.nodes.size()) return QB200_ERR_ARG;
+    std::memcpy(nodes_out, t.nodes.data(), t.nodes.size() * sizeof(KdNode));
+  }
+  if (order_out)
+    for (size_t i = 0; i < K; i++) order_out[i] = t.order[i];
+  if (margin_out) *margin_out = t.min_margin;
+  return QB200_OK;
+}
+
 int qb200_debug_level_codebook(qb200_ctx *ctx, int level, double *codebook_out) {
   if (!ctx || !codebook_out || level < 0 || level > 23) return QB200_ERR_ARG;
   NOT_ON_MULTI("qb200_debug_level_codebook");
