@@ -264,6 +264,30 @@ def cpp_compress_leg(band, xs, ys, w, h, nbits, steps, n_total, cb_expect):
             "codebook_bytes_equal_c_abi_run": same, "report_mse": d.value, "bits_per_pixel": bpp.value}
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs: keep this rank's host thread - and so the first touch of its pinned buffers - on the NUMA node
+    its GPU hangs off (sysfs numa_node of the device's PCI address).  Returns the node, or None when it is unknown or
+    the binding is not possible; never fatal."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if len(allowed) < 2:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args):
     import torch
     import quant_b200 as qb
@@ -275,6 +299,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference)")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("QB200_BENCH_NUMA", "1") != "0" else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -501,6 +526,7 @@ def run_gpu_arm(args):
                                      if args.centroids == "auto" else "from integer per-cell sums (<= 4e-16 relative of the reference's)"),
                        "allreduce": (None if world == 1 else "NCCL via torch.distributed callback" if args.nccl else
                                      "libqb200 peer-memory all-reduce (qb200_comm.cu), CUDA IPC between the rank processes"),
+                       "host_numa_node_rank0": numa_node,   # multi-rank: host thread + pinned buffers bound to the GPU's node
                        "l2": "512 MiB flush (memset) before every timed step, outside the timed events"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(host_band.numel()) * world,

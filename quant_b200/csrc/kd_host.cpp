@@ -164,7 +164,7 @@ class Builder {
       // every point against the cutting plane.  A point AT the plane is harmless when the plane was clamped onto
       // the data range (then the plane is that point's own coordinate and moves with it), or when point and plane
       // are both bit-reproducible numbers.
-      const bool clamped = cut == mn || cut == mx;
+      const bool clamped = mid < mn || mid > mx;  // (not "cut == mn || cut == mx": an unclamped midpoint can coincide with an extreme)
       if (mn == mx && mn != 0.0 && !(mn_exact && mx_exact)) out_.min_margin = 0.0;  // all points equal along the cut
       size_t at_cut = 0, at_cut_inexact = 0;
       for (size_t i = 0; i < count; i++) {
@@ -182,7 +182,7 @@ class Builder {
       // clamped plane shared by several points, not all of them bit-reproducible: in the other codebook they may sit an
       // ulp apart, and how many are <= the plane (planeSplit's second limit) changes
       if (clamped && at_cut > 1 && at_cut_inexact > 0 && cut != 0.0) out_.min_margin = 0.0;
-      if (!clamped && !(mid_exact && mn_exact && mx_exact)) {  // the clamp decisions themselves
+      if (!(mid_exact && mn_exact && mx_exact)) {  // the clamp decisions themselves (far from flipping when clamped by a lot)
         note(mid, mn);
         note(mid, mx);
       }
@@ -191,8 +191,9 @@ class Builder {
     partition(first, count, feat, cut, lim1, lim2);
     static const bool trace = std::getenv("QB200_KD_TRACE") != nullptr;  // diagnostics: one line per inner node
     if (trace)
-      std::fprintf(stderr, "kd node first=%zu count=%zu feat=%d cut=%.17g (exact %d) lim1=%zu lim2=%zu margin=%.3g\n", first, count, feat,
-                   cut, (int)cut_exact_, lim1, lim2, out_.min_margin);
+      std::fprintf(stderr, "kd node first=%zu count=%zu feat=%d cut=%.17g (exact %d) lim1=%zu lim2=%zu margin=%.3g  box [%.17g (%d), %.17g (%d)] data [%.17g (%d), %.17g (%d)]\n",
+                   first, count, feat, cut, (int)cut_exact_, lim1, lim2, out_.min_margin, box[feat].lo, (int)box[feat].lo_exact, box[feat].hi,
+                   (int)box[feat].hi_exact, mn, (int)mn_exact, mx, (int)mx_exact);
     if (lim1 > count / 2) return lim1;
     if (lim2 < count / 2) return lim2;
     return count / 2;

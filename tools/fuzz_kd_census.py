@@ -55,22 +55,30 @@ def kahan_mean(ts):
 
 def make_level(rng):
     """One split level: (ours, reference, flags) for 2 * cells codevectors."""
-    dim = int(rng.choice([3, 6, 9, 12, 27]))
-    cells = int(rng.choice([8, 16, 32, 64, 128]))
+    dim = int(rng.choice([3, 3, 6, 9, 12, 12, 27, 48]))
+    cells = int(rng.choice([8, 16, 32, 64, 128, 256]))
     n_colours = int(rng.choice([2, 3, 4, 6, 16, 256]))
     palette = np.sort(rng.choice(256, n_colours, replace=False)) if n_colours < 256 else np.arange(256)
     ours = np.zeros((cells, dim))
     ref = np.zeros((cells, dim))
     flag = np.zeros(cells, np.uint8)
     shared = palette[rng.integers(0, len(palette), dim)]   # a vector many cells are built around
+    flat = rng.random() < 0.35
     for k in range(cells):
         kind = rng.random()
         if kind < 0.08:                                   # dead cell
             flag[k] = 1
             continue
-        n = int(rng.choice([1, 1, 2, 2, 3, 5, 8, 9, 12, 40]))
+        n = int(rng.choice([1, 1, 2, 2, 3, 5, 8, 9, 10, 12, 16, 40, 150]))
         ts = palette[rng.integers(0, len(palette), (n, dim))].astype(np.int64)
-        if rng.random() < 0.5:                            # most coordinates equal to the shared vector's
+        if flat:                                          # a flat image with outliers: copies of one vector, few strays
+            stray = ts.copy()
+            ts[:] = shared
+            for m in range(n):
+                if rng.random() < (0.5 if n == 1 else 0.12):
+                    px = int(rng.integers(0, dim // 3)) * 3   # one stray pixel (3 coordinates)
+                    ts[m, px:px + 3] = stray[m, px:px + 3]
+        elif rng.random() < 0.5:                          # most coordinates equal to the shared vector's
             keep = rng.random(dim) < 0.7
             ts[:, keep] = shared[keep]
         if rng.random() < 0.2:
