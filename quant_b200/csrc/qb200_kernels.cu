@@ -953,7 +953,9 @@ __global__ void __launch_bounds__(128)
       // within a few ulps when the tree's shape is robust (KdHostTree::min_margin) and every step of the descent is.
       if (sensitive && lane == 0 && near2 > 1) {
         const bool order_safe = tree_robust && all_exact && n_cand <= 32 && !fragile;
-        if (inexact2 > 0 || (at_min > 1 && !order_safe)) atomicAdd(sensitive, 1u);
+        // (at_min < near2: bit-reproducible candidates at DISTINCT distances inside the band - which of them the walk
+        //  returns can hinge on the rounding of its pruning bounds, i.e. on plane coordinates of other codevectors)
+        if (inexact2 > 0 || at_min < near2 || (at_min > 1 && !order_safe)) atomicAdd(sensitive, 1u);
         // diagnostics: sensitive[1] counts the first kind, sensitive[2] collects why a visiting order was not safe
         if (inexact2 > 0) atomicAdd(sensitive + 1, 1u);
         if (inexact2 == 0 && at_min > 1 && !order_safe)
