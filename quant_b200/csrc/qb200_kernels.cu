@@ -953,9 +953,12 @@ __global__ void __launch_bounds__(128)
       // within a few ulps when the tree's shape is robust (KdHostTree::min_margin) and every step of the descent is.
       if (sensitive && lane == 0 && near2 > 1) {
         const bool order_safe = tree_robust && all_exact && n_cand <= 32 && !fragile;
-        // (at_min < near2: bit-reproducible candidates at DISTINCT distances inside the band - which of them the walk
-        //  returns can hinge on the rounding of its pruning bounds, i.e. on plane coordinates of other codevectors)
-        if (inexact2 > 0 || at_min < near2 || (at_min > 1 && !order_safe)) atomicAdd(sensitive, 1u);
+        // (Bit-reproducible candidates at DISTINCT distances inside the band are taken as decided by the exact search:
+        //  it returns the smaller one unless the walk's pruning bound for that candidate's subtree is within ~2^-46 dmax
+        //  of its full distance - a box corner reached along every dimension - AND the bound's plane coordinates differ
+        //  between the codebooks.  Counting them as sensitive was tried: the 1.2c / 0.8c pair of a two-member cell is
+        //  such a pair, an ulp apart, and every large noise train would take the exact repeat for it.)
+        if (inexact2 > 0 || (at_min > 1 && !order_safe)) atomicAdd(sensitive, 1u);
         // diagnostics: sensitive[1] counts the first kind, sensitive[2] collects why a visiting order was not safe
         if (inexact2 > 0) atomicAdd(sensitive + 1, 1u);
         if (inexact2 == 0 && at_min > 1 && !order_safe)
