@@ -418,7 +418,9 @@ def run_gpu_arm(args):
     # queries through the exact FP64 resolver and its tree walk than noise does (and the reference's KD search is
     # faster there), so the noise headline alone would flatter the comparison.  Reported next to it.
     natural = None
-    if args.data == "noise" and not args.no_natural:
+    # (one GPU by default; `--natural` asks for it at N > 1 too - there it takes the sharded exact repeat, whose chains
+    #  run rank after rank, and was not timed under torchrun this round)
+    if args.data == "noise" and not args.no_natural and (world == 1 or args.natural):
         host_band.numpy()[:] = natural_band(bx, ys, rank * bx).reshape(-1)
         n_steps = min(args.steps, 3)
         ms_nr, reps_n, _, _, _, d_nat = timed("resident", n_steps, 3)
@@ -685,6 +687,7 @@ def main():
                          "peer-memory all-reduce")
     ap.add_argument("--no-cpp", action="store_true", help="skip the C++ CompressedImage::compress end-to-end leg")
     ap.add_argument("--no-natural", action="store_true", help="skip the natural-image leg")
+    ap.add_argument("--natural", action="store_true", help="run the natural-image leg under torchrun (N > 1) as well")
     ap.add_argument("--centroids", default="auto", choices=["auto", "integer"],
                     help="auto (the library's default): integer-sum centroids, repeated with the reference's compensated sums "
                          "when the train had tie-sensitive decisions; integer: integer sums only")
