@@ -10,6 +10,6 @@ from .quantizer import (AbstractQuantizer, LBGQuantizer, Quantizers, getQuantize
                         vectors_to_lattice_bytes)
 from .compressor import (ColorSpaces, CompressedImage, CompressionRaport,
                          getBlocksAsVectorsFromImage, getImageFromVectors,
-                         pack_indices, unpack_indices, vectorsToCharVectorsColorSpaced)
+                         pack_indices, unpack_indices, huffman_lengths, huffman_encode, huffman_decode, vectorsToCharVectorsColorSpaced)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -44,6 +44,105 @@ def unpack_indices(stream, n: int, bits: int) -> np.ndarray:
     b = np.unpackbits(np.asarray(stream, np.uint8), bitorder="little")[:n * bits].reshape(n, bits).astype(np.uint64)
     return (b << np.arange(bits, dtype=np.uint64)[None, :]).sum(1).astype(np.uint64)
 
+MAX_CODE_LEN = 32
+
+
+def huffman_lengths(counts) -> np.ndarray:
+    """Code lengths (0 for unused symbols, at most MAX_CODE_LEN) of a Huffman code for `counts`."""
+    import heapq
+    counts = np.asarray(counts, np.uint64)
+    length = np.zeros(counts.size, np.uint8)
+    used = np.nonzero(counts)[0]
+    if used.size == 0:
+        return length
+    if used.size == 1:
+        length[used[0]] = 1
+        return length
+    heap = [(int(counts[k]), i, None) for i, k in enumerate(used)]   # (weight, tie-break, children)
+    heapq.heapify(heap)
+    parent, nxt = {}, used.size
+    while len(heap) > 1:
+        a = heapq.heappop(heap)
+        b = heapq.heappop(heap)
+        parent[a[1]] = parent[b[1]] = nxt
+        heapq.heappush(heap, (a[0] + b[0], nxt, None))
+        nxt += 1
+    depth = {}
+    for node in range(nxt - 1, -1, -1):          # parents carry larger numbers than their children
+        depth[node] = 0 if node not in parent else depth[parent[node]] + 1
+    for i, k in enumerate(used):
+        length[k] = min(depth[i], MAX_CODE_LEN)
+    kraft = sum(1 << (MAX_CODE_LEN - int(l)) for l in length[used])
+    while kraft > (1 << MAX_CODE_LEN):           # lengthen the longest codes still short of the limit
+        cand = used[length[used] < MAX_CODE_LEN]
+        k = cand[np.argmax(length[cand])]
+        kraft -= 1 << (MAX_CODE_LEN - int(length[k]) - 1)
+        length[k] += 1
+    return length
+
+
+def canonical_codes(length):
+    """(code per symbol, symbols sorted by (length, index), first_code / first_pos / count per length)."""
+    length = np.asarray(length, np.int64)
+    if length.size and length.max() > MAX_CODE_LEN:
+        raise ValueError("code length out of range")
+    n_of = np.bincount(length, minlength=MAX_CODE_LEN + 2)
+    n_of[0] = 0
+    first_code = np.zeros(MAX_CODE_LEN + 2, np.int64)
+    first_pos = np.zeros(MAX_CODE_LEN + 2, np.int64)
+    code = pos = 0
+    for l in range(1, MAX_CODE_LEN + 1):
+        code <<= 1
+        first_code[l], first_pos[l] = code, pos
+        code += int(n_of[l])
+        pos += int(n_of[l])
+        if code > (1 << l):
+            raise ValueError("code lengths oversubscribed")
+    used = np.nonzero(length)[0]
+    order = used[np.lexsort((used, length[used]))]
+    codes = np.zeros(length.size, np.int64)
+    rank = np.arange(order.size) - first_pos[length[order]]
+    codes[order] = first_code[length[order]] + rank
+    return codes, order, first_code, first_pos, n_of
+
+
+def huffman_encode(indices, length) -> np.ndarray:
+    """The indices as canonical Huffman codes, MSB first, zero padded to a whole byte."""
+    a = np.asarray(indices, np.int64)
+    length = np.asarray(length, np.int64)
+    codes, _, _, _, _ = canonical_codes(length)
+    ls, cs = length[a], codes[a]
+    if a.size and ls.min() == 0:
+        raise ValueError("an index without a code")
+    start = np.concatenate([[0], np.cumsum(ls)[:-1]]) if a.size else np.zeros(0, np.int64)
+    total = int(ls.sum())
+    bits = np.zeros(((total + 7) // 8) * 8, np.uint8)
+    for b in range(int(ls.max()) if a.size else 0):
+        m = ls > b
+        bits[start[m] + b] = (cs[m] >> (ls[m] - 1 - b)) & 1
+    return np.packbits(bits)
+
+
+def huffman_decode(stream, n: int, length) -> np.ndarray:
+    length = np.asarray(length, np.int64)
+    _, order, first_code, first_pos, n_of = canonical_codes(length)
+    bits = np.unpackbits(np.asarray(stream, np.uint8)).tolist()
+    fc, fp, cnt, out, at = first_code.tolist(), first_pos.tolist(), n_of.tolist(), np.zeros(n, np.uint64), 0
+    order = order.tolist()
+    for i in range(n):
+        code = l = 0
+        while True:
+            if at >= len(bits) or l >= MAX_CODE_LEN:
+                raise ValueError("corrupt entropy-coded index stream")
+            code = (code << 1) | bits[at]
+            at += 1
+            l += 1
+            if cnt[l] and 0 <= code - fc[l] < cnt[l]:
+                break
+        out[i] = order[fp[l] + code - fc[l]]
+    return out
+
+
 
 def _block_index_map(xSize: int, ySize: int, w: int, h: int):
     """img index of every (vector, pixel-in-block) pair: (N, w*h) int64, per src/Compressor.cpp:44-50."""
@@ -196,9 +295,25 @@ class CompressedImage:
                                                self.xSize, self.ySize, self.blockWidth, self.blockHeight)
         return hdr + np.ascontiguousarray(self.codeVectors, np.uint8).tobytes() + pack_indices(self.assignedCodeVector, bits).tobytes()
 
+    def to_bytes_entropy(self) -> bytes:
+        """Extension (`quant --entropy`): header "QH1 ... <stream bytes>", codebook, one code length per codevector, and
+        the indices as canonical Huffman codes of their own histogram (quant_b200/host/src/Compressor.cpp)."""
+        K = len(self.codeVectors)
+        bits = _smallest_pow2(K)
+        a = np.asarray(self.assignedCodeVector, np.int64)
+        length = huffman_lengths(np.bincount(a, minlength=K))
+        stream = huffman_encode(a, length)
+        hdr = b"QH1 %d %d %d %d %d %d %d %d\n" % (bits, int(self.colorSpace), a.size, self.xSize, self.ySize,
+                                                  self.blockWidth, self.blockHeight, stream.size)
+        return hdr + np.ascontiguousarray(self.codeVectors, np.uint8).tobytes() + length.tobytes() + stream.tobytes()
+
     def saveToFile(self, path: str):
         with open(path, "wb") as f:
             f.write(self.to_bytes())
+
+    def saveToFileEntropy(self, path: str):
+        with open(path, "wb") as f:
+            f.write(self.to_bytes_entropy())
 
     def saveToFilePacked(self, path: str):
         with open(path, "wb") as f:
@@ -209,10 +324,10 @@ class CompressedImage:
             data = f.read()
         nl = data.index(b"\n")
         fields = data[:nl].split()
-        packed = fields[0] == b"QP1"
-        if packed:
+        packed, entropy = fields[0] == b"QP1", fields[0] == b"QH1"
+        if packed or entropy:
             fields = fields[1:]
-        bits, cs, n, xs, ys, bw, bh = (int(t) for t in fields)
+        bits, cs, n, xs, ys, bw, bh = (int(t) for t in fields[:7])
         self.xSize, self.ySize, self.blockWidth, self.blockHeight = xs, ys, bw, bh
         try:
             self.colorSpace = ColorSpaces(cs)
@@ -222,6 +337,11 @@ class CompressedImage:
         pos = nl + 1
         self.codeVectors = np.frombuffer(data, np.uint8, K * dim, pos).reshape(K, dim).copy()
         pos += K * dim
+        if entropy:
+            length = np.frombuffer(data, np.uint8, K, pos)
+            stream = np.frombuffer(data, np.uint8, int(fields[7]), pos + K)
+            self.assignedCodeVector = huffman_decode(stream, n, length)
+            return
         if packed:
             stream = np.frombuffer(data, np.uint8, (n * bits + 7) // 8, pos)
             self.assignedCodeVector = unpack_indices(stream, n, bits)

@@ -52,6 +52,10 @@ class CompressedImage {
   // starts with "QP1 " so that the two cannot be confused.  Index i occupies stream bits [i*bits, (i+1)*bits),
   // LSB first - exactly the size sizeInBits() has always reported.
   void saveToFilePacked(const std::string &path);
+  // Extension (`quant --entropy`): header "QH1 ..." and the indices as canonical Huffman codes of their own histogram
+  // (code lengths stored per codevector) - smaller than the packed container wherever some cells are much more
+  // populated than others (flat areas of natural images); see Compressor.cpp for the layout.
+  void saveToFileEntropy(const std::string &path);
   size_t sizeInBits();                         // bit-packed size estimate the report uses
 };
 

@@ -21,6 +21,7 @@ struct ProgramParameters {
 
   // --- extension, not in the reference ---------------------------------------------------------------------
   bool pack;           // --pack : write the bit-packed .quant container (Compressor.hpp)      (default false)
+  bool entropy;        // --entropy : write the Huffman-coded .quant container                 (default false)
 };
 
 // The process-wide instance, and a reset to the defaults listed above.

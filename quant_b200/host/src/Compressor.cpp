@@ -7,6 +7,7 @@
 // for reading and writing files; none of them is on the accelerated path.
 #include "Compressor.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -233,18 +234,149 @@ void CompressedImage::saveToFilePacked(const std::string &path) {
   out.write(reinterpret_cast<const char *>(stream.data()), (std::streamsize)stream.size());
 }
 
+// Entropy-coded container (extension; `quant --entropy`):
+//   "QH1 <bits> <colorSpace> <N> <xSize> <ySize> <blockW> <blockH> <stream bytes>\n", K * dim codebook bytes, K bytes
+//   of code lengths (0: index never used), then the indices as canonical Huffman codes, MSB first, zero padded to a byte.
+// Canonical: symbols ordered by (length, index); the first code of the shortest length is 0, each next code is the
+// previous + 1, shifted left when the length grows - so the lengths alone define the code.
+namespace {
+
+constexpr int kMaxCodeLen = 32;
+
+// Huffman code lengths for the given counts (0 for unused symbols), limited to kMaxCodeLen.
+std::vector<unsigned char> huffman_lengths(const std::vector<unsigned long long> &count) {
+  const size_t K = count.size();
+  std::vector<unsigned char> len(K, 0);
+  struct Node {
+    unsigned long long w;
+    int parent;
+  };
+  std::vector<Node> nodes;
+  std::vector<int> leaf_of;  // node index -> symbol (leaves first)
+  for (size_t k = 0; k < K; k++)
+    if (count[k]) {
+      nodes.push_back({count[k], -1});
+      leaf_of.push_back((int)k);
+    }
+  const size_t n_leaves = nodes.size();
+  if (n_leaves == 0) return len;
+  if (n_leaves == 1) {
+    len[(size_t)leaf_of[0]] = 1;
+    return len;
+  }
+  // two-queue construction: leaves sorted by weight, internal nodes are created in non-decreasing weight order
+  std::vector<int> order(n_leaves);
+  for (size_t i = 0; i < n_leaves; i++) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nodes[(size_t)a].w < nodes[(size_t)b].w; });
+  size_t qa = 0, qb = n_leaves;  // next unused leaf (in `order`), next unused internal node (index into nodes)
+  auto take = [&]() {
+    const bool leaf = qa < n_leaves && (qb >= nodes.size() || nodes[(size_t)order[qa]].w <= nodes[qb].w);
+    return leaf ? order[qa++] : (int)qb++;
+  };
+  while ((n_leaves - qa) + (nodes.size() - qb) > 1) {
+    const int a = take(), b = take();
+    nodes.push_back({nodes[(size_t)a].w + nodes[(size_t)b].w, -1});
+    nodes[(size_t)a].parent = nodes[(size_t)b].parent = (int)nodes.size() - 1;
+  }
+  std::vector<int> depth(nodes.size(), 0);
+  for (size_t i = nodes.size() - 1; i-- > 0;) depth[i] = depth[(size_t)nodes[i].parent] + 1;  // parents have larger indices
+  for (size_t i = 0; i < n_leaves; i++) len[(size_t)leaf_of[i]] = (unsigned char)std::min(depth[i], 255);
+  // length limit: clamp, then lengthen the longest codes that are still short of the limit until Kraft's sum fits
+  unsigned long long kraft = 0;  // in units of 2^-kMaxCodeLen
+  for (size_t k = 0; k < K; k++)
+    if (len[k]) {
+      if (len[k] > kMaxCodeLen) len[k] = kMaxCodeLen;
+      kraft += 1ull << (kMaxCodeLen - len[k]);
+    }
+  while (kraft > (1ull << kMaxCodeLen)) {
+    size_t best = K;
+    for (size_t k = 0; k < K; k++)
+      if (len[k] && len[k] < kMaxCodeLen && (best == K || len[k] > len[best])) best = k;
+    if (best == K) throw std::logic_error("huffman_lengths: cannot limit the code length");
+    kraft -= 1ull << (kMaxCodeLen - len[best] - 1);
+    len[best]++;
+  }
+  return len;
+}
+
+// canonical codes from lengths; first_code / first_pos / n_of per length serve the decoder
+struct CanonicalCode {
+  std::vector<unsigned int> code;     // per symbol
+  std::vector<unsigned int> sorted;   // symbols by (length, index)
+  unsigned long long first_code[kMaxCodeLen + 2];
+  size_t first_pos[kMaxCodeLen + 2], n_of[kMaxCodeLen + 2];
+};
+CanonicalCode canonical_code(const std::vector<unsigned char> &len) {
+  CanonicalCode c;
+  c.code.assign(len.size(), 0);
+  for (int l = 0; l <= kMaxCodeLen + 1; l++) c.first_code[l] = c.first_pos[l] = c.n_of[l] = 0;
+  for (unsigned char l : len) {
+    if (l > kMaxCodeLen) throw std::runtime_error("entropy container: code length out of range");
+    c.n_of[l]++;
+  }
+  c.n_of[0] = 0;
+  unsigned long long code = 0;
+  size_t pos = 0;
+  for (int l = 1; l <= kMaxCodeLen; l++) {
+    code <<= 1;
+    c.first_code[l] = code;
+    c.first_pos[l] = pos;
+    code += c.n_of[l];
+    pos += c.n_of[l];
+    if (code > (1ull << l)) throw std::runtime_error("entropy container: code lengths oversubscribed");
+  }
+  c.sorted.assign(pos, 0);
+  std::vector<size_t> next(c.first_pos, c.first_pos + kMaxCodeLen + 2);
+  for (size_t k = 0; k < len.size(); k++)
+    if (len[k]) {
+      c.code[k] = (unsigned int)(c.first_code[len[k]] + (next[len[k]] - c.first_pos[len[k]]));
+      c.sorted[next[len[k]]++] = (unsigned int)k;
+    }
+  return c;
+}
+
+}  // namespace
+
+void CompressedImage::saveToFileEntropy(const std::string &path) {
+  std::ofstream out(path, std::ios::binary);
+  if (!out) throw std::runtime_error("cannot write " + path);
+  const size_t K = codeVectors.size(), bits = index_bits(K), n = assignedCodeVector.size();
+  std::vector<unsigned long long> count(K, 0);
+  for (size_t idx : assignedCodeVector) count.at(idx)++;
+  const std::vector<unsigned char> len = huffman_lengths(count);
+  const CanonicalCode cc = canonical_code(len);
+  unsigned long long total_bits = 0;
+  for (size_t k = 0; k < K; k++) total_bits += count[k] * len[k];
+  std::vector<unsigned char> stream((size_t)((total_bits + 7) / 8), 0);
+  unsigned long long at = 0;
+  for (size_t idx : assignedCodeVector) {
+    const unsigned int code = cc.code[idx];
+    for (int b = len[idx] - 1; b >= 0; b--, at++)
+      if ((code >> b) & 1u) stream[(size_t)(at >> 3)] |= (unsigned char)(0x80u >> (at & 7));
+  }
+  out << "QH1 " << bits << " " << (int)colorSpace << " " << n << " " << xSize << " " << ySize << " " << blockWidth << " "
+      << blockHeight << " " << stream.size() << "\n";
+  for (const CharVector &c : codeVectors) out.write(c.data(), (std::streamsize)c.size());
+  out.write(reinterpret_cast<const char *>(len.data()), (std::streamsize)len.size());
+  out.write(reinterpret_cast<const char *>(stream.data()), (std::streamsize)stream.size());
+}
+
 void CompressedImage::loadFromFile(const std::string &path) {
   std::ifstream in(path, std::ios::binary);
   if (!in) throw std::runtime_error("cannot open " + path);
   size_t bits = 0, n = 0;
   long long cs = 0;
-  const bool packed = in.peek() == 'Q';
-  if (packed) {
+  bool packed = false, entropy = false;
+  size_t stream_bytes = 0;
+  if (in.peek() == 'Q') {
     std::string magic;
     in >> magic;
-    if (magic != "QP1") throw std::runtime_error(path + ": unknown container " + magic);
+    packed = magic == "QP1";
+    entropy = magic == "QH1";
+    if (!packed && !entropy) throw std::runtime_error(path + ": unknown container " + magic);
   }
   in >> bits >> cs >> n >> xSize >> ySize >> blockWidth >> blockHeight;
+  if (entropy) in >> stream_bytes;
   if (!in || bits > 24 || blockWidth == 0 || blockHeight == 0) throw std::runtime_error(path + ": bad .quant header");
   in.get();  // '\n'
   // files written by the reference carry an uninitialised value in this field; decoding never uses it
@@ -252,6 +384,29 @@ void CompressedImage::loadFromFile(const std::string &path) {
   const size_t K = (size_t)1 << bits, dim = blockWidth * blockHeight * 3, bpi = ceil_div(bits, 8);
   codeVectors.assign(K, CharVector(dim));
   for (CharVector &c : codeVectors) in.read(c.data(), (std::streamsize)dim);
+  if (entropy) {
+    std::vector<unsigned char> len(K), stream(stream_bytes);
+    in.read(reinterpret_cast<char *>(len.data()), (std::streamsize)K);
+    in.read(reinterpret_cast<char *>(stream.data()), (std::streamsize)stream_bytes);
+    if (!in) throw std::runtime_error(path + ": truncated .quant file");
+    const CanonicalCode cc = canonical_code(len);
+    assignedCodeVector.assign(n, 0);
+    const unsigned long long avail = (unsigned long long)stream_bytes * 8;
+    unsigned long long at = 0;
+    for (size_t i = 0; i < n; i++) {
+      unsigned long long code = 0;
+      int l = 0;
+      for (;;) {
+        if (at >= avail || l >= kMaxCodeLen) throw std::runtime_error(path + ": corrupt entropy-coded index stream");
+        code = (code << 1) | ((stream[(size_t)(at >> 3)] >> (7 - (at & 7))) & 1u);
+        at++;
+        l++;
+        if (cc.n_of[l] && code >= cc.first_code[l] && code - cc.first_code[l] < cc.n_of[l]) break;
+      }
+      assignedCodeVector[i] = cc.sorted[cc.first_pos[l] + (size_t)(code - cc.first_code[l])];
+    }
+    return;
+  }
   std::vector<unsigned char> raw(packed ? ceil_div(n * bits, 8) : n * bpi);
   in.read(reinterpret_cast<char *>(raw.data()), (std::streamsize)raw.size());
   if (!in) throw std::runtime_error(path + ": truncated .quant file");

@@ -18,6 +18,7 @@ void paramsInitialize() {
   g_params.quantizer = (int)Quantizers::LBG;
   g_params.colorspace = (int)ColorSpaces::SCALED;
   g_params.pack = false;
+  g_params.entropy = false;
   g_params.file.clear();
   g_params.saveto.clear();
 }

@@ -37,7 +37,9 @@ void usage() {
                "  -r arg (=0)            Print raport to std::out\n"
                "  -q [ --quantizer ] arg (=0)  Pick quantizer\n"
                "  --c [ --colorspace ] arg (=1) Pick ColorSpace\n"
-               "  --pack                 (extension) bit-packed indices in the .quant file\n";
+               "  --pack                 (extension) bit-packed indices in the .quant file\n"
+               "  --entropy              (extension) Huffman-coded indices in the .quant file\n"
+               "                         (.quant -> .quant re-writes a file in the chosen container)\n";
 }
 
 bool parse_bool(const std::string &v) { return v == "1" || v == "true" || v == "yes" || v == "on"; }
@@ -65,6 +67,7 @@ int main(int argc, char **argv) {
       else if (a == "-q" || a == "--quantizer") par->quantizer = std::stoi(value());
       else if (a == "--c" || a == "--colorspace") par->colorspace = std::stoi(value());
       else if (a == "--pack") par->pack = true;
+      else if (a == "--entropy") par->entropy = true;
       else if (!a.empty() && a[0] == '-') throw std::runtime_error("unrecognised option '" + a + "'");
       else par->file = a;  // positional: the input file
     }
@@ -89,7 +92,15 @@ int main(int argc, char **argv) {
       CompressedImage::decompress(c).saveToFile(par->saveto);
     } else if (from == FileType::PPM && to == FileType::QUANT) {
       CompressedImage c = run_compression();
-      if (par->pack) c.saveToFilePacked(par->saveto); else c.saveToFile(par->saveto);
+      if (par->entropy) c.saveToFileEntropy(par->saveto);
+      else if (par->pack) c.saveToFilePacked(par->saveto);
+      else c.saveToFile(par->saveto);
+    } else if (from == FileType::QUANT && to == FileType::QUANT) {  // (extension) re-write in another container: host only
+      CompressedImage c;
+      c.loadFromFile(par->file);
+      if (par->entropy) c.saveToFileEntropy(par->saveto);
+      else if (par->pack) c.saveToFilePacked(par->saveto);
+      else c.saveToFile(par->saveto);
     } else {
       std::cerr << "File type not supported" << std::endl;
       return 1;

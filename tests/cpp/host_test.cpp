@@ -1,6 +1,8 @@
 // C++ checks of the drop-in host layer, written like the reference's only unit test
 // (/root/reference/src/test.cpp:5-62, compressor_test.something) plus the plugin entry on a GPU.
 //   host_test layout                CPU only: block -> vector -> char vector -> image round trips
+//   host_test entropy <tmp.quant>   CPU only: the Huffman-coded container on an index histogram whose optimal code is
+//                                   deeper than the 32-bit limit (Fibonacci counts), on a one-symbol and an empty image
 //   host_test quantize <in.ppm> w h n [cs]  needs a B200: getQuantizer(LBG)->quantize(vectors) must agree with
 //                                   CompressedImage::compress(image) (codebook bytes, indices)
 //   host_test multi xs ys w h n ndev [exact]  needs ndev B200s: one image trained on ONE device and on a
@@ -26,6 +28,46 @@ static int failures = 0;
       failures++;                                                           \
     }                                                                       \
   } while (0)
+
+// saveToFileEntropy / loadFromFile round trips where the code-length limit matters.
+static int test_entropy(const char *path) {
+  auto roundtrip = [&](CompressedImage &c) {
+    c.saveToFileEntropy(path);
+    CompressedImage b;
+    b.loadFromFile(path);
+    EXPECT(b.assignedCodeVector == c.assignedCodeVector);
+    EXPECT(b.codeVectors == c.codeVectors);
+    EXPECT(b.xSize == c.xSize && b.ySize == c.ySize && b.blockWidth == c.blockWidth && b.blockHeight == c.blockHeight);
+  };
+  CompressedImage c;
+  c.blockWidth = c.blockHeight = 1;
+  c.colorSpace = ColorSpaces::SCALED;
+  c.quantizer = Quantizers::LBG;
+  c.codeVectors.assign(64, CharVector(3));
+  for (size_t k = 0; k < 64; k++) c.codeVectors[k][0] = (char)k;
+  // Fibonacci counts for 35 of the 64 codevectors: the unrestricted Huffman tree is a 34-deep comb
+  size_t fa = 1, fb = 1;
+  for (size_t k = 0; k < 35; k++) {
+    c.assignedCodeVector.insert(c.assignedCodeVector.end(), fa, k + 3);
+    const size_t next = fa + fb;
+    fa = fb;
+    fb = next;
+  }
+  c.xSize = c.assignedCodeVector.size();
+  c.ySize = 1;
+  // interleave a little so that long and short codes alternate in the stream
+  for (size_t i = 0; i + 1 < c.assignedCodeVector.size(); i += 97) std::swap(c.assignedCodeVector[i], c.assignedCodeVector[c.assignedCodeVector.size() - 1 - i]);
+  roundtrip(c);
+  CompressedImage one = c;   // a single used codevector: one-bit codes
+  one.assignedCodeVector.assign(1000, 17);
+  one.xSize = 1000;
+  roundtrip(one);
+  CompressedImage none = c;  // no blocks at all
+  none.assignedCodeVector.clear();
+  none.xSize = 0;
+  roundtrip(none);
+  return failures;
+}
 
 static int test_layout() {
   // 4x4 image of letters, ColorSpaces::NORMAL; 1x3 exercises the y-overflow wrap
@@ -158,6 +200,7 @@ int main(int argc, char **argv) {
       return test_multi(std::atoi(argv[2]), std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6]),
                         std::atoi(argv[7]), argc >= 9 ? std::atoi(argv[8]) : 0) ? 1 : (std::puts("multi ok"), 0);
     if (argc >= 2 && std::strcmp(argv[1], "layout") == 0) return test_layout() ? 1 : (std::puts("layout ok"), 0);
+    if (argc >= 3 && std::strcmp(argv[1], "entropy") == 0) return test_entropy(argv[2]) ? 1 : (std::puts("entropy ok"), 0);
     if (argc >= 6 && std::strcmp(argv[1], "quantize") == 0)
       return test_quantize(argv[2], std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]),
                            argc >= 7 ? (ColorSpaces)std::atoi(argv[6]) : ColorSpaces::SCALED) ? 1

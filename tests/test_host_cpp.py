@@ -157,6 +157,63 @@ def test_packed_container_roundtrip_and_cross_reading(host_built, tmp_path):
         assert s.size == (1001 * bits + 7) // 8 and np.array_equal(qb.unpack_indices(s, 1001, bits), a)
 
 
+def test_entropy_container_code_length_limit_in_cpp(host_built, tmp_path):
+    """Fibonacci index counts (optimal Huffman depth 34 > the 32-bit limit), a single used codevector, an empty image."""
+    out = subprocess.run([HOST_TEST, "entropy", str(tmp_path / "e.quant")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_entropy_container_roundtrip_and_cross_reading(host_built, tmp_path):
+    """Extension (second half): the Huffman-coded .quant container "QH1".  Python writes / C++ reads
+    and decodes, C++ re-writes a plain file as QH1 (`quant a.quant -o b.quant --entropy`, host code only) / Python
+    reads; both decode to the reference's image; the index payload is within 1 % + 1 byte of the indices' empirical
+    entropy and smaller than the bit-packed container on a natural image."""
+    import quant_b200 as qb
+    g = load_golden("kodim01_crop_2x2_n10")
+    ci = qb.CompressedImage()
+    ci.codeVectors, ci.assignedCodeVector = g.z["codebook_bytes"], g.z["assign"].astype(np.uint64)
+    ci.xSize, ci.ySize, ci.blockWidth, ci.blockHeight, ci.colorSpace = g.xs, g.ys, g.w, g.h, qb.ColorSpaces.SCALED
+    plain, packed, coded = ci.to_bytes(), ci.to_bytes_packed(), ci.to_bytes_entropy()
+    assert coded.startswith(b"QH1 10 ") and len(coded) < len(packed) < len(plain)
+    a = ci.assignedCodeVector.astype(np.int64)
+    p = np.bincount(a, minlength=1024) / a.size
+    entropy_bits = float(-(p[p > 0] * np.log2(p[p > 0])).sum()) * a.size
+    payload = int(coded[:coded.index(b"\n")].split()[-1])
+    assert entropy_bits / 8 <= payload <= 1.01 * entropy_bits / 8 + 1 + a.size / 8     # Huffman: < 1 bit per index above
+    f_plain, f_py, f_cpp, out = (str(tmp_path / n) for n in ("a.quant", "py.quant", "cpp.quant", "o.ppm"))
+    open(f_plain, "wb").write(plain)
+    ci.saveToFileEntropy(f_py)
+    back = qb.CompressedImage()
+    back.loadFromFile(f_py)
+    assert np.array_equal(back.assignedCodeVector, ci.assignedCodeVector) and np.array_equal(back.codeVectors, ci.codeVectors)
+    r = subprocess.run([QUANT, f_py, "-o", out], capture_output=True, text=True)            # C++ decodes the Python-written file
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(ppm_payload(out, g.xs, g.ys)).hexdigest() == str(g.z["decoded_sha"])
+    r = subprocess.run([QUANT, f_plain, "-o", f_cpp, "--entropy"], capture_output=True, text=True)   # C++ writes QH1
+    assert r.returncode == 0, r.stderr
+    assert open(f_cpp, "rb").read(4) == b"QH1 " and os.path.getsize(f_cpp) < len(packed)
+    back2 = qb.CompressedImage()
+    back2.loadFromFile(f_cpp)                                                              # Python reads the C++-written file
+    assert np.array_equal(back2.assignedCodeVector, ci.assignedCodeVector) and np.array_equal(back2.codeVectors, ci.codeVectors)
+    f_back = str(tmp_path / "back.quant")
+    r = subprocess.run([QUANT, f_cpp, "-o", f_back], capture_output=True, text=True)       # ... and C++ turns it back into
+    assert r.returncode == 0, r.stderr                                                     # the reference's container
+    assert hashlib.sha256(open(f_back, "rb").read()).hexdigest() == str(g.z["quant_sha"])
+    # degenerate histograms: one symbol only, two symbols, a long geometric tail (length limit), empty
+    for counts in ([0, 7, 0, 0], [3, 0, 9, 0], [2 ** i for i in range(40)], [0, 0]):
+        L = qb.huffman_lengths(counts)
+        assert L.max(initial=0) <= 32 and sum(2.0 ** -int(l) for l in L if l) <= 1.0
+        rng = np.random.default_rng(len(counts))
+        used = np.nonzero(counts)[0]
+        idx = rng.choice(used, 500).astype(np.uint64) if used.size else np.zeros(0, np.uint64)
+        assert np.array_equal(qb.huffman_decode(qb.huffman_encode(idx, L), idx.size, L), idx)
+    # a corrupt stream is an error, not garbage
+    bad = bytearray(coded)
+    del bad[-200:]
+    open(f_py, "wb").write(bytes(bad))
+    assert subprocess.run([QUANT, f_py, "-o", out], capture_output=True).returncode != 0
+
+
 @pytest.mark.gpu
 def test_cli_pack_flag_and_device_side_packing(host_built, tmp_path):
     import quant_b200 as qb
