@@ -158,6 +158,65 @@ def census_descent(nodes, order, inv, pts, x, cands):
     return int(order[min(pos)]), fragile
 
 
+def our_level(L, assign, K_prev):
+    """(codebook of the next split level in OUR arithmetic, reproducibility flags) from a level's assignment.
+    L: N x dim values t = 0..255 (SCALED value t / 255); assign: index per vector into K_prev cells."""
+    dim = L.shape[1]
+    cent = np.zeros((K_prev, dim))
+    flag = np.zeros(K_prev, np.uint8)
+    order = np.argsort(assign, kind="stable")
+    bounds = np.searchsorted(assign[order], np.arange(K_prev + 1))
+    for k in range(K_prev):
+        mem = L[order[bounds[k]:bounds[k + 1]]]          # members in ascending vector order
+        n = len(mem)
+        if n == 0:
+            flag[k] = 1
+        elif n <= SMALL:
+            cent[k] = kahan_mean(mem)
+            flag[k] = 1
+        elif (mem == mem[0]).all():
+            cent[k] = (float(n) * (mem[0].astype(np.float64) / 255.0)) / float(n)
+            flag[k] = 1
+        else:
+            cent[k] = (mem.sum(0).astype(np.float64) / 255.0) / float(n)
+    f_up, f_dn = 1 + 0.2, 1 - 0.2
+    return np.concatenate([cent * f_up, cent * f_dn]), np.concatenate([flag, flag])
+
+
+def check_level(lib, ours, flags, ref, queries):
+    """The three census checks on one level; returns (robust, order-safe ties checked) or raises AssertionError."""
+    same_bits = (ours.view(np.uint64) == ref.view(np.uint64)).all(axis=1)
+    assert same_bits[flags == 1].all(), "a codevector flagged reproducible differs from the reference's bits"
+    no, oo, margin = build(lib, ours, flags)
+    nr, orr, _ = build(lib, ref, None)
+    robust = margin > 1e-9
+    if robust:
+        assert same_shape(no, nr, oo, orr), f"census margin {margin:.3g} but the trees differ"
+    K = ours.shape[0]
+    inv_o = np.empty(K, np.int64)
+    inv_o[oo] = np.arange(K)
+    inv_r = np.empty(K, np.int64)
+    inv_r[orr] = np.arange(K)
+    d = ((queries[:, None, :] - ours[None, :, :]) ** 2).sum(2)
+    dmin, dmax = d.min(1), d.max(1)
+    band = d <= (dmin + dmax * 5.6843418860808015e-14)[:, None]
+    ties = 0
+    for q in np.nonzero(band.sum(1) > 1)[0]:
+        cands = np.nonzero(d[q] == dmin[q])[0]
+        in_band = np.nonzero(band[q])[0]
+        if len(cands) < 2 or len(cands) > 32 or len(cands) != len(in_band) or not flags[in_band].all():
+            continue
+        win, fragile = census_descent(no, oo, inv_o, ours, queries[q], cands)
+        if not robust or fragile:
+            continue
+        dr = np.array([l2(queries[q], c) for c in ref])
+        cr = np.nonzero(dr == dr.min())[0]
+        ref_win = int(orr[first_visited(nr, orr, queries[q], {int(inv_r[k]) for k in cr})])
+        assert ref_win == win, f"tie among {cands.tolist()} called safe: ours {win}, reference {ref_win}"
+        ties += 1
+    return robust, ties
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 30.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
