@@ -67,6 +67,11 @@ class Builder {
     const double scale = std::max(std::fabs(a), std::fabs(b));
     const double m = scale > 0 ? std::fabs(a - b) / scale : 0.0;
     if (m < out_.min_margin) out_.min_margin = m;
+    if (m < node_margin_) node_margin_ = m;
+  }
+  void no_margin() {  // a comparison that is a coin toss between the two centroid arithmetics
+    out_.min_margin = 0.0;
+    node_margin_ = 0.0;
   }
   double via(size_t pos, int d) const { return at(out_.order[pos], d); }
 
@@ -124,6 +129,7 @@ class Builder {
   size_t choose_split(size_t first, size_t count, const std::vector<Range> &box, int &feat,
                       double &cut) {
     const double kEps = static_cast<double>(0.00001);
+    node_margin_ = 1.0;  // the smallest margin of the comparisons made for THIS node (subdivide turns it into a census bit)
     double max_span = box[0].hi - box[0].lo;
     for (int d = 1; d < dim_; d++) {
       double span = box[d].hi - box[d].lo;
@@ -165,7 +171,7 @@ class Builder {
       // the data range (then the plane is that point's own coordinate and moves with it), or when point and plane
       // are both bit-reproducible numbers.
       const bool clamped = mid < mn || mid > mx;  // (not "cut == mn || cut == mx": an unclamped midpoint can coincide with an extreme)
-      if (mn == mx && mn != 0.0 && !(mn_exact && mx_exact)) out_.min_margin = 0.0;  // all points equal along the cut
+      if (mn == mx && mn != 0.0 && !(mn_exact && mx_exact)) no_margin();  // all points equal along the cut
       size_t at_cut = 0, at_cut_inexact = 0;
       for (size_t i = 0; i < count; i++) {
         const double v = via(first + i, feat);
@@ -177,11 +183,11 @@ class Builder {
         if (v != cut)
           note(v, cut);
         else if (!clamped)
-          out_.min_margin = 0.0;
+          no_margin();
       }
       // clamped plane shared by several points, not all of them bit-reproducible: in the other codebook they may sit an
       // ulp apart, and how many are <= the plane (planeSplit's second limit) changes
-      if (clamped && at_cut > 1 && at_cut_inexact > 0 && cut != 0.0) out_.min_margin = 0.0;
+      if (clamped && at_cut > 1 && at_cut_inexact > 0 && cut != 0.0) no_margin();
       if (!(mid_exact && mn_exact && mx_exact)) {  // the clamp decisions themselves (far from flipping when clamped by a lot)
         note(mid, mn);
         note(mid, mx);
@@ -223,6 +229,7 @@ class Builder {
     double cut;
     size_t nleft = choose_split(first, last - first, box, feat, cut);
     const bool cut_exact = cut_exact_;
+    const double split_margin = node_margin_;  // (the recursion below overwrites the member)
     std::vector<Range> lbox(box);
     lbox[feat].hi = cut;
     lbox[feat].hi_exact = cut_exact;
@@ -234,7 +241,7 @@ class Builder {
     // census only: are the two plane coordinates numbers both codebooks share bit for bit?  divlow is the largest
     // coordinate of the left child, divhigh the smallest of the right one (span_of: attained only by bit-reproducible
     // points, no other point within rounding noise of it).  Kept in bits 16 / 17 of the node's `a`.
-    int div_flags = 0;
+    int div_flags = split_margin <= kKdRobustMargin ? kKdNodeFragile : 0;
     if (exact_) {
       double mn, mx;
       bool mn_e, mx_e;
@@ -270,6 +277,7 @@ class Builder {
   };
   std::vector<Spread> spreads_;  // census scratch of choose_split: the eligible dimensions of the node
   bool cut_exact_ = false;      // of the plane choose_split just returned
+  double node_margin_ = 1.0;    // smallest census margin among the comparisons of the node choose_split just handled
 };
 
 }  // namespace

@@ -135,6 +135,10 @@ __device__ __forceinline__ void gather_lattice(const VecSource &s, unsigned long
 constexpr int kKdFeatMask = 0xffff;      // inner node: a & kKdFeatMask = divfeat
 constexpr int kKdDivLowExact = 1 << 16;  // inner node, census of the auto centroid mode only: divlow / divhigh is a number
 constexpr int kKdDivHighExact = 1 << 17; // the integer-sum and the compensated-sum codebooks share bit for bit
+constexpr int kKdNodeFragile = 1 << 18;  // inner node, census only: a comparison that shaped this node's split is within
+                                         // kKdRobustMargin of flipping - everything UNDER the node may be arranged differently
+                                         // in the reference's tree (nothing outside it is affected)
+constexpr double kKdRobustMargin = 1e-9;
 struct KdNode {
   int child1, child2;  // -1/-1: leaf
   int a;               // inner: divfeat (+ the two census bits above); leaf: left (first position in vind)

@@ -899,12 +899,16 @@ __global__ void __launch_bounds__(128)
         inexact2 = __reduce_add_sync(0xffffffffu, inexact2);
       }
       bool fragile = false;  // a step of the descent below within rounding noise of going the other way
+      bool path_fragile = false;  // an inner node on the way to the first-visited candidate whose split the host's census
+                                  // calls fragile (kKdNodeFragile): only what lies UNDER such a node can be arranged
+                                  // differently in the reference's tree
       const bool all_exact = __all_sync(0xffffffffu, exact);
       if (all_exact && n_cand <= 32) {
         int node = 0, lo = 0, hi = K;
         for (int guard = 0; guard < 4096; guard++) {
           const KdNode nd = tree.nodes[node];
           if (nd.child1 < 0 && nd.child2 < 0) break;
+          path_fragile = path_fragile || (nd.a & kKdNodeFragile) != 0;
           const int mid = nd.b;
           const bool in1 = my_pos != 0xffffffffu && (int)my_pos >= lo && (int)my_pos < mid;
           const bool in2 = my_pos != 0xffffffffu && (int)my_pos >= mid && (int)my_pos < hi;
@@ -950,9 +954,11 @@ __global__ void __launch_bounds__(128)
       // Sensitive to the last bits of the codebook?  Yes when a codevector in the 2^-44 band is not reproduced bit for
       // bit by the integer path.  When they all are and the minimum is attained once, no (the exact search returns
       // it).  When it is attained several times the visiting order decides: that order is the same for any codebook
-      // within a few ulps when the tree's shape is robust (KdHostTree::min_margin) and every step of the descent is.
+      // within a few ulps when every step of the descent is robust and the tree's shape is - as a whole
+      // (KdHostTree::min_margin) or at least at every node from the root to the winner's leaf: a fragile split only
+      // rearranges its own subtree, which the walk enters after the winner's unless it lies on that path.
       if (sensitive && lane == 0 && near2 > 1) {
-        const bool order_safe = tree_robust && all_exact && n_cand <= 32 && !fragile;
+        const bool order_safe = (tree_robust || !path_fragile) && all_exact && n_cand <= 32 && !fragile;
         // (Bit-reproducible candidates at DISTINCT distances inside the band are taken as decided by the exact search:
         //  it returns the smaller one unless the walk's pruning bound for that candidate's subtree is within ~2^-46 dmax
         //  of its full distance - a box corner reached along every dimension - AND the bound's plane coordinates differ

@@ -43,7 +43,7 @@ def main():
     lib = _lib.load()
     P = PortLib()
     t_end = time.time() + budget
-    trains = levels = robust = ties = bad = 0
+    trains = levels = robust = ties = bad = repeat_per_level = repeat_per_path = 0
     while time.time() < t_end:
         w, h = int(rng.integers(1, 5)), int(rng.integers(1, 5))
         if rng.random() < 0.05:
@@ -58,17 +58,22 @@ def main():
         if len(Xu) > 400:
             Xu = Xu[rng.choice(len(Xu), 400, replace=False)]
         trains += 1
+        stats = {}
         for l in range(1, len(lv)):
             ours, flags = F.our_level(L, lv[l - 1]["assign"].astype(np.int64), lv[l - 1]["K"])
             levels += 1
             try:
-                r, t = F.check_level(lib, ours, flags, lv[l]["cb_pre"], Xu)
+                r, t = F.check_level(lib, ours, flags, lv[l]["cb_pre"], Xu, stats)
                 robust += r
                 ties += t
             except AssertionError as e:
                 bad += 1
                 np.savez(f"/tmp/census_train_fail_{bad}.npz", rgb=rgb, xs=xs, ys=ys, w=w, h=h, nbits=nbits, level=l)
                 print(f"VIOLATION kind={kind} xs={xs} ys={ys} w={w} h={h} nbits={nbits} level {l}: {e}", flush=True)
+        repeat_per_level += stats.get("unsafe_per_level", 0) > 0
+        repeat_per_path += stats.get("unsafe_per_path", 0) > 0
+    print(f"trains with an order-unsafe exact tie among reproducible candidates (-> exact repeat): {repeat_per_level} under one margin "
+          f"per level, {repeat_per_path} under the per-path rule")
     print(f"census train fuzz: {trains} trains, {levels} levels ({robust} robust), {ties} order-safe ties checked, {bad} violations - seed {seed}")
     sys.exit(1 if bad else 0)
 

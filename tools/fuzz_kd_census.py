@@ -22,7 +22,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quant_b200 import _lib
 
 NODE = np.dtype([("c1", "<i4"), ("c2", "<i4"), ("a", "<i4"), ("b", "<i4"), ("lo", "<f8"), ("hi", "<f8")])
-FEAT_MASK, LOW_EXACT, HIGH_EXACT = 0xFFFF, 1 << 16, 1 << 17
+FEAT_MASK, LOW_EXACT, HIGH_EXACT, NODE_FRAGILE = 0xFFFF, 1 << 16, 1 << 17, 1 << 18
+PER_PATH = os.environ.get("KD_FUZZ_PER_PATH", "1") == "1"   # 0: the one-margin-per-level rule the per-path rule replaced
 SMALL = 8
 IGNORE_BITS = os.environ.get("KD_FUZZ_IGNORE_PLANE_BITS") == "1"   # self-test: the census as it was before the plane bits
 
@@ -130,13 +131,15 @@ def first_visited(nodes, order, x, cand_pos):
 
 
 def census_descent(nodes, order, inv, pts, x, cands):
-    """resolve_bruteforce_kernel's descent among exactly tied candidates: (winner, fragile)."""
+    """resolve_bruteforce_kernel's descent among exactly tied candidates: (winner, fragile descent step, fragile node
+    on the path from the root to the winner's leaf)."""
     pos = {int(inv[k]) for k in cands}
-    node, lo, hi, fragile = 0, 0, len(order), False
+    node, lo, hi, fragile, path_fragile = 0, 0, len(order), False, False
     while True:
         nd = nodes[node]
         if nd["c1"] < 0:
             break
+        path_fragile = path_fragile or bool(nd["a"] & NODE_FRAGILE)
         mid = int(nd["b"])
         in1 = {p for p in pos if lo <= p < mid}
         in2 = {p for p in pos if mid <= p < hi}
@@ -155,7 +158,7 @@ def census_descent(nodes, order, inv, pts, x, cands):
             node, hi, pos = int(nd["c1"]), mid, in1
         else:
             node, lo, pos = int(nd["c2"]), mid, in2
-    return int(order[min(pos)]), fragile
+    return int(order[min(pos)]), fragile, path_fragile
 
 
 def our_level(L, assign, K_prev):
@@ -183,7 +186,7 @@ def our_level(L, assign, K_prev):
     return np.concatenate([cent * f_up, cent * f_dn]), np.concatenate([flag, flag])
 
 
-def check_level(lib, ours, flags, ref, queries):
+def check_level(lib, ours, flags, ref, queries, stats=None):
     """The three census checks on one level; returns (robust, order-safe ties checked) or raises AssertionError."""
     same_bits = (ours.view(np.uint64) == ref.view(np.uint64)).all(axis=1)
     assert same_bits[flags == 1].all(), "a codevector flagged reproducible differs from the reference's bits"
@@ -206,8 +209,11 @@ def check_level(lib, ours, flags, ref, queries):
         in_band = np.nonzero(band[q])[0]
         if len(cands) < 2 or len(cands) > 32 or len(cands) != len(in_band) or not flags[in_band].all():
             continue
-        win, fragile = census_descent(no, oo, inv_o, ours, queries[q], cands)
-        if not robust or fragile:
+        win, fragile, path_fragile = census_descent(no, oo, inv_o, ours, queries[q], cands)
+        if stats is not None:   # ties the per-level rule / the per-path rule would send to the exact repeat
+            stats["unsafe_per_level"] = stats.get("unsafe_per_level", 0) + int(fragile or not robust)
+            stats["unsafe_per_path"] = stats.get("unsafe_per_path", 0) + int(fragile or not (robust or not path_fragile))
+        if fragile or not (robust or (PER_PATH and not path_fragile)):
             continue
         dr = np.array([l2(queries[q], c) for c in ref])
         cr = np.nonzero(dr == dr.min())[0]
@@ -255,8 +261,8 @@ def main():
             if len(cands) < 2 or len(cands) > 32 or not flags[np.nonzero(band)[0]].all() or (d_o[band] != dmin).any():
                 continue                                  # the census calls these sensitive without looking at the order
             ties += 1
-            win, fragile = census_descent(no, oo, inv_o, ours, x, cands)
-            if not (is_robust and not fragile):
+            win, fragile, path_fragile = census_descent(no, oo, inv_o, ours, x, cands)
+            if fragile or not (is_robust or (PER_PATH and not path_fragile)):
                 continue
             tie_safe += 1
             # the reference: its own codebook, its own tree; the tied candidates are the same numbers there
